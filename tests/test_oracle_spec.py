@@ -1,0 +1,199 @@
+"""Pins the pure-Python spec oracle against the reference's own vectors (CPU only)."""
+import random
+import pytest
+from oracle import gl_spec as S
+from oracle import sm_all
+
+P = S.P
+
+
+def test_poseidon_kats():
+    # test/poseidon.test.js:13-38 (also test/glwasm.test.js:143-187)
+    assert S.poseidon([0] * 8) == [0x3c18a9786cb0b359, 0xc4055e3364a246c3, 0x7953db0ab48808f4, 0xc71603f33a1144ca]
+    assert S.poseidon(list(range(8)), [8, 9, 10, 11]) == [
+        0xd64e1e3efc5b8e9e, 0x53666633020aaa47, 0xd40285597c6a8825, 0x613a4f81e81231d2]
+    assert S.poseidon([P - 1] * 8, [P - 1] * 4) == [
+        0xbe0085cfc57a8357, 0xd95af71847d05c09, 0xcf55a13d33c1c953, 0x95803a74f4530e82]
+
+
+def test_f3_kats():
+    # test/f3g.test.js:13-38
+    assert S.f3_mul([1, 2, 3], [4, 5, P - 1]) == [17, 23, 18]
+    a = [random.randrange(P) for _ in range(3)]
+    assert S.f3_mul(a, S.f3_inv(a)) == [1, 0, 0]
+    assert pow(S.W32, 1 << 31, P) == P - 1
+    assert S.SHIFT_INV == 2635249152773512046
+
+
+def test_ntt_roundtrip_and_definition():
+    # test/fft.test.js:16-34 (round trip) + the DFT definition
+    rnd = random.Random(1)
+    a = [rnd.randrange(P) for _ in range(16)]
+    A = S.ntt(a)
+    w = S.root_of_unity(4)
+    for k in range(16):
+        assert A[k] == sum(a[j] * pow(w, j * k, P) for j in range(16)) % P
+    assert S.intt(A) == a
+    a3 = [[rnd.randrange(P) for _ in range(3)] for _ in range(64)]
+    assert S.intt(S.ntt(a3)) == a3
+
+
+def test_extend_pol_is_coset_evaluation():
+    rnd = random.Random(2)
+    a = [rnd.randrange(P) for _ in range(8)]
+    coefs = S.intt(a)
+    ext = S.extend_pol(a, 1)
+    w = S.root_of_unity(4)
+    for j in range(16):
+        x = (S.SHIFT * pow(w, j, P)) % P
+        assert ext[j] == sum(c * pow(x, i, P) for i, c in enumerate(coefs)) % P
+
+
+def test_merkle_layout_sizes():
+    # power-of-two heights: 8h-4 words; h=1 quirk: 8 words, root = zeros
+    for k in range(1, 12):
+        assert S.merkle_n_nodes(4 << k) == 8 * (1 << k) - 4
+    assert S.merkle_n_nodes(4) == 8
+    t = S.merkelize(list(range(1, 10)), 9, 1)
+    assert S.merkle_root(t) == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("n,npols", [(256, 3), (256, 9), (33, 6), (5, 17), (2, 1)])
+def test_merkle_selfconsistency(n, npols, split):
+    # test/merklehash_p.test.js shapes incl. the non-power-of-two (33,6) case
+    buff = [i + j * 1000 for i in range(n) for j in range(npols)]
+    tree = S.merkelize(buff, npols, n, split)
+    for idx in {0, 3 % n, n - 1, n // 2}:
+        v, mp = S.get_group_proof(tree, idx)
+        assert S.verify_group_proof(S.merkle_root(tree), mp, idx, v, split)
+    with pytest.raises(IndexError):
+        S.get_group_proof(tree, n)
+
+
+def test_split_hash_shapes():
+    # widths of test/glwasm.test.js:198-230; structural checks of linearhash_gpu.js:31-67
+    for w in [0, 1, 2, 3, 4]:
+        v = list(range(1, w + 1))
+        assert S.linear_hash(v, True) == v + [0] * (4 - w)
+    v = list(range(1, 9))           # one batch of 8 -> single sponge digest, passthrough of 4 words
+    assert S.linear_hash(v, True) == S.linear_hash(v, False)
+    v = list(range(1, 51))          # batch = 13 -> 4 batches -> 16 words -> sponge
+    d = []
+    for b in range(0, 50, 13):
+        d += S.linear_hash(v[b:b + 13], False)
+    assert S.linear_hash(v, True) == S.linear_hash(d, False)
+
+
+# ------------------------------------------------------------------------------------------------
+# Golden proof: test/compressor/verifier.proof.zkin.json
+# ------------------------------------------------------------------------------------------------
+def _transcript(golden):
+    """Challenge order: test/compressor/verifier.circom:90-235 (== src/prover/prover.js:42-122)."""
+    t = S.Transcript()
+    r = golden["roots"]
+    t.put(r["const"]); t.put(golden["publics"]); t.put(r["stage1"])
+    ch = {"stage2": [t.get_field(), t.get_field()]}
+    t.put(r["stage2"])
+    ch["stage3"] = [t.get_field() for _ in range(3)]
+    t.put(r["stage3"])
+    ch["Q"] = t.get_field()
+    t.put(r["stageQ"])
+    ch["xi"] = t.get_field()
+    for e in golden["evals"]:
+        t.put(e)
+    ch["fri"] = [t.get_field(), t.get_field()]
+    steps = [t.get_field()]
+    t.put(r["fri1"]); steps.append(t.get_field())
+    t.put(r["fri2"]); steps.append(t.get_field())
+    for e in golden["final_pol"]:
+        t.put(e)
+    steps.append(t.get_field())
+    ch["fri_steps"] = steps
+    t2 = S.Transcript()
+    t2.put(steps[3])
+    ch["queries"] = t2.get_permutations(8, 11)
+    return ch
+
+
+def test_golden_transcript_queries(golden):
+    assert _transcript(golden)["queries"] == [891, 1628, 1228, 1991, 1856, 415, 833, 296]
+
+
+def test_golden_root1_and_rootC(golden):
+    buff, w = sm_all.committed_trace((1, 2))
+    assert buff[(sm_all.N - 1) * w + 0] == golden["publics"][2] == 74469561660084004
+    ext = S.interpolate(buff, w, 10, 11)
+    tree1 = S.merkelize(ext, w, 2048)
+    assert S.merkle_root(tree1) == golden["roots"]["stage1"]
+    cbuff, cw = sm_all.constant_trace()
+    cext = S.interpolate(cbuff, cw, 10, 11)
+    treec = S.merkelize(cext, cw, 2048)
+    assert S.merkle_root(treec) == golden["roots"]["const"]
+    # the opened rows and paths of the proof are exactly what get_group_proof returns
+    q = _transcript(golden)["queries"]
+    for k, idx in enumerate(q):
+        v, mp = S.get_group_proof(tree1, idx)
+        assert v == golden["layer0"]["stage1"]["rows"][k]
+        assert mp == golden["layer0"]["stage1"]["siblings"][k]
+        v, mp = S.get_group_proof(treec, idx)
+        assert v == golden["layer0"]["const"]["rows"][k]
+        assert mp == golden["layer0"]["const"]["siblings"][k]
+
+
+def test_golden_all_merkle_paths(golden):
+    q = _transcript(golden)["queries"]
+    for name in ["const", "stage1", "stage2", "stage3", "stageQ"]:
+        for k, idx in enumerate(q):
+            assert S.verify_group_proof(golden["roots"][name], golden["layer0"][name]["siblings"][k], idx,
+                                        golden["layer0"][name]["rows"][k])
+    for k, idx in enumerate(q):
+        assert S.verify_group_proof(golden["roots"]["fri1"], golden["fri1"]["siblings"][k], idx % 128,
+                                    golden["fri1"]["rows"][k])
+        assert S.verify_group_proof(golden["roots"]["fri2"], golden["fri2"]["siblings"][k], idx % 8,
+                                    golden["fri2"]["rows"][k])
+
+
+def test_golden_fri_fold_links(golden):
+    # fri.js:107-174 on the fixture: s1 group --challenge[1]--> element of s2 group --challenge[2]--> finalPol
+    ch = _transcript(golden)
+    q = ch["queries"]
+    steps = [11, 7, 3]
+    for k, q0 in enumerate(q):
+        g1 = [golden["fri1"]["rows"][k][3 * i:3 * i + 3] for i in range(16)]
+        q1 = q0 % 128
+        shift1 = S.SHIFT                                            # polBits = 11, no squaring yet
+        ev = S.fri_verify_fold(g1, steps[0], shift1, ch["fri_steps"][1], q1)
+        g2 = [golden["fri2"]["rows"][k][3 * i:3 * i + 3] for i in range(16)]
+        q2 = q1 % 8
+        assert g2[q1 // 8] == ev
+        shift2 = pow(S.SHIFT, 1 << 4, P)                            # squared (11-7) times
+        ev2 = S.fri_verify_fold(g2, steps[1], shift2, ch["fri_steps"][2], q2)
+        assert golden["final_pol"][q2] == ev2
+
+
+def test_fri_fold_prover_matches_verifier():
+    # prover-side fold (fri.js:22-81) against the verifier-side link on a synthetic chain
+    rnd = random.Random(5)
+    steps = [8, 5, 2]
+    pol = [[rnd.randrange(P) for _ in range(3)] for _ in range(256)]
+    ch = [[rnd.randrange(P) for _ in range(3)] for _ in range(3)]
+    r0 = S.fri_fold(steps, 0, pol, ch[0])
+    assert r0["pol"] == pol
+    r1 = S.fri_fold(steps, 1, r0["pol"], ch[1])
+    r2 = S.fri_fold(steps, 2, r1["pol"], ch[2])
+    assert r2["tree"] is None and len(r2["proof"]) == 4
+    for q0 in [0, 7, 100, 255]:
+        q1 = q0 % 32
+        v, mp = S.get_group_proof(r0["tree"], q1)
+        assert S.verify_group_proof(r0["proof"]["root"], mp, q1, v)
+        grp = [v[3 * i:3 * i + 3] for i in range(8)]
+        assert grp == [pol[q1 + 32 * j] for j in range(8)]
+        ev = S.fri_verify_fold(grp, 8, S.SHIFT, ch[1], q1)
+        assert ev == r1["pol"][q1]
+        q2 = q1 % 4
+        v2, mp2 = S.get_group_proof(r1["tree"], q2)
+        grp2 = [v2[3 * i:3 * i + 3] for i in range(8)]
+        assert grp2[q1 // 4] == ev
+        ev2 = S.fri_verify_fold(grp2, 5, pow(S.SHIFT, 8, P), ch[2], q2)
+        assert ev2 == r2["pol"][q2]
