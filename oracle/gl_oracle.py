@@ -1,0 +1,111 @@
+"""ctypes front-end of the C oracle (oracle/gl_oracle.c).  TEST INFRASTRUCTURE ONLY."""
+import ctypes, os, pathlib, subprocess
+import numpy as np
+
+_DIR = pathlib.Path(__file__).resolve().parent
+_SO = _DIR / "_build" / "libgloracle.so"
+_U64P = ctypes.POINTER(ctypes.c_uint64)
+
+
+def build(force=False):
+    src = _DIR / "gl_oracle.c"
+    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+        # -march=native is avoided: the .so is built in one container and also used on the GPU box
+        subprocess.check_call(["make", "-C", str(_DIR), "CFLAGS=-O3 -fPIC -Wall -Wextra -pthread"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(str(_SO))
+        L.orc_ntt.argtypes = [_U64P, _U64P, ctypes.c_uint64, ctypes.c_uint, ctypes.c_int, ctypes.c_int]
+        L.orc_lde.argtypes = [_U64P, _U64P, ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint, ctypes.c_int]
+        L.orc_poseidon_perm.argtypes = [_U64P, _U64P]
+        L.orc_poseidon_perm.restype = None
+        L.orc_linear_hash.argtypes = [_U64P, ctypes.c_uint64, ctypes.c_int, _U64P]
+        L.orc_linear_hash.restype = None
+        L.orc_merkle_nnodes.argtypes = [ctypes.c_uint64]
+        L.orc_merkle_nnodes.restype = ctypes.c_uint64
+        L.orc_merkelize.argtypes = [_U64P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, _U64P, ctypes.c_int]
+        L.orc_group_proof.argtypes = [_U64P, _U64P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, _U64P, _U64P]
+        L.orc_fri_fold.argtypes = [_U64P, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_uint, _U64P, _U64P,
+                                   _U64P, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(_U64P)
+
+
+def _arr(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def default_threads():
+    return max(1, os.cpu_count() or 1)
+
+
+def ntt(src, n_pols, n_bits, inverse=False, threads=None):
+    src = _arr(src); dst = np.empty_like(src)
+    assert src.size == n_pols << n_bits
+    lib().orc_ntt(_p(src), _p(dst), n_pols, n_bits, int(inverse), threads or default_threads())
+    return dst
+
+
+def lde(src, n_pols, n_bits, n_bits_ext, threads=None):
+    src = _arr(src); dst = np.empty(n_pols << n_bits_ext, dtype=np.uint64)
+    assert src.size == n_pols << n_bits
+    rc = lib().orc_lde(_p(src), _p(dst), n_pols, n_bits, n_bits_ext, threads or default_threads())
+    assert rc == 0
+    return dst
+
+
+def poseidon_perm(state12):
+    s = _arr(state12); o = np.empty(12, dtype=np.uint64)
+    lib().orc_poseidon_perm(_p(s), _p(o))
+    return o
+
+
+def linear_hash(vals, split=False):
+    v = _arr(vals); o = np.empty(4, dtype=np.uint64)
+    lib().orc_linear_hash(_p(v) if v.size else None, v.size, int(split), _p(o))
+    return o
+
+
+def merkle_nnodes(height):
+    return int(lib().orc_merkle_nnodes(height))
+
+
+def merkelize(elems, width, height, split=False, threads=None):
+    e = _arr(elems)
+    assert e.size == width * height
+    nodes = np.empty(merkle_nnodes(height), dtype=np.uint64)
+    lib().orc_merkelize(_p(e), width, height, int(split), _p(nodes), threads or default_threads())
+    return nodes
+
+
+def group_proof(elems, nodes, width, height, idx):
+    e = _arr(elems); nd = _arr(nodes)
+    row = np.empty(width, dtype=np.uint64); sib = np.empty(4 * 64, dtype=np.uint64)
+    d = lib().orc_group_proof(_p(e), _p(nd), width, height, idx, _p(row), _p(sib))
+    if d < 0:
+        raise IndexError("Out of range")
+    return row, sib[:4 * d].reshape(d, 4).copy()
+
+
+def fri_fold(pol, prev_bits, cur_bits, next_bits, step0_bits, challenge, threads=None):
+    """pol: (2^prev, 3) uint64.  next_bits None => last step (no rows).  Returns (pol2, rows|None)."""
+    pol = _arr(pol).reshape(-1)
+    assert pol.size == 3 << prev_bits
+    ch = _arr(challenge)
+    pol2 = np.empty(3 << cur_bits, dtype=np.uint64)
+    rows = np.empty(3 << cur_bits, dtype=np.uint64) if next_bits is not None else None
+    lib().orc_fri_fold(_p(pol), prev_bits, cur_bits, 0 if next_bits is None else next_bits + 1, step0_bits, _p(ch),
+                       _p(pol2), _p(rows) if rows is not None else None, threads or default_threads())
+    return pol2.reshape(-1, 3), rows
