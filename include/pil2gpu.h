@@ -1,0 +1,133 @@
+/*
+ * pil2gpu -- C ABI of the B200-native commit-phase library (libpil2gpu.so).
+ *
+ * Drop-in boundary for the three JavaScript modules of pil2-stark-js that make up the STARK commit phase.  Every
+ * entry point names the reference interface it replaces (paths relative to the reference repo root); the N-API
+ * addon (napi/pil2gpu_addon.cc), the JS shims (js/*.js) and the Python mirror (pil2_stark_js_b200/) all bind
+ * exactly these symbols.
+ *
+ * Conventions
+ *   - All field data are little-endian u64 Goldilocks elements (p = 2^64 - 2^32 + 1); outputs are always canonical
+ *     (< p).  Inputs should be canonical (the reference requires it: src/helpers/f3g.js:61-66); values >= p are
+ *     interpreted mod p.
+ *   - Buffers are row-major: buff[row * nPols + col]  (pilcom BigBuffer / BigUint64Array layout).
+ *   - Every function returns 0 on success and a negative PIL2GPU_E_* code on failure; pil2gpu_last_error() returns
+ *     a thread-local message.  Nothing throws or aborts across the boundary.
+ *   - Pointers without a _dev suffix are HOST pointers; *_dev functions take DEVICE pointers (on ctx's device) and
+ *     only enqueue work on ctx's stream (call pil2gpu_sync, or sync the stream you supplied, before reading).
+ *   - Host-pointer functions are synchronous.  A ctx is bound to one GPU and one stream; use one ctx per thread.
+ *   - There is no CPU fallback: without a CUDA device pil2gpu_create fails with PIL2GPU_E_CUDA.
+ */
+#ifndef PIL2GPU_H
+#define PIL2GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIL2GPU_OK 0
+#define PIL2GPU_E_INVALID (-1)   /* bad argument (sizes, aliasing, null pointers) */
+#define PIL2GPU_E_RANGE (-2)     /* "Out of range" (merklehash_p.js:143) */
+#define PIL2GPU_E_CUDA (-3)      /* CUDA runtime error (no device, launch failure, ...) */
+#define PIL2GPU_E_NOMEM (-4)     /* device or pinned-host allocation failed */
+#define PIL2GPU_E_UNSUPPORTED (-5)
+
+typedef struct pil2gpu_ctx pil2gpu_ctx;
+typedef struct pil2gpu_tree pil2gpu_tree;   /* device-resident {elements, nodes, width, height} */
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream) or NULL to let the ctx
+ * create its own non-blocking stream.  Replaces the per-call workerpool.pool()/terminate() of fft_p.js:121,175
+ * and merklehash_p.js:53,105 (no threads are left alive between calls; the ctx only owns twiddle tables). */
+int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out);
+void pil2gpu_destroy(pil2gpu_ctx* ctx);
+const char* pil2gpu_last_error(void);
+const char* pil2gpu_version(void);
+int pil2gpu_sync(pil2gpu_ctx* ctx);
+/* Number of kernels of this library launched through ctx since creation (bench.py "gpu_launches"). */
+uint64_t pil2gpu_launch_count(const pil2gpu_ctx* ctx);
+
+/* ---- memory helpers (so JS / Python hosts need no CUDA binding of their own) ---------------------------- */
+int pil2gpu_dev_alloc(pil2gpu_ctx* ctx, size_t bytes, void** dptr);
+int pil2gpu_dev_free(pil2gpu_ctx* ctx, void* dptr);
+int pil2gpu_host_alloc(size_t bytes, void** hptr);   /* pinned host memory for BigBuffer pages */
+int pil2gpu_host_free(void* hptr);
+int pil2gpu_h2d(pil2gpu_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);   /* async on ctx stream */
+int pil2gpu_d2h(pil2gpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);   /* async on ctx stream */
+
+/* ---- NTT: src/helpers/fft/fft_p.js ------------------------------------------------------------------------ */
+/* fft(buffSrc,nPols,nBits,buffDst) / ifft(...)  fft_p.js:178-184.  dst = per-column NTT (inverse != 0: INTT) of
+ * the 2^nBits x nPols buffer, natural order in and out.  src and dst must not overlap. */
+int pil2gpu_ntt(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, int inverse);
+int pil2gpu_ntt_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t* dst_dev, uint64_t nPols, uint32_t nBits, int inverse);
+/* interpolate(buffSrc,nPols,nBits,buffDst,nBitsExt)  fft_p.js:187-297: dst[j*nPols+c] = P_c(7 * w_ext^j) where P_c
+ * interpolates column c of src on <w_n>.  dst holds 2^nBitsExt rows and is fully overwritten (its prior contents are
+ * ignored, unlike the reference which needs a zeroed dst: fft_p.js:265).  No scratch buffer is used. */
+int pil2gpu_lde(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt);
+int pil2gpu_lde_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t* dst_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt);
+/* BigBuffer twin (pilcom BigBuffer = list of BigUint64Array pages): page p holds page_words[p] u64. */
+int pil2gpu_lde_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const uint64_t* src_page_words, uint32_t n_src_pages,
+                      uint64_t* const* dst_pages, const uint64_t* dst_page_words, uint32_t n_dst_pages, uint64_t nPols,
+                      uint32_t nBits, uint32_t nBitsExt);
+
+/* ---- hashing: src/helpers/hash/poseidon/poseidon.js, linearhash/*.js -------------------------------------- */
+/* poseidon(inputs[8], capacity[4], nOuts) poseidon.js:57-108: full 12-word permutation of in12 = inputs || capacity. */
+int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[12]);
+/* LinearHash.hash linearhash.js:8-42 (split == 0) / LinearHashGPU.hash linearhash_gpu.js:31-67 (split != 0). */
+int pil2gpu_linear_hash(pil2gpu_ctx* ctx, const uint64_t* vals, uint64_t width, int split, uint64_t out4[4]);
+
+/* ---- Merkle: src/helpers/hash/merklehash/merklehash_p.js --------------------------------------------------- */
+/* _getNNodes(height*4) merklehash_p.js:28-42: number of u64 words in tree.nodes. */
+uint64_t pil2gpu_merkle_nnodes(uint64_t height);
+/* Number of sibling levels of a proof (length of getGroupProof(...)[1]). */
+uint32_t pil2gpu_merkle_depth(uint64_t height);
+/* merkelize(buff,width,height) merklehash_p.js:44-133 with the ctor flag splitLinearHash (:20-26).  Writes
+ * pil2gpu_merkle_nnodes(height) words to nodes (reference layout, root = last 4 words). */
+int pil2gpu_merkelize(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, uint64_t* nodes);
+int pil2gpu_merkelize_dev(pil2gpu_ctx* ctx, const uint64_t* elems_dev, uint64_t width, uint64_t height, int split, uint64_t* nodes_dev);
+int pil2gpu_merkelize_paged(pil2gpu_ctx* ctx, const uint64_t* const* elem_pages, const uint64_t* page_words, uint32_t n_pages,
+                            uint64_t width, uint64_t height, int split, uint64_t* nodes);
+
+/* ---- device-resident commit (extendAndMerkelize, src/stark/stark_gen_helpers.js:388-412; buildConstTree,
+ *      src/stark/stark_buildConstTree.js:17-33): interpolate + merkelize without the LDE ever leaving HBM ---- */
+int pil2gpu_commit(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
+                   pil2gpu_tree** tree_out, uint64_t root_out[4]);
+int pil2gpu_commit_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
+                       pil2gpu_tree** tree_out, uint64_t root_out[4]);
+/* Wrap / build trees over existing data.  tree_from_host uploads elements and merkelizes them on the device. */
+int pil2gpu_tree_from_host(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, pil2gpu_tree** tree_out);
+int pil2gpu_tree_width(const pil2gpu_tree* t, uint64_t* width, uint64_t* height);
+const uint64_t* pil2gpu_tree_elements_dev(const pil2gpu_tree* t);
+const uint64_t* pil2gpu_tree_nodes_dev(const pil2gpu_tree* t);
+/* root(tree) merklehash_p.js:224 */
+int pil2gpu_tree_root(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t root_out[4]);
+/* getGroupProof(tree, idx) merklehash_p.js:142-168 for n_idx leaves at once: rows_out[q*width ..] = row values,
+ * siblings_out[(q*depth + level)*4 ..] = sibling at each level.  Any idx >= height -> PIL2GPU_E_RANGE ("Out of range"). */
+int pil2gpu_tree_group_proofs(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uint64_t* idxs, uint32_t n_idx, uint64_t* rows_out,
+                              uint64_t* siblings_out);
+/* Copy back to the host layout of the reference tree object {elements, nodes}; either pointer may be NULL. */
+int pil2gpu_tree_download(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t* elems_out, uint64_t* nodes_out);
+void pil2gpu_tree_free(pil2gpu_ctx* ctx, pil2gpu_tree* t);
+
+/* ---- FRI: src/stark/fri.js --------------------------------------------------------------------------------- */
+/* One FRI.fold(step > 0, pol, challenge) fri.js:22-81.  pol: 2^prevBits F3 values (3 words each); pol_out: 2^curBits.
+ * step0Bits = steps[0].nBits (fixes the coset shift, fri.js:31-36).  nextBits >= 0: also produce the transposed rows
+ * (getTransposedBuffer fri.js:187-202; rows_out: 2^nextBits x 3*2^(curBits-nextBits) words) and their Merkle nodes
+ * (nodes_out: pil2gpu_merkle_nnodes(2^nextBits) words); nextBits < 0 is the last step (rows_out/nodes_out ignored).
+ * Step 0 (identity fold, fri.js:48-49, followed by the first layer commit :63-71) is prevBits == curBits. */
+int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
+                     const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out);
+int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol_dev, uint32_t prevBits, uint32_t curBits, int32_t nextBits,
+                         uint32_t step0Bits, const uint64_t challenge[3], int split, uint64_t* pol_out_dev, uint64_t* rows_out_dev,
+                         uint64_t* nodes_out_dev);
+/* Wrap device buffers produced by the *_dev FRI calls into a tree handle (not owned: tree_free leaves them alone). */
+int pil2gpu_tree_wrap_dev(pil2gpu_ctx* ctx, const uint64_t* elems_dev, const uint64_t* nodes_dev, uint64_t width, uint64_t height,
+                          pil2gpu_tree** tree_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIL2GPU_H */

@@ -1,0 +1,94 @@
+"""ctypes binding of libpil2gpu.so (include/pil2gpu.h).  No fallback: if the library cannot be loaded, or no
+CUDA device is present, every operation raises."""
+import ctypes
+import pathlib
+
+_PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libpil2gpu.so"
+
+OK, E_INVALID, E_RANGE, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u64pp = ctypes.POINTER(u64p)
+vp = ctypes.c_void_p
+c_u64, c_u32, c_i32, c_int, c_size = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32, ctypes.c_int, ctypes.c_size_t
+
+
+class Pil2GpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pil2gpu error {code}: {msg}")
+        self.code = code
+        self.message = msg
+
+
+class OutOfRange(Pil2GpuError, IndexError):
+    """Mirrors `throw new Error("Out of range")` of merklehash_p.js:143."""
+
+
+_SIGS = {
+    # name: (restype, [argtypes])
+    "pil2gpu_create": (c_int, [c_int, vp, ctypes.POINTER(vp)]),
+    "pil2gpu_destroy": (None, [vp]),
+    "pil2gpu_last_error": (ctypes.c_char_p, []),
+    "pil2gpu_version": (ctypes.c_char_p, []),
+    "pil2gpu_sync": (c_int, [vp]),
+    "pil2gpu_launch_count": (c_u64, [vp]),
+    "pil2gpu_dev_alloc": (c_int, [vp, c_size, ctypes.POINTER(vp)]),
+    "pil2gpu_dev_free": (c_int, [vp, vp]),
+    "pil2gpu_host_alloc": (c_int, [c_size, ctypes.POINTER(vp)]),
+    "pil2gpu_host_free": (c_int, [vp]),
+    "pil2gpu_h2d": (c_int, [vp, vp, vp, c_size]),
+    "pil2gpu_d2h": (c_int, [vp, vp, vp, c_size]),
+    "pil2gpu_ntt": (c_int, [vp, vp, vp, c_u64, c_u32, c_int]),
+    "pil2gpu_ntt_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_int]),
+    "pil2gpu_lde": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32]),
+    "pil2gpu_lde_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32]),
+    "pil2gpu_lde_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u32, c_u32]),
+    "pil2gpu_poseidon": (c_int, [vp, vp, vp]),
+    "pil2gpu_linear_hash": (c_int, [vp, vp, c_u64, c_int, vp]),
+    "pil2gpu_merkle_nnodes": (c_u64, [c_u64]),
+    "pil2gpu_merkle_depth": (c_u32, [c_u64]),
+    "pil2gpu_merkelize": (c_int, [vp, vp, c_u64, c_u64, c_int, vp]),
+    "pil2gpu_merkelize_dev": (c_int, [vp, vp, c_u64, c_u64, c_int, vp]),
+    "pil2gpu_merkelize_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u64, c_int, vp]),
+    "pil2gpu_commit": (c_int, [vp, vp, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), vp]),
+    "pil2gpu_commit_dev": (c_int, [vp, vp, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), vp]),
+    "pil2gpu_tree_from_host": (c_int, [vp, vp, c_u64, c_u64, c_int, ctypes.POINTER(vp)]),
+    "pil2gpu_tree_width": (c_int, [vp, u64p, u64p]),
+    "pil2gpu_tree_elements_dev": (vp, [vp]),
+    "pil2gpu_tree_nodes_dev": (vp, [vp]),
+    "pil2gpu_tree_root": (c_int, [vp, vp, vp]),
+    "pil2gpu_tree_group_proofs": (c_int, [vp, vp, vp, c_u32, vp, vp]),
+    "pil2gpu_tree_download": (c_int, [vp, vp, vp, vp]),
+    "pil2gpu_tree_free": (None, [vp, vp]),
+    "pil2gpu_tree_wrap_dev": (c_int, [vp, vp, vp, c_u64, c_u64, ctypes.POINTER(vp)]),
+    "pil2gpu_fri_fold": (c_int, [vp, vp, c_u32, c_u32, c_i32, c_u32, vp, c_int, vp, vp, vp]),
+    "pil2gpu_fri_fold_dev": (c_int, [vp, vp, c_u32, c_u32, c_i32, c_u32, vp, c_int, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libpil2gpu.so (built in-tree by pil2_stark_js_b200/build.py).  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m pil2_stark_js_b200.build` (needs nvcc). "
+                "There is no CPU fallback for the commit path.")
+        L = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)          # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        msg = load().pil2gpu_last_error().decode("utf-8", "replace")
+        if rc == E_RANGE:
+            raise OutOfRange(rc, msg)
+        raise Pil2GpuError(rc, msg)

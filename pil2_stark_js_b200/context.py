@@ -1,0 +1,192 @@
+"""GPU context: one per (device, stream).  Mirrors nothing in the reference (which spins up a workerpool per call,
+fft_p.js:121 / merklehash_p.js:53); it exists so twiddle tables are built once per process."""
+import ctypes
+import numpy as np
+
+from . import _lib
+from ._lib import vp, check
+
+
+def _as_u64(a, name="buffer"):
+    if not isinstance(a, np.ndarray) or a.dtype != np.uint64 or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"{name} must be a C-contiguous numpy uint64 array (BigUint64Array layout)")
+    return a
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        self._L = _lib.load()
+        h = vp()
+        check(self._L.pil2gpu_create(int(device), vp(stream) if stream else None, ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pil2gpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("context is closed")
+        return self._h
+
+    def sync(self):
+        check(self._L.pil2gpu_sync(self.handle))
+
+    @property
+    def launch_count(self):
+        return int(self._L.pil2gpu_launch_count(self.handle))
+
+    # ---- host-buffer entry points (numpy uint64 in / out) ----
+    def ntt(self, src, n_pols, n_bits, dst, inverse=False):
+        _as_u64(src, "buffSrc"); _as_u64(dst, "buffDst")
+        if src.size != n_pols << n_bits or dst.size != n_pols << n_bits:
+            raise ValueError("buffer size does not match nPols * 2^nBits")
+        check(self._L.pil2gpu_ntt(self.handle, _ptr(src), _ptr(dst), n_pols, n_bits, int(inverse)))
+
+    def lde(self, src, n_pols, n_bits, dst, n_bits_ext):
+        _as_u64(src, "buffSrc"); _as_u64(dst, "buffDst")
+        if src.size != n_pols << n_bits or dst.size != n_pols << n_bits_ext:
+            raise ValueError("buffer size does not match nPols * 2^nBits / 2^nBitsExt")
+        check(self._L.pil2gpu_lde(self.handle, _ptr(src), _ptr(dst), n_pols, n_bits, n_bits_ext))
+
+    def poseidon(self, in12):
+        a = np.ascontiguousarray(in12, dtype=np.uint64)
+        if a.size != 12:
+            raise ValueError("poseidon state must have 12 words")
+        o = np.empty(12, dtype=np.uint64)
+        check(self._L.pil2gpu_poseidon(self.handle, _ptr(a), _ptr(o)))
+        return o
+
+    def linear_hash(self, vals, split=False):
+        a = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1)
+        o = np.empty(4, dtype=np.uint64)
+        check(self._L.pil2gpu_linear_hash(self.handle, _ptr(a) if a.size else None, a.size, int(split), _ptr(o)))
+        return o
+
+    def merkle_nnodes(self, height):
+        return int(self._L.pil2gpu_merkle_nnodes(height))
+
+    def merkelize(self, elems, width, height, split=False):
+        _as_u64(elems, "buff")
+        if elems.size != width * height:
+            raise ValueError("buffer size does not match width * height")
+        nodes = np.empty(self.merkle_nnodes(height), dtype=np.uint64)
+        check(self._L.pil2gpu_merkelize(self.handle, _ptr(elems), width, height, int(split), _ptr(nodes)))
+        return nodes
+
+    def fri_fold(self, pol, prev_bits, cur_bits, next_bits, step0_bits, challenge, split=False):
+        """pol: (2^prev, 3) uint64.  next_bits=None: last step.  Returns (pol2 (2^cur,3), rows|None, nodes|None)."""
+        pol = np.ascontiguousarray(pol, dtype=np.uint64).reshape(-1)
+        if pol.size != 3 << prev_bits:
+            raise ValueError("Invalid polynomial size")
+        ch = np.ascontiguousarray(challenge, dtype=np.uint64).reshape(-1)
+        pol2 = np.empty(3 << cur_bits, dtype=np.uint64)
+        rows = nodes = None
+        if next_bits is not None:
+            rows = np.empty(3 << cur_bits, dtype=np.uint64)
+            nodes = np.empty(self.merkle_nnodes(1 << next_bits), dtype=np.uint64)
+        check(self._L.pil2gpu_fri_fold(self.handle, _ptr(pol), prev_bits, cur_bits, -1 if next_bits is None else next_bits,
+                                       step0_bits, _ptr(ch), int(split), _ptr(pol2),
+                                       _ptr(rows) if rows is not None else None, _ptr(nodes) if nodes is not None else None))
+        return pol2.reshape(-1, 3), rows, nodes
+
+    # ---- device-resident commit ----
+    def commit(self, src, n_pols, n_bits, n_bits_ext, split=False):
+        """interpolate + merkelize with the LDE kept in HBM.  Returns (DeviceTree, root[4])."""
+        _as_u64(src, "buffSrc")
+        if src.size != n_pols << n_bits:
+            raise ValueError("buffer size does not match nPols * 2^nBits")
+        t = vp()
+        root = np.empty(4, dtype=np.uint64)
+        check(self._L.pil2gpu_commit(self.handle, _ptr(src), n_pols, n_bits, n_bits_ext, int(split), ctypes.byref(t), _ptr(root)))
+        return DeviceTree(self, t), root
+
+    def commit_dev(self, src_dev_ptr, n_pols, n_bits, n_bits_ext, split=False):
+        t = vp()
+        root = np.empty(4, dtype=np.uint64)
+        check(self._L.pil2gpu_commit_dev(self.handle, vp(src_dev_ptr), n_pols, n_bits, n_bits_ext, int(split), ctypes.byref(t),
+                                         _ptr(root)))
+        return DeviceTree(self, t), root
+
+    def tree_from_host(self, elems, width, height, split=False):
+        _as_u64(elems, "buff")
+        t = vp()
+        check(self._L.pil2gpu_tree_from_host(self.handle, _ptr(elems), width, height, int(split), ctypes.byref(t)))
+        return DeviceTree(self, t)
+
+
+class DeviceTree:
+    """Device-resident {elements, nodes, width, height} (the tree object of merklehash_p.js:46-51)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        w, h = ctypes.c_uint64(), ctypes.c_uint64()
+        check(ctx._L.pil2gpu_tree_width(handle, ctypes.byref(w), ctypes.byref(h)))
+        self.width, self.height = int(w.value), int(h.value)
+
+    def root(self):
+        r = np.empty(4, dtype=np.uint64)
+        check(self.ctx._L.pil2gpu_tree_root(self.ctx.handle, self._h, _ptr(r)))
+        return r
+
+    def group_proofs(self, idxs):
+        idxs = [int(i) for i in idxs]
+        if any(i < 0 for i in idxs):
+            raise _lib.OutOfRange(_lib.E_RANGE, "Out of range")
+        ia = np.asarray(idxs, dtype=np.uint64)
+        depth = int(self.ctx._L.pil2gpu_merkle_depth(self.height))
+        rows = np.empty((len(idxs), self.width), dtype=np.uint64)
+        sib = np.empty((len(idxs), depth, 4), dtype=np.uint64)
+        check(self.ctx._L.pil2gpu_tree_group_proofs(self.ctx.handle, self._h, _ptr(ia) if len(idxs) else None, len(idxs), _ptr(rows),
+                                                    _ptr(sib)))
+        return rows, sib
+
+    def download(self, elements=True, nodes=True):
+        e = np.empty(self.width * self.height, dtype=np.uint64) if elements else None
+        n = np.empty(self.ctx.merkle_nnodes(self.height), dtype=np.uint64) if nodes else None
+        check(self.ctx._L.pil2gpu_tree_download(self.ctx.handle, self._h, _ptr(e) if e is not None else None,
+                                                _ptr(n) if n is not None else None))
+        return e, n
+
+    @property
+    def elements_ptr(self):
+        return self.ctx._L.pil2gpu_tree_elements_dev(self._h)
+
+    @property
+    def nodes_ptr(self):
+        return self.ctx._L.pil2gpu_tree_nodes_dev(self._h)
+
+    def free(self):
+        if self._h:
+            self.ctx._L.pil2gpu_tree_free(self.ctx.handle, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+_default = {}
+
+
+def default_context(device=0):
+    """Process-wide context on `device` (created on first use; raises without a CUDA device)."""
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]

@@ -1,0 +1,222 @@
+// Poseidon-GL linear hash, Merkle tree and group-proof gather for sm_100a.
+//
+// Replaces (semantics, not structure):
+//   linear hash        src/helpers/hash/linearhash/linearhash.js:8-42, linearhash_gpu.js:31-67,
+//                      width<=4 passthrough src/helpers/hash/merklehash/merklehash_worker.js:42-49
+//   merkelize          src/helpers/hash/merklehash/merklehash_p.js:44-133 (node layout _getNNodes :28-42)
+//   getGroupProof      src/helpers/hash/merklehash/merklehash_p.js:142-168
+// One row (or one batch of a row in split mode) per thread; the tree is reduced level by level with the last
+// <= MERKLE_TAIL pairs finished inside a single CTA.  `nodes` uses the reference layout exactly: level l starts
+// right after level l-1, every level is padded with a zero node to an even node count, the root is the last 4
+// words; a tree of height 1 is L(row) followed by four zero words (reference quirk, root = 0).
+#pragma once
+#include "poseidon.cuh"
+
+#define MERKLE_THREADS 128
+#define MERKLE_TAIL 512    // pairs handled by the single-CTA tail kernel (512 threads keeps 128 regs/thread)
+
+// _getNNodes(height*4) of merklehash_p.js:28-42, in words.
+static inline u64 merkle_nnodes_words(u64 height) {
+    u64 n = height * 4;
+    u64 next = ((n - 1) / 8 + 1) * 4;
+    u64 acc = next * 2;
+    while (n > 4) {
+        n = next;
+        next = ((n - 1) / 8 + 1) * 4;
+        if (n > 4) acc += next * 2; else acc += 4;
+    }
+    return acc;
+}
+static inline int merkle_depth(u64 height) {
+    int d = 0;
+    u64 n = height * 4;
+    while (n > 4) { n = ((n - 1) / 8 + 1) * 4; d++; }
+    return d;
+}
+
+// Sponge over `w` words at `v` (stride 1): st = H(chunk, st) per 8 words, last chunk zero padded; w <= 4 is copied.
+// Works for global or shared pointers.  Output canonical.
+GL_D void merkle_sponge(const u64* __restrict__ v, u64 w, u64 out[4]) {
+    if (w <= 4) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = (u64)i < w ? v[i] : 0;
+        return;
+    }
+    u64 x[12];
+#pragma unroll
+    for (int i = 8; i < 12; i++) x[i] = 0;
+    for (u64 off = 0; off < w; off += 8) {
+        if (off + 8 <= w) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = v[off + i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = (off + i < w) ? v[off + i] : 0;
+        }
+        poseidon_permute(x);
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[8 + i] = x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = gl_canon(x[8 + i]);
+}
+
+// Standard linear hash of every row: nodes[4*row ..] = L(elems[row*width ..]).
+__global__ void __launch_bounds__(MERKLE_THREADS) merkle_leaf_kernel(const u64* __restrict__ elems, u64 width, u64 height,
+                                                                     u64* __restrict__ nodes) {
+    const u64 row = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
+    if (row >= height) return;
+    u64 d[4];
+    merkle_sponge(elems + row * width, width, d);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(nodes + 4 * row);
+    o[0] = make_ulonglong2(d[0], d[1]);
+    o[1] = make_ulonglong2(d[2], d[3]);
+}
+
+// Split linear hash, stage 1: one thread per (row, batch): digests[(row*nb + b)*4 ..] = L(row[b*batch .. ]).
+__global__ void __launch_bounds__(MERKLE_THREADS) merkle_batch_kernel(const u64* __restrict__ elems, u64 width, u64 height, u64 batch,
+                                                                      u64 nb, u64* __restrict__ digests) {
+    const u64 id = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
+    if (id >= height * nb) return;
+    const u64 row = id / nb, b = id % nb;
+    const u64 off = b * batch;
+    const u64 sz = (width - off < batch) ? (width - off) : batch;
+    u64 d[4];
+    merkle_sponge(elems + row * width + off, sz, d);
+#pragma unroll
+    for (int i = 0; i < 4; i++) digests[id * 4 + i] = d[i];
+}
+
+// One tree level: out[i] = H(in[2i] || in[2i+1], cap = 0), i < pairs (merkelizeLevel, glwasm.js:1220-1254).
+GL_D void merkle_pair(const u64* __restrict__ in, u64* __restrict__ out, u64 i) {
+    u64 x[12];
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + 8 * i);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        ulonglong2 v = p[k];
+        x[2 * k] = v.x;
+        x[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for (int k = 8; k < 12; k++) x[k] = 0;
+    poseidon_permute(x);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
+    o[0] = make_ulonglong2(gl_canon(x[0]), gl_canon(x[1]));
+    o[1] = make_ulonglong2(gl_canon(x[2]), gl_canon(x[3]));
+}
+__global__ void __launch_bounds__(MERKLE_THREADS) merkle_level_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 pairs) {
+    const u64 i = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
+    if (i < pairs) merkle_pair(in, out, i);
+}
+// All remaining levels inside one CTA (pairs <= MERKLE_TAIL at entry).  nodes + p_in is the current level.
+__global__ void __launch_bounds__(MERKLE_TAIL) merkle_tail_kernel(u64* __restrict__ nodes, u64 p_in, u64 n64) {
+    u64 next = ((n64 - 1) / 8 + 1) * 4;
+    u64 p_out = p_in + next * 2;
+    while (n64 > 4) {
+        const u64 pairs = next / 4;
+        if (threadIdx.x < pairs) merkle_pair(nodes + p_in, nodes + p_out, threadIdx.x);
+        __syncthreads();
+        n64 = next;
+        next = ((n64 - 1) / 8 + 1) * 4;
+        p_in = p_out;
+        p_out = p_in + next * 2;
+    }
+}
+
+// Zero the padding node of every odd level (and the height-1 quirk node).
+__global__ void merkle_pad_kernel(u64* __restrict__ nodes, u64 height) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u64 p_in = 0, n64 = height * 4;
+    u64 next = ((n64 - 1) / 8 + 1) * 4;
+    if (n64 <= 4) {   // height 1: nodes = L(row) || 0^4
+        for (int i = 0; i < 4; i++) nodes[4 + i] = 0;
+        return;
+    }
+    while (n64 > 4) {
+        if (next * 2 != n64) for (u64 i = n64; i < next * 2; i++) nodes[p_in + i] = 0;
+        p_in += next * 2;
+        n64 = next;
+        next = ((n64 - 1) / 8 + 1) * 4;
+    }
+}
+
+// Reduce leaf digests already stored at nodes[0 .. 4*height) to the root.  Returns launches or -1.
+static int merkle_launch_tree(u64* nodes, u64 height, cudaStream_t st) {
+    int launches = 0;
+    merkle_pad_kernel<<<1, 32, 0, st>>>(nodes, height);
+    launches++;
+    u64 p_in = 0, n64 = height * 4;
+    u64 next = ((n64 - 1) / 8 + 1) * 4;
+    u64 p_out = p_in + next * 2;
+    while (n64 > 4) {
+        const u64 pairs = next / 4;
+        if (pairs <= MERKLE_TAIL) {
+            merkle_tail_kernel<<<1, MERKLE_TAIL, 0, st>>>(nodes, p_in, n64);
+            launches++;
+            break;
+        }
+        merkle_level_kernel<<<(unsigned)((pairs + MERKLE_THREADS - 1) / MERKLE_THREADS), MERKLE_THREADS, 0, st>>>(nodes + p_in, nodes + p_out,
+                                                                                                                  pairs);
+        launches++;
+        n64 = next;
+        next = ((n64 - 1) / 8 + 1) * 4;
+        p_in = p_out;
+        p_out = p_in + next * 2;
+    }
+    return launches;
+}
+
+// Full merkelize of device-resident rows.  `scratch` (split mode only) holds height*nb*4 words.
+static inline u64 merkle_split_batch(u64 width) { u64 b = (width + 3) / 4; return b < 8 ? 8 : b; }   // linearhash_gpu.js:42-44
+static inline u64 merkle_split_scratch_words(u64 width, u64 height) {
+    if (width <= 4) return 0;
+    u64 batch = merkle_split_batch(width);
+    return height * ((width + batch - 1) / batch) * 4;
+}
+static int merkle_launch(const u64* elems, u64 width, u64 height, int split, u64* nodes, u64* scratch, cudaStream_t st) {
+    int launches = 0;
+    if (height == 0) return 0;
+    const unsigned blocks = (unsigned)((height + MERKLE_THREADS - 1) / MERKLE_THREADS);
+    if (!split || width <= 4) {
+        merkle_leaf_kernel<<<blocks, MERKLE_THREADS, 0, st>>>(elems, width, height, nodes);
+        launches++;
+    } else {
+        const u64 batch = merkle_split_batch(width);
+        const u64 nb = (width + batch - 1) / batch;
+        const u64 total = height * nb;
+        merkle_batch_kernel<<<(unsigned)((total + MERKLE_THREADS - 1) / MERKLE_THREADS), MERKLE_THREADS, 0, st>>>(elems, width, height, batch, nb,
+                                                                                                                  scratch);
+        merkle_leaf_kernel<<<blocks, MERKLE_THREADS, 0, st>>>(scratch, nb * 4, height, nodes);
+        launches += 2;
+    }
+    int t = merkle_launch_tree(nodes, height, st);
+    return t < 0 ? -1 : launches + t;
+}
+
+// Group proofs for a batch of leaf indices: row values + one 4-word sibling per level (merklehash_p.js:142-168).
+// One CTA per query; rows_out[q*width ..], sib_out[q*depth*4 ..].
+__global__ void merkle_group_proof_kernel(const u64* __restrict__ elems, const u64* __restrict__ nodes, u64 width, u64 height,
+                                          const u64* __restrict__ idxs, int depth, u64* __restrict__ rows_out, u64* __restrict__ sib_out) {
+    const u64 q = blockIdx.x;
+    u64 idx = idxs[q];
+    for (u64 i = threadIdx.x; i < width; i += blockDim.x) rows_out[q * width + i] = elems[idx * width + i];
+    if (threadIdx.x < 4) {
+        u64 off = 0, n = height * 4;
+        for (int d = 0; d < depth; d++) {
+            sib_out[(q * depth + d) * 4 + threadIdx.x] = nodes[off + (idx ^ 1) * 4 + threadIdx.x];
+            const u64 next = ((n - 1) / 8 + 1) * 4;
+            idx >>= 1;
+            off += next * 2;
+            n = next;
+        }
+    }
+}
+
+// Single permutation / single row hash (test hooks and the host-side transcript).
+__global__ void poseidon_single_kernel(const u64* __restrict__ in12, u64* __restrict__ out12) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u64 x[12];
+    for (int i = 0; i < 12; i++) x[i] = in12[i];
+    poseidon_permute(x);
+    for (int i = 0; i < 12; i++) out12[i] = gl_canon(x[i]);
+}

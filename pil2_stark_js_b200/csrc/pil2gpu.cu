@@ -1,0 +1,572 @@
+// libpil2gpu.so -- C ABI over the sm_100a kernels (see include/pil2gpu.h for the contract and the reference
+// interfaces each entry point replaces).  Unity build: the kernels live in the .cuh files included below.
+// There is deliberately no CPU implementation behind any entry point: every failure to reach the GPU is an error.
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pil2gpu.h"
+#include "fri.cuh"
+#include "gl.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? PIL2GPU_E_NOMEM : PIL2GPU_E_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                         \
+    } while (0)
+
+struct pil2gpu_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    u64* tables;      // bytepow[1024] | tw_fwd[2048] | tw_inv[2048]
+    u64* coset;       // LDE coset scale scratch: (B_max << TMAX) + B_max words, grown on demand
+    size_t coset_words;
+    uint64_t launches;
+    NttTables tb;
+};
+
+struct pil2gpu_tree {
+    u64* elems;
+    u64* nodes;
+    uint64_t width, height;
+    bool own_elems, own_nodes;
+};
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+#define ENTER(ctx)                                                        \
+    if (!(ctx)) return fail(PIL2GPU_E_INVALID, "null context");           \
+    DeviceGuard guard__((ctx)->device);                                   \
+    if (!guard__.ok) return fail(PIL2GPU_E_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
+
+static int check_launch(pil2gpu_ctx* ctx, int launches, const char* what) {
+    if (launches < 0) return fail(PIL2GPU_E_CUDA, "%s: kernel configuration failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
+    ctx->launches += (uint64_t)launches;
+    return PIL2GPU_OK;
+}
+
+extern "C" {
+
+const char* pil2gpu_last_error(void) { return g_last_error.c_str(); }
+const char* pil2gpu_version(void) { return "pil2gpu 0.1 (sm_100a)"; }
+
+int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
+    if (!out) return fail(PIL2GPU_E_INVALID, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PIL2GPU_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(PIL2GPU_E_INVALID, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(PIL2GPU_E_CUDA, "cudaSetDevice(%d) failed", device);
+    pil2gpu_ctx* ctx = new (std::nothrow) pil2gpu_ctx();
+    if (!ctx) return fail(PIL2GPU_E_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->launches = 0;
+    ctx->coset = nullptr;
+    ctx->coset_words = 0;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->own_stream = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return fail(PIL2GPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        ctx->own_stream = true;
+    }
+    const size_t words = 1024 + 2 * (1u << (NTT_TW_BITS - 1));
+    e = cudaMalloc(&ctx->tables, words * sizeof(u64));
+    if (e != cudaSuccess) { pil2gpu_destroy(ctx); return fail(PIL2GPU_E_NOMEM, "cudaMalloc(tables): %s", cudaGetErrorString(e)); }
+    u64* tw_fwd = ctx->tables + 1024;
+    u64* tw_inv = tw_fwd + (1u << (NTT_TW_BITS - 1));
+    ntt_setup_tables<<<(1u << (NTT_TW_BITS - 1)) / 256, 256, 0, ctx->stream>>>(ctx->tables, tw_fwd, tw_inv);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        pil2gpu_destroy(ctx);
+        return fail(PIL2GPU_E_CUDA, "table setup kernel failed: %s (is this an sm_100a device?)", cudaGetErrorString(e));
+    }
+    ctx->launches++;
+    ctx->tb.bytepow = ctx->tables;
+    ctx->tb.tw_fwd = tw_fwd;
+    ctx->tb.tw_inv = tw_inv;
+    *out = ctx;
+    return PIL2GPU_OK;
+}
+
+void pil2gpu_destroy(pil2gpu_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->tables) cudaFree(ctx->tables);
+    if (ctx->coset) cudaFree(ctx->coset);
+    delete ctx;
+}
+
+int pil2gpu_sync(pil2gpu_ctx* ctx) {
+    ENTER(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+uint64_t pil2gpu_launch_count(const pil2gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pil2gpu_dev_alloc(pil2gpu_ctx* ctx, size_t bytes, void** dptr) {
+    ENTER(ctx);
+    if (!dptr) return fail(PIL2GPU_E_INVALID, "null dptr");
+    CU(cudaMalloc(dptr, bytes ? bytes : 8));
+    return PIL2GPU_OK;
+}
+int pil2gpu_dev_free(pil2gpu_ctx* ctx, void* dptr) {
+    ENTER(ctx);
+    if (dptr) CU(cudaFree(dptr));
+    return PIL2GPU_OK;
+}
+int pil2gpu_host_alloc(size_t bytes, void** hptr) {
+    if (!hptr) return fail(PIL2GPU_E_INVALID, "null hptr");
+    CU(cudaHostAlloc(hptr, bytes ? bytes : 8, cudaHostAllocPortable));
+    return PIL2GPU_OK;
+}
+int pil2gpu_host_free(void* hptr) {
+    if (hptr) CU(cudaFreeHost(hptr));
+    return PIL2GPU_OK;
+}
+int pil2gpu_h2d(pil2gpu_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    ENTER(ctx);
+    if (bytes) CU(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return PIL2GPU_OK;
+}
+int pil2gpu_d2h(pil2gpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    ENTER(ctx);
+    if (bytes) CU(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return PIL2GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// NTT / LDE
+// ------------------------------------------------------------------------------------------------------------
+static int check_ntt_args(const void* src, const void* dst, uint64_t nPols, uint32_t nBits) {
+    if (!src || !dst) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (nPols == 0) return fail(PIL2GPU_E_INVALID, "nPols must be > 0");
+    if (nBits > 32) return fail(PIL2GPU_E_INVALID, "nBits %u exceeds the 2-adicity of the field (32)", nBits);
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_ntt_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, int inverse) {
+    ENTER(ctx);
+    int rc = check_ntt_args(src, dst, nPols, nBits);
+    if (rc) return rc;
+    const size_t words = (size_t)nPols << nBits;
+    if ((const u64*)src < (const u64*)dst + words && (const u64*)dst < (const u64*)src + words)
+        return fail(PIL2GPU_E_INVALID, "src and dst overlap");
+    int l = ntt_launch_transform((const u64*)src, (u64*)dst, nPols, (int)nBits, inverse != 0, ctx->tb, ctx->stream);
+    return check_launch(ctx, l, "ntt");
+}
+
+static int ensure_coset(pil2gpu_ctx* ctx, size_t words) {
+    if (ctx->coset_words >= words) return PIL2GPU_OK;
+    if (ctx->coset) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(ctx->coset)); ctx->coset = nullptr; ctx->coset_words = 0; }
+    CU(cudaMalloc(&ctx->coset, words * sizeof(u64)));
+    ctx->coset_words = words;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_lde_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt) {
+    ENTER(ctx);
+    int rc = check_ntt_args(src, dst, nPols, nBitsExt);
+    if (rc) return rc;
+    if (nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "nBitsExt (%u) < nBits (%u)", nBitsExt, nBits);
+    if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
+    const size_t sw = (size_t)nPols << nBits, dw = (size_t)nPols << nBitsExt;
+    if ((const u64*)src < (const u64*)dst + dw && (const u64*)dst < (const u64*)src + sw) return fail(PIL2GPU_E_INVALID, "src and dst overlap");
+    const size_t B = (size_t)1 << (nBitsExt - nBits);
+    rc = ensure_coset(ctx, (B << NTT_TMAX) + B);
+    if (rc) return rc;
+    int l = ntt_launch_lde((const u64*)src, (u64*)dst, nPols, (int)nBits, (int)nBitsExt, ctx->coset, ctx->coset + (B << NTT_TMAX), ctx->tb,
+                           ctx->stream);
+    return check_launch(ctx, l, "lde");
+}
+
+// Gather a paged host buffer into device memory / scatter back (async on the ctx stream).
+static int pages_to_dev(pil2gpu_ctx* ctx, u64* dev, const uint64_t* const* pages, const uint64_t* page_words, uint32_t n_pages, size_t expect) {
+    size_t off = 0;
+    for (uint32_t p = 0; p < n_pages; p++) {
+        if (off + page_words[p] > expect) return fail(PIL2GPU_E_INVALID, "pages hold more than %zu words", expect);
+        if (page_words[p]) CU(cudaMemcpyAsync(dev + off, pages[p], page_words[p] * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        off += page_words[p];
+    }
+    if (off != expect) return fail(PIL2GPU_E_INVALID, "pages hold %zu words, expected %zu", off, expect);
+    return PIL2GPU_OK;
+}
+static int dev_to_pages(pil2gpu_ctx* ctx, const u64* dev, uint64_t* const* pages, const uint64_t* page_words, uint32_t n_pages, size_t expect) {
+    size_t off = 0;
+    for (uint32_t p = 0; p < n_pages; p++) {
+        if (off + page_words[p] > expect) return fail(PIL2GPU_E_INVALID, "pages hold more than %zu words", expect);
+        if (page_words[p]) CU(cudaMemcpyAsync(pages[p], dev + off, page_words[p] * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        off += page_words[p];
+    }
+    if (off != expect) return fail(PIL2GPU_E_INVALID, "pages hold %zu words, expected %zu", off, expect);
+    return PIL2GPU_OK;
+}
+
+struct DevBuf {   // RAII device allocation for the host-pointer entry points
+    u64* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t words) { return cudaMalloc(&p, (words ? words : 1) * sizeof(u64)); }
+};
+
+int pil2gpu_ntt(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, int inverse) {
+    ENTER(ctx);
+    int rc = check_ntt_args(src, dst, nPols, nBits);
+    if (rc) return rc;
+    const size_t words = (size_t)nPols << nBits;
+    DevBuf a, b;
+    CU(a.alloc(words));
+    CU(b.alloc(words));
+    CU(cudaMemcpyAsync(a.p, src, words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pil2gpu_ntt_dev(ctx, a.p, b.p, nPols, nBits, inverse);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, b.p, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_lde(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt) {
+    const uint64_t sw = nPols << nBits, dw = nPols << nBitsExt;
+    const uint64_t* sp[1] = {src};
+    uint64_t* dp[1] = {dst};
+    if (!src || !dst) return fail(PIL2GPU_E_INVALID, "null buffer");
+    return pil2gpu_lde_paged(ctx, sp, &sw, 1, dp, &dw, 1, nPols, nBits, nBitsExt);
+}
+
+int pil2gpu_lde_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const uint64_t* src_page_words, uint32_t n_src_pages,
+                      uint64_t* const* dst_pages, const uint64_t* dst_page_words, uint32_t n_dst_pages, uint64_t nPols, uint32_t nBits,
+                      uint32_t nBitsExt) {
+    ENTER(ctx);
+    if (!src_pages || !dst_pages || !src_page_words || !dst_page_words) return fail(PIL2GPU_E_INVALID, "null page list");
+    if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad LDE shape");
+    const size_t sw = (size_t)nPols << nBits, dw = (size_t)nPols << nBitsExt;
+    DevBuf a, b;
+    CU(a.alloc(sw));
+    CU(b.alloc(dw));
+    int rc = pages_to_dev(ctx, a.p, src_pages, src_page_words, n_src_pages, sw);
+    if (rc) return rc;
+    rc = pil2gpu_lde_dev(ctx, a.p, b.p, nPols, nBits, nBitsExt);
+    if (rc) return rc;
+    rc = dev_to_pages(ctx, b.p, dst_pages, dst_page_words, n_dst_pages, dw);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Hashing / Merkle
+// ------------------------------------------------------------------------------------------------------------
+uint64_t pil2gpu_merkle_nnodes(uint64_t height) { return height == 0 ? 0 : merkle_nnodes_words(height); }
+uint32_t pil2gpu_merkle_depth(uint64_t height) { return height == 0 ? 0 : (uint32_t)merkle_depth(height); }
+
+int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[12]) {
+    ENTER(ctx);
+    if (!in12 || !out12) return fail(PIL2GPU_E_INVALID, "null buffer");
+    DevBuf d;
+    CU(d.alloc(24));
+    CU(cudaMemcpyAsync(d.p, in12, 96, cudaMemcpyHostToDevice, ctx->stream));
+    poseidon_single_kernel<<<1, 32, 0, ctx->stream>>>(d.p, d.p + 12);
+    int rc = check_launch(ctx, 1, "poseidon");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out12, d.p + 12, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_merkelize_dev(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, uint64_t* nodes) {
+    ENTER(ctx);
+    if (!nodes || (!elems && width * height)) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (height == 0) return fail(PIL2GPU_E_INVALID, "height must be > 0");
+    u64* scratch = nullptr;
+    const u64 sw = (split && width > 4) ? merkle_split_scratch_words(width, height) : 0;
+    if (sw) CU(cudaMallocAsync(&scratch, sw * sizeof(u64), ctx->stream));
+    int l = merkle_launch((const u64*)elems, width, height, split, (u64*)nodes, scratch, ctx->stream);
+    if (scratch) CU(cudaFreeAsync(scratch, ctx->stream));
+    return check_launch(ctx, l, "merkelize");
+}
+
+int pil2gpu_linear_hash(pil2gpu_ctx* ctx, const uint64_t* vals, uint64_t width, int split, uint64_t out4[4]) {
+    ENTER(ctx);
+    if (!out4 || (!vals && width)) return fail(PIL2GPU_E_INVALID, "null buffer");
+    DevBuf e, n;
+    CU(e.alloc(width));
+    CU(n.alloc(8));
+    if (width) CU(cudaMemcpyAsync(e.p, vals, width * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = pil2gpu_merkelize_dev(ctx, e.p, width, 1, split, n.p);   // height-1 tree: nodes[0..4) is the leaf digest
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out4, n.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_merkelize_paged(pil2gpu_ctx* ctx, const uint64_t* const* elem_pages, const uint64_t* page_words, uint32_t n_pages,
+                            uint64_t width, uint64_t height, int split, uint64_t* nodes) {
+    ENTER(ctx);
+    if (!nodes || !elem_pages || !page_words) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (height == 0) return fail(PIL2GPU_E_INVALID, "height must be > 0");
+    const size_t ew = (size_t)width * height, nw = merkle_nnodes_words(height);
+    DevBuf e, n;
+    CU(e.alloc(ew));
+    CU(n.alloc(nw));
+    int rc = pages_to_dev(ctx, e.p, elem_pages, page_words, n_pages, ew);
+    if (rc) return rc;
+    rc = pil2gpu_merkelize_dev(ctx, e.p, width, height, split, n.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(nodes, n.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_merkelize(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, uint64_t* nodes) {
+    const uint64_t ew = width * height;
+    const uint64_t* pages[1] = {elems};
+    if (!elems && ew) return fail(PIL2GPU_E_INVALID, "null buffer");
+    return pil2gpu_merkelize_paged(ctx, pages, &ew, 1, width, height, split, nodes);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Trees / commit
+// ------------------------------------------------------------------------------------------------------------
+static pil2gpu_tree* new_tree() {
+    pil2gpu_tree* t = new (std::nothrow) pil2gpu_tree();
+    if (t) { t->elems = t->nodes = nullptr; t->width = t->height = 0; t->own_elems = t->own_nodes = false; }
+    return t;
+}
+
+void pil2gpu_tree_free(pil2gpu_ctx* ctx, pil2gpu_tree* t) {
+    if (!t) return;
+    if (ctx) {
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (t->own_elems && t->elems) cudaFree(t->elems);
+        if (t->own_nodes && t->nodes) cudaFree(t->nodes);
+    }
+    delete t;
+}
+
+int pil2gpu_tree_wrap_dev(pil2gpu_ctx* ctx, const uint64_t* elems_dev, const uint64_t* nodes_dev, uint64_t width, uint64_t height,
+                          pil2gpu_tree** tree_out) {
+    if (!ctx || !tree_out || !nodes_dev || height == 0) return fail(PIL2GPU_E_INVALID, "bad tree description");
+    pil2gpu_tree* t = new_tree();
+    if (!t) return fail(PIL2GPU_E_NOMEM, "out of host memory");
+    t->elems = (u64*)elems_dev;
+    t->nodes = (u64*)nodes_dev;
+    t->width = width;
+    t->height = height;
+    *tree_out = t;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_tree_width(const pil2gpu_tree* t, uint64_t* width, uint64_t* height) {
+    if (!t) return fail(PIL2GPU_E_INVALID, "null tree");
+    if (width) *width = t->width;
+    if (height) *height = t->height;
+    return PIL2GPU_OK;
+}
+const uint64_t* pil2gpu_tree_elements_dev(const pil2gpu_tree* t) { return t ? (const uint64_t*)t->elems : nullptr; }
+const uint64_t* pil2gpu_tree_nodes_dev(const pil2gpu_tree* t) { return t ? (const uint64_t*)t->nodes : nullptr; }
+
+int pil2gpu_tree_root(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t root_out[4]) {
+    ENTER(ctx);
+    if (!t || !root_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    const u64 nw = merkle_nnodes_words(t->height);
+    CU(cudaMemcpyAsync(root_out, t->nodes + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+static int commit_common(pil2gpu_ctx* ctx, u64* src_dev_owned, const u64* src_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
+                         int split, pil2gpu_tree** tree_out, uint64_t root_out[4]) {
+    (void)src_dev_owned;
+    pil2gpu_tree* t = new_tree();
+    if (!t) return fail(PIL2GPU_E_NOMEM, "out of host memory");
+    t->width = nPols;
+    t->height = 1ULL << nBitsExt;
+    t->own_elems = t->own_nodes = true;
+    cudaError_t e = cudaMalloc(&t->elems, ((size_t)nPols << nBitsExt) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&t->nodes, merkle_nnodes_words(t->height) * 8);
+    if (e != cudaSuccess) {
+        pil2gpu_tree_free(ctx, t);
+        return fail(PIL2GPU_E_NOMEM, "device allocation for the committed tree failed: %s", cudaGetErrorString(e));
+    }
+    int rc = pil2gpu_lde_dev(ctx, src_dev, t->elems, nPols, nBits, nBitsExt);
+    if (!rc) rc = pil2gpu_merkelize_dev(ctx, t->elems, nPols, t->height, split, t->nodes);
+    if (!rc && root_out) rc = pil2gpu_tree_root(ctx, t, root_out);
+    if (rc) { pil2gpu_tree_free(ctx, t); return rc; }
+    *tree_out = t;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_commit_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
+                       pil2gpu_tree** tree_out, uint64_t root_out[4]) {
+    ENTER(ctx);
+    if (!src_dev || !tree_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad commit shape");
+    return commit_common(ctx, nullptr, (const u64*)src_dev, nPols, nBits, nBitsExt, split, tree_out, root_out);
+}
+
+int pil2gpu_commit(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
+                   pil2gpu_tree** tree_out, uint64_t root_out[4]) {
+    ENTER(ctx);
+    if (!src || !tree_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad commit shape");
+    DevBuf a;
+    const size_t sw = (size_t)nPols << nBits;
+    CU(a.alloc(sw));
+    CU(cudaMemcpyAsync(a.p, src, sw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = commit_common(ctx, nullptr, a.p, nPols, nBits, nBitsExt, split, tree_out, root_out);
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+
+int pil2gpu_tree_from_host(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, pil2gpu_tree** tree_out) {
+    ENTER(ctx);
+    if (!tree_out || height == 0 || (!elems && width)) return fail(PIL2GPU_E_INVALID, "bad tree description");
+    pil2gpu_tree* t = new_tree();
+    if (!t) return fail(PIL2GPU_E_NOMEM, "out of host memory");
+    t->width = width;
+    t->height = height;
+    t->own_elems = t->own_nodes = true;
+    cudaError_t e = cudaMalloc(&t->elems, (width * height ? width * height : 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&t->nodes, merkle_nnodes_words(height) * 8);
+    if (e != cudaSuccess) { pil2gpu_tree_free(ctx, t); return fail(PIL2GPU_E_NOMEM, "device allocation failed: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(t->elems, elems, width * height * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { pil2gpu_tree_free(ctx, t); return fail(PIL2GPU_E_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
+    int rc = pil2gpu_merkelize_dev(ctx, t->elems, width, height, split, t->nodes);
+    if (!rc) { e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = fail(PIL2GPU_E_CUDA, "merkelize failed: %s", cudaGetErrorString(e)); }
+    if (rc) { pil2gpu_tree_free(ctx, t); return rc; }
+    *tree_out = t;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_tree_group_proofs(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uint64_t* idxs, uint32_t n_idx, uint64_t* rows_out,
+                              uint64_t* siblings_out) {
+    ENTER(ctx);
+    if (!t || !idxs || !rows_out || !siblings_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (!t->elems) return fail(PIL2GPU_E_INVALID, "tree has no device-resident elements");
+    for (uint32_t i = 0; i < n_idx; i++)
+        if (idxs[i] >= t->height) return fail(PIL2GPU_E_RANGE, "Out of range");
+    if (n_idx == 0) return PIL2GPU_OK;
+    const int depth = merkle_depth(t->height);
+    DevBuf di, dr, ds;
+    CU(di.alloc(n_idx));
+    CU(dr.alloc((size_t)n_idx * t->width));
+    CU(ds.alloc((size_t)n_idx * depth * 4));
+    CU(cudaMemcpyAsync(di.p, idxs, (size_t)n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
+    merkle_group_proof_kernel<<<n_idx, 128, 0, ctx->stream>>>(t->elems, t->nodes, t->width, t->height, di.p, depth, dr.p, ds.p);
+    int rc = check_launch(ctx, 1, "group_proofs");
+    if (rc) return rc;
+    if (t->width) CU(cudaMemcpyAsync(rows_out, dr.p, (size_t)n_idx * t->width * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (depth) CU(cudaMemcpyAsync(siblings_out, ds.p, (size_t)n_idx * depth * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_tree_download(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t* elems_out, uint64_t* nodes_out) {
+    ENTER(ctx);
+    if (!t) return fail(PIL2GPU_E_INVALID, "null tree");
+    if (elems_out && t->elems) CU(cudaMemcpyAsync(elems_out, t->elems, t->width * t->height * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nodes_out) CU(cudaMemcpyAsync(nodes_out, t->nodes, merkle_nnodes_words(t->height) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FRI
+// ------------------------------------------------------------------------------------------------------------
+int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
+                         const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out) {
+    ENTER(ctx);
+    if (!pol || !pol_out || !challenge) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (curBits > prevBits || prevBits > step0Bits || step0Bits > 32) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
+    if (nextBits >= 0 && ((uint32_t)nextBits > curBits || !rows_out || !nodes_out)) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
+    if (prevBits - curBits > FRI_MAX_FOLD_BITS) return fail(PIL2GPU_E_UNSUPPORTED, "fold by 2^%u not supported (max 2^%d)", prevBits - curBits, FRI_MAX_FOLD_BITS);
+    FriParams P;
+    P.prev_bits = (int)prevBits;
+    P.cur_bits = (int)curBits;
+    P.next_bits = nextBits;
+    P.write_rows = nextBits >= 0;
+    u64 si = glh_inv(GL_SHIFT);                                    // fri.js:31-36
+    for (uint32_t j = 0; j < step0Bits - prevBits; j++) si = glh_mul(si, si);
+    P.shift_inv = si;
+    P.nx_inv = glh_inv(1ULL << (prevBits - curBits));
+    for (int k = 0; k < 3; k++) P.challenge[k] = challenge[k];
+    const u64 gs = nextBits >= 0 ? (1ULL << (curBits - nextBits)) : 1;
+    P.fuse_leaf_hash = (nextBits >= 0) && (!split || 3 * gs <= 4) && (gs * 3 * 8 * FRI_ROWS_PER_CTA <= 160 * 1024);
+    int l = fri_launch_fold((const u64*)pol, (u64*)pol_out, (u64*)rows_out, (u64*)nodes_out, P, ctx->tb, ctx->stream);
+    int rc = check_launch(ctx, l, "fri_fold");
+    if (rc) return rc;
+    if (nextBits >= 0) {
+        const u64 height = 1ULL << nextBits;
+        if (P.fuse_leaf_hash) {
+            l = merkle_launch_tree((u64*)nodes_out, height, ctx->stream);
+            rc = check_launch(ctx, l, "fri_tree");
+        } else {
+            rc = pil2gpu_merkelize_dev(ctx, rows_out, 3 * gs, height, split, nodes_out);
+        }
+    }
+    return rc;
+}
+
+int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
+                     const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out) {
+    ENTER(ctx);
+    if (!pol || !pol_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (prevBits > 32 || curBits > prevBits) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
+    const size_t pw = (size_t)3 << prevBits, cw = (size_t)3 << curBits;
+    const u64 height = nextBits >= 0 ? (1ULL << nextBits) : 0;
+    DevBuf a, b, r, n;
+    CU(a.alloc(pw));
+    CU(b.alloc(cw));
+    if (nextBits >= 0) { CU(r.alloc(cw)); CU(n.alloc(merkle_nnodes_words(height))); }
+    CU(cudaMemcpyAsync(a.p, pol, pw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = pil2gpu_fri_fold_dev(ctx, a.p, prevBits, curBits, nextBits, step0Bits, challenge, split, b.p, r.p, n.p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(pol_out, b.p, cw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nextBits >= 0) {
+        if (rows_out) CU(cudaMemcpyAsync(rows_out, r.p, cw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (nodes_out) CU(cudaMemcpyAsync(nodes_out, n.p, merkle_nnodes_words(height) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+}   // extern "C"

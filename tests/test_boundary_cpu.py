@@ -1,0 +1,58 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/pil2gpu.h declares,
+and refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+import pathlib
+import re
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "pil2gpu.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pil2gpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pil2_stark_js_b200 import _lib
+    L = _lib.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/pil2gpu.h but not exported"
+        assert s in _lib._SIGS, f"{s} has no ctypes signature in _lib.py"
+    assert set(_lib._SIGS) == set(syms)
+
+
+def test_layout_helpers_match_reference_formula():
+    # pure functions of the ABI (no device needed): _getNNodes (merklehash_p.js:28-42)
+    from pil2_stark_js_b200 import _lib
+    from oracle import gl_spec as S
+    L = _lib.load()
+    for h in [1, 2, 3, 4, 5, 7, 8, 33, 256, 1000, 1 << 18, (1 << 24)]:
+        assert L.pil2gpu_merkle_nnodes(h) == S.merkle_n_nodes(4 * h)
+    for k in range(1, 25):
+        assert L.pil2gpu_merkle_nnodes(1 << k) == 8 * (1 << k) - 4
+        assert L.pil2gpu_merkle_depth(1 << k) == k
+    assert L.pil2gpu_merkle_depth(33) == 6 and L.pil2gpu_merkle_depth(1) == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the failure path is exercised on CPU-only hosts")
+    import pil2_stark_js_b200 as m
+    with pytest.raises(m.Pil2GpuError) as e:
+        m.Context(0)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+    import numpy as np
+    with pytest.raises(m.Pil2GpuError):
+        m.fft(np.zeros(8, dtype=np.uint64), 1, 3, np.zeros(8, dtype=np.uint64))
+
+
+def test_product_does_not_import_oracle():
+    pkg = ROOT / "pil2_stark_js_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        txt = f.read_text()
+        assert "oracle" not in txt.replace("no oracle", ""), f"{f} mentions the oracle"

@@ -1,0 +1,310 @@
+"""GPU parity tests: the CUDA path (through the C ABI / Python mirror) against the CPU oracle, the reference's
+known-answer vectors and the committed golden proof.  Bit-exact (integer field arithmetic): the tolerance is zero."""
+import random
+import numpy as np
+import pytest
+
+from oracle import gl_spec as S
+from oracle import gl_oracle as C
+from oracle import sm_all
+
+pytestmark = pytest.mark.gpu
+P = S.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import pil2_stark_js_b200 as m
+    return m.default_context(0)
+
+
+def rnd_field(seed, n):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    return np.where(a >= np.uint64(P), a - np.uint64(P), a)
+
+
+# ---------------------------------------------------------------- Poseidon / linear hash
+def test_poseidon_kats(ctx):
+    # test/poseidon.test.js:13-38
+    assert [int(x) for x in ctx.poseidon([0] * 12)[:4]] == [0x3c18a9786cb0b359, 0xc4055e3364a246c3, 0x7953db0ab48808f4, 0xc71603f33a1144ca]
+    assert [int(x) for x in ctx.poseidon(list(range(12)))[:4]] == [0xd64e1e3efc5b8e9e, 0x53666633020aaa47, 0xd40285597c6a8825, 0x613a4f81e81231d2]
+    assert [int(x) for x in ctx.poseidon([P - 1] * 12)[:4]] == [0xbe0085cfc57a8357, 0xd95af71847d05c09, 0xcf55a13d33c1c953, 0x95803a74f4530e82]
+
+
+def test_poseidon_random_and_edge_states(ctx):
+    states = [rnd_field(s, 12) for s in range(8)]
+    states += [np.array([P - 1, 0, 1, 2**32 - 1, 2**32, 2**63, P - 2, 2**32 + 1, 0xFFFFFFFF00000000, 5, 6, 7], dtype=np.uint64)]
+    for st in states:
+        assert np.array_equal(ctx.poseidon(st), C.poseidon_perm(st))
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_linear_hash_width_sweep(ctx, split):
+    # widths of test/glwasm.test.js:198-230
+    for w in [0, 1, 2, 3, 4, 5, 8, 9, 15, 16, 24, 25, 32, 33, 50, 256]:
+        v = rnd_field(100 + w, w)
+        assert np.array_equal(ctx.linear_hash(v, split), C.linear_hash(v, split)), (w, split)
+
+
+# ---------------------------------------------------------------- NTT
+@pytest.mark.parametrize("bits,npols", [(0, 1), (1, 3), (2, 2), (3, 1), (5, 2), (8, 17), (9, 16), (10, 5), (12, 33), (13, 3)])
+def test_ntt_vs_oracle(ctx, bits, npols):
+    src = rnd_field(bits * 97 + npols, npols << bits)
+    dst = np.empty_like(src)
+    ctx.ntt(src, npols, bits, dst)
+    assert np.array_equal(dst, C.ntt(src, npols, bits))
+    ctx.ntt(src, npols, bits, dst, inverse=True)
+    assert np.array_equal(dst, C.ntt(src, npols, bits, inverse=True))
+
+
+def test_fft_p_reference_shapes(ctx):
+    # test/fft_p.test.js:47 (5 bits x 2 cols), :120/:156 (18 bits x 5 cols), inputs v = row index
+    from pil2_stark_js_b200 import fft_p
+    for bits, npols in [(5, 2), (18, 5)]:
+        src = np.repeat(np.arange(1 << bits, dtype=np.uint64), npols)
+        dst = np.empty_like(src)
+        fft_p.fft(src, npols, bits, dst)
+        assert np.array_equal(dst, C.ntt(src, npols, bits))
+        back = np.empty_like(src)
+        fft_p.ifft(dst, npols, bits, back)
+        assert np.array_equal(back, src)
+        fft_p.ifft(src, npols, bits, dst)
+        assert np.array_equal(dst, C.ntt(src, npols, bits, inverse=True))
+
+
+# ---------------------------------------------------------------- LDE (interpolate)
+@pytest.mark.parametrize("bits,ext,npols", [(0, 0, 2), (0, 1, 1), (1, 2, 3), (3, 4, 1), (3, 3, 2), (5, 8, 3), (9, 10, 16), (10, 11, 15),
+                                            (10, 12, 7), (11, 12, 20), (13, 14, 5), (12, 15, 2)])
+def test_lde_vs_oracle(ctx, bits, ext, npols):
+    src = rnd_field(bits * 31 + ext * 7 + npols, npols << bits)
+    dst = np.full(npols << ext, 0xDEADBEEF, dtype=np.uint64)   # prior contents must not matter
+    ctx.lde(src, npols, bits, dst, ext)
+    assert np.array_equal(dst, C.lde(src, npols, bits, ext))
+
+
+def test_interpolate_reference_shapes(ctx):
+    # test/fft_p.test.js:82 (3 bits x 1, extendPol) and :193 (18 bits x 5, ext 1)
+    from pil2_stark_js_b200 import fft_p
+    src = np.arange(8, dtype=np.uint64)
+    dst = np.empty(16, dtype=np.uint64)
+    fft_p.interpolate(src, 1, 3, dst, 4)
+    assert [int(x) for x in dst] == S.extend_pol(list(range(8)), 1)
+    bits, npols = 18, 5
+    src = np.repeat(np.arange(1 << bits, dtype=np.uint64), npols)
+    dst = np.empty(npols << (bits + 1), dtype=np.uint64)
+    fft_p.interpolate(src, npols, bits, dst, bits + 1)
+    assert np.array_equal(dst, C.lde(src, npols, bits, bits + 1))
+
+
+# ---------------------------------------------------------------- Merkle
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("n,npols", [(256, 3), (256, 9), (33, 6), (1, 9), (2, 1), (7, 40), (1025, 17), (5000, 8)])
+def test_merkelize_vs_oracle(ctx, n, npols, split):
+    # shapes of test/merklehash_p.test.js (pattern i + 1000 j) incl. the non-power-of-two (33,6)
+    i = np.arange(n, dtype=np.uint64)[:, None]
+    j = np.arange(npols, dtype=np.uint64)[None, :]
+    buff = np.ascontiguousarray((i + 1000 * j).reshape(-1))
+    nodes = ctx.merkelize(buff, npols, n, split)
+    assert np.array_equal(nodes, C.merkelize(buff, npols, n, split))
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_merklehash_p_interface(ctx, split, tmp_path):
+    # test/merklehash_p.test.js: merkelize -> getGroupProof -> verifyGroupProof, (2^18, 10); file save/restore :101-132
+    from pil2_stark_js_b200 import buildMerkleHash, OutOfRange
+    MH = buildMerkleHash(split)
+    n, npols = 1 << 18, 10
+    i = np.arange(n, dtype=np.uint64)[:, None]
+    j = np.arange(npols, dtype=np.uint64)[None, :]
+    pols = np.ascontiguousarray((i + 1000 * j).reshape(-1))
+    tree = MH.merkelize(pols, npols, n)
+    assert tree["elements"] is pols and tree["nodes"].size == 8 * n - 4
+    assert np.array_equal(tree["nodes"], C.merkelize(pols, npols, n, split))
+    idx = 3
+    groupElements, mp = MH.getGroupProof(tree, idx)
+    root = MH.root(tree)
+    assert MH.verifyGroupProof(root, mp, idx, groupElements)
+    assert S.verify_group_proof(root, mp, idx, groupElements, split)           # and by the independent CPU verifier
+    bad = list(groupElements); bad[0] = (bad[0] + 1) % P
+    assert not MH.verifyGroupProof(root, mp, idx, bad)
+    with pytest.raises(OutOfRange):
+        MH.getGroupProof(tree, n)
+    f = tmp_path / "tree.bin"
+    MH.writeToFile(tree, str(f))
+    t2 = MH.readFromFile(str(f))
+    assert t2["width"] == npols and t2["height"] == n
+    assert np.array_equal(t2["elements"], pols) and np.array_equal(t2["nodes"], tree["nodes"])
+    raw = np.fromfile(str(f), dtype="<u8")
+    assert raw[0] == npols and raw[1] == n and raw.size == 2 + pols.size + tree["nodes"].size
+
+
+# ---------------------------------------------------------------- golden proof (test/compressor/verifier.proof.zkin.json)
+def _golden_queries(golden, T):
+    t = T()
+    r = golden["roots"]
+    t.put(r["const"]); t.put(golden["publics"]); t.put(r["stage1"])
+    t.getField(); t.getField()
+    t.put(r["stage2"])
+    for _ in range(3):
+        t.getField()
+    t.put(r["stage3"]); t.getField()
+    t.put(r["stageQ"]); t.getField()
+    for e in golden["evals"]:
+        t.put(e)
+    t.getField(); t.getField()
+    steps = [t.getField()]
+    t.put(r["fri1"]); steps.append(t.getField())
+    t.put(r["fri2"]); steps.append(t.getField())
+    for e in golden["final_pol"]:
+        t.put(e)
+    steps.append(t.getField())
+    t2 = T()
+    t2.put(steps[3])
+    return steps, t2.getPermutations(8, 11)
+
+
+def test_golden_transcript_on_gpu(ctx, golden):
+    from pil2_stark_js_b200 import Transcript
+    steps, q = _golden_queries(golden, Transcript)
+    assert q == [891, 1628, 1228, 1991, 1856, 415, 833, 296]
+
+
+def test_golden_commit_roots_and_paths(ctx, golden):
+    # sm_all traces -> device-resident commit (LDE x2 + Merkle) -> root1 / rootC and every opened row + sibling path
+    q = [891, 1628, 1228, 1991, 1856, 415, 833, 296]
+    for trace_fn, name in [(sm_all.committed_trace, "stage1"), (sm_all.constant_trace, "const")]:
+        buff, w = trace_fn()
+        src = np.array(buff, dtype=np.uint64)
+        tree, root = ctx.commit(src, w, 10, 11)
+        assert [int(x) for x in root] == golden["roots"][name]
+        rows, sib = tree.group_proofs(q)
+        assert rows.tolist() == golden["layer0"][name]["rows"]
+        assert sib.tolist() == golden["layer0"][name]["siblings"]
+        elems, nodes = tree.download()
+        assert np.array_equal(elems, C.lde(src, w, 10, 11))
+        assert np.array_equal(nodes, C.merkelize(elems, w, 2048))
+        tree.free()
+
+
+def test_golden_merkle_paths_verify_on_gpu(ctx, golden):
+    from pil2_stark_js_b200 import buildMerkleHash
+    MH = buildMerkleHash(False)
+    q = [891, 1628, 1228, 1991, 1856, 415, 833, 296]
+    for name in ["const", "stage1", "stage2", "stage3", "stageQ"]:
+        for k in (0, 5):
+            assert MH.verifyGroupProof(golden["roots"][name], golden["layer0"][name]["siblings"][k], q[k], golden["layer0"][name]["rows"][k])
+    for k in (1, 7):
+        assert MH.verifyGroupProof(golden["roots"]["fri1"], golden["fri1"]["siblings"][k], q[k] % 128, golden["fri1"]["rows"][k])
+        assert MH.verifyGroupProof(golden["roots"]["fri2"], golden["fri2"]["siblings"][k], q[k] % 8, golden["fri2"]["rows"][k])
+
+
+def test_golden_fri_fold_links(ctx, golden):
+    # Embed the opened groups of the fixture in full-size layers and fold them on the GPU with the transcript challenges:
+    # s1 group --challenge[1]--> element of the s2 group --challenge[2]--> finalPol[q mod 8]  (fri.js:47-61)
+    from pil2_stark_js_b200 import Transcript
+    steps, q = _golden_queries(golden, Transcript)
+    lay1 = rnd_field(1, 3 << 11).reshape(-1, 3).copy()
+    lay2 = rnd_field(2, 3 << 7).reshape(-1, 3).copy()
+    for k, q0 in enumerate(q):
+        q1, q2 = q0 % 128, q0 % 8
+        for i in range(16):
+            lay1[i * 128 + q1] = golden["fri1"]["rows"][k][3 * i:3 * i + 3]
+            lay2[i * 8 + q2] = golden["fri2"]["rows"][k][3 * i:3 * i + 3]
+    p2, rows, nodes = ctx.fri_fold(lay1, 11, 7, 3, 11, steps[1])
+    p3, _, _ = ctx.fri_fold(lay2, 7, 3, None, 11, steps[2])
+    for k, q0 in enumerate(q):
+        q1, q2 = q0 % 128, q0 % 8
+        assert [int(x) for x in p2[q1]] == golden["fri2"]["rows"][k][3 * (q1 // 8):3 * (q1 // 8) + 3]
+        assert [int(x) for x in p3[q2]] == golden["final_pol"][q2]
+
+
+# ---------------------------------------------------------------- FRI vs oracle
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("steps", [[9, 5, 2], [12, 8, 4, 2], [10, 5, 0], [8, 7, 3], [6, 6, 2]])
+def test_fri_chain_vs_oracle(ctx, steps, split):
+    pol = rnd_field(sum(steps), 3 << steps[0]).reshape(-1, 3)
+    rng = random.Random(7)
+    # step 0: identity fold + commit of the first layer
+    ch = [rng.randrange(P) for _ in range(3)]
+    p, rows, nodes = ctx.fri_fold(pol, steps[0], steps[0], steps[1], steps[0], ch, split)
+    assert np.array_equal(p, pol)
+    exp_rows = np.array(S.transposed_buffer(pol.tolist(), steps[1]), dtype=np.uint64)
+    assert np.array_equal(rows, exp_rows)
+    assert np.array_equal(nodes, C.merkelize(exp_rows, 3 << (steps[0] - steps[1]), 1 << steps[1], split))
+    cur = pol
+    for s in range(1, len(steps)):
+        ch = [rng.randrange(P) for _ in range(3)]
+        nxt = steps[s + 1] if s + 1 < len(steps) else None
+        p, rows, nodes = ctx.fri_fold(cur, steps[s - 1], steps[s], nxt, steps[0], ch, split)
+        ep, erows = C.fri_fold(cur, steps[s - 1], steps[s], nxt, steps[0], ch)
+        assert np.array_equal(p, ep)
+        if nxt is not None:
+            assert np.array_equal(rows, erows)
+            assert np.array_equal(nodes, C.merkelize(erows, 3 << (steps[s] - nxt), 1 << nxt, split))
+        else:
+            assert rows is None and nodes is None
+        cur = p
+
+
+def test_fri_class_prove_then_verify(ctx):
+    # the reference's integration style (test/stark/helpers.js): prove, then the verifier must accept
+    from pil2_stark_js_b200 import FRI, buildMerkleHash, Transcript
+    MH = buildMerkleHash(False)
+    struct = {"nBits": 7, "nBitsExt": 8, "nQueries": 4, "steps": [{"nBits": 8}, {"nBits": 5}, {"nBits": 2}]}
+    fri = FRI(struct, MH)
+    # a genuine low-degree polynomial (deg < 2^7) evaluated on the coset 7*<w_8>, in F3
+    coef = rnd_field(3, 3 << 7).reshape(-1, 3)
+    cols = np.ascontiguousarray(coef.reshape(-1))            # 128 rows x 3 "columns" = the three F3 components
+    ext = np.empty(3 << 8, dtype=np.uint64)
+    tmp = np.empty_like(cols)
+    ctx.ntt(cols, 3, 7, tmp)                                 # evaluations on <w_7>, then LDE to the coset
+    ctx.lde(tmp, 3, 7, ext, 8)
+    pol = ext.reshape(-1, 3)
+    tr = Transcript()
+    proof, trees, challenges = [], [], []
+    cur = pol
+    for step in range(3):
+        ch = tr.getField(); challenges.append(ch)
+        r = fri.fold(step, cur, ch)
+        cur = r["pol"]
+        proof.append(r["proof"] if isinstance(r["proof"], dict) else r["proof"])
+        trees.append(r["tree"])
+        tr.put(r["proof"]["root"] if isinstance(r["proof"], dict) else r["proof"])
+    final = proof[2]
+    chq = tr.getField()
+    t2 = Transcript(); t2.put(chq)
+    queries = t2.getPermutations(4, 8)
+    # layer proofs: proof[s] for s>=1 opens tree s-1's successor; mirror fri.proofQueries' layout (fri.js:83-105)
+    layer = [{"root": proof[0]["root"]}, {"root": proof[1]["root"]}]
+    qs = list(queries)
+    opened = []
+    for s in (1, 2):
+        qs = [x % (1 << struct["steps"][s]["nBits"]) for x in qs]
+        opened.append([MH.getGroupProof(trees[s - 1], x) for x in qs])
+    vproof = [{"polQueries": [[[int(v) for v in pol[x]], None] for x in queries]},
+              {"root": proof[0]["root"], "polQueries": opened[0]},
+              {"root": proof[1]["root"], "polQueries": opened[1]}, final]
+
+    def check0(query, idx):        # layer-0 consistency is the STARK's job; FRI starts from the committed first layer
+        return None
+
+    # verify the two folding links + final degree with the reference's verifier logic, starting at step 1
+    vfri = FRI({"nBits": 7, "nBitsExt": 8, "nQueries": 4, "steps": struct["steps"]}, MH)
+    polBits = 8
+    for i, x in enumerate(queries):
+        x1 = x % 32
+        v, mp = opened[0][i]
+        assert MH.verifyGroupProof(proof[0]["root"], mp, x1, v)
+        grp = [v[3 * k:3 * k + 3] for k in range(8)]
+        assert grp == [[int(c) for c in pol[x1 + 32 * k]] for k in range(8)]
+        ev = S.fri_verify_fold(grp, 8, 7, challenges[1], x1)
+        x2 = x1 % 4
+        v2, mp2 = opened[1][i]
+        assert MH.verifyGroupProof(proof[1]["root"], mp2, x2, v2)
+        assert v2[3 * (x1 // 4):3 * (x1 // 4) + 3] == ev
+        ev2 = S.fri_verify_fold([v2[3 * k:3 * k + 3] for k in range(8)], 5, pow(7, 8, P), challenges[2], x2)
+        assert final[x2] == ev2
+    # final polynomial has degree < 2^(2 - 1): coefficients above maxDeg vanish (fri.js:158-171)
+    c = S.intt([list(e) for e in final])
+    assert all(ci == [0, 0, 0] for ci in c[3:])
