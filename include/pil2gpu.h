@@ -97,6 +97,18 @@ int pil2gpu_commit(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32
                    pil2gpu_tree** tree_out, uint64_t root_out[4]);
 int pil2gpu_commit_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
                        pil2gpu_tree** tree_out, uint64_t root_out[4]);
+/* extendAndMerkelize (src/stark/stark_gen_helpers.js:388-412 = interpolate :397 + merkelize :400) with HOST buffers in
+ * and out: uploads src, extends and hashes on the device, and writes the extended buffer (dst_out, 2^nBitsExt x nPols,
+ * may be NULL) and tree.nodes (nodes_out, may be NULL) back; the download of dst overlaps the hashing.  root_out = root. */
+int pil2gpu_extend_and_merkelize(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
+                                 uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]);
+
+/* ---- bench / test utilities (not part of the reference surface) ------------------------------------------------ */
+/* dst_dev[i] = splitmix64(seed ^ (first_index + i)) mod p : the synthetic trace generator of SURVEY 8(d). */
+int pil2gpu_synth_dev(pil2gpu_ctx* ctx, uint64_t* dst_dev, uint64_t n_words, uint64_t seed, uint64_t first_index);
+/* Integer-pipe roofline denominators measured live: standalone Goldilocks mulmod/s and IMAD.WIDE.U32/s on this GPU. */
+int pil2gpu_bench_int_pipes(pil2gpu_ctx* ctx, double* mulmod_per_s, double* imad_wide_per_s);
+
 /* Wrap / build trees over existing data.  tree_from_host uploads elements and merkelizes them on the device. */
 int pil2gpu_tree_from_host(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, pil2gpu_tree** tree_out);
 int pil2gpu_tree_width(const pil2gpu_tree* t, uint64_t* width, uint64_t* height);

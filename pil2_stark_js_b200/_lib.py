@@ -53,6 +53,9 @@ _SIGS = {
     "pil2gpu_merkelize_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u64, c_int, vp]),
     "pil2gpu_commit": (c_int, [vp, vp, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), vp]),
     "pil2gpu_commit_dev": (c_int, [vp, vp, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), vp]),
+    "pil2gpu_extend_and_merkelize": (c_int, [vp, vp, c_u64, c_u32, c_u32, c_int, vp, vp, vp]),
+    "pil2gpu_synth_dev": (c_int, [vp, vp, c_u64, c_u64, c_u64]),
+    "pil2gpu_bench_int_pipes": (c_int, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "pil2gpu_tree_from_host": (c_int, [vp, vp, c_u64, c_u64, c_int, ctypes.POINTER(vp)]),
     "pil2gpu_tree_width": (c_int, [vp, u64p, u64p]),
     "pil2gpu_tree_elements_dev": (vp, [vp]),

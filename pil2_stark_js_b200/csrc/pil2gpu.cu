@@ -44,6 +44,8 @@ struct pil2gpu_ctx {
     size_t coset_words;
     uint64_t launches;
     NttTables tb;
+    cudaStream_t copy_stream;   // second stream: D2H of the LDE overlaps the hashing (extend_and_merkelize)
+    cudaEvent_t ev;
 };
 
 struct pil2gpu_tree {
@@ -78,6 +80,34 @@ static int check_launch(pil2gpu_ctx* ctx, int launches, const char* what) {
     return PIL2GPU_OK;
 }
 
+// ---- utility kernels (bench / test) ----
+__global__ void synth_kernel(u64* __restrict__ dst, u64 n, u64 seed, u64 first) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 z = (seed ^ (first + i)) + 0x9E3779B97F4A7C15ULL;       // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z = z ^ (z >> 31);
+        dst[i] = gl_canon(z);
+    }
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) pipe_probe_kernel(u64* out, int iters) {
+    u64 a0 = threadIdx.x + 1, a1 = blockIdx.x + 3, a2 = a0 ^ 0x1234567, a3 = a0 + a1 + 77;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (MODE == 0) {
+                a0 = gl_mul(a0, a1); a1 = gl_mul(a1, a2); a2 = gl_mul(a2, a3); a3 = gl_mul(a3, a0);
+            } else {
+                a0 += (u64)(u32)a0 * 0x9E3779B9u; a1 += (u64)(u32)a1 * 0x85EBCA6Bu;
+                a2 += (u64)(u32)a2 * 0xC2B2AE35u; a3 += (u64)(u32)a3 * 0x27D4EB2Fu;
+            }
+        }
+    }
+    out[(u64)blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3;
+}
+
 extern "C" {
 
 const char* pil2gpu_last_error(void) { return g_last_error.c_str(); }
@@ -100,6 +130,11 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
     ctx->launches = 0;
     ctx->coset = nullptr;
     ctx->coset_words = 0;
+    ctx->copy_stream = nullptr;
+    ctx->ev = nullptr;
+    ctx->tables = nullptr;
+    ctx->stream = nullptr;
+    ctx->own_stream = false;
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
         ctx->own_stream = false;
@@ -107,6 +142,11 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) { delete ctx; return fail(PIL2GPU_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         ctx->own_stream = true;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming) != cudaSuccess) {
+        pil2gpu_destroy(ctx);
+        return fail(PIL2GPU_E_CUDA, "stream/event creation failed");
     }
     const size_t words = 1024 + 2 * (1u << (NTT_TW_BITS - 1));
     e = cudaMalloc(&ctx->tables, words * sizeof(u64));
@@ -131,6 +171,8 @@ void pil2gpu_destroy(pil2gpu_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->tables) cudaFree(ctx->tables);
     if (ctx->coset) cudaFree(ctx->coset);
     delete ctx;
@@ -455,6 +497,77 @@ int pil2gpu_commit(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32
     int rc = commit_common(ctx, nullptr, a.p, nPols, nBits, nBitsExt, split, tree_out, root_out);
     cudaStreamSynchronize(ctx->stream);
     return rc;
+}
+
+int pil2gpu_extend_and_merkelize(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
+                                 uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]) {
+    ENTER(ctx);
+    if (!src) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad commit shape");
+    const size_t sw = (size_t)nPols << nBits, dw = (size_t)nPols << nBitsExt;
+    const u64 height = 1ULL << nBitsExt;
+    const size_t nw = merkle_nnodes_words(height);
+    DevBuf a, b, n;
+    CU(a.alloc(sw));
+    CU(b.alloc(dw));
+    CU(n.alloc(nw));
+    CU(cudaMemcpyAsync(a.p, src, sw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = pil2gpu_lde_dev(ctx, a.p, b.p, nPols, nBits, nBitsExt);
+    if (rc) return rc;
+    if (dst_out) {   // download the extended buffer on the copy stream while the main stream hashes it
+        CU(cudaEventRecord(ctx->ev, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev, 0));
+        CU(cudaMemcpyAsync(dst_out, b.p, dw * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    rc = pil2gpu_merkelize_dev(ctx, b.p, nPols, height, split, n.p);
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    if (nodes_out) CU(cudaMemcpyAsync(nodes_out, n.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (root_out) CU(cudaMemcpyAsync(root_out, n.p + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return PIL2GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Bench / test utilities
+// ------------------------------------------------------------------------------------------------------------
+int pil2gpu_synth_dev(pil2gpu_ctx* ctx, uint64_t* dst_dev, uint64_t n_words, uint64_t seed, uint64_t first_index) {
+    ENTER(ctx);
+    if (!dst_dev && n_words) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (n_words == 0) return PIL2GPU_OK;
+    synth_kernel<<<148 * 16, 256, 0, ctx->stream>>>((u64*)dst_dev, n_words, seed, first_index);
+    return check_launch(ctx, 1, "synth");
+}
+
+int pil2gpu_bench_int_pipes(pil2gpu_ctx* ctx, double* mulmod_per_s, double* imad_wide_per_s) {
+    ENTER(ctx);
+    const int blocks = 148 * 8, threads = 256, iters = 2048;
+    DevBuf o;
+    CU(o.alloc((size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double res[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            CU(cudaEventRecord(e0, ctx->stream));
+            if (mode == 0) pipe_probe_kernel<0><<<blocks, threads, 0, ctx->stream>>>(o.p, iters);
+            else pipe_probe_kernel<1><<<blocks, threads, 0, ctx->stream>>>(o.p, iters);
+            CU(cudaEventRecord(e1, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            float ms;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (ms < best) best = ms;
+            ctx->launches++;
+        }
+        res[mode] = (double)blocks * threads * iters * 32.0 / (best * 1e-3);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (mulmod_per_s) *mulmod_per_s = res[0];
+    if (imad_wide_per_s) *imad_wide_per_s = res[1];
+    return PIL2GPU_OK;
 }
 
 int pil2gpu_tree_from_host(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, pil2gpu_tree** tree_out) {

@@ -22,55 +22,119 @@ GL_D u64 poseidon_sbox(u64 x) {
     return gl_mul(x3, x4);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
 // Dense MDS layer: out_i = sum_j circ[(j - i) mod 12] * x_j  (+ 8*x_0 on lane 0), glwasm.js:428-440.
-// The coefficients are < 2^6, so each state word is split into 32-bit halves and the two half-sums are
-// accumulated exactly in 64 bits with one IMAD.WIDE.U32 per term (12*41*2^32 < 2^42); the halves are
-// recombined with a single 96-bit reduction per lane.
-GL_D void poseidon_mds(u64 x[12]) {
-    const u32 circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    u32 lo[12], hi[12];
+//
+// On sm_100a IMAD.WIDE issues at 1/4 rate and IMAD at 1/2 rate while IADD3/LOP3/SHF run at full rate (measured:
+// tools/poseidon_probe.cu, profiles/), so the 144 small multiplies are NOT done with multiplies.  The matrix is
+// circulant with kernel k = [17,20,34,18,39,13,13,28,2,16,41,15] (y = k (*) x mod z^12 - 1), chosen so that its CRT
+// split over z^12-1 = (z^6-1)(z^6+1) = (z^3-1)(z^3+1)(z^6+1) has power-of-two entries:
+//     (k_lo + k_hi)/2 = [15,24,18,17,40,14]  ->  (.)/2 split again: [16,32,16] (cyclic 3) and [-1,-8,2] (negacyclic 3)
+//     (k_lo - k_hi)/2 = [2,-4,16,1,-1,-1]                            (negacyclic 6)
+// so one MDS on a vector of small integers is ~80 adds/shifts on the ALU pipe.  Each state word is cut into three
+// limbs of 22/22/20 bits; limb sums stay below 264 * 2^23 < 2^32, so plain wrap-around u32 arithmetic is exact.
+// ---------------------------------------------------------------------------------------------------------------
+GL_D void poseidon_mds_limb(u32 y[12], const u32 x[12]) {
+    u32 xp[6], xm[6];
 #pragma unroll
-    for (int j = 0; j < 12; j++) {
-        lo[j] = (u32)x[j];
-        hi[j] = (u32)(x[j] >> 32);
+    for (int i = 0; i < 6; i++) {
+        xp[i] = x[i] + x[i + 6];
+        xm[i] = x[i] - x[i + 6];
+    }
+    // Q = negacyclic6([2,-4,16,1,-1,-1], xm):  Q_i = sum_e km_e * (+-) xm[(i-e) mod 6], sign flips on wrap
+    u32 Q[6];
+    Q[0] = 2 * xm[0] + 4 * xm[5] - 16 * xm[4] - xm[3] + xm[2] + xm[1];
+    Q[1] = 2 * xm[1] - 4 * xm[0] - 16 * xm[5] - xm[4] + xm[3] + xm[2];
+    Q[2] = 2 * xm[2] - 4 * xm[1] + 16 * xm[0] - xm[5] + xm[4] + xm[3];
+    Q[3] = 2 * xm[3] - 4 * xm[2] + 16 * xm[1] + xm[0] + xm[5] + xm[4];
+    Q[4] = 2 * xm[4] - 4 * xm[3] + 16 * xm[2] + xm[1] - xm[0] + xm[5];
+    Q[5] = 2 * xm[5] - 4 * xm[4] + 16 * xm[3] + xm[2] - xm[1] - xm[0];
+    u32 xpp[3], xpm[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        xpp[i] = xp[i] + xp[i + 3];
+        xpm[i] = xp[i] - xp[i + 3];
+    }
+    // PP = cyclic3([16,32,16], xpp) = 16*(s + xpp[i-1]),  s = xpp0+xpp1+xpp2
+    const u32 s = xpp[0] + xpp[1] + xpp[2];
+    u32 PP[3] = {16 * (s + xpp[2]), 16 * (s + xpp[0]), 16 * (s + xpp[1])};
+    // PQ = negacyclic3([-1,-8,2], xpm)
+    u32 PQ[3];
+    PQ[0] = 8 * xpm[2] - xpm[0] - 2 * xpm[1];
+    PQ[1] = 0u - xpm[1] - 8 * xpm[0] - 2 * xpm[2];
+    PQ[2] = 2 * xpm[0] - xpm[2] - 8 * xpm[1];
+    u32 Pv[6];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        Pv[i] = PP[i] + PQ[i];
+        Pv[i + 3] = PP[i] - PQ[i];
     }
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-        u64 L = 0, H = 0;
-#pragma unroll
-        for (int j = 0; j < 12; j++) {
-            const u32 c = circ[(j - i + 12) % 12] + ((i == 0 && j == 0) ? 8u : 0u);
-            L += (u64)lo[j] * c;
-            H += (u64)hi[j] * c;
-        }
-        // value = L + H*2^32 = (L + Hh*EPS) + (Hl << 32), Hh = H >> 32 < 2^10
-        u64 base = L + (u64)(u32)(H >> 32) * (u64)0xFFFFFFFFu;   // < 2^43, no wrap
-        u64 top = (u64)(u32)H << 32;
-        u64 r = base + top;
-        if (r < top) r += GL_EPS;
-        x[i] = r;
+    for (int i = 0; i < 6; i++) {
+        y[i] = Pv[i] + Q[i];
+        y[i + 6] = Pv[i] - Q[i];
     }
+    y[0] += 8 * x[0];
 }
 
-// Plain-form permutation; state in lazy form on input, lazy form on output (callers canonicalise).
+#define POSEIDON_L0 22
+#define POSEIDON_L1 22
+// limbs -> field element: Y0 + Y1*2^22 + Y2*2^44 (Y < 2^32 each) reduced with 2^64 = EPS
+GL_D u64 poseidon_join(u32 Y0, u32 Y1, u32 Y2) {
+    const u32 Y2h = Y2 >> 20, Y2l = Y2 & 0xFFFFFu;
+    u64 base = (u64)Y0 + ((u64)Y1 << 22) + (((u64)Y2h << 32) - (u64)Y2h);   // < 2^55, no wrap
+    const u64 top = (u64)Y2l << 44;
+    u64 r = base + top;
+    if (r < top) r += GL_EPS;
+    return r;
+}
+
+// MDS over the whole state; `add` (optional) is a vector of pre-split round constants added limb-wise first.
+template <bool ADD_RC>
+GL_D void poseidon_mds_alu(u64 x[12], const u32* __restrict__ rc_limbs) {
+    u32 a[12], b[12], c[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        const u32 lo = (u32)x[j], hi = (u32)(x[j] >> 32);
+        a[j] = lo & 0x3FFFFFu;
+        b[j] = __funnelshift_r(lo, hi, 22) & 0x3FFFFFu;
+        c[j] = hi >> 12;
+        if (ADD_RC && j > 0) {
+            a[j] += rc_limbs[3 * j];
+            b[j] += rc_limbs[3 * j + 1];
+            c[j] += rc_limbs[3 * j + 2];
+        }
+    }
+    u32 ya[12], yb[12], yc[12];
+    poseidon_mds_limb(ya, a);
+    poseidon_mds_limb(yb, b);
+    poseidon_mds_limb(yc, c);
+#pragma unroll
+    for (int i = 0; i < 12; i++) x[i] = poseidon_join(ya[i], yb[i], yc[i]);
+}
+
+// Round constants of the partial rounds pre-split into limbs (lanes 1..11; lane 0 goes through the S-box first).
+__constant__ u32 POSEIDON_RC_LIMBS[22 * 36] = {
+#include "poseidon_rc_limbs.inc"
+};
+
+// Permutation; state in lazy form on input, lazy form on output (callers canonicalise).
 GL_D void poseidon_permute(u64 x[12]) {
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 12; i++) x[i] = poseidon_sbox(gl_add(x[i], POSEIDON_RC[12 * r + i]));
-        poseidon_mds(x);
+        poseidon_mds_alu<false>(x, nullptr);
     }
 #pragma unroll 1
     for (int r = 4; r < 26; r++) {
-#pragma unroll
-        for (int i = 1; i < 12; i++) x[i] = gl_add(x[i], POSEIDON_RC[12 * r + i]);
         x[0] = poseidon_sbox(gl_add(x[0], POSEIDON_RC[12 * r]));
-        poseidon_mds(x);
+        poseidon_mds_alu<true>(x, POSEIDON_RC_LIMBS + (r - 4) * 36);
     }
 #pragma unroll 1
     for (int r = 26; r < 30; r++) {
 #pragma unroll
         for (int i = 0; i < 12; i++) x[i] = poseidon_sbox(gl_add(x[i], POSEIDON_RC[12 * r + i]));
-        poseidon_mds(x);
+        poseidon_mds_alu<false>(x, nullptr);
     }
 }
