@@ -46,16 +46,32 @@ GL_D u64 gl_sub(u64 a, u64 b) {
 
 GL_D u64 gl_neg(u64 a) { return gl_sub(0, a); }
 
-// 128 -> 64 bits: hi*2^64 + lo  ==  lo - (hi >> 32) + (hi & EPS) * EPS   (2^64 = 2^32 - 1, 2^96 = -1 mod p)
+// 128 -> 64 bits with 2^64 = 2^32 - 1 and 2^96 = -1 (mod p):
+//     hi*2^64 + lo  ==  V = lo + h0*2^32 - h0 - h1     (h0 = low word of hi, h1 = high word of hi)
+// V is computed exactly in three 32-bit words (top word v2 in {-1,0,1}) with carry chains, then v2*2^64 = v2*EPS is
+// folded once; no second wrap is possible (V <= 2^65 - 2^33 and V >= -(2^32 - 1)).  12 ALU-pipe instructions, no
+// multiply and no compare/select pairs (the compiler's version of the same identity costs ~17 incl. one IMAD.WIDE).
 GL_D u64 gl_reduce128(u64 hi, u64 lo) {
-    u32 hh = (u32)(hi >> 32);
-    u32 hl = (u32)hi;
-    u64 t0 = lo - hh;
-    if (lo < (u64)hh) t0 -= GL_EPS;          // cannot underflow: wrapped t0 >= 2^64 - 2^32
-    u64 t1 = (u64)hl * (u64)0xFFFFFFFFu;     // one IMAD.WIDE.U32
-    u64 r = t0 + t1;
-    if (r < t1) r += GL_EPS;                 // cannot wrap again: t1 <= 2^64 - 2^33 + 1
-    return r;
+    const u32 l0 = (u32)lo, l1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32);
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 v0, v1, v2, t, m;\n\t"
+        "sub.cc.u32  v0, %2, %4;\n\t"
+        "subc.cc.u32 v1, %3, 0;\n\t"
+        "subc.u32    v2, 0, 0;\n\t"
+        "sub.cc.u32  v0, v0, %5;\n\t"
+        "subc.cc.u32 v1, v1, 0;\n\t"
+        "subc.u32    v2, v2, 0;\n\t"
+        "add.cc.u32  v1, v1, %4;\n\t"
+        "addc.u32    v2, v2, 0;\n\t"
+        "neg.s32     t, v2;\n\t"
+        "shr.s32     m, v2, 31;\n\t"
+        "add.cc.u32  %0, v0, t;\n\t"
+        "addc.u32    %1, v1, m;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
+    return ((u64)r1 << 32) | r0;
 }
 
 GL_D u64 gl_mul(u64 a, u64 b) { return gl_reduce128(__umul64hi(a, b), a * b); }

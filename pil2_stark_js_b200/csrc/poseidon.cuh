@@ -89,8 +89,7 @@ GL_D u64 poseidon_join(u32 Y0, u32 Y1, u32 Y2) {
     return r;
 }
 
-// MDS over the whole state; `add` (optional) is a vector of pre-split round constants added limb-wise first.
-template <bool ADD_RC>
+// MDS over the whole state followed by the limb-wise addition of the NEXT round's constants (rc_limbs: [lane][limb]).
 GL_D void poseidon_mds_alu(u64 x[12], const u32* __restrict__ rc_limbs) {
     u32 a[12], b[12], c[12];
 #pragma unroll
@@ -99,42 +98,33 @@ GL_D void poseidon_mds_alu(u64 x[12], const u32* __restrict__ rc_limbs) {
         a[j] = lo & 0x3FFFFFu;
         b[j] = __funnelshift_r(lo, hi, 22) & 0x3FFFFFu;
         c[j] = hi >> 12;
-        if (ADD_RC && j > 0) {
-            a[j] += rc_limbs[3 * j];
-            b[j] += rc_limbs[3 * j + 1];
-            c[j] += rc_limbs[3 * j + 2];
-        }
     }
     u32 ya[12], yb[12], yc[12];
     poseidon_mds_limb(ya, a);
     poseidon_mds_limb(yb, b);
     poseidon_mds_limb(yc, c);
 #pragma unroll
-    for (int i = 0; i < 12; i++) x[i] = poseidon_join(ya[i], yb[i], yc[i]);
+    for (int i = 0; i < 12; i++)
+        x[i] = poseidon_join(ya[i] + rc_limbs[3 * i], yb[i] + rc_limbs[3 * i + 1], yc[i] + rc_limbs[3 * i + 2]);
 }
 
-// Round constants of the partial rounds pre-split into limbs (lanes 1..11; lane 0 goes through the S-box first).
-__constant__ u32 POSEIDON_RC_LIMBS[22 * 36] = {
+// Constants of round r+1 pre-split into limbs, added after the MDS of round r (row 29 = 0): one code path for all rounds.
+__constant__ u32 POSEIDON_RC_LIMBS[30 * 36] = {
 #include "poseidon_rc_limbs.inc"
 };
 
-// Permutation; state in lazy form on input, lazy form on output (callers canonicalise).
+// Permutation; state in lazy form on input, lazy form on output (callers canonicalise).  A single 30-iteration loop
+// keeps one copy of the S-box layer and one copy of the MDS in the instruction cache (~30 KB of SASS).
 GL_D void poseidon_permute(u64 x[12]) {
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) x[i] = poseidon_sbox(gl_add(x[i], POSEIDON_RC[12 * r + i]));
-        poseidon_mds_alu<false>(x, nullptr);
-    }
+    for (int i = 0; i < 12; i++) x[i] = gl_add(x[i], POSEIDON_RC[i]);
 #pragma unroll 1
-    for (int r = 4; r < 26; r++) {
-        x[0] = poseidon_sbox(gl_add(x[0], POSEIDON_RC[12 * r]));
-        poseidon_mds_alu<true>(x, POSEIDON_RC_LIMBS + (r - 4) * 36);
-    }
-#pragma unroll 1
-    for (int r = 26; r < 30; r++) {
+    for (int r = 0; r < 30; r++) {
+        x[0] = poseidon_sbox(x[0]);
+        if (r < 4 || r >= 26) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) x[i] = poseidon_sbox(gl_add(x[i], POSEIDON_RC[12 * r + i]));
-        poseidon_mds_alu<false>(x, nullptr);
+            for (int i = 1; i < 12; i++) x[i] = poseidon_sbox(x[i]);
+        }
+        poseidon_mds_alu(x, POSEIDON_RC_LIMBS + r * 36);
     }
 }
