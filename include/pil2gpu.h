@@ -88,6 +88,13 @@ uint32_t pil2gpu_merkle_depth(uint64_t height);
  * pil2gpu_merkle_nnodes(height) words to nodes (reference layout, root = last 4 words). */
 int pil2gpu_merkelize(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, uint64_t* nodes);
 int pil2gpu_merkelize_dev(pil2gpu_ctx* ctx, const uint64_t* elems_dev, uint64_t width, uint64_t height, int split, uint64_t* nodes_dev);
+/* Multi-GPU building blocks.  After the column->row all-to-all a rank holds its rows as n_tiles column
+ * tiles (one per source rank): element (row, c) at tiles + (c / tile_cols) * tile_stride + row * tile_cols + c % tile_cols.
+ * merkelize_tiled hashes them in place (width = n_tiles * tile_cols; tile_cols % 8 == 0); tree_from_digests builds the
+ * levels above `height` leaf digests already stored at nodes[0 .. 4*height) (the gathered sub-roots). */
+int pil2gpu_merkelize_tiled_dev(pil2gpu_ctx* ctx, const uint64_t* tiles_dev, uint32_t n_tiles, uint64_t tile_cols, uint64_t tile_stride,
+                                uint64_t height, int split, uint64_t* nodes_dev);
+int pil2gpu_merkle_tree_from_digests_dev(pil2gpu_ctx* ctx, uint64_t* nodes_dev, uint64_t height);
 int pil2gpu_merkelize_paged(pil2gpu_ctx* ctx, const uint64_t* const* elem_pages, const uint64_t* page_words, uint32_t n_pages,
                             uint64_t width, uint64_t height, int split, uint64_t* nodes);
 
@@ -103,9 +110,14 @@ int pil2gpu_commit_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t nPols
 int pil2gpu_extend_and_merkelize(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
                                  uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]);
 
+int pil2gpu_tree_wrap_tiled_dev(pil2gpu_ctx* ctx, const uint64_t* tiles_dev, uint32_t n_tiles, uint64_t tile_cols, uint64_t tile_stride,
+                                const uint64_t* nodes_dev, uint64_t height, pil2gpu_tree** tree_out);
+
 /* ---- bench / test utilities (not part of the reference surface) ------------------------------------------------ */
 /* dst_dev[i] = splitmix64(seed ^ (first_index + i)) mod p : the synthetic trace generator of SURVEY 8(d). */
 int pil2gpu_synth_dev(pil2gpu_ctx* ctx, uint64_t* dst_dev, uint64_t n_words, uint64_t seed, uint64_t first_index);
+/* Column slab of the same generator: dst[r*cols + c] = splitmix64(seed ^ (r*row_stride + col0 + c)) mod p. */
+int pil2gpu_synth2d_dev(pil2gpu_ctx* ctx, uint64_t* dst_dev, uint64_t rows, uint64_t cols, uint64_t row_stride, uint64_t col0, uint64_t seed);
 /* Integer-pipe roofline denominators measured live: standalone Goldilocks mulmod/s and IMAD.WIDE.U32/s on this GPU. */
 int pil2gpu_bench_int_pipes(pil2gpu_ctx* ctx, double* mulmod_per_s, double* imad_wide_per_s);
 

@@ -50,6 +50,10 @@ _SIGS = {
     "pil2gpu_merkle_depth": (c_u32, [c_u64]),
     "pil2gpu_merkelize": (c_int, [vp, vp, c_u64, c_u64, c_int, vp]),
     "pil2gpu_merkelize_dev": (c_int, [vp, vp, c_u64, c_u64, c_int, vp]),
+    "pil2gpu_merkelize_tiled_dev": (c_int, [vp, vp, c_u32, c_u64, c_u64, c_u64, c_int, vp]),
+    "pil2gpu_merkle_tree_from_digests_dev": (c_int, [vp, vp, c_u64]),
+    "pil2gpu_tree_wrap_tiled_dev": (c_int, [vp, vp, c_u32, c_u64, c_u64, vp, c_u64, ctypes.POINTER(vp)]),
+    "pil2gpu_synth2d_dev": (c_int, [vp, vp, c_u64, c_u64, c_u64, c_u64, c_u64]),
     "pil2gpu_merkelize_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u64, c_int, vp]),
     "pil2gpu_commit": (c_int, [vp, vp, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), vp]),
     "pil2gpu_commit_dev": (c_int, [vp, vp, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), vp]),

@@ -61,28 +61,67 @@ GL_D void merkle_sponge(const u64* __restrict__ v, u64 w, u64 out[4]) {
     for (int i = 0; i < 4; i++) out[i] = gl_canon(x[8 + i]);
 }
 
-// Standard linear hash of every row: nodes[4*row ..] = L(elems[row*width ..]).
-__global__ void __launch_bounds__(MERKLE_THREADS) merkle_leaf_kernel(const u64* __restrict__ elems, u64 width, u64 height,
-                                                                     u64* __restrict__ nodes) {
+// Column-tiled row storage: element (row, c) lives at base + (c / tile_cols) * tile_stride + row * tile_cols + c % tile_cols.
+// A plain row-major buffer is the one-tile case (tile_cols = width).  Tiled buffers are what the multi-GPU all-to-all
+// delivers (one tile per source rank); hashing them in place saves a repacking pass.
+struct RowTiles {
+    const u64* base;
+    u64 tile_cols;     // columns per tile (multiple of 8 unless there is a single tile)
+    u64 tile_stride;   // words between consecutive tiles
+};
+GL_D const u64* tiles_ptr(const RowTiles& t, u64 row, u64 c) {
+    const u64 tile = c / t.tile_cols;
+    return t.base + tile * t.tile_stride + row * t.tile_cols + (c - tile * t.tile_cols);
+}
+
+// Sponge over columns [c0, c0 + w) of one row of a tiled buffer (every 8-word chunk lies inside one tile).
+GL_D void merkle_sponge_tiled(const RowTiles& t, u64 row, u64 c0, u64 w, u64 out[4]) {
+    if (w <= 4) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = (u64)i < w ? *tiles_ptr(t, row, c0 + i) : 0;
+        return;
+    }
+    u64 x[12];
+#pragma unroll
+    for (int i = 8; i < 12; i++) x[i] = 0;
+    for (u64 off = 0; off < w; off += 8) {
+        const u64* v = tiles_ptr(t, row, c0 + off);
+        if (off + 8 <= w) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = v[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = (off + i < w) ? v[i] : 0;
+        }
+        poseidon_permute(x);
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[8 + i] = x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = gl_canon(x[8 + i]);
+}
+
+// Standard linear hash of every row: nodes[4*row ..] = L(row).
+__global__ void __launch_bounds__(MERKLE_THREADS) merkle_leaf_kernel(RowTiles t, u64 width, u64 height, u64* __restrict__ nodes) {
     const u64 row = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
     if (row >= height) return;
     u64 d[4];
-    merkle_sponge(elems + row * width, width, d);
+    merkle_sponge_tiled(t, row, 0, width, d);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(nodes + 4 * row);
     o[0] = make_ulonglong2(d[0], d[1]);
     o[1] = make_ulonglong2(d[2], d[3]);
 }
 
 // Split linear hash, stage 1: one thread per (row, batch): digests[(row*nb + b)*4 ..] = L(row[b*batch .. ]).
-__global__ void __launch_bounds__(MERKLE_THREADS) merkle_batch_kernel(const u64* __restrict__ elems, u64 width, u64 height, u64 batch,
-                                                                      u64 nb, u64* __restrict__ digests) {
+__global__ void __launch_bounds__(MERKLE_THREADS) merkle_batch_kernel(RowTiles t, u64 width, u64 height, u64 batch, u64 nb,
+                                                                      u64* __restrict__ digests) {
     const u64 id = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
     if (id >= height * nb) return;
     const u64 row = id / nb, b = id % nb;
     const u64 off = b * batch;
     const u64 sz = (width - off < batch) ? (width - off) : batch;
     u64 d[4];
-    merkle_sponge(elems + row * width + off, sz, d);
+    merkle_sponge_tiled(t, row, off, sz, d);
 #pragma unroll
     for (int i = 0; i < 4; i++) digests[id * 4 + i] = d[i];
 }
@@ -173,33 +212,33 @@ static inline u64 merkle_split_scratch_words(u64 width, u64 height) {
     u64 batch = merkle_split_batch(width);
     return height * ((width + batch - 1) / batch) * 4;
 }
-static int merkle_launch(const u64* elems, u64 width, u64 height, int split, u64* nodes, u64* scratch, cudaStream_t st) {
+static int merkle_launch(RowTiles t, u64 width, u64 height, int split, u64* nodes, u64* scratch, cudaStream_t st) {
     int launches = 0;
     if (height == 0) return 0;
     const unsigned blocks = (unsigned)((height + MERKLE_THREADS - 1) / MERKLE_THREADS);
     if (!split || width <= 4) {
-        merkle_leaf_kernel<<<blocks, MERKLE_THREADS, 0, st>>>(elems, width, height, nodes);
+        merkle_leaf_kernel<<<blocks, MERKLE_THREADS, 0, st>>>(t, width, height, nodes);
         launches++;
     } else {
         const u64 batch = merkle_split_batch(width);
         const u64 nb = (width + batch - 1) / batch;
         const u64 total = height * nb;
-        merkle_batch_kernel<<<(unsigned)((total + MERKLE_THREADS - 1) / MERKLE_THREADS), MERKLE_THREADS, 0, st>>>(elems, width, height, batch, nb,
-                                                                                                                  scratch);
-        merkle_leaf_kernel<<<blocks, MERKLE_THREADS, 0, st>>>(scratch, nb * 4, height, nodes);
+        merkle_batch_kernel<<<(unsigned)((total + MERKLE_THREADS - 1) / MERKLE_THREADS), MERKLE_THREADS, 0, st>>>(t, width, height, batch, nb, scratch);
+        RowTiles d = {scratch, nb * 4, 0};
+        merkle_leaf_kernel<<<blocks, MERKLE_THREADS, 0, st>>>(d, nb * 4, height, nodes);
         launches += 2;
     }
-    int t = merkle_launch_tree(nodes, height, st);
-    return t < 0 ? -1 : launches + t;
+    int tl = merkle_launch_tree(nodes, height, st);
+    return tl < 0 ? -1 : launches + tl;
 }
 
 // Group proofs for a batch of leaf indices: row values + one 4-word sibling per level (merklehash_p.js:142-168).
 // One CTA per query; rows_out[q*width ..], sib_out[q*depth*4 ..].
-__global__ void merkle_group_proof_kernel(const u64* __restrict__ elems, const u64* __restrict__ nodes, u64 width, u64 height,
+__global__ void merkle_group_proof_kernel(RowTiles t, const u64* __restrict__ nodes, u64 width, u64 height,
                                           const u64* __restrict__ idxs, int depth, u64* __restrict__ rows_out, u64* __restrict__ sib_out) {
     const u64 q = blockIdx.x;
     u64 idx = idxs[q];
-    for (u64 i = threadIdx.x; i < width; i += blockDim.x) rows_out[q * width + i] = elems[idx * width + i];
+    for (u64 i = threadIdx.x; i < width; i += blockDim.x) rows_out[q * width + i] = *tiles_ptr(t, idx, i);
     if (threadIdx.x < 4) {
         u64 off = 0, n = height * 4;
         for (int d = 0; d < depth; d++) {

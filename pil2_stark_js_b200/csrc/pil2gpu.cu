@@ -52,6 +52,7 @@ struct pil2gpu_tree {
     u64* elems;
     u64* nodes;
     uint64_t width, height;
+    uint64_t tile_cols, tile_stride;   // column tiling of elems (tile_cols == width: plain row-major)
     bool own_elems, own_nodes;
 };
 
@@ -91,6 +92,18 @@ __global__ void synth_kernel(u64* __restrict__ dst, u64 n, u64 seed, u64 first) 
         dst[i] = gl_canon(z);
     }
 }
+__global__ void synth2d_kernel(u64* __restrict__ dst, u64 rows, u64 cols, u64 row_stride, u64 col0, u64 seed) {
+    const u64 n = rows * cols, stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 r = i / cols, c = i - r * cols;
+        u64 z = (seed ^ (r * row_stride + col0 + c)) + 0x9E3779B97F4A7C15ULL;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z = z ^ (z >> 31);
+        dst[i] = gl_canon(z);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) pipe_probe_kernel(u64* out, int iters) {
     u64 a0 = threadIdx.x + 1, a1 = blockIdx.x + 3, a2 = a0 ^ 0x1234567, a3 = a0 + a1 + 77;
@@ -353,16 +366,42 @@ int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[1
     return PIL2GPU_OK;
 }
 
+static int merkelize_tiles(pil2gpu_ctx* ctx, RowTiles t, uint64_t width, uint64_t height, int split, uint64_t* nodes) {
+    u64* scratch = nullptr;
+    const u64 sw = (split && width > 4) ? merkle_split_scratch_words(width, height) : 0;
+    if (sw) CU(cudaMallocAsync(&scratch, sw * sizeof(u64), ctx->stream));
+    int l = merkle_launch(t, width, height, split, (u64*)nodes, scratch, ctx->stream);
+    if (scratch) CU(cudaFreeAsync(scratch, ctx->stream));
+    return check_launch(ctx, l, "merkelize");
+}
+
 int pil2gpu_merkelize_dev(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, uint64_t* nodes) {
     ENTER(ctx);
     if (!nodes || (!elems && width * height)) return fail(PIL2GPU_E_INVALID, "null buffer");
     if (height == 0) return fail(PIL2GPU_E_INVALID, "height must be > 0");
-    u64* scratch = nullptr;
-    const u64 sw = (split && width > 4) ? merkle_split_scratch_words(width, height) : 0;
-    if (sw) CU(cudaMallocAsync(&scratch, sw * sizeof(u64), ctx->stream));
-    int l = merkle_launch((const u64*)elems, width, height, split, (u64*)nodes, scratch, ctx->stream);
-    if (scratch) CU(cudaFreeAsync(scratch, ctx->stream));
-    return check_launch(ctx, l, "merkelize");
+    RowTiles t = {(const u64*)elems, width ? width : 1, 0};
+    return merkelize_tiles(ctx, t, width, height, split, nodes);
+}
+
+int pil2gpu_merkelize_tiled_dev(pil2gpu_ctx* ctx, const uint64_t* tiles, uint32_t n_tiles, uint64_t tile_cols, uint64_t tile_stride,
+                                uint64_t height, int split, uint64_t* nodes) {
+    ENTER(ctx);
+    if (!nodes || !tiles) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (height == 0 || n_tiles == 0 || tile_cols == 0) return fail(PIL2GPU_E_INVALID, "bad tile description");
+    if (n_tiles > 1 && (tile_cols % 8) != 0) return fail(PIL2GPU_E_UNSUPPORTED, "tile_cols must be a multiple of 8 (got %llu)", (unsigned long long)tile_cols);
+    if (n_tiles > 1 && split) {
+        const u64 width = tile_cols * n_tiles, batch = merkle_split_batch(width);
+        if (batch % 8) return fail(PIL2GPU_E_UNSUPPORTED, "split hash over tiles needs a batch size that is a multiple of 8");
+    }
+    RowTiles t = {(const u64*)tiles, tile_cols, tile_stride};
+    return merkelize_tiles(ctx, t, tile_cols * n_tiles, height, split, nodes);
+}
+
+int pil2gpu_merkle_tree_from_digests_dev(pil2gpu_ctx* ctx, uint64_t* nodes, uint64_t height) {
+    ENTER(ctx);
+    if (!nodes || height == 0) return fail(PIL2GPU_E_INVALID, "bad arguments");
+    int l = merkle_launch_tree((u64*)nodes, height, ctx->stream);
+    return check_launch(ctx, l, "tree_from_digests");
 }
 
 int pil2gpu_linear_hash(pil2gpu_ctx* ctx, const uint64_t* vals, uint64_t width, int split, uint64_t out4[4]) {
@@ -409,7 +448,7 @@ int pil2gpu_merkelize(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, u
 // ------------------------------------------------------------------------------------------------------------
 static pil2gpu_tree* new_tree() {
     pil2gpu_tree* t = new (std::nothrow) pil2gpu_tree();
-    if (t) { t->elems = t->nodes = nullptr; t->width = t->height = 0; t->own_elems = t->own_nodes = false; }
+    if (t) { t->elems = t->nodes = nullptr; t->width = t->height = 0; t->tile_cols = t->tile_stride = 0; t->own_elems = t->own_nodes = false; }
     return t;
 }
 
@@ -433,7 +472,17 @@ int pil2gpu_tree_wrap_dev(pil2gpu_ctx* ctx, const uint64_t* elems_dev, const uin
     t->nodes = (u64*)nodes_dev;
     t->width = width;
     t->height = height;
+    t->tile_cols = width ? width : 1;
     *tree_out = t;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_tree_wrap_tiled_dev(pil2gpu_ctx* ctx, const uint64_t* tiles_dev, uint32_t n_tiles, uint64_t tile_cols, uint64_t tile_stride,
+                                const uint64_t* nodes_dev, uint64_t height, pil2gpu_tree** tree_out) {
+    int rc = pil2gpu_tree_wrap_dev(ctx, tiles_dev, nodes_dev, tile_cols * n_tiles, height, tree_out);
+    if (rc) return rc;
+    (*tree_out)->tile_cols = tile_cols;
+    (*tree_out)->tile_stride = tile_stride;
     return PIL2GPU_OK;
 }
 
@@ -461,6 +510,7 @@ static int commit_common(pil2gpu_ctx* ctx, u64* src_dev_owned, const u64* src_de
     pil2gpu_tree* t = new_tree();
     if (!t) return fail(PIL2GPU_E_NOMEM, "out of host memory");
     t->width = nPols;
+    t->tile_cols = nPols;
     t->height = 1ULL << nBitsExt;
     t->own_elems = t->own_nodes = true;
     cudaError_t e = cudaMalloc(&t->elems, ((size_t)nPols << nBitsExt) * 8);
@@ -539,6 +589,14 @@ int pil2gpu_synth_dev(pil2gpu_ctx* ctx, uint64_t* dst_dev, uint64_t n_words, uin
     return check_launch(ctx, 1, "synth");
 }
 
+int pil2gpu_synth2d_dev(pil2gpu_ctx* ctx, uint64_t* dst_dev, uint64_t rows, uint64_t cols, uint64_t row_stride, uint64_t col0, uint64_t seed) {
+    ENTER(ctx);
+    if (!dst_dev && rows * cols) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (rows * cols == 0) return PIL2GPU_OK;
+    synth2d_kernel<<<148 * 16, 256, 0, ctx->stream>>>((u64*)dst_dev, rows, cols, row_stride, col0, seed);
+    return check_launch(ctx, 1, "synth2d");
+}
+
 int pil2gpu_bench_int_pipes(pil2gpu_ctx* ctx, double* mulmod_per_s, double* imad_wide_per_s) {
     ENTER(ctx);
     const int blocks = 148 * 8, threads = 256, iters = 2048;
@@ -576,6 +634,7 @@ int pil2gpu_tree_from_host(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t wid
     pil2gpu_tree* t = new_tree();
     if (!t) return fail(PIL2GPU_E_NOMEM, "out of host memory");
     t->width = width;
+    t->tile_cols = width ? width : 1;
     t->height = height;
     t->own_elems = t->own_nodes = true;
     cudaError_t e = cudaMalloc(&t->elems, (width * height ? width * height : 1) * 8);
@@ -604,7 +663,8 @@ int pil2gpu_tree_group_proofs(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uin
     CU(dr.alloc((size_t)n_idx * t->width));
     CU(ds.alloc((size_t)n_idx * depth * 4));
     CU(cudaMemcpyAsync(di.p, idxs, (size_t)n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
-    merkle_group_proof_kernel<<<n_idx, 128, 0, ctx->stream>>>(t->elems, t->nodes, t->width, t->height, di.p, depth, dr.p, ds.p);
+    RowTiles rt = {t->elems, t->tile_cols ? t->tile_cols : 1, t->tile_stride};
+    merkle_group_proof_kernel<<<n_idx, 128, 0, ctx->stream>>>(rt, t->nodes, t->width, t->height, di.p, depth, dr.p, ds.p);
     int rc = check_launch(ctx, 1, "group_proofs");
     if (rc) return rc;
     if (t->width) CU(cudaMemcpyAsync(rows_out, dr.p, (size_t)n_idx * t->width * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -616,6 +676,7 @@ int pil2gpu_tree_group_proofs(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uin
 int pil2gpu_tree_download(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t* elems_out, uint64_t* nodes_out) {
     ENTER(ctx);
     if (!t) return fail(PIL2GPU_E_INVALID, "null tree");
+    if (elems_out && t->elems && t->tile_cols != t->width) return fail(PIL2GPU_E_UNSUPPORTED, "download of a column-tiled tree is not supported");
     if (elems_out && t->elems) CU(cudaMemcpyAsync(elems_out, t->elems, t->width * t->height * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (nodes_out) CU(cudaMemcpyAsync(nodes_out, t->nodes, merkle_nnodes_words(t->height) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

@@ -1,5 +1,212 @@
-"""Multi-GPU commit: column-sharded LDE -> all-to-all -> row-sharded hashing -> gathered tree top (placeholder, see below)."""
+"""Multi-GPU commit (one process per GPU, torch.distributed for the plumbing) -- SURVEY 8(e).
+
+    rank g owns columns [g*C/G, (g+1)*C/G) of the trace            (columns are independent NTTs: no communication)
+    1. LDE of the column slab on the local GPU                       N x C/G  ->  E x C/G
+    2. ONE all-to-all over NVLink: rank g sends rows [h*E/G, (h+1)*E/G) of its slab to rank h; rank h receives G tiles
+       (one per source rank) of E/G rows x C/G columns -- its row range across all columns, kept as column tiles
+    3. leaf hashing + subtree of the E/G local rows straight from the tiles (pil2gpu_merkelize_tiled_dev, no repack)
+    4. all-gather of the G sub-roots (G x 32 bytes); the top log2(G) levels are hashed redundantly on every rank
+The root (and every node) equals the single-GPU tree: contiguous leaf ranges make each local root the level-log2(E/G)
+node of the reference layout.  The reference has no counterpart (it is single-process, workerpool threads).
+
+The choreography is written against a small `engine` interface so that the same code runs on CUDA tensors through the
+C ABI (GpuEngine) and, in the CPU tests, on a stand-in engine under the gloo backend.
+"""
+import ctypes
+
+import numpy as np
 
 
+class GpuEngine:
+    """Device work through libpil2gpu.so; tensors are torch int64 CUDA tensors holding u64 bit patterns."""
+
+    def __init__(self, torch, device_index):
+        from . import _lib
+        self.torch, self.L, self.check = torch, _lib.load(), _lib.check
+        h = ctypes.c_void_p()
+        self.check(self.L.pil2gpu_create(device_index, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), ctypes.byref(h)))
+        self.h = h
+        self.device = torch.device("cuda", device_index)
+
+    def empty(self, words):
+        return self.torch.empty(int(words), dtype=self.torch.int64, device=self.device)
+
+    def _p(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def nnodes(self, height):
+        return int(self.L.pil2gpu_merkle_nnodes(height))
+
+    def lde(self, src, cols, n_bits, ext_bits, dst):
+        self.check(self.L.pil2gpu_lde_dev(self.h, self._p(src), self._p(dst), cols, n_bits, ext_bits))
+
+    def merkelize_tiled(self, tiles, n_tiles, tile_cols, rows, nodes, split=False):
+        self.check(self.L.pil2gpu_merkelize_tiled_dev(self.h, self._p(tiles), n_tiles, tile_cols, rows * tile_cols, rows, int(split),
+                                                      self._p(nodes)))
+
+    def tree_from_digests(self, nodes, height):
+        self.check(self.L.pil2gpu_merkle_tree_from_digests_dev(self.h, self._p(nodes), height))
+
+    def launches(self):
+        return int(self.L.pil2gpu_launch_count(self.h))
+
+
+class ShardedCommit:
+    """Column-sharded LDE -> all-to-all -> row-sharded hashing -> gathered tree top."""
+
+    def __init__(self, engine, dist, rank, world):
+        self.e, self.dist, self.rank, self.world = engine, dist, rank, world
+
+    def shard_cols(self, cols):
+        if cols % self.world:
+            raise ValueError(f"nPols ({cols}) must be divisible by the number of GPUs ({self.world})")
+        cg = cols // self.world
+        if self.world > 1 and cg % 8:
+            raise ValueError("columns per GPU must be a multiple of 8 (sponge chunks must not straddle tiles)")
+        return cg
+
+    def buffers(self, cols, n_bits, ext_bits):
+        cg = self.shard_cols(cols)
+        rows_local = (1 << ext_bits) // self.world
+        e = self.e
+        return {"dst": e.empty(cg << ext_bits), "recv": e.empty(cg << ext_bits), "nodes": e.empty(e.nnodes(rows_local)),
+                "top": e.empty(max(8, e.nnodes(self.world))), "sub": e.empty(4 * self.world)}
+
+    def commit(self, src_slab, cols, n_bits, ext_bits, buf, split=False):
+        """src_slab: this rank's N x C/G column slab (row-major).  Returns the 4-word root tensor (on every rank)."""
+        G, e = self.world, self.e
+        cg = self.shard_cols(cols)
+        E = 1 << ext_bits
+        if E % G:
+            raise ValueError("extended height must be divisible by the number of GPUs")
+        rows_local = E // G
+        e.lde(src_slab, cg, n_bits, ext_bits, buf["dst"])
+        if G > 1:
+            self.dist.all_to_all_single(buf["recv"], buf["dst"])            # equal splits: chunk h = rows of rank h
+            tiles = buf["recv"]
+        else:
+            tiles = buf["dst"]
+        e.merkelize_tiled(tiles, G, cg, rows_local, buf["nodes"], split)
+        if G == 1:
+            return buf["nodes"][-4:]
+        nn = e.nnodes(rows_local)
+        local_root = buf["nodes"][nn - 4:nn]
+        self.dist.all_gather_into_tensor(buf["sub"], local_root.contiguous())
+        buf["top"][:4 * G].copy_(buf["sub"])
+        e.tree_from_digests(buf["top"], G)
+        nt = e.nnodes(G)
+        return buf["top"][nt - 4:nt]
+
+
+def assemble_nodes(local_nodes_per_rank, top_nodes, rows_local, world, nnodes_fn):
+    """Host-side helper (tests / downloads): stitch per-rank subtree node arrays and the top tree into the reference
+    `nodes` layout of the full tree (power-of-two sizes)."""
+    E = rows_local * world
+    out = np.zeros(nnodes_fn(E), dtype=np.uint64)
+    # levels of the local subtrees: level l has rows_local >> l nodes per rank, stored contiguously per rank
+    off_local, off_global, n = 0, 0, rows_local
+    while n >= 1:
+        for r in range(world):
+            out[off_global + r * n * 4: off_global + (r + 1) * n * 4] = local_nodes_per_rank[r][off_local:off_local + n * 4]
+        if n == 1:
+            break
+        off_local += n * 4
+        off_global += n * world * 4
+        n >>= 1
+    # levels above the sub-roots come from the top tree (its leaf level is the sub-root level just written)
+    top_off, m = 0, world
+    while m > 1:
+        top_off += m * 4
+        off_global += m * 4
+        m >>= 1
+        out[off_global:off_global + m * 4] = top_nodes[top_off:top_off + m * 4]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# bench.py --gpus N entry (launched under torchrun, one rank per GPU)
+# ------------------------------------------------------------------------------------------------------------------
 def bench_main(args, rank, world, local_rank, dist, bench):
-    raise SystemExit("multi-GPU path not built yet")
+    import json
+    import torch
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng = GpuEngine(torch, local_rank)
+    L, check, vp = eng.L, eng.check, ctypes.c_void_p
+    n_bits, cols, blow = bench.WORKLOADS[args.workload]
+    ext_bits = n_bits + blow
+    sc = ShardedCommit(eng, dist, rank, world)
+    cg = sc.shard_cols(cols)
+    seed = 0x5EED0000 + 3
+    src = eng.empty(cg << n_bits)
+    check(L.pil2gpu_synth2d_dev(eng.h, vp(src.data_ptr()), 1 << n_bits, cg, cols, rank * cg, seed))
+    buf = sc.buffers(cols, n_bits, ext_bits)
+    # FRI chain + queries run on rank 0 (layers shrink 16x per step; the chain is ~2% of the commit)
+    steps = bench.fri_steps(ext_bits)
+    fri = None
+    if rank == 0:
+        fri = {"pol": [eng.empty(3 << b) for b in steps], "rows": [eng.empty(3 << steps[s]) for s in range(len(steps) - 1)],
+               "nodes": [eng.empty(eng.nnodes(1 << steps[s + 1])) for s in range(len(steps) - 1)],
+               "chal": [np.ascontiguousarray(bench.splitmix_field(seed + 2 + s, 0, 3)) for s in range(len(steps))]}
+        check(L.pil2gpu_synth_dev(eng.h, vp(fri["pol"][0].data_ptr()), 3 << steps[0], seed + 1, 0))
+    npp = lambda a: vp(a.ctypes.data)
+    P = lambda t: vp(t.data_ptr())
+
+    def fri_chain():
+        f = fri
+        check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol"][0]), steps[0], steps[0], steps[1], steps[0], npp(f["chal"][0]), 0, P(f["pol"][0]),
+                                     P(f["rows"][0]), P(f["nodes"][0])))
+        for s in range(1, len(steps)):
+            last = s == len(steps) - 1
+            check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol"][s - 1]), steps[s - 1], steps[s], -1 if last else steps[s + 1], steps[0],
+                                         npp(f["chal"][s]), 0, P(f["pol"][s]), None if last else P(f["rows"][s]),
+                                         None if last else P(f["nodes"][s])))
+
+    root_host = torch.empty(4, dtype=torch.int64, pin_memory=True)
+
+    def step():
+        root = sc.commit(src, cols, n_bits, ext_bits, buf)
+        if rank == 0:
+            fri_chain()
+        root_host.copy_(root, non_blocking=True)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = bench.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.barrier()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([eng.launches() - l0], device="cuda")
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+    if rank == 0:
+        clocks = sampler.stop()
+        sec = float(ms.item()) / 1e3 / args.steps
+        root = [int(x) & 0xFFFFFFFFFFFFFFFF for x in root_host.tolist()]
+        a2a = 8 * (cg << ext_bits) * (world - 1) // world
+        line = {
+            "metric": bench.METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks, integer pipes)", "data": "synthetic", "config": bench.config_dict(args.workload, world),
+            "rows_per_s": (1 << n_bits) / sec, "all_to_all_bytes_per_gpu": a2a, "gpu_launches": int(launches.item()), "clocks": clocks,
+            "root": root,
+            "e2e": None, "cpu_baseline": None,
+            "roofline": {"kernel": "merkle_leaf_kernel (per-rank share): Poseidon-GL", "bound": "int",
+                         "note": "per-kernel roofline is reported by the N=1 run; N>1 adds one NCCL all-to-all of "
+                                 f"{a2a >> 20} MiB per GPU between the LDE and the hashing"},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

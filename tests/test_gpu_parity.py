@@ -308,3 +308,56 @@ def test_fri_class_prove_then_verify(ctx):
     # final polynomial has degree < 2^(2 - 1): coefficients above maxDeg vanish (fri.js:158-171)
     c = S.intt([list(e) for e in final])
     assert all(ci == [0, 0, 0] for ci in c[3:])
+
+
+# ---------------------------------------------------------------- multi-GPU (runs when the box has >= 2 GPUs)
+def _mgpu_worker(rank, world, port, n_bits, blow, cols, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from pil2_stark_js_b200.sharded import GpuEngine, ShardedCommit
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rng = np.random.default_rng(5)
+        full = rng.integers(0, P, size=(1 << n_bits, cols), dtype=np.uint64)
+        sc = ShardedCommit(GpuEngine(torch, rank), dist, rank, world)
+        cg = sc.shard_cols(cols)
+        slab = torch.from_numpy(np.ascontiguousarray(full[:, rank * cg:(rank + 1) * cg]).reshape(-1).view(np.int64)).cuda()
+        buf = sc.buffers(cols, n_bits, n_bits + blow)
+        root = sc.commit(slab, cols, n_bits, n_bits + blow, buf)
+        torch.cuda.synchronize()
+        q.put((rank, root.cpu().numpy().view(np.uint64).copy(), buf["nodes"].cpu().numpy().view(np.uint64).copy(),
+               buf["top"].cpu().numpy().view(np.uint64).copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_commit_two_gpus():
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from pil2_stark_js_b200.sharded import assemble_nodes
+    world, n_bits, blow, cols = 2, 12, 1, 64
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx_mp = mp.get_context("spawn")
+    q = ctx_mp.Queue()
+    procs = [ctx_mp.Process(target=_mgpu_worker, args=(r, world, port, n_bits, blow, cols, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(5)
+    full = rng.integers(0, P, size=(1 << n_bits, cols), dtype=np.uint64)
+    nodes = C.merkelize(C.lde(full.reshape(-1), cols, n_bits, n_bits + blow), cols, 1 << (n_bits + blow))
+    for _, root, _, _ in res:
+        assert np.array_equal(root, nodes[-4:])
+    stitched = assemble_nodes([r[2] for r in res], res[0][3], (1 << (n_bits + blow)) // world, world, C.merkle_nnodes)
+    assert np.array_equal(stitched, nodes)
