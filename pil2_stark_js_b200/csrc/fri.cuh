@@ -37,8 +37,8 @@ GL_D gl3 fri_fold_point(const u64* __restrict__ pol, u64 g, int cur_bits, gl3 be
     for (int j = 0; j < NX / 2; j++) {
         const gl3 a = fri_load3(pol + 3 * (((u64)j << cur_bits) + g));
         const gl3 b = fri_load3(pol + 3 * (((u64)(j + NX / 2) << cur_bits) + g));
-        const u64 wj = tw_inv[(size_t)j << (NTT_TW_BITS - FOLD)];   // w_NX^-j
-        e[j] = gl3_add(gl3_add(a, b), gl3_mul(beta, gl3_scale(gl3_sub(a, b), wj)));
+        const u64 wj = tw_inv[(NX / 2) + j];                         // w_NX^-j (Montgomery form)
+        e[j] = gl3_add(gl3_add(a, b), gl3_mul(beta, gl3_mscale(gl3_sub(a, b), wj)));
     }
 #pragma unroll
     for (int lvl = 1; lvl < FOLD; lvl++) {
@@ -48,8 +48,8 @@ GL_D gl3 fri_fold_point(const u64* __restrict__ pol, u64 g, int cur_bits, gl3 be
         for (int j = 0; j < NX / 2; j++) {
             if (j < n / 2) {
                 const gl3 a = e[j], b = e[j + n / 2];
-                const u64 wj = tw_inv[(size_t)j << (NTT_TW_BITS - FOLD + lvl)];   // w_n^-j
-                e[j] = gl3_add(gl3_add(a, b), gl3_mul(beta, gl3_scale(gl3_sub(a, b), wj)));
+                const u64 wj = tw_inv[(n / 2) + j];                         // w_n^-j (Montgomery form)
+                e[j] = gl3_add(gl3_add(a, b), gl3_mul(beta, gl3_mscale(gl3_sub(a, b), wj)));
             }
         }
     }
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(FOLD >= 5 ? 256 : 512) fri_fold_kernel(const u
         const u64 g = i + (j << next_bits);
         // sinv_g = shift_inv * w_prev^-g
         const u32 E = P.prev_bits == 0 ? 0u : (0u - ((u32)g << (32 - P.prev_bits)));
-        const u64 sinv = gl_mul(P.shift_inv, ntt_root_pow(tb.bytepow, E));
+        const u64 sinv = gl_mmul(P.shift_inv, ntt_root_pow(tb.bytepow, E));   // root in Montgomery form: plain product
         gl3 v = fri_fold_point<FOLD>(pol, g, P.cur_bits, gl3_scale(alpha, sinv), tb.tw_inv);
         v = gl3_canon(gl3_scale(v, P.nx_inv));
         pol2[3 * g] = v.c[0]; pol2[3 * g + 1] = v.c[1]; pol2[3 * g + 2] = v.c[2];

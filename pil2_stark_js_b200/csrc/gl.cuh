@@ -85,6 +85,89 @@ GL_D u64 gl_reduce96(u32 hi, u64 lo) {
     return r;
 }
 
+// ---- Montgomery multiply (R = 2^64) and one-canonical-operand add/sub ------------------------------------------
+// sm_100a executes integer work on two half-rate pipes per SM sub-partition: "alu" (IADD3/LOP3/SHF) and "fmaheavy"
+// (IMAD, IMAD.WIDE = 2 slots).  A Goldilocks product is 4 IMAD.WIDE; what decides throughput is how many ALU-pipe
+// instructions the reduction needs.  The Montgomery reduction below needs 9 (the 2^64 = 2^32 - 1 fold above needs 12) and
+// returns a canonical value whenever one factor is canonical, which lets the add/sub that follow skip the second wrap
+// check.  Constants (twiddles, round constants, 2^128 mod p) are stored pre-multiplied by 2^64, so that
+// gl_mmul(x, c * 2^64) = x * c with no domain change for x.  Measured (tools/probe/gl_probe.cu, B200): butterfly
+// 0.54 -> 0.90 T/s, multiply 1.28 -> 1.41 T/s.
+//
+// NOTE on carry chains: ptxas models CC.CF as the hardware carry, so `subc` after `add.cc` sees the inverted flag.
+// Every chain below stays inside one family (add.cc -> addc, sub.cc -> subc).
+
+// x * 2^-64 mod p for x = hi:lo.  m = lo * (2^32 + 1) mod 2^64 = {a1, l0} with (e, a1) = l1 + l0;
+// q = (m * p) >> 64 = m - a1 - e;  r = hi - q (+ p on borrow).  Any u64 in, u64 out; canonical out when hi < p.
+GL_D u64 gl_mont_reduce(u64 hi, u64 lo) {
+    const u32 l0 = (u32)lo, l1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32);
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 a1, ae, b0, b1, m, t0, t1;\n\t"
+        "add.cc.u32  a1, %3, %2;\n\t"      // a1 = l1 + l0, CF = e
+        "addc.u32    ae, a1, 0;\n\t"       // a1 + e (never wraps: l0 + l1 <= 2^33 - 2)
+        "sub.cc.u32  b0, %2, ae;\n\t"      // q = {a1, l0} - (a1 + e)
+        "subc.u32    b1, a1, 0;\n\t"
+        "sub.cc.u32  t0, %4, b0;\n\t"      // r = hi - q, CF = borrow
+        "subc.cc.u32 t1, %5, b1;\n\t"
+        "subc.u32    m, 0, 0;\n\t"         // m = borrow ? 0xFFFFFFFF : 0
+        "sub.cc.u32  %0, t0, m;\n\t"       // r -= borrow * EPS  (== r + p mod 2^64)
+        "subc.u32    %1, t1, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
+    return ((u64)r1 << 32) | r0;
+}
+GL_D u64 gl_mmul(u64 a, u64 b) { return gl_mont_reduce(__umul64hi(a, b), a * b); }   // a * b * 2^-64
+GL_D u64 gl_msqr(u64 a) { return gl_mmul(a, a); }
+// x * 2^64 mod p = x0 * EPS - x1 (x = x1 * 2^32 + x0): 1 IMAD.WIDE + 5 ALU.  Any u64 in, u64 out.
+GL_D u64 gl_to_mont(u64 x) {
+    const u64 t = (u64)(u32)x * 0xFFFFFFFFu;
+    const u32 t0 = (u32)t, t1 = (u32)(t >> 32), x1 = (u32)(x >> 32);
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 s0, s1, m;\n\t"
+        "sub.cc.u32  s0, %2, %4;\n\t"
+        "subc.cc.u32 s1, %3, 0;\n\t"
+        "subc.u32    m, 0, 0;\n\t"
+        "sub.cc.u32  %0, s0, m;\n\t"
+        "subc.u32    %1, s1, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(t0), "r"(t1), "r"(x1));
+    return ((u64)r1 << 32) | r0;
+}
+GL_D u64 gl_from_mont(u64 x) { return gl_mont_reduce(0, x); }   // canonical
+#define GL_MONT_ONE 0xFFFFFFFFULL   // 1 * 2^64 mod p
+
+// a + t with t <= p - 1 (a any u64): the wrapped sum is < t, so adding EPS once cannot wrap again.  3 ALU + 1 IMAD.WIDE.
+GL_D u64 gl_addc(u64 a, u64 t) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), t0 = (u32)t, t1 = (u32)(t >> 32);
+    u32 s0, s1, c;
+    asm("add.cc.u32  %0, %3, %5;\n\t"
+        "addc.cc.u32 %1, %4, %6;\n\t"
+        "addc.u32    %2, 0, 0;"
+        : "=r"(s0), "=r"(s1), "=r"(c)
+        : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
+    return (u64)c * 0xFFFFFFFFu + (((u64)s1 << 32) | s0);
+}
+// a - t with t <= p - 1 (a any u64).  5 ALU.
+GL_D u64 gl_subc(u64 a, u64 t) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), t0 = (u32)t, t1 = (u32)(t >> 32);
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 s0, s1, m;\n\t"
+        "sub.cc.u32  s0, %2, %4;\n\t"
+        "subc.cc.u32 s1, %3, %5;\n\t"
+        "subc.u32    m, 0, 0;\n\t"
+        "sub.cc.u32  %0, s0, m;\n\t"
+        "subc.u32    %1, s1, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(a0), "r"(a1), "r"(t0), "r"(t1));
+    return ((u64)r1 << 32) | r0;
+}
+
 GL_D u64 gl_pow(u64 a, u64 e) {
     u64 r = 1;
     while (e) {
@@ -104,6 +187,8 @@ struct gl3 {
 GL_D gl3 gl3_add(const gl3& a, const gl3& b) { return gl3{{gl_add(a.c[0], b.c[0]), gl_add(a.c[1], b.c[1]), gl_add(a.c[2], b.c[2])}}; }
 GL_D gl3 gl3_sub(const gl3& a, const gl3& b) { return gl3{{gl_sub(a.c[0], b.c[0]), gl_sub(a.c[1], b.c[1]), gl_sub(a.c[2], b.c[2])}}; }
 GL_D gl3 gl3_scale(const gl3& a, u64 s) { return gl3{{gl_mul(a.c[0], s), gl_mul(a.c[1], s), gl_mul(a.c[2], s)}}; }
+// s_mont = s * 2^64 (canonical): plain product a * s
+GL_D gl3 gl3_mscale(const gl3& a, u64 s_mont) { return gl3{{gl_mmul(a.c[0], s_mont), gl_mmul(a.c[1], s_mont), gl_mmul(a.c[2], s_mont)}}; }
 GL_D gl3 gl3_canon(const gl3& a) { return gl3{{gl_canon(a.c[0]), gl_canon(a.c[1]), gl_canon(a.c[2])}}; }
 GL_D gl3 gl3_mul(const gl3& a, const gl3& b) {
     // Karatsuba-style product modulo x^3 - x - 1, same operation count as f3g.js:94-102
@@ -136,6 +221,7 @@ static inline u64 glh_pow(u64 a, u64 e) {
     return r;
 }
 static inline u64 glh_inv(u64 a) { return glh_pow(a, GL_P - 2); }
+static inline u64 glh_to_mont(u64 a) { return glh_mul(a % GL_P, 0xFFFFFFFFULL); }   // a * 2^64 mod p
 static inline u64 glh_root(unsigned s) {  // w[s], order 2^s (fft.js:45-50)
     u64 w = GL_W32;
     for (unsigned i = 32; i > s; i--) w = glh_mul(w, w);

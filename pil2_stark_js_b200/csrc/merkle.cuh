@@ -48,17 +48,17 @@ GL_D void merkle_sponge(const u64* __restrict__ v, u64 w, u64 out[4]) {
     for (u64 off = 0; off < w; off += 8) {
         if (off + 8 <= w) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[i] = v[off + i];
+            for (int i = 0; i < 8; i++) x[i] = gl_to_mont(v[off + i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[i] = (off + i < w) ? v[off + i] : 0;
+            for (int i = 0; i < 8; i++) x[i] = (off + i < w) ? gl_to_mont(v[off + i]) : 0;
         }
-        poseidon_permute(x);
+        poseidon_permute_mont(x);      // the capacity words stay in Montgomery form between absorptions
 #pragma unroll
         for (int i = 0; i < 4; i++) x[8 + i] = x[i];
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = gl_canon(x[8 + i]);
+    for (int i = 0; i < 4; i++) out[i] = gl_from_mont(x[8 + i]);
 }
 
 // Column-tiled row storage: element (row, c) lives at base + (c / tile_cols) * tile_stride + row * tile_cols + c % tile_cols.
@@ -88,17 +88,17 @@ GL_D void merkle_sponge_tiled(const RowTiles& t, u64 row, u64 c0, u64 w, u64 out
         const u64* v = tiles_ptr(t, row, c0 + off);
         if (off + 8 <= w) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[i] = v[i];
+            for (int i = 0; i < 8; i++) x[i] = gl_to_mont(v[i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[i] = (off + i < w) ? v[i] : 0;
+            for (int i = 0; i < 8; i++) x[i] = (off + i < w) ? gl_to_mont(v[i]) : 0;
         }
-        poseidon_permute(x);
+        poseidon_permute_mont(x);
 #pragma unroll
         for (int i = 0; i < 4; i++) x[8 + i] = x[i];
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = gl_canon(x[8 + i]);
+    for (int i = 0; i < 4; i++) out[i] = gl_from_mont(x[8 + i]);
 }
 
 // Standard linear hash of every row: nodes[4*row ..] = L(row).
@@ -133,15 +133,15 @@ GL_D void merkle_pair(const u64* __restrict__ in, u64* __restrict__ out, u64 i) 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         ulonglong2 v = p[k];
-        x[2 * k] = v.x;
-        x[2 * k + 1] = v.y;
+        x[2 * k] = gl_to_mont(v.x);
+        x[2 * k + 1] = gl_to_mont(v.y);
     }
 #pragma unroll
     for (int k = 8; k < 12; k++) x[k] = 0;
-    poseidon_permute(x);
+    poseidon_permute_mont(x);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
-    o[0] = make_ulonglong2(gl_canon(x[0]), gl_canon(x[1]));
-    o[1] = make_ulonglong2(gl_canon(x[2]), gl_canon(x[3]));
+    o[0] = make_ulonglong2(gl_from_mont(x[0]), gl_from_mont(x[1]));
+    o[1] = make_ulonglong2(gl_from_mont(x[2]), gl_from_mont(x[3]));
 }
 __global__ void __launch_bounds__(MERKLE_THREADS) merkle_level_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 pairs) {
     const u64 i = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
@@ -257,5 +257,5 @@ __global__ void poseidon_single_kernel(const u64* __restrict__ in12, u64* __rest
     u64 x[12];
     for (int i = 0; i < 12; i++) x[i] = in12[i];
     poseidon_permute(x);
-    for (int i = 0; i < 12; i++) out12[i] = gl_canon(x[i]);
+    for (int i = 0; i < 12; i++) out12[i] = x[i];
 }

@@ -39,9 +39,7 @@ struct pil2gpu_ctx {
     int device;
     cudaStream_t stream;
     bool own_stream;
-    u64* tables;      // bytepow[1024] | tw_fwd[2048] | tw_inv[2048]
-    u64* coset;       // LDE coset scale scratch: (B_max << TMAX) + B_max words, grown on demand
-    size_t coset_words;
+    u64* tables;      // bytepow[1024] | tw_fwd[2^TMAX] | tw_inv[2^TMAX] | pow7[32]  (Montgomery form, see ntt.cuh)
     uint64_t launches;
     NttTables tb;
     cudaStream_t copy_stream;   // second stream: D2H of the LDE overlaps the hashing (extend_and_merkelize)
@@ -141,8 +139,6 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
     if (!ctx) return fail(PIL2GPU_E_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->launches = 0;
-    ctx->coset = nullptr;
-    ctx->coset_words = 0;
     ctx->copy_stream = nullptr;
     ctx->ev = nullptr;
     ctx->tables = nullptr;
@@ -161,12 +157,13 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
         pil2gpu_destroy(ctx);
         return fail(PIL2GPU_E_CUDA, "stream/event creation failed");
     }
-    const size_t words = 1024 + 2 * (1u << (NTT_TW_BITS - 1));
+    const size_t words = NTT_TABLE_WORDS;
     e = cudaMalloc(&ctx->tables, words * sizeof(u64));
     if (e != cudaSuccess) { pil2gpu_destroy(ctx); return fail(PIL2GPU_E_NOMEM, "cudaMalloc(tables): %s", cudaGetErrorString(e)); }
     u64* tw_fwd = ctx->tables + 1024;
-    u64* tw_inv = tw_fwd + (1u << (NTT_TW_BITS - 1));
-    ntt_setup_tables<<<(1u << (NTT_TW_BITS - 1)) / 256, 256, 0, ctx->stream>>>(ctx->tables, tw_fwd, tw_inv);
+    u64* tw_inv = tw_fwd + (1u << NTT_TMAX);
+    u64* pow7 = tw_inv + (1u << NTT_TMAX);
+    ntt_setup_tables<<<4, 256, 0, ctx->stream>>>(ctx->tables, tw_fwd, tw_inv, pow7);
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         pil2gpu_destroy(ctx);
@@ -176,6 +173,7 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
     ctx->tb.bytepow = ctx->tables;
     ctx->tb.tw_fwd = tw_fwd;
     ctx->tb.tw_inv = tw_inv;
+    ctx->tb.pow7 = pow7;
     *out = ctx;
     return PIL2GPU_OK;
 }
@@ -187,7 +185,6 @@ void pil2gpu_destroy(pil2gpu_ctx* ctx) {
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->tables) cudaFree(ctx->tables);
-    if (ctx->coset) cudaFree(ctx->coset);
     delete ctx;
 }
 
@@ -250,14 +247,6 @@ int pil2gpu_ntt_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64
     return check_launch(ctx, l, "ntt");
 }
 
-static int ensure_coset(pil2gpu_ctx* ctx, size_t words) {
-    if (ctx->coset_words >= words) return PIL2GPU_OK;
-    if (ctx->coset) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaFree(ctx->coset)); ctx->coset = nullptr; ctx->coset_words = 0; }
-    CU(cudaMalloc(&ctx->coset, words * sizeof(u64)));
-    ctx->coset_words = words;
-    return PIL2GPU_OK;
-}
-
 int pil2gpu_lde_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt) {
     ENTER(ctx);
     int rc = check_ntt_args(src, dst, nPols, nBitsExt);
@@ -266,11 +255,7 @@ int pil2gpu_lde_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64
     if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
     const size_t sw = (size_t)nPols << nBits, dw = (size_t)nPols << nBitsExt;
     if ((const u64*)src < (const u64*)dst + dw && (const u64*)dst < (const u64*)src + sw) return fail(PIL2GPU_E_INVALID, "src and dst overlap");
-    const size_t B = (size_t)1 << (nBitsExt - nBits);
-    rc = ensure_coset(ctx, (B << NTT_TMAX) + B);
-    if (rc) return rc;
-    int l = ntt_launch_lde((const u64*)src, (u64*)dst, nPols, (int)nBits, (int)nBitsExt, ctx->coset, ctx->coset + (B << NTT_TMAX), ctx->tb,
-                           ctx->stream);
+    int l = ntt_launch_lde((const u64*)src, (u64*)dst, nPols, (int)nBits, (int)nBitsExt, ctx->tb, ctx->stream);
     return check_launch(ctx, l, "lde");
 }
 

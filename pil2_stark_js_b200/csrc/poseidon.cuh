@@ -4,37 +4,42 @@
 //   plain 30-round form      src/helpers/glwasm.js:359-390 (MDS :428-440, round constants :536-627)
 //   optimised (sparse) form  src/helpers/hash/poseidon/poseidon.js:57-108
 // One permutation per thread, the 12-word state lives in 24 registers, round constants come from
-// __constant__ memory (warp-uniform index -> constant-cache broadcast).  The kernel is bound by the
-// integer pipes (IMAD.WIDE.U32 / IADD3), not by HBM: see DESIGN.md "Poseidon".
+// __constant__ memory (warp-uniform index -> constant-cache broadcast).  The kernel is bound by the two
+// half-rate integer pipes (alu: IADD3/LOP3/SHF, fmaheavy: IMAD/IMAD.WIDE), not by HBM: see DESIGN.md "Poseidon".
 #pragma once
 #include "gl.cuh"
 
-// 30 rounds x 12 lanes, plain form (generated: tools/gen_poseidon_rc.py)
-__constant__ u64 POSEIDON_RC[360] = {
+// Round-0 constants (added before the first S-box layer), Montgomery form (generated: tools/gen_poseidon_rc.py)
+__constant__ u64 POSEIDON_RC0[12] = {
 #include "poseidon_rc.inc"
 };
 
+// The state is kept in Montgomery form (x * 2^64 mod p, any 64-bit representative): the S-box then costs 4 gl_mmul whose
+// reductions are 9 ALU-pipe instructions each instead of 12, and the linear layer does not care about the scaling.
 // x -> x^7 : 4 multiplications (2 of them squarings)
 GL_D u64 poseidon_sbox(u64 x) {
-    u64 x2 = gl_sqr(x);
-    u64 x3 = gl_mul(x2, x);
-    u64 x4 = gl_sqr(x2);
-    return gl_mul(x3, x4);
+    u64 x2 = gl_msqr(x);
+    u64 x3 = gl_mmul(x2, x);
+    u64 x4 = gl_msqr(x2);
+    return gl_mmul(x3, x4);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Dense MDS layer: out_i = sum_j circ[(j - i) mod 12] * x_j  (+ 8*x_0 on lane 0), glwasm.js:428-440.
 //
-// On sm_100a IMAD.WIDE issues at 1/4 rate and IMAD at 1/2 rate while IADD3/LOP3/SHF run at full rate (measured:
-// tools/poseidon_probe.cu, profiles/), so the 144 small multiplies are NOT done with multiplies.  The matrix is
-// circulant with kernel k = [17,20,34,18,39,13,13,28,2,16,41,15] (y = k (*) x mod z^12 - 1), chosen so that its CRT
-// split over z^12-1 = (z^6-1)(z^6+1) = (z^3-1)(z^3+1)(z^6+1) has power-of-two entries:
+// The 144 small multiplies are NOT done with multiplies.  The matrix is circulant with kernel
+// k = [17,20,34,18,39,13,13,28,2,16,41,15] (y = k (*) x mod z^12 - 1), and its CRT split over
+// z^12-1 = (z^6-1)(z^6+1) = (z^3-1)(z^3+1)(z^6+1) has power-of-two entries:
 //     (k_lo + k_hi)/2 = [15,24,18,17,40,14]  ->  (.)/2 split again: [16,32,16] (cyclic 3) and [-1,-8,2] (negacyclic 3)
 //     (k_lo - k_hi)/2 = [2,-4,16,1,-1,-1]                            (negacyclic 6)
-// so one MDS on a vector of small integers is ~80 adds/shifts on the ALU pipe.  Each state word is cut into three
-// limbs of 22/22/20 bits; limb sums stay below 264 * 2^23 < 2^32, so plain wrap-around u32 arithmetic is exact.
+// so one MDS on a vector of small integers is ~76 shift-adds, which ptxas spreads over the alu pipe (IADD3/LEA) and the
+// fmaheavy pipe (IMAD.IADD / IMAD with a power-of-two immediate).  Each state word is cut into three limbs of 22/22/20
+// bits; limb sums stay below 264 * 2^22 + 2^22 < 2^31, so plain wrap-around u32 arithmetic is exact.  The round constant of
+// the NEXT round rides on the last butterfly as the third operand of an IADD3.
+// Alternatives measured on B200 (tools/probe/gl_probe.cu, Gperm/s): this 1.26; two 64-bit lanes with carries 1.20; adds
+// forced onto the fmaheavy pipe 1.20; the same CRT on the FP64 pipe (exact, DFMA/DADD) 1.22; previous non-Montgomery 1.11.
 // ---------------------------------------------------------------------------------------------------------------
-GL_D void poseidon_mds_limb(u32 y[12], const u32 x[12]) {
+GL_D void poseidon_mds_limb(u32 y[12], const u32 x[12], const u32* __restrict__ rc) {
     u32 xp[6], xm[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -71,26 +76,35 @@ GL_D void poseidon_mds_limb(u32 y[12], const u32 x[12]) {
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        y[i] = Pv[i] + Q[i];
-        y[i + 6] = Pv[i] - Q[i];
+        y[i] = Pv[i] + Q[i] + rc[3 * i];
+        y[i + 6] = Pv[i] - Q[i] + rc[3 * (i + 6)];
     }
     y[0] += 8 * x[0];
 }
 
-#define POSEIDON_L0 22
-#define POSEIDON_L1 22
-// limbs -> field element: Y0 + Y1*2^22 + Y2*2^44 (Y < 2^32 each) reduced with 2^64 = EPS
+// limbs -> field element: Y0 + Y1*2^22 + Y2*2^44 (Y < 2^32 each) mod p, with 2^64 = EPS.  3 IMAD.WIDE + 5 ALU.
 GL_D u64 poseidon_join(u32 Y0, u32 Y1, u32 Y2) {
-    const u32 Y2h = Y2 >> 20, Y2l = Y2 & 0xFFFFFu;
-    u64 base = (u64)Y0 + ((u64)Y1 << 22) + (((u64)Y2h << 32) - (u64)Y2h);   // < 2^55, no wrap
-    const u64 top = (u64)Y2l << 44;
-    u64 r = base + top;
-    if (r < top) r += GL_EPS;
-    return r;
+    const u64 v = (u64)Y1 * (1u << 22) + Y0;             // < 2^55
+    const u64 w = (u64)Y2 * (1u << 12);                  // Y2 * 2^44 = w * 2^32, w < 2^44
+    const u32 w0 = (u32)w, w1 = (u32)(w >> 32);          // value = v + w0 * 2^32 + w1 * 2^64
+    const u64 s = (u64)w1 * 0xFFFFFFFFu + v;             // w1 * 2^64 = w1 * EPS (w1 < 2^12): no overflow
+    const u32 s0 = (u32)s, s1 = (u32)(s >> 32);
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 t1, c, m;\n\t"
+        "add.cc.u32  t1, %3, %4;\n\t"      // + w0 * 2^32
+        "addc.u32    c, 0, 0;\n\t"
+        "neg.s32     m, c;\n\t"            // carry ? 0xFFFFFFFF : 0
+        "add.cc.u32  %0, %2, m;\n\t"       // + carry * EPS (the wrapped value is < 2^56: no second wrap)
+        "addc.u32    %1, t1, 0;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(s0), "r"(s1), "r"(w0));
+    return ((u64)r1 << 32) | r0;
 }
 
-// MDS over the whole state followed by the limb-wise addition of the NEXT round's constants (rc_limbs: [lane][limb]).
-GL_D void poseidon_mds_alu(u64 x[12], const u32* __restrict__ rc_limbs) {
+// MDS over the whole state + limb-wise addition of the NEXT round's constants (rc_limbs: [lane][limb]).
+GL_D void poseidon_mds(u64 x[12], const u32* __restrict__ rc_limbs) {
     u32 a[12], b[12], c[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) {
@@ -100,24 +114,24 @@ GL_D void poseidon_mds_alu(u64 x[12], const u32* __restrict__ rc_limbs) {
         c[j] = hi >> 12;
     }
     u32 ya[12], yb[12], yc[12];
-    poseidon_mds_limb(ya, a);
-    poseidon_mds_limb(yb, b);
-    poseidon_mds_limb(yc, c);
+    poseidon_mds_limb(ya, a, rc_limbs);
+    poseidon_mds_limb(yb, b, rc_limbs + 1);
+    poseidon_mds_limb(yc, c, rc_limbs + 2);
 #pragma unroll
-    for (int i = 0; i < 12; i++)
-        x[i] = poseidon_join(ya[i] + rc_limbs[3 * i], yb[i] + rc_limbs[3 * i + 1], yc[i] + rc_limbs[3 * i + 2]);
+    for (int i = 0; i < 12; i++) x[i] = poseidon_join(ya[i], yb[i], yc[i]);
 }
 
-// Constants of round r+1 pre-split into limbs, added after the MDS of round r (row 29 = 0): one code path for all rounds.
+// Montgomery-form constants of round r+1 pre-split into limbs, added after the MDS of round r (row 29 = 0): one code
+// path for all rounds.
 __constant__ u32 POSEIDON_RC_LIMBS[30 * 36] = {
 #include "poseidon_rc_limbs.inc"
 };
 
-// Permutation; state in lazy form on input, lazy form on output (callers canonicalise).  A single 30-iteration loop
-// keeps one copy of the S-box layer and one copy of the MDS in the instruction cache (~30 KB of SASS).
-GL_D void poseidon_permute(u64 x[12]) {
+// Permutation of a MONTGOMERY-FORM state (x * 2^64 mod p, any 64-bit representative in and out).  A single 30-iteration
+// loop keeps one copy of the S-box layer and one copy of the MDS in the instruction cache.
+GL_D void poseidon_permute_mont(u64 x[12]) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) x[i] = gl_add(x[i], POSEIDON_RC[i]);
+    for (int i = 0; i < 12; i++) x[i] = gl_addc(x[i], POSEIDON_RC0[i]);
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
         x[0] = poseidon_sbox(x[0]);
@@ -125,6 +139,15 @@ GL_D void poseidon_permute(u64 x[12]) {
 #pragma unroll
             for (int i = 1; i < 12; i++) x[i] = poseidon_sbox(x[i]);
         }
-        poseidon_mds_alu(x, POSEIDON_RC_LIMBS + r * 36);
+        poseidon_mds(x, POSEIDON_RC_LIMBS + r * 36);
     }
+}
+
+// Permutation of a plain state; output canonical.  (Test hook / transcript: hashing kernels stay in Montgomery form.)
+GL_D void poseidon_permute(u64 x[12]) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) x[i] = gl_to_mont(x[i]);
+    poseidon_permute_mont(x);
+#pragma unroll
+    for (int i = 0; i < 12; i++) x[i] = gl_from_mont(x[i]);
 }
