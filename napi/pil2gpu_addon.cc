@@ -1,0 +1,133 @@
+// Node N-API addon: marshals BigUint64Array / BigBuffer pages to the C ABI of include/pil2gpu.h.  No arithmetic here.
+// Build (on a machine with Node >= 16 and node-gyp; this repo's build container has neither, so this file is
+// compile-checked only where node_api.h exists):   cd napi && node-gyp configure build
+// Every exported function maps to exactly one pil2gpu_* entry point; failures become JS Errors carrying
+// pil2gpu_last_error() ("Out of range" for PIL2GPU_E_RANGE, as merklehash_p.js:143 throws).
+#include <node_api.h>
+#include <cstdint>
+#include <vector>
+#include "../include/pil2gpu.h"
+
+#define NAPI_OK(call) do { if ((call) != napi_ok) { napi_throw_error(env, nullptr, "pil2gpu addon: N-API call failed: " #call); return nullptr; } } while (0)
+
+static napi_value fail(napi_env env) { napi_throw_error(env, nullptr, pil2gpu_last_error()); return nullptr; }
+
+static bool get_u64_array(napi_env env, napi_value v, uint64_t** data, size_t* len) {
+    napi_typedarray_type ty; napi_value ab; size_t off;
+    bool is_ta = false;
+    if (napi_is_typedarray(env, v, &is_ta) != napi_ok || !is_ta) return false;
+    if (napi_get_typedarray_info(env, v, &ty, len, (void**)data, &ab, &off) != napi_ok) return false;
+    return ty == napi_biguint64_array;
+}
+static bool get_pages(napi_env env, napi_value arr, std::vector<uint64_t*>& pages, std::vector<uint64_t>& words) {
+    uint32_t n = 0;
+    if (napi_get_array_length(env, arr, &n) != napi_ok) return false;
+    for (uint32_t i = 0; i < n; i++) {
+        napi_value e; uint64_t* d; size_t l;
+        if (napi_get_element(env, arr, i, &e) != napi_ok || !get_u64_array(env, e, &d, &l)) return false;
+        pages.push_back(d); words.push_back(l);
+    }
+    return true;
+}
+static pil2gpu_ctx* get_ctx(napi_env env, napi_value v) { void* p = nullptr; napi_get_value_external(env, v, &p); return (pil2gpu_ctx*)p; }
+static uint32_t u32_of(napi_env env, napi_value v) { uint32_t x = 0; napi_get_value_uint32(env, v, &x); return x; }
+static int32_t i32_of(napi_env env, napi_value v) { int32_t x = 0; napi_get_value_int32(env, v, &x); return x; }
+static uint64_t u64_of(napi_env env, napi_value v) { double d = 0; napi_get_value_double(env, v, &d); return (uint64_t)d; }
+
+static void ctx_finalize(napi_env, void* data, void*) { pil2gpu_destroy((pil2gpu_ctx*)data); }
+
+// create(device) -> external
+static napi_value Create(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    pil2gpu_ctx* ctx = nullptr;
+    if (pil2gpu_create(i32_of(env, a[0]), nullptr, &ctx)) return fail(env);
+    napi_value ext; NAPI_OK(napi_create_external(env, ctx, ctx_finalize, nullptr, &ext));
+    return ext;
+}
+// nttPaged(ctx, srcPages, dstPages, nPols, nBits, inverse): single-page buffers go straight to pil2gpu_ntt
+static napi_value NttPaged(napi_env env, napi_callback_info info) {
+    size_t argc = 6; napi_value a[6]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    std::vector<uint64_t*> sp, dp; std::vector<uint64_t> sw, dw;
+    if (!get_pages(env, a[1], sp, sw) || !get_pages(env, a[2], dp, dw)) { napi_throw_type_error(env, nullptr, "expected arrays of BigUint64Array"); return nullptr; }
+    if (sp.size() != 1 || dp.size() != 1) { napi_throw_error(env, nullptr, "fft/ifft on multi-page BigBuffers: use interpolate or concatenate (pages > 2^28 words)"); return nullptr; }
+    if (pil2gpu_ntt(get_ctx(env, a[0]), sp[0], dp[0], u64_of(env, a[3]), u32_of(env, a[4]), i32_of(env, a[5]))) return fail(env);
+    return nullptr;
+}
+// ldePaged(ctx, srcPages, dstPages, nPols, nBits, nBitsExt) -> pil2gpu_lde_paged
+static napi_value LdePaged(napi_env env, napi_callback_info info) {
+    size_t argc = 6; napi_value a[6]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    std::vector<uint64_t*> sp, dp; std::vector<uint64_t> sw, dw;
+    if (!get_pages(env, a[1], sp, sw) || !get_pages(env, a[2], dp, dw)) { napi_throw_type_error(env, nullptr, "expected arrays of BigUint64Array"); return nullptr; }
+    if (pil2gpu_lde_paged(get_ctx(env, a[0]), (const uint64_t* const*)sp.data(), sw.data(), (uint32_t)sp.size(), dp.data(), dw.data(),
+                          (uint32_t)dp.size(), u64_of(env, a[3]), u32_of(env, a[4]), u32_of(env, a[5]))) return fail(env);
+    return nullptr;
+}
+// merkleNNodes(heightBigInt) -> BigInt
+static napi_value MerkleNNodes(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value a[1]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    uint64_t h = 0; bool lossless = false; NAPI_OK(napi_get_value_bigint_uint64(env, a[0], &h, &lossless));
+    napi_value r; NAPI_OK(napi_create_bigint_uint64(env, pil2gpu_merkle_nnodes(h), &r));
+    return r;
+}
+// merkelizePaged(ctx, elemPages, width, height, split, nodes) -> pil2gpu_merkelize_paged
+static napi_value MerkelizePaged(napi_env env, napi_callback_info info) {
+    size_t argc = 6; napi_value a[6]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    std::vector<uint64_t*> ep; std::vector<uint64_t> ew; uint64_t* nodes; size_t nlen;
+    if (!get_pages(env, a[1], ep, ew) || !get_u64_array(env, a[5], &nodes, &nlen)) { napi_throw_type_error(env, nullptr, "expected BigUint64Array buffers"); return nullptr; }
+    const uint64_t height = u64_of(env, a[3]);
+    if (nlen < pil2gpu_merkle_nnodes(height)) { napi_throw_range_error(env, nullptr, "nodes buffer too small"); return nullptr; }
+    if (pil2gpu_merkelize_paged(get_ctx(env, a[0]), (const uint64_t* const*)ep.data(), ew.data(), (uint32_t)ep.size(), u64_of(env, a[2]), height,
+                                i32_of(env, a[4]), nodes)) return fail(env);
+    return nullptr;
+}
+// poseidon(ctx, in12) -> BigUint64Array(12);  linearHash(ctx, vals, split) -> BigUint64Array(4)
+static napi_value make_u64_array(napi_env env, const uint64_t* src, size_t n) {
+    napi_value ab, ta; void* data;
+    if (napi_create_arraybuffer(env, n * 8, &data, &ab) != napi_ok) return nullptr;
+    for (size_t i = 0; i < n; i++) ((uint64_t*)data)[i] = src[i];
+    if (napi_create_typedarray(env, napi_biguint64_array, n, ab, 0, &ta) != napi_ok) return nullptr;
+    return ta;
+}
+static napi_value Poseidon(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value a[2]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    uint64_t* in; size_t n; uint64_t out[12];
+    if (!get_u64_array(env, a[1], &in, &n) || n != 12) { napi_throw_type_error(env, nullptr, "expected BigUint64Array(12)"); return nullptr; }
+    if (pil2gpu_poseidon(get_ctx(env, a[0]), in, out)) return fail(env);
+    return make_u64_array(env, out, 12);
+}
+static napi_value LinearHash(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value a[3]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    uint64_t* in; size_t n; uint64_t out[4];
+    if (!get_u64_array(env, a[1], &in, &n)) { napi_throw_type_error(env, nullptr, "expected BigUint64Array"); return nullptr; }
+    if (pil2gpu_linear_hash(get_ctx(env, a[0]), in, n, i32_of(env, a[2]), out)) return fail(env);
+    return make_u64_array(env, out, 4);
+}
+// friFold(ctx, pol, prevBits, curBits, nextBits, step0Bits, challenge, split, polOut, rowsOut|null, nodesOut|null)
+static napi_value FriFold(napi_env env, napi_callback_info info) {
+    size_t argc = 11; napi_value a[11]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    uint64_t *pol, *ch, *po, *rows = nullptr, *nodes = nullptr; size_t l;
+    if (!get_u64_array(env, a[1], &pol, &l) || !get_u64_array(env, a[6], &ch, &l) || l != 3 || !get_u64_array(env, a[8], &po, &l)) {
+        napi_throw_type_error(env, nullptr, "expected BigUint64Array buffers"); return nullptr;
+    }
+    get_u64_array(env, a[9], &rows, &l);     // null on the last step
+    get_u64_array(env, a[10], &nodes, &l);
+    if (pil2gpu_fri_fold(get_ctx(env, a[0]), pol, u32_of(env, a[2]), u32_of(env, a[3]), i32_of(env, a[4]), u32_of(env, a[5]), ch, i32_of(env, a[7]),
+                         po, rows, nodes)) return fail(env);
+    return nullptr;
+}
+
+static napi_value Init(napi_env env, napi_value exports) {
+    const napi_property_descriptor props[] = {
+        {"create", nullptr, Create, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"nttPaged", nullptr, NttPaged, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"ldePaged", nullptr, LdePaged, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"merkleNNodes", nullptr, MerkleNNodes, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"merkelizePaged", nullptr, MerkelizePaged, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"poseidon", nullptr, Poseidon, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"linearHash", nullptr, LinearHash, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"friFold", nullptr, FriFold, nullptr, nullptr, nullptr, napi_default, nullptr},
+    };
+    napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
+    return exports;
+}
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)

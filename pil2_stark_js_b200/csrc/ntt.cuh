@@ -109,6 +109,16 @@ __device__ __forceinline__ void ntt_build_tw(u64* __restrict__ TW, u64* __restri
     __syncthreads();
 }
 
+
+// ---- tile load ---------------------------------------------------------------------------------------------------
+// 16-byte cp.async (LDGSTS) copies: every thread puts all of its row segments in flight at once and the data never
+// passes through registers, so one DRAM latency covers the whole tile while the CTA builds its twiddle table.
+GL_D void ntt_cp_async16(u64* smem_dst, const u64* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+GL_D void ntt_cp_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
 // ---- butterflies -----------------------------------------------------------------------------------------------
 // canonical a, b -> canonical (a + b) mod p:  a - (p - b), + p on borrow.  7 ALU.
 GL_D u64 ntt_cadd(u64 a, u64 b) { return gl_subc(a, GL_P - b); }
@@ -218,17 +228,30 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __rest
     const u64 pos0 = ((u64)base_hi << (lo + t)) | base_lo;
 
     // loads first (they are in flight while the twiddle table is built)
-    for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
-        u64 v = 0;
-        if (c < cw) {
-            u64 pos = pos0 | ((u64)k << lo);
-            if (P.bitrev_in) pos = (P.n == 0) ? 0 : (u64)(__brevll(pos) >> (64 - P.n));
-            v = in[(pos * P.in_mul + z) * P.C + c0 + c];
-            if (DIF && P.canon_in) v = gl_canon(v);
+    const bool async_ok = !P.bitrev_in && cw == NTT_W && (P.C % 2 == 0) && ((((size_t)in) & 15) == 0);
+    if (async_ok) {
+        const int cp = threadIdx.x % (NTT_W / 2);
+        for (int k = threadIdx.x / (NTT_W / 2); k < rows; k += NTT_THREADS / (NTT_W / 2)) {
+            const u64 pos = pos0 | ((u64)k << lo);
+            ntt_cp_async16(tile + k * NTT_W + 2 * cp, in + (pos * P.in_mul + z) * P.C + c0 + 2 * cp);
         }
-        tile[k * NTT_W + c] = v;
+    } else {
+        for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
+            u64 v = 0;
+            if (c < cw) {
+                u64 pos = pos0 | ((u64)k << lo);
+                if (P.bitrev_in) pos = (P.n == 0) ? 0 : (u64)(__brevll(pos) >> (64 - P.n));
+                v = in[(pos * P.in_mul + z) * P.C + c0 + c];
+            }
+            tile[k * NTT_W + c] = v;
+        }
     }
     ntt_build_tw<INVERSE>(TW, G, t, lo, base_lo, P.coset ? (int)z : -1, P.n, P.ext_bits, tb);   // ends with a barrier
+    if (async_ok) { ntt_cp_async_wait(); __syncthreads(); }
+    if (DIF && P.canon_in) {   // the caller's buffer may hold non-canonical words; DIF butterflies need canonical inputs
+        for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile[i] = gl_canon(tile[i]);
+        __syncthreads();
+    }
     ntt_tile_transform<DIF>(tile, TW, t);
     for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
         if (c < cw) {
@@ -259,24 +282,35 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_lde_fused_kernel(const u64* _
     const int cw = (int)((C - c0 < NTT_W) ? (C - c0) : NTT_W);
     const int rows = 1 << t;
     const int c = threadIdx.x % NTT_W;
-    for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
-        u64 v = 0;
-        if (c < cw) {
-            v = in[((q0 | (u64)k) * in_mul) * C + c0 + c];
-            if (canon_in) v = gl_canon(v);
-        }
-        tile[k * NTT_W + c] = v;
+    const bool async_ok = cw == NTT_W && (C % 2 == 0) && ((((size_t)in) & 15) == 0);
+    if (async_ok) {
+        const int cp = threadIdx.x % (NTT_W / 2);
+        for (int k = threadIdx.x / (NTT_W / 2); k < rows; k += NTT_THREADS / (NTT_W / 2))
+            ntt_cp_async16(tile + k * NTT_W + 2 * cp, in + ((q0 | (u64)k) * in_mul) * C + c0 + 2 * cp);
+    } else {
+        for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W)
+            tile[k * NTT_W + c] = (c < cw) ? in[((q0 | (u64)k) * in_mul) * C + c0 + c] : 0;
     }
     ntt_build_tw<true>(TW, G, t, 0, 0, -1, n, ext_bits, tb);
-    ntt_tile_transform<true>(tile, TW, t);          // coefficients, bit-reversed: position q holds a_{bitrev_n(q)}
-    for (int r = 0; r < B; r++) {
-        ntt_build_tw<false>(TW, G, t, 0, 0, r, n, ext_bits, tb);   // all threads passed the trailing barrier of the transform
-        for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile2[i] = gl_mmul(tile[i], n_inv_mont);
+    if (async_ok) { ntt_cp_async_wait(); __syncthreads(); }
+    if (canon_in) {
+        for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile[i] = gl_canon(tile[i]);
         __syncthreads();
-        ntt_tile_transform<false>(tile2, TW, t);
+    }
+    ntt_tile_transform<true>(tile, TW, t);          // coefficients, bit-reversed: position q holds a_{bitrev_n(q)}
+    for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile[i] = gl_mmul(tile[i], n_inv_mont);   // * 1/N, once
+    for (int r = 0; r < B; r++) {
+        ntt_build_tw<false>(TW, G, t, 0, 0, r, n, ext_bits, tb);   // ends with a barrier (also orders the scale pass above)
+        u64* work = tile;                                          // the last coset transforms the coefficients in place
+        if (r + 1 < B) {
+            work = tile2;
+            for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile2[i] = tile[i];
+            __syncthreads();
+        }
+        ntt_tile_transform<false>(work, TW, t);
         for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
             if (c < cw) {
-                u64 v = tile2[k * NTT_W + c];
+                u64 v = work[k * NTT_W + c];
                 if (canon_out) v = gl_canon(v);
                 out[(((q0 | (u64)k) << (ext_bits - n)) + r) * C + c0 + c] = v;
             }

@@ -1,11 +1,13 @@
 // Stand-alone probe: arithmetic / Poseidon candidates vs the shipped versions (correctness + throughput on one GPU).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I pil2_stark_js_b200/csrc -I tools/probe tools/probe/gl_probe.cu -o tools/bin/gl_probe
+// Results of the rounds of experiments are kept in profiles/r01_probe_*.log and summarised in DESIGN.md section 4.0.
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include "poseidon.cuh"
-#include "poseidon_steer.cuh"
+#include "poseidon_mont.cuh"
 #include "poseidon_fp64.cuh"
+#include "poseidon_z.cuh"
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
@@ -13,18 +15,13 @@ __device__ __forceinline__ u64 splitmix(u64 z) {
     z += 0x9E3779B97F4A7C15ULL; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31);
 }
 
-// VAR: 0 shipped, 1 mont + 64-bit lanes, 2 mont + 3 limbs (compiler-placed), 3 mont + 3 limbs steered
+// VAR: 0 shipped, 1 64-bit lanes, 2 FP64-pipe MDS, 3 shipped with two-input adds forced to IADD3
 template <int VAR>
-__device__ __forceinline__ void permute_var(u64 x[12]) {
-    if (VAR == 0) { poseidon_permute(x); return; }
-#pragma unroll
-    for (int i = 0; i < 12; i++) x[i] = gl_to_mont(x[i]);
-    if (VAR == 1) poseidon_permute_mont(x);
-    if (VAR == 2) poseidon_permute_steer<0>(x);
-    if (VAR == 3) poseidon_permute_steer<1>(x);
-    if (VAR == 4) poseidon_permute_fp64(x);
-#pragma unroll
-    for (int i = 0; i < 12; i++) x[i] = gl_from_mont(x[i]);
+__device__ __forceinline__ void permute_mont_var(u64 x[12]) {
+    if (VAR == 0) poseidon_permute_mont(x);
+    if (VAR == 1) poseidon_permute_lanes64(x);
+    if (VAR == 2) poseidon_permute_fp64(x);
+    if (VAR == 3) poseidon_permute_mont_z(x);
 }
 
 template <int VAR>
@@ -34,30 +31,25 @@ __global__ void __launch_bounds__(256) k_check(u64* out, u64 seed, int lazy) {
 #pragma unroll
     for (int i = 0; i < 12; i++) { u64 v = seed ? splitmix(seed + tid * 12 + i) : (u64)i; x[i] = lazy ? v : gl_canon(v); }
     if (seed && tid % 7 == 0) { x[3] = GL_P - 1; x[4] = 0; x[5] = 0xFFFFFFFFULL; x[6] = lazy ? 0xFFFFFFFFFFFFFFFFULL : 1; }
-    permute_var<VAR>(x);
 #pragma unroll
-    for (int i = 0; i < 12; i++) out[tid * 12 + i] = gl_canon(x[i]);
+    for (int i = 0; i < 12; i++) x[i] = gl_to_mont(x[i]);
+    permute_mont_var<VAR>(x);
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[tid * 12 + i] = gl_from_mont(x[i]);
 }
 
-// throughput: the state stays in the variant's own domain across iterations (as in a sponge)
 template <int VAR>
 __global__ void __launch_bounds__(256) k_chain(u64* out, int iters) {
     u64 x[12];
     u64 tid = blockIdx.x * (u64)blockDim.x + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < 12; i++) x[i] = tid * 12 + i;
-    for (int it = 0; it < iters; it++) {
-        if (VAR == 0) poseidon_permute(x);
-        if (VAR == 1) poseidon_permute_mont(x);
-        if (VAR == 2) poseidon_permute_steer<0>(x);
-        if (VAR == 3) poseidon_permute_steer<1>(x);
-        if (VAR == 4) poseidon_permute_fp64(x);
-    }
+    for (int it = 0; it < iters; it++) permute_mont_var<VAR>(x);
 #pragma unroll
     for (int i = 0; i < 12; i++) out[tid * 12 + i] = x[i];
 }
 
-// MODE 0: gl_mul chain, 1: gl_mmul chain, 2: shipped butterfly (gl_mul/gl_add/gl_sub), 3: mont butterfly
+// MODE 0: gl_mul chain, 1: gl_mmul chain, 2: legacy butterfly (gl_mul/gl_add/gl_sub), 3: Montgomery butterfly, 4 DFMA, 5 DADD
 template <int MODE>
 __global__ void __launch_bounds__(256) k_arith(u64* out, int iters, u64 w) {
     u64 a0 = threadIdx.x + 1, a1 = blockIdx.x + 3, a2 = a0 ^ 0x1234567, a3 = a0 + a1 + 77;
@@ -72,35 +64,34 @@ __global__ void __launch_bounds__(256) k_arith(u64* out, int iters, u64 w) {
                 t = gl_mul(a2, w); a2 = gl_sub(a0, t); a0 = gl_add(a0, t);
                 t = gl_mul(a3, w); a3 = gl_sub(a1, t); a1 = gl_add(a1, t);
             }
-            if (MODE == 4) {   // FP64 pipe: 4 independent DFMA chains
-                double d0 = __longlong_as_double(a0), d1 = __longlong_as_double(a1), d2 = __longlong_as_double(a2), d3 = __longlong_as_double(a3);
-                d0 = fma(d0, 1.0000001, d1); d1 = fma(d1, 0.9999999, d2); d2 = fma(d2, 1.0000002, d3); d3 = fma(d3, 0.9999998, d0);
-                a0 = __double_as_longlong(d0); a1 = __double_as_longlong(d1); a2 = __double_as_longlong(d2); a3 = __double_as_longlong(d3);
-            }
-            if (MODE == 5) {   // FP64 pipe: DADD
-                double d0 = __longlong_as_double(a0), d1 = __longlong_as_double(a1), d2 = __longlong_as_double(a2), d3 = __longlong_as_double(a3);
-                d0 = d0 + d1; d1 = d1 + d2; d2 = d2 + d3; d3 = d3 + d0;
-                a0 = __double_as_longlong(d0); a1 = __double_as_longlong(d1); a2 = __double_as_longlong(d2); a3 = __double_as_longlong(d3);
-            }
             if (MODE == 3) {
                 u64 t = gl_mmul(a1, w); a1 = gl_subc(a0, t); a0 = gl_addc(a0, t);
                 t = gl_mmul(a3, w); a3 = gl_subc(a2, t); a2 = gl_addc(a2, t);
                 t = gl_mmul(a2, w); a2 = gl_subc(a0, t); a0 = gl_addc(a0, t);
                 t = gl_mmul(a3, w); a3 = gl_subc(a1, t); a1 = gl_addc(a1, t);
             }
+            if (MODE == 4) {
+                double d0 = __longlong_as_double(a0), d1 = __longlong_as_double(a1), d2 = __longlong_as_double(a2), d3 = __longlong_as_double(a3);
+                d0 = fma(d0, 1.0000001, d1); d1 = fma(d1, 0.9999999, d2); d2 = fma(d2, 1.0000002, d3); d3 = fma(d3, 0.9999998, d0);
+                a0 = __double_as_longlong(d0); a1 = __double_as_longlong(d1); a2 = __double_as_longlong(d2); a3 = __double_as_longlong(d3);
+            }
+            if (MODE == 5) {
+                double d0 = __longlong_as_double(a0), d1 = __longlong_as_double(a1), d2 = __longlong_as_double(a2), d3 = __longlong_as_double(a3);
+                d0 = d0 + d1; d1 = d1 + d2; d2 = d2 + d3; d3 = d3 + d0;
+                a0 = __double_as_longlong(d0); a1 = __double_as_longlong(d1); a2 = __double_as_longlong(d2); a3 = __double_as_longlong(d3);
+            }
         }
     }
     out[(u64)blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3;
 }
 
-// arithmetic self-check against __int128 on the host
 __global__ void k_arith_check(const u64* a, const u64* b, u64* o, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    o[4 * i] = gl_mmul(a[i], b[i]);                    // a*b*2^-64 (b canonical -> result canonical)
+    o[4 * i] = gl_mmul(a[i], b[i]);
     o[4 * i + 1] = gl_addc(a[i], b[i]);
     o[4 * i + 2] = gl_subc(a[i], b[i]);
-    o[4 * i + 3] = gl_mmul(a[i], a[i]);                // lazy * lazy
+    o[4 * i + 3] = gl_mmul(a[i], a[i]);
 }
 static u64 hmul(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) % GL_P); }
 static u64 hpow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = hmul(r, a); a = hmul(a, a); e >>= 1; } return r; }
@@ -113,7 +104,6 @@ int main() {
     const int blocks = pr.multiProcessorCount * 8, threads = 256;
     const size_t n = (size_t)blocks * threads;
     u64 *o0, *o1; CK(cudaMalloc(&o0, n * 12 * 8)); CK(cudaMalloc(&o1, n * 12 * 8));
-    // ---- arithmetic self-check
     {
         const int N = 1 << 16;
         u64 *ha = (u64*)malloc(N * 8), *hb = (u64*)malloc(N * 8), *ho = (u64*)malloc(N * 32);
@@ -140,21 +130,19 @@ int main() {
         }
         printf("arith check: %ld mismatches, %ld non-canonical mmul outputs (of %d)\n", bad, noncanon, N);
     }
-    // ---- Poseidon correctness: KAT and variants vs shipped
     {
         k_check<0><<<1, 32>>>(o0, 0, 0); CK(cudaDeviceSynchronize());
-        u64 h[12]; CK(cudaMemcpy(h, o0, 96, cudaMemcpyDeviceToHost));
+        unsigned long long h[12]; CK(cudaMemcpy(h, o0, 96, cudaMemcpyDeviceToHost));
         printf("shipped perm(0..11)[0..3] = %016llx %016llx %016llx %016llx (expect d64e1e3efc5b8e9e 53666633020aaa47 d40285597c6a8825 613a4f81e81231d2)\n",
                h[0], h[1], h[2], h[3]);
         u64* h0 = (u64*)malloc(n * 96); u64* h1 = (u64*)malloc(n * 96);
         for (int lazy = 0; lazy < 2; lazy++) {
             k_check<0><<<blocks, threads>>>(o0, 777 + lazy, lazy); CK(cudaDeviceSynchronize());
             CK(cudaMemcpy(h0, o0, n * 96, cudaMemcpyDeviceToHost));
-            for (int var = 1; var <= 4; var++) {
+            for (int var = 1; var <= 3; var++) {
                 if (var == 1) k_check<1><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 if (var == 2) k_check<2><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 if (var == 3) k_check<3><<<blocks, threads>>>(o1, 777 + lazy, lazy);
-                if (var == 4) k_check<4><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 CK(cudaDeviceSynchronize());
                 CK(cudaMemcpy(h1, o1, n * 96, cudaMemcpyDeviceToHost));
                 long bad = 0;
@@ -163,9 +151,8 @@ int main() {
             }
         }
     }
-    // ---- Poseidon throughput
-    const char* pn[5] = {"shipped (3 limbs, ALU MDS)", "mont + 64-bit lanes", "mont + 3 limbs", "mont + 3 limbs steered", "mont + FP64-pipe MDS"};
-    for (int var = 0; var < 5; var++) {
+    const char* pn[4] = {"shipped (mont, 3 limbs)", "64-bit lanes", "FP64-pipe MDS", "3 limbs, adds forced to IADD3"};
+    for (int var = 0; var < 4; var++) {
         float best = 1e30f; int iters = 64;
         for (int rep = 0; rep < 3; rep++) {
             CK(cudaEventRecord(e0));
@@ -173,14 +160,12 @@ int main() {
             if (var == 1) k_chain<1><<<blocks, threads>>>(o0, iters);
             if (var == 2) k_chain<2><<<blocks, threads>>>(o0, iters);
             if (var == 3) k_chain<3><<<blocks, threads>>>(o0, iters);
-            if (var == 4) k_chain<4><<<blocks, threads>>>(o0, iters);
             CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
         }
-        printf("poseidon %-28s %.3f ms  %.3f Gperm/s\n", pn[var], best, (double)n * iters / best / 1e6);
+        printf("poseidon %-32s %.3f ms  %.3f Gperm/s\n", pn[var], best, (double)n * iters / best / 1e6);
     }
-    // ---- arithmetic throughput
-    const char* an[6] = {"gl_mul", "gl_mmul (Montgomery)", "butterfly shipped", "butterfly mont", "DFMA", "DADD"};
+    const char* an[6] = {"gl_mul (2^64=2^32-1 fold)", "gl_mmul (Montgomery)", "butterfly legacy", "butterfly mont", "DFMA", "DADD"};
     for (int mode = 0; mode < 6; mode++) {
         float best = 1e30f; int iters = 2048;
         for (int rep = 0; rep < 3; rep++) {
@@ -195,7 +180,7 @@ int main() {
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
         }
         double ops = (double)n * iters * 8 * 4;
-        printf("%-24s %.3f ms  %.1f Gop/s\n", an[mode], best, ops / best / 1e6);
+        printf("%-28s %.3f ms  %.1f Gop/s\n", an[mode], best, ops / best / 1e6);
     }
     return 0;
 }

@@ -1,19 +1,12 @@
 // Candidate Poseidon-GL permutation for the probe: Montgomery-form state, MDS on 64-bit lanes (lo/hi halves).
 #pragma once
-#include "gl_mont.cuh"
+#include "poseidon.cuh"
 
-#ifndef POSEIDON_RC_MONT_DEFINED
 __constant__ u64 POSEIDON_RC_MONT[372] = {   // RC[r][i] * 2^64 mod p; rows 1..30 used post-MDS (row 30 = 0)
 #include "poseidon_rc_mont.inc"
 };
-#endif
 
-GL_D u64 poseidon_sbox_mont(u64 x) {
-    u64 x2 = gl_msqr(x);
-    u64 x3 = gl_mmul(x2, x);
-    u64 x4 = gl_msqr(x2);
-    return gl_mmul(x3, x4);
-}
+#define poseidon_sbox_mont poseidon_sbox
 
 // y = circ-MDS * x on lanes of type T (wrap-around arithmetic; true results are non-negative and small)
 template <typename T>
@@ -94,7 +87,7 @@ GL_D void poseidon_mds_mont(u64 x[12], const u64* __restrict__ rc) {
 }
 
 // Permutation on a Montgomery-form state (x~ = x * 2^64 mod p, any 64-bit representative).
-GL_D void poseidon_permute_mont(u64 x[12]) {
+GL_D void poseidon_permute_lanes64(u64 x[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) x[i] = gl_addc(x[i], POSEIDON_RC_MONT[i]);
 #pragma unroll 1
@@ -108,6 +101,3 @@ GL_D void poseidon_permute_mont(u64 x[12]) {
     }
 }
 
-#define GL_R2 0xFFFFFFFE00000001ULL   // 2^128 mod p
-GL_D u64 gl_to_mont(u64 x) { return gl_mmul(x, GL_R2); }
-GL_D u64 gl_from_mont(u64 x) { return gl_mmul(x, 1ULL); }
