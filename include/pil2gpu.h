@@ -47,6 +47,9 @@ void pil2gpu_destroy(pil2gpu_ctx* ctx);
 const char* pil2gpu_last_error(void);
 const char* pil2gpu_version(void);
 int pil2gpu_sync(pil2gpu_ctx* ctx);
+/* The host-pointer entry points keep a grow-only device workspace in the ctx between calls (allocating and freeing tens
+ * of GiB per call costs more than the kernels); this returns it to the driver. */
+int pil2gpu_release_workspace(pil2gpu_ctx* ctx);
 /* Number of kernels of this library launched through ctx since creation (bench.py "gpu_launches"). */
 uint64_t pil2gpu_launch_count(const pil2gpu_ctx* ctx);
 

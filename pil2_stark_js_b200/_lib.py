@@ -32,6 +32,7 @@ _SIGS = {
     "pil2gpu_last_error": (ctypes.c_char_p, []),
     "pil2gpu_version": (ctypes.c_char_p, []),
     "pil2gpu_sync": (c_int, [vp]),
+    "pil2gpu_release_workspace": (c_int, [vp]),
     "pil2gpu_launch_count": (c_u64, [vp]),
     "pil2gpu_dev_alloc": (c_int, [vp, c_size, ctypes.POINTER(vp)]),
     "pil2gpu_dev_free": (c_int, [vp, vp]),

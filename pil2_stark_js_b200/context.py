@@ -103,6 +103,19 @@ class Context:
                                        _ptr(rows) if rows is not None else None, _ptr(nodes) if nodes is not None else None))
         return pol2.reshape(-1, 3), rows, nodes
 
+    def extend_and_merkelize(self, src, n_pols, n_bits, n_bits_ext, split=False, want_dst=True, want_nodes=True):
+        """extendAndMerkelize (stark_gen_helpers.js:388-412) with host buffers: returns (dst|None, nodes|None, root[4]).
+        Wide standard-hash traces go through the column-slab pipeline (H2D | LDE + hashing | D2H overlapped)."""
+        _as_u64(src, "buffSrc")
+        if src.size != n_pols << n_bits:
+            raise ValueError("buffer size does not match nPols * 2^nBits")
+        dst = np.empty(n_pols << n_bits_ext, dtype=np.uint64) if want_dst else None
+        nodes = np.empty(self.merkle_nnodes(1 << n_bits_ext), dtype=np.uint64) if want_nodes else None
+        root = np.empty(4, dtype=np.uint64)
+        check(self._L.pil2gpu_extend_and_merkelize(self.handle, _ptr(src), n_pols, n_bits, n_bits_ext, int(split),
+                                                   _ptr(dst) if want_dst else None, _ptr(nodes) if want_nodes else None, _ptr(root)))
+        return dst, nodes, root
+
     # ---- device-resident commit ----
     def commit(self, src, n_pols, n_bits, n_bits_ext, split=False):
         """interpolate + merkelize with the LDE kept in HBM.  Returns (DeviceTree, root[4])."""

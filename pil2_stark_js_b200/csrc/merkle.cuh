@@ -112,6 +112,47 @@ __global__ void __launch_bounds__(MERKLE_THREADS) merkle_leaf_kernel(RowTiles t,
     o[1] = make_ulonglong2(d[2], d[3]);
 }
 
+// Incremental standard linear hash for the column-slab pipeline (pil2gpu.cu: pipelined extend-and-merkelize): absorbs
+// `cols` more columns of every row (a row-major slab [height][cols], cols % 8 == 0 except for the last slab) into the
+// running sponge state.  state[row*4 ..] holds the capacity words in Montgomery form between slabs; the last slab
+// writes the canonical digest to nodes[row*4 ..].  Equivalent to merkle_sponge over the concatenated slabs (total > 4).
+__global__ void __launch_bounds__(MERKLE_THREADS) merkle_absorb_kernel(const u64* __restrict__ slab, u64 cols, u64 height,
+                                                                       u64* __restrict__ state, int first, int last, u64* __restrict__ nodes) {
+    const u64 row = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
+    if (row >= height) return;
+    u64 x[12];
+    if (first) {
+#pragma unroll
+        for (int i = 8; i < 12; i++) x[i] = 0;
+    } else {
+        const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(state + 4 * row);
+        const ulonglong2 a = sp[0], b = sp[1];
+        x[8] = a.x; x[9] = a.y; x[10] = b.x; x[11] = b.y;
+    }
+    const u64* __restrict__ v = slab + row * cols;
+    for (u64 off = 0; off < cols; off += 8) {
+        if (off + 8 <= cols) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = gl_to_mont(v[off + i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = (off + i < cols) ? gl_to_mont(v[off + i]) : 0;
+        }
+        poseidon_permute_mont(x);
+#pragma unroll
+        for (int i = 0; i < 4; i++) x[8 + i] = x[i];
+    }
+    if (last) {
+        ulonglong2* o = reinterpret_cast<ulonglong2*>(nodes + 4 * row);
+        o[0] = make_ulonglong2(gl_from_mont(x[8]), gl_from_mont(x[9]));
+        o[1] = make_ulonglong2(gl_from_mont(x[10]), gl_from_mont(x[11]));
+    } else {
+        ulonglong2* o = reinterpret_cast<ulonglong2*>(state + 4 * row);
+        o[0] = make_ulonglong2(x[8], x[9]);
+        o[1] = make_ulonglong2(x[10], x[11]);
+    }
+}
+
 // Split linear hash, stage 1: one thread per (row, batch): digests[(row*nb + b)*4 ..] = L(row[b*batch .. ]).
 __global__ void __launch_bounds__(MERKLE_THREADS) merkle_batch_kernel(RowTiles t, u64 width, u64 height, u64 batch, u64 nb,
                                                                       u64* __restrict__ digests) {

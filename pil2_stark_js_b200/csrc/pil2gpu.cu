@@ -42,8 +42,11 @@ struct pil2gpu_ctx {
     u64* tables;      // bytepow[1024] | tw_fwd[2^TMAX] | tw_inv[2^TMAX] | pow7[32]  (Montgomery form, see ntt.cuh)
     uint64_t launches;
     NttTables tb;
-    cudaStream_t copy_stream;   // second stream: D2H of the LDE overlaps the hashing (extend_and_merkelize)
+    cudaStream_t copy_stream;   // D2H stream: downloads of finished slabs overlap the compute (extend_and_merkelize)
+    cudaStream_t in_stream;     // H2D stream: uploads of the next slab overlap the compute
     cudaEvent_t ev;
+    u64* ws;                    // grow-only device workspace of the host-pointer entry points (cudaMalloc/cudaFree of tens of GiB
+    size_t ws_words;            // per call cost ~0.3 s at cfg3); released by pil2gpu_destroy / pil2gpu_release_workspace
 };
 
 struct pil2gpu_tree {
@@ -140,7 +143,10 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
     ctx->device = device;
     ctx->launches = 0;
     ctx->copy_stream = nullptr;
+    ctx->in_stream = nullptr;
     ctx->ev = nullptr;
+    ctx->ws = nullptr;
+    ctx->ws_words = 0;
     ctx->tables = nullptr;
     ctx->stream = nullptr;
     ctx->own_stream = false;
@@ -153,6 +159,7 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
         ctx->own_stream = true;
     }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming) != cudaSuccess) {
         pil2gpu_destroy(ctx);
         return fail(PIL2GPU_E_CUDA, "stream/event creation failed");
@@ -183,8 +190,10 @@ void pil2gpu_destroy(pil2gpu_ctx* ctx) {
     DeviceGuard guard(ctx->device);
     if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->in_stream) { cudaStreamSynchronize(ctx->in_stream); cudaStreamDestroy(ctx->in_stream); }
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->tables) cudaFree(ctx->tables);
+    if (ctx->ws) cudaFree(ctx->ws);
     delete ctx;
 }
 
@@ -194,6 +203,30 @@ int pil2gpu_sync(pil2gpu_ctx* ctx) {
     return PIL2GPU_OK;
 }
 uint64_t pil2gpu_launch_count(const pil2gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static inline size_t ev2(size_t w) { return (w + 1) & ~(size_t)1; }   // keep 16-byte alignment of workspace carve-outs
+static int ensure_ws(pil2gpu_ctx* ctx, size_t words) {
+    if (ctx->ws_words >= words) return PIL2GPU_OK;
+    if (ctx->ws) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_words = 0;
+    }
+    CU(cudaMalloc(&ctx->ws, words * sizeof(u64)));
+    ctx->ws_words = words;
+    return PIL2GPU_OK;
+}
+int pil2gpu_release_workspace(pil2gpu_ctx* ctx) {
+    ENTER(ctx);
+    if (ctx->ws) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_words = 0;
+    }
+    return PIL2GPU_OK;
+}
 
 int pil2gpu_dev_alloc(pil2gpu_ctx* ctx, size_t bytes, void** dptr) {
     ENTER(ctx);
@@ -292,9 +325,9 @@ int pil2gpu_ntt(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t n
     int rc = check_ntt_args(src, dst, nPols, nBits);
     if (rc) return rc;
     const size_t words = (size_t)nPols << nBits;
-    DevBuf a, b;
-    CU(a.alloc(words));
-    CU(b.alloc(words));
+    rc = ensure_ws(ctx, 2 * ev2(words));
+    if (rc) return rc;
+    struct { u64* p; } a = {ctx->ws}, b = {ctx->ws + ev2(words)};
     CU(cudaMemcpyAsync(a.p, src, words * 8, cudaMemcpyHostToDevice, ctx->stream));
     rc = pil2gpu_ntt_dev(ctx, a.p, b.p, nPols, nBits, inverse);
     if (rc) return rc;
@@ -318,10 +351,10 @@ int pil2gpu_lde_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const 
     if (!src_pages || !dst_pages || !src_page_words || !dst_page_words) return fail(PIL2GPU_E_INVALID, "null page list");
     if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad LDE shape");
     const size_t sw = (size_t)nPols << nBits, dw = (size_t)nPols << nBitsExt;
-    DevBuf a, b;
-    CU(a.alloc(sw));
-    CU(b.alloc(dw));
-    int rc = pages_to_dev(ctx, a.p, src_pages, src_page_words, n_src_pages, sw);
+    int rc = ensure_ws(ctx, ev2(sw) + dw);
+    if (rc) return rc;
+    struct { u64* p; } a = {ctx->ws}, b = {ctx->ws + ev2(sw)};
+    rc = pages_to_dev(ctx, a.p, src_pages, src_page_words, n_src_pages, sw);
     if (rc) return rc;
     rc = pil2gpu_lde_dev(ctx, a.p, b.p, nPols, nBits, nBitsExt);
     if (rc) return rc;
@@ -409,10 +442,10 @@ int pil2gpu_merkelize_paged(pil2gpu_ctx* ctx, const uint64_t* const* elem_pages,
     if (!nodes || !elem_pages || !page_words) return fail(PIL2GPU_E_INVALID, "null buffer");
     if (height == 0) return fail(PIL2GPU_E_INVALID, "height must be > 0");
     const size_t ew = (size_t)width * height, nw = merkle_nnodes_words(height);
-    DevBuf e, n;
-    CU(e.alloc(ew));
-    CU(n.alloc(nw));
-    int rc = pages_to_dev(ctx, e.p, elem_pages, page_words, n_pages, ew);
+    int rc = ensure_ws(ctx, ev2(ew) + nw);
+    if (rc) return rc;
+    struct { u64* p; } e = {ctx->ws}, n = {ctx->ws + ev2(ew)};
+    rc = pages_to_dev(ctx, e.p, elem_pages, page_words, n_pages, ew);
     if (rc) return rc;
     rc = pil2gpu_merkelize_dev(ctx, e.p, width, height, split, n.p);
     if (rc) return rc;
@@ -534,20 +567,106 @@ int pil2gpu_commit(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32
     return rc;
 }
 
+// Column-slab pipeline behind pil2gpu_extend_and_merkelize: the trace is cut into slabs of PIPE_COLS columns (columns are
+// independent NTTs and the standard linear hash absorbs columns left to right), and three streams overlap
+//     H2D of slab s+1   |   LDE + sponge absorption of slab s   |   D2H of the extended slab s-1
+// so the call costs max(PCIe down, PCIe up, compute) instead of their sum.  Strided 2D copies of >= 256-byte row
+// segments run at the full PCIe rate (measured 55.6 / 57.2 GB/s up / down, 98.7 GB/s both ways: tools/probe/pcie_probe.cu).
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    ~EventPool() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    bool timing = false;
+    cudaError_t make(cudaEvent_t* out) {
+        cudaError_t e = cudaEventCreateWithFlags(out, timing ? cudaEventDefault : cudaEventDisableTiming);
+        if (e == cudaSuccess) ev.push_back(*out);
+        return e;
+    }
+};
+
+static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, uint64_t cs,
+                                          uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]) {
+    const u64 N = 1ULL << nBits, E = 1ULL << nBitsExt;
+    const size_t nw = merkle_nnodes_words(E);
+    const u64 nslabs = nPols / cs;
+    // workspace: the whole trace (so the upload runs ahead at full rate and then leaves PCIe to the download, which is the
+    // longer of the two), two extended slabs, the sponge states and the nodes
+    int wrc = ensure_ws(ctx, N * nPols + 2 * E * cs + 4 * E + nw);
+    if (wrc) return wrc;
+    struct { u64* p; } sall = {ctx->ws}, dbuf[2] = {{ctx->ws + N * nPols}, {ctx->ws + N * nPols + E * cs}}, state = {ctx->ws + N * nPols + 2 * E * cs},
+                       nodes = {ctx->ws + N * nPols + 2 * E * cs + 4 * E};
+    EventPool pool;
+    const bool trace = getenv("PIL2GPU_TRACE") != nullptr;   // diagnostic: print the slab timeline after the call
+    pool.timing = trace;
+    std::vector<cudaEvent_t> ev_in(nslabs), ev_lde(nslabs), ev_out(nslabs), ev_abs(nslabs);
+    for (u64 s = 0; s < nslabs; s++) { CU(pool.make(&ev_in[s])); CU(pool.make(&ev_lde[s])); CU(pool.make(&ev_out[s])); CU(pool.make(&ev_abs[s])); }
+    cudaEvent_t ev_start;
+    CU(pool.make(&ev_start));
+    CU(cudaEventRecord(ev_start, ctx->stream));                // the copy streams must not run ahead of prior work on ctx->stream
+    CU(cudaStreamWaitEvent(ctx->in_stream, ev_start, 0));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ev_start, 0));
+    const unsigned blocks = (unsigned)((E + MERKLE_THREADS - 1) / MERKLE_THREADS);
+    int rc = PIL2GPU_OK;
+    for (u64 s = 0; s < nslabs && rc == PIL2GPU_OK; s++) {
+        const int b = (int)(s & 1);
+        u64* sslab = sall.p + s * N * cs;
+        CU(cudaMemcpy2DAsync(sslab, cs * 8, src + s * cs, nPols * 8, cs * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
+        CU(cudaEventRecord(ev_in[s], ctx->in_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
+        if (s >= 2 && dst_out) CU(cudaStreamWaitEvent(ctx->stream, ev_out[s - 2], 0));   // dbuf[b] was downloaded
+        rc = pil2gpu_lde_dev(ctx, sslab, dbuf[b].p, cs, nBits, nBitsExt);
+        if (rc) break;
+        CU(cudaEventRecord(ev_lde[s], ctx->stream));
+        if (dst_out) {
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ev_lde[s], 0));
+            CU(cudaMemcpy2DAsync(dst_out + s * cs, nPols * 8, dbuf[b].p, cs * 8, cs * 8, E, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CU(cudaEventRecord(ev_out[s], ctx->copy_stream));
+        }
+        merkle_absorb_kernel<<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(dbuf[b].p, cs, E, state.p, s == 0, s + 1 == nslabs, nodes.p);
+        rc = check_launch(ctx, 1, "absorb");
+        if (trace) CU(cudaEventRecord(ev_abs[s], ctx->stream));
+    }
+    if (rc == PIL2GPU_OK) {
+        int l = merkle_launch_tree(nodes.p, E, ctx->stream);
+        rc = check_launch(ctx, l, "tree");
+    }
+    if (rc == PIL2GPU_OK) {
+        if (nodes_out) CU(cudaMemcpyAsync(nodes_out, nodes.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (root_out) CU(cudaMemcpyAsync(root_out, nodes.p + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    // every stream must drain before the workspace is reused, on the error paths too
+    cudaError_t e1 = cudaStreamSynchronize(ctx->in_stream), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(ctx->copy_stream);
+    if (rc) return rc;
+    if (trace && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
+        for (u64 s = 0; s < nslabs; s++) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, ev_start, ev_in[s]); cudaEventElapsedTime(&b, ev_start, ev_lde[s]); cudaEventElapsedTime(&c, ev_start, ev_abs[s]);
+            if (dst_out) cudaEventElapsedTime(&d, ev_start, ev_out[s]);
+            fprintf(stderr, "[pil2gpu] slab %llu: h2d done %.1f ms, lde done %.1f, absorb done %.1f, d2h done %.1f\n", (unsigned long long)s, a, b, c, d);
+        }
+    }
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(PIL2GPU_E_CUDA, "pipelined commit failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return PIL2GPU_OK;
+}
+
 int pil2gpu_extend_and_merkelize(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
                                  uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]) {
     ENTER(ctx);
     if (!src) return fail(PIL2GPU_E_INVALID, "null argument");
     if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad commit shape");
+    if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
+    // slab pipeline: standard hash only (split batches do not align with slabs), wide traces only
+    const uint64_t cs = (nPols % 32 == 0) ? 32 : 16;
+    if (!split && nPols % 16 == 0 && nPols / cs >= 4 && nBits >= 12)
+        return extend_and_merkelize_pipelined(ctx, src, nPols, nBits, nBitsExt, cs, dst_out, nodes_out, root_out);
     const size_t sw = (size_t)nPols << nBits, dw = (size_t)nPols << nBitsExt;
     const u64 height = 1ULL << nBitsExt;
     const size_t nw = merkle_nnodes_words(height);
-    DevBuf a, b, n;
-    CU(a.alloc(sw));
-    CU(b.alloc(dw));
-    CU(n.alloc(nw));
+    int rc = ensure_ws(ctx, ev2(sw) + ev2(dw) + nw);
+    if (rc) return rc;
+    struct { u64* p; } a = {ctx->ws}, b = {ctx->ws + ev2(sw)}, n = {ctx->ws + ev2(sw) + ev2(dw)};
     CU(cudaMemcpyAsync(a.p, src, sw * 8, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = pil2gpu_lde_dev(ctx, a.p, b.p, nPols, nBits, nBitsExt);
+    rc = pil2gpu_lde_dev(ctx, a.p, b.p, nPols, nBits, nBitsExt);
     if (rc) return rc;
     if (dst_out) {   // download the extended buffer on the copy stream while the main stream hashes it
         CU(cudaEventRecord(ctx->ev, ctx->stream));
@@ -712,12 +831,11 @@ int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, u
     if (prevBits > 32 || curBits > prevBits) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
     const size_t pw = (size_t)3 << prevBits, cw = (size_t)3 << curBits;
     const u64 height = nextBits >= 0 ? (1ULL << nextBits) : 0;
-    DevBuf a, b, r, n;
-    CU(a.alloc(pw));
-    CU(b.alloc(cw));
-    if (nextBits >= 0) { CU(r.alloc(cw)); CU(n.alloc(merkle_nnodes_words(height))); }
+    int rc = ensure_ws(ctx, ev2(pw) + 2 * ev2(cw) + (nextBits >= 0 ? merkle_nnodes_words(height) : 0));
+    if (rc) return rc;
+    struct { u64* p; } a = {ctx->ws}, b = {ctx->ws + ev2(pw)}, r = {ctx->ws + ev2(pw) + ev2(cw)}, n = {ctx->ws + ev2(pw) + 2 * ev2(cw)};
     CU(cudaMemcpyAsync(a.p, pol, pw * 8, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = pil2gpu_fri_fold_dev(ctx, a.p, prevBits, curBits, nextBits, step0Bits, challenge, split, b.p, r.p, n.p);
+    rc = pil2gpu_fri_fold_dev(ctx, a.p, prevBits, curBits, nextBits, step0Bits, challenge, split, b.p, r.p, n.p);
     if (rc) return rc;
     CU(cudaMemcpyAsync(pol_out, b.p, cw * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (nextBits >= 0) {
