@@ -29,6 +29,7 @@ METRIC = "s per commit (GL NTT LDE+Poseidon Merkle+FRI) @2^23 rows x 256 cols, b
 WORKLOADS = {   # name: (nBits, nCols, blowup bits)
     "tiny": (14, 32, 1),
     "cfg2": (20, 64, 1),
+    "slab": (23, 32, 1),    # one column slab of cfg3 (same pass structure 8/8/7): used for ncu captures of the NTT kernels
     "cfg3": (23, 256, 1),
     "cfg5": (22, 512, 2),
 }

@@ -123,19 +123,31 @@ GL_D void ntt_cp_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async
 // canonical a, b -> canonical (a + b) mod p:  a - (p - b), + p on borrow.  7 ALU.
 GL_D u64 ntt_cadd(u64 a, u64 b) { return gl_subc(a, GL_P - b); }
 
-// tile: [2^t][NTT_W] u64 in shared memory.  TW: per-tile table (see ntt_build_tw).
-// One "step" handles R consecutive layers in registers; `low` is the lowest k-bit of the step.
+// ---- tile layout --------------------------------------------------------------------------------------------
+// A tile holds 2^t rows x NTT_W columns.  In shared memory it is stored as NTT_CP = NTT_W/2 column-pair regions, one per
+// warp: region cp holds the 16-byte elements (row k, columns 2cp, 2cp+1) at padded index k + (k >> 3).  Every butterfly of
+// a column stays inside one region, so a warp transforms its two columns with __syncwarp only -- no CTA barrier between
+// the radix steps -- and every shared-memory access is conflict-free (the pad makes rows 8, 64, ...
+// apart land in different bank groups; regions are an odd number of elements long so that the 8 column pairs of one row,
+// written by one quarter-warp of cp.async, land in 8 different bank groups too).
+#define NTT_CP (NTT_W / 2)
+__host__ __device__ __forceinline__ int ntt_pad(int k) { return k + (k >> 3); }
+__host__ __device__ __forceinline__ int ntt_region_elems(int t) { return ((1 << t) + ((1 << t) >> 3)) | 1; }
+
+// One "step" handles R consecutive layers in registers; `low` is the lowest k-bit of the step.  Lane l works on column
+// (l & 1) of the pair, so a half-warp touches 8 whole 16-byte elements per access: conflict-free 64-bit LDS/STS, and a
+// thread keeps only 2^R values live (44-50 registers -> 4-5 CTAs per SM).
 template <int R, bool DIF>
-__device__ __forceinline__ void ntt_tile_step(u64* __restrict__ tile, const u64* __restrict__ TW, int t, int low) {
-    const int groups = 1 << (t - R);
-    const int c = threadIdx.x % NTT_W;
-    for (int g = threadIdx.x / NTT_W; g < groups; g += NTT_THREADS / NTT_W) {
+__device__ __forceinline__ void ntt_warp_step(ulonglong2* __restrict__ reg, const u64* __restrict__ TW, int t, int low) {
+    const int items = 2 << (t - R);
+    for (int item = threadIdx.x & 31; item < items; item += 32) {
+        const int g = item >> 1;
         const int glow = g & ((1 << low) - 1);
         const int kbase = ((g >> low) << (low + R)) | glow;
-        u64* __restrict__ p = tile + kbase * NTT_W + c;
+        u64* __restrict__ p = reinterpret_cast<u64*>(reg) + (item & 1);
         u64 v[1 << R];
 #pragma unroll
-        for (int i = 0; i < (1 << R); i++) v[i] = p[(i << low) * NTT_W];
+        for (int i = 0; i < (1 << R); i++) v[i] = p[ntt_pad(kbase + (i << low)) * 2];
         if (DIF) {
 #pragma unroll
             for (int lb = R - 1; lb >= 0; lb--) {
@@ -166,31 +178,77 @@ __device__ __forceinline__ void ntt_tile_step(u64* __restrict__ tile, const u64*
             }
         }
 #pragma unroll
-        for (int i = 0; i < (1 << R); i++) p[(i << low) * NTT_W] = v[i];
+        for (int i = 0; i < (1 << R); i++) p[ntt_pad(kbase + (i << low)) * 2] = v[i];
     }
+    __syncwarp();
 }
 
-// Full in-tile transform of 2^t points per column.  DIF: natural -> bit-reversed (layers from the top), canonical in/out;
-// DIT: bit-reversed -> natural (layers from the bottom), any u64 in/out.  Caller syncs before; this syncs after every step.
-template <bool DIF>
-__device__ __forceinline__ void ntt_tile_transform(u64* tile, const u64* TW, int t) {
+// Full transform of the warp's region (2^t points of two columns).  DIF: natural -> bit-reversed (layers from the top),
+// canonical in/out; DIT: bit-reversed -> natural (layers from the bottom), any u64 in/out.  Steps are radix-8 when that
+// keeps all 32 lanes busy (t >= 7), radix-4 / radix-2 for smaller tiles.
+template <bool DIF, int R>
+__device__ __forceinline__ void ntt_warp_transform_r(ulonglong2* reg, const u64* TW, int t) {
     if (DIF) {
-        int top = t;   // bits [0, top) still to do
-        while (top >= 3) { ntt_tile_step<3, true>(tile, TW, t, top - 3); top -= 3; __syncthreads(); }
-        if (top == 2) { ntt_tile_step<2, true>(tile, TW, t, 0); __syncthreads(); }
-        if (top == 1) { ntt_tile_step<1, true>(tile, TW, t, 0); __syncthreads(); }
+        int top = t;
+        while (top >= R) { ntt_warp_step<R, true>(reg, TW, t, top - R); top -= R; }
+        if (R > 2 && top == 2) ntt_warp_step<2, true>(reg, TW, t, 0);
+        if (R > 1 && top == 1) ntt_warp_step<1, true>(reg, TW, t, 0);
     } else {
         int low = 0;
-        const int rem = t % 3;
-        if (rem == 1) { ntt_tile_step<1, false>(tile, TW, t, 0); low = 1; __syncthreads(); }
-        if (rem == 2) { ntt_tile_step<2, false>(tile, TW, t, 0); low = 2; __syncthreads(); }
-        while (low < t) { ntt_tile_step<3, false>(tile, TW, t, low); low += 3; __syncthreads(); }
+        const int rem = t % R;
+        if (R > 1 && rem == 1) { ntt_warp_step<1, false>(reg, TW, t, 0); low = 1; }
+        if (R > 2 && rem == 2) { ntt_warp_step<2, false>(reg, TW, t, 0); low = 2; }
+        while (low < t) { ntt_warp_step<R, false>(reg, TW, t, low); low += R; }
+    }
+}
+// Compile-time chains for the tile sizes the planner actually produces (6..9 bits): with t and `low` constant every
+// shared-memory offset and twiddle index folds into an immediate (measured: 40 -> ~31 instructions per butterfly).
+template <int T, int TOP, int R>
+__device__ __forceinline__ void ntt_dif_chain(ulonglong2* reg, const u64* TW) {
+    if constexpr (TOP >= R) {
+        ntt_warp_step<R, true>(reg, TW, T, TOP - R);
+        ntt_dif_chain<T, TOP - R, R>(reg, TW);
+    } else if constexpr (TOP == 2) {
+        ntt_warp_step<2, true>(reg, TW, T, 0);
+    } else if constexpr (TOP == 1) {
+        ntt_warp_step<1, true>(reg, TW, T, 0);
+    }
+}
+template <int T, int LOW, int R>
+__device__ __forceinline__ void ntt_dit_chain(ulonglong2* reg, const u64* TW) {
+    if constexpr (LOW < T) {
+        ntt_warp_step<R, false>(reg, TW, T, LOW);
+        ntt_dit_chain<T, LOW + R, R>(reg, TW);
+    }
+}
+template <bool DIF, int T>
+__device__ __forceinline__ void ntt_warp_transform_c(ulonglong2* reg, const u64* TW) {
+    constexpr int R = (T >= 7) ? 3 : 2;
+    if constexpr (DIF) {
+        ntt_dif_chain<T, T, R>(reg, TW);
+    } else {
+        constexpr int rem = T % R;
+        if constexpr (rem == 1) ntt_warp_step<1, false>(reg, TW, T, 0);
+        if constexpr (rem == 2) ntt_warp_step<2, false>(reg, TW, T, 0);
+        ntt_dit_chain<T, rem, R>(reg, TW);
+    }
+}
+template <bool DIF>
+__device__ __forceinline__ void ntt_warp_transform(ulonglong2* reg, const u64* TW, int t) {
+    switch (t) {
+        case 9: ntt_warp_transform_c<DIF, 9>(reg, TW); break;
+        case 8: ntt_warp_transform_c<DIF, 8>(reg, TW); break;
+        case 7: ntt_warp_transform_c<DIF, 7>(reg, TW); break;
+        case 6: ntt_warp_transform_c<DIF, 6>(reg, TW); break;
+        default:
+            if (t >= 2) ntt_warp_transform_r<DIF, 2>(reg, TW, t);
+            else if (t == 1) ntt_warp_transform_r<DIF, 1>(reg, TW, t);
     }
 }
 
-// Shared-memory layout: tile | [tile2] | TW (2^t) | G (16)
+// Shared-memory layout: tile (NTT_CP regions) | [tile2] | TW (2^t) | G (16)
 static inline size_t ntt_smem_bytes(int t, bool two_tiles) {
-    const size_t words = ((size_t)NTT_W << t) * (two_tiles ? 2 : 1) + ((size_t)1 << t) + 16;
+    const size_t words = (size_t)NTT_CP * ntt_region_elems(t) * 2 * (two_tiles ? 2 : 1) + ((size_t)1 << t) + 16;
     return words * sizeof(u64);
 }
 
@@ -206,16 +264,79 @@ struct NttPass {
     u64 scale;         // Montgomery-form factor applied on store (plain INTT: 1/N), 0 = none
 };
 
+// Tile load: tile row k comes from buffer row (row0 + k * row_step), or, for the first DIT pass of a natural -> natural
+// transform, from the bit-reversed position.  Full, aligned chunks use one 16-byte cp.async per (row, column pair) with a
+// running pointer (no 64-bit multiplies in the loop); everything else takes scalar loads.  Callers wait with
+// ntt_cp_async_wait + barrier when this returns true.
+__device__ __forceinline__ bool ntt_tile_load(ulonglong2* __restrict__ tile, const u64* __restrict__ in, u64 C, u64 c0, int cw, int t, u64 row0,
+                                              u64 row_step, int bitrev_n) {
+    const int rows = 1 << t, RS = ntt_region_elems(t);
+    const bool async_ok = bitrev_n < 0 && cw == NTT_W && (C % 2 == 0) && ((((size_t)in) & 15) == 0);
+    if (async_ok) {
+        const int cp = threadIdx.x % NTT_CP, k0 = threadIdx.x / NTT_CP;
+        const u64* __restrict__ src = in + (row0 + (u64)k0 * row_step) * C + c0 + 2 * cp;
+        const u64 step = row_step * C * (NTT_THREADS / NTT_CP);
+        ulonglong2* __restrict__ dst = tile + cp * RS;
+        for (int k = k0; k < rows; k += NTT_THREADS / NTT_CP, src += step) ntt_cp_async16(reinterpret_cast<u64*>(dst + ntt_pad(k)), src);
+    } else {
+        const int c = threadIdx.x % NTT_W;
+        u64* __restrict__ tw = reinterpret_cast<u64*>(tile) + (c >> 1) * RS * 2 + (c & 1);
+        for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
+            u64 row = row0 + (u64)k * row_step;
+            if (bitrev_n >= 0) row = (bitrev_n == 0) ? 0 : (u64)(__brevll(row) >> (64 - bitrev_n));   // row0/row_step describe positions here
+            tw[ntt_pad(k) * 2] = (c < cw) ? in[row * C + c0 + c] : 0;
+        }
+    }
+    return async_ok;
+}
+
+// Tile store to buffer rows (row0 + k * row_step); FIX: 0 = as is, 1 = canonicalise, 2 = multiply by `scale` (Montgomery form).
+template <int FIX>
+__device__ __forceinline__ void ntt_tile_store_fix(const ulonglong2* __restrict__ tile, u64* __restrict__ out, u64 C, u64 c0, int cw, int t, u64 scale,
+                                                   u64 row0, u64 row_step) {
+    const int rows = 1 << t, RS = ntt_region_elems(t);
+    if (cw == NTT_W && (C % 2 == 0) && ((((size_t)out) & 15) == 0)) {
+        const int cp = threadIdx.x % NTT_CP, k0 = threadIdx.x / NTT_CP;
+        u64* __restrict__ dst = out + (row0 + (u64)k0 * row_step) * C + c0 + 2 * cp;
+        const u64 step = row_step * C * (NTT_THREADS / NTT_CP);
+        const ulonglong2* __restrict__ src = tile + cp * RS;
+        for (int k = k0; k < rows; k += NTT_THREADS / NTT_CP, dst += step) {
+            ulonglong2 v = src[ntt_pad(k)];
+            if (FIX == 2) { v.x = gl_mmul(v.x, scale); v.y = gl_mmul(v.y, scale); }
+            if (FIX == 1) { v.x = gl_canon(v.x); v.y = gl_canon(v.y); }
+            *reinterpret_cast<ulonglong2*>(dst) = v;
+        }
+    } else {
+        const int c = threadIdx.x % NTT_W;
+        const u64* __restrict__ tw = reinterpret_cast<const u64*>(tile) + (c >> 1) * RS * 2 + (c & 1);
+        for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
+            if (c < cw) {
+                u64 v = tw[ntt_pad(k) * 2];
+                if (FIX == 2) v = gl_mmul(v, scale);
+                if (FIX == 1) v = gl_canon(v);
+                out[(row0 + (u64)k * row_step) * C + c0 + c] = v;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void ntt_tile_store(const ulonglong2* __restrict__ tile, u64* __restrict__ out, u64 C, u64 c0, int cw, int t, int fix, u64 scale,
+                                               u64 row0, u64 row_step) {
+    if (fix == 2) ntt_tile_store_fix<2>(tile, out, C, c0, cw, t, scale, row0, row_step);
+    else if (fix == 1) ntt_tile_store_fix<1>(tile, out, C, c0, cw, t, scale, row0, row_step);
+    else ntt_tile_store_fix<0>(tile, out, C, c0, cw, t, scale, row0, row_step);
+}
+
 // ---- generic pass ------------------------------------------------------------------------------------------
 // One pass over bits [lo, lo+t) of a 2^n-point transform of every column.
 //   position(k) = (base_hi << (lo+t)) | (k << lo) | base_lo,   tile id = (base_hi << lo) | base_lo
 // gridDim.x = 2^(n-t) tiles, gridDim.y = ceil(C / NTT_W) column chunks, gridDim.z = cosets.
 template <bool DIF, bool INVERSE>
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __restrict__ in, u64* __restrict__ out, NttPass P, NttTables tb) {
-    extern __shared__ u64 ntt_smem[];
+    extern __shared__ __align__(16) u64 ntt_smem[];
     const int t = P.t, lo = P.lo;
-    u64* tile = ntt_smem;
-    u64* TW = tile + ((size_t)NTT_W << t);
+    const int RS = ntt_region_elems(t);
+    ulonglong2* tile = reinterpret_cast<ulonglong2*>(ntt_smem);
+    u64* TW = ntt_smem + (size_t)NTT_CP * RS * 2;
     u64* G = TW + ((size_t)1 << t);
     const u32 tile_id = blockIdx.x;
     const u32 base_lo = tile_id & ((1u << lo) - 1);
@@ -223,45 +344,25 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __rest
     const u64 c0 = (u64)blockIdx.y * NTT_W;
     const int cw = (int)((P.C - c0 < NTT_W) ? (P.C - c0) : NTT_W);
     const u64 z = blockIdx.z;
-    const int rows = 1 << t;
-    const int c = threadIdx.x % NTT_W;
     const u64 pos0 = ((u64)base_hi << (lo + t)) | base_lo;
-
-    // loads first (they are in flight while the twiddle table is built)
-    const bool async_ok = !P.bitrev_in && cw == NTT_W && (P.C % 2 == 0) && ((((size_t)in) & 15) == 0);
-    if (async_ok) {
-        const int cp = threadIdx.x % (NTT_W / 2);
-        for (int k = threadIdx.x / (NTT_W / 2); k < rows; k += NTT_THREADS / (NTT_W / 2)) {
-            const u64 pos = pos0 | ((u64)k << lo);
-            ntt_cp_async16(tile + k * NTT_W + 2 * cp, in + (pos * P.in_mul + z) * P.C + c0 + 2 * cp);
-        }
-    } else {
-        for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
-            u64 v = 0;
-            if (c < cw) {
-                u64 pos = pos0 | ((u64)k << lo);
-                if (P.bitrev_in) pos = (P.n == 0) ? 0 : (u64)(__brevll(pos) >> (64 - P.n));
-                v = in[(pos * P.in_mul + z) * P.C + c0 + c];
-            }
-            tile[k * NTT_W + c] = v;
-        }
-    }
+    // loads first: they are in flight while the twiddle table is built.  position(k) = pos0 + (k << lo); buffer row =
+    // position * mul + z (bit-reversed gather: the helper reverses the position itself, mul is 1 and z is 0 there)
+    const bool async = P.bitrev_in ? ntt_tile_load(tile, in, P.C, c0, cw, t, pos0, (u64)1 << lo, P.n)
+                                   : ntt_tile_load(tile, in, P.C, c0, cw, t, pos0 * P.in_mul + z, P.in_mul << lo, -1);
     ntt_build_tw<INVERSE>(TW, G, t, lo, base_lo, P.coset ? (int)z : -1, P.n, P.ext_bits, tb);   // ends with a barrier
-    if (async_ok) { ntt_cp_async_wait(); __syncthreads(); }
+    if (async) { ntt_cp_async_wait(); __syncthreads(); }
+    ulonglong2* reg = tile + (threadIdx.x >> 5) * RS;      // this warp's column pair
     if (DIF && P.canon_in) {   // the caller's buffer may hold non-canonical words; DIF butterflies need canonical inputs
-        for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile[i] = gl_canon(tile[i]);
-        __syncthreads();
-    }
-    ntt_tile_transform<DIF>(tile, TW, t);
-    for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
-        if (c < cw) {
-            u64 v = tile[k * NTT_W + c];
-            if (P.scale) v = gl_mmul(v, P.scale);
-            else if (!DIF && P.canon_out) v = gl_canon(v);
-            const u64 pos = pos0 | ((u64)k << lo);
-            out[(pos * P.out_mul + z) * P.C + c0 + c] = v;
+        for (int k = threadIdx.x & 31; k < (1 << t); k += 32) {
+            ulonglong2 v = reg[ntt_pad(k)];
+            v.x = gl_canon(v.x); v.y = gl_canon(v.y);
+            reg[ntt_pad(k)] = v;
         }
+        __syncwarp();
     }
+    ntt_warp_transform<DIF>(reg, TW, t);
+    __syncthreads();
+    ntt_tile_store(tile, out, P.C, c0, cw, t, P.scale ? 2 : ((!DIF && P.canon_out) ? 1 : 0), P.scale, pos0 * P.out_mul + z, P.out_mul << lo);
 }
 
 // ---- fused LDE middle kernel ---------------------------------------------------------------------------------
@@ -271,51 +372,49 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __rest
 __global__ void __launch_bounds__(NTT_THREADS) ntt_lde_fused_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 C, int n,
                                                                     int ext_bits, int t, u64 in_mul, u64 n_inv_mont, int canon_in,
                                                                     int canon_out, NttTables tb) {
-    extern __shared__ u64 ntt_smem[];
-    u64* tile = ntt_smem;
-    u64* tile2 = tile + ((size_t)NTT_W << t);
-    u64* TW = tile2 + ((size_t)NTT_W << t);
+    extern __shared__ __align__(16) u64 ntt_smem[];
+    const int RS = ntt_region_elems(t);
+    ulonglong2* tile = reinterpret_cast<ulonglong2*>(ntt_smem);
+    ulonglong2* tile2 = tile + (size_t)NTT_CP * RS;
+    u64* TW = ntt_smem + (size_t)NTT_CP * RS * 4;
     u64* G = TW + ((size_t)1 << t);
     const int B = 1 << (ext_bits - n);
     const u64 q0 = (u64)blockIdx.x << t;
     const u64 c0 = (u64)blockIdx.y * NTT_W;
     const int cw = (int)((C - c0 < NTT_W) ? (C - c0) : NTT_W);
     const int rows = 1 << t;
-    const int c = threadIdx.x % NTT_W;
-    const bool async_ok = cw == NTT_W && (C % 2 == 0) && ((((size_t)in) & 15) == 0);
-    if (async_ok) {
-        const int cp = threadIdx.x % (NTT_W / 2);
-        for (int k = threadIdx.x / (NTT_W / 2); k < rows; k += NTT_THREADS / (NTT_W / 2))
-            ntt_cp_async16(tile + k * NTT_W + 2 * cp, in + ((q0 | (u64)k) * in_mul) * C + c0 + 2 * cp);
-    } else {
-        for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W)
-            tile[k * NTT_W + c] = (c < cw) ? in[((q0 | (u64)k) * in_mul) * C + c0 + c] : 0;
-    }
+    const bool async = ntt_tile_load(tile, in, C, c0, cw, t, q0 * in_mul, in_mul, -1);
     ntt_build_tw<true>(TW, G, t, 0, 0, -1, n, ext_bits, tb);
-    if (async_ok) { ntt_cp_async_wait(); __syncthreads(); }
+    if (async) { ntt_cp_async_wait(); __syncthreads(); }
+    ulonglong2* reg = tile + (threadIdx.x >> 5) * RS;
+    ulonglong2* reg2 = tile2 + (threadIdx.x >> 5) * RS;
     if (canon_in) {
-        for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile[i] = gl_canon(tile[i]);
-        __syncthreads();
+        for (int k = threadIdx.x & 31; k < rows; k += 32) {
+            ulonglong2 v = reg[ntt_pad(k)];
+            v.x = gl_canon(v.x); v.y = gl_canon(v.y);
+            reg[ntt_pad(k)] = v;
+        }
+        __syncwarp();
     }
-    ntt_tile_transform<true>(tile, TW, t);          // coefficients, bit-reversed: position q holds a_{bitrev_n(q)}
-    for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile[i] = gl_mmul(tile[i], n_inv_mont);   // * 1/N, once
+    ntt_warp_transform<true>(reg, TW, t);          // coefficients, bit-reversed: position q holds a_{bitrev_n(q)}
+    for (int k = threadIdx.x & 31; k < rows; k += 32) {   // * 1/N, once (warp-private region)
+        ulonglong2 v = reg[ntt_pad(k)];
+        v.x = gl_mmul(v.x, n_inv_mont); v.y = gl_mmul(v.y, n_inv_mont);
+        reg[ntt_pad(k)] = v;
+    }
+    __syncwarp();
     for (int r = 0; r < B; r++) {
-        ntt_build_tw<false>(TW, G, t, 0, 0, r, n, ext_bits, tb);   // ends with a barrier (also orders the scale pass above)
-        u64* work = tile;                                          // the last coset transforms the coefficients in place
+        __syncthreads();                                           // every warp is done with the previous twiddle table
+        ntt_build_tw<false>(TW, G, t, 0, 0, r, n, ext_bits, tb);   // ends with a barrier
+        ulonglong2* work = reg;                                    // the last coset transforms the coefficients in place
         if (r + 1 < B) {
-            work = tile2;
-            for (int i = threadIdx.x; i < rows * NTT_W; i += NTT_THREADS) tile2[i] = tile[i];
-            __syncthreads();
+            work = reg2;
+            for (int k = threadIdx.x & 31; k < rows; k += 32) reg2[ntt_pad(k)] = reg[ntt_pad(k)];
+            __syncwarp();
         }
-        ntt_tile_transform<false>(work, TW, t);
-        for (int k = threadIdx.x / NTT_W; k < rows; k += NTT_THREADS / NTT_W) {
-            if (c < cw) {
-                u64 v = work[k * NTT_W + c];
-                if (canon_out) v = gl_canon(v);
-                out[(((q0 | (u64)k) << (ext_bits - n)) + r) * C + c0 + c] = v;
-            }
-        }
+        ntt_warp_transform<false>(work, TW, t);
         __syncthreads();
+        ntt_tile_store((r + 1 < B) ? tile2 : tile, out, C, c0, cw, t, canon_out ? 1 : 0, 0, (q0 << (ext_bits - n)) + r, (u64)B);
     }
 }
 

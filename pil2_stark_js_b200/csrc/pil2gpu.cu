@@ -808,7 +808,9 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
     P.nx_inv = glh_inv(1ULL << (prevBits - curBits));
     for (int k = 0; k < 3; k++) P.challenge[k] = challenge[k];
     const u64 gs = nextBits >= 0 ? (1ULL << (curBits - nextBits)) : 1;
-    P.fuse_leaf_hash = (nextBits >= 0) && (!split || 3 * gs <= 4) && (gs * 3 * 8 * FRI_ROWS_PER_CTA <= 160 * 1024);
+    // The in-kernel leaf hash runs on FRI_ROWS_PER_CTA threads of each CTA: worth it only for small layers, where it saves
+    // a launch; big layers (the first FRI tree has 2^20 leaves at cfg3) go through the full-width leaf kernel instead.
+    P.fuse_leaf_hash = (nextBits >= 0) && (!split || 3 * gs <= 4) && (gs * 3 * 8 * FRI_ROWS_PER_CTA <= 160 * 1024) && nextBits <= 12;
     int l = fri_launch_fold((const u64*)pol, (u64*)pol_out, (u64*)rows_out, (u64*)nodes_out, P, ctx->tb, ctx->stream);
     int rc = check_launch(ctx, l, "fri_fold");
     if (rc) return rc;
