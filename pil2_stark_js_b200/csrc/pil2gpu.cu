@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(u64* out, int iters) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             if (MODE == 0) {
-                a0 = gl_mul(a0, a1); a1 = gl_mul(a1, a2); a2 = gl_mul(a2, a3); a3 = gl_mul(a3, a0);
+                a0 = gl_mmul(a0, a1); a1 = gl_mmul(a1, a2); a2 = gl_mmul(a2, a3); a3 = gl_mmul(a3, a0);
             } else {
                 a0 += (u64)(u32)a0 * 0x9E3779B9u; a1 += (u64)(u32)a1 * 0x85EBCA6Bu;
                 a2 += (u64)(u32)a2 * 0xC2B2AE35u; a3 += (u64)(u32)a3 * 0x27D4EB2Fu;

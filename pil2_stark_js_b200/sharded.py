@@ -191,6 +191,52 @@ def bench_main(args, rank, world, local_rank, dist, bench):
     launches = torch.tensor([eng.launches() - l0], device="cuda")
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     torch.cuda.synchronize()
+    # ---- e2e: the same sharded commit with HOST buffers: every rank uploads its column slab from pinned memory and
+    # downloads its share of the extended rows and of the nodes; rank 0 also moves the FRI polynomial and layers ----
+    e2e = None
+    if not args.no_e2e:
+        import time
+        pin = lambda t: torch.empty(t.numel(), dtype=torch.int64, pin_memory=True)
+        src_host = pin(src)
+        src_host.copy_(src)
+        ext_dev = buf["recv"] if world > 1 else buf["dst"]
+        out_host, nodes_host = pin(ext_dev), pin(buf["nodes"])
+        fri_host = None
+        if rank == 0:
+            fri_host = {"pol0": pin(fri["pol"][0]), "pol": [pin(t) for t in fri["pol"]], "rows": [pin(t) for t in fri["rows"]],
+                        "nodes": [pin(t) for t in fri["nodes"]]}
+            fri_host["pol0"].copy_(fri["pol"][0])
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            src.copy_(src_host, non_blocking=True)
+            root = sc.commit(src, cols, n_bits, ext_bits, buf)
+            out_host.copy_(ext_dev, non_blocking=True)
+            nodes_host.copy_(buf["nodes"], non_blocking=True)
+            if rank == 0:
+                fri["pol"][0].copy_(fri_host["pol0"], non_blocking=True)
+                fri_chain()
+                for d, h in zip(fri["pol"] + fri["rows"] + fri["nodes"], fri_host["pol"] + fri_host["rows"] + fri_host["nodes"]):
+                    h.copy_(d, non_blocking=True)
+            root_host.copy_(root, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        n_e2e = max(1, min(args.steps, 3))
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = 8 * (cols << n_bits) + 8 * (3 << steps[0])
+        d2h = 8 * (cols << ext_bits) + 8 * world * buf["nodes"].numel() + 32
+        d2h += 8 * sum(3 << b for b in steps) + 8 * sum(3 << steps[s] for s in range(len(steps) - 1)) + 8 * sum(eng.nnodes(1 << steps[s + 1]) for s in range(len(steps) - 1))
+        e2e = {"value": float(dt.item()), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+               "call": "per rank: pinned host slab -> device, ShardedCommit.commit, extended rows + nodes -> pinned host; rank 0 also the FRI chain "
+                       "(polynomial up, layers down)"}
     if rank == 0:
         clocks = sampler.stop()
         sec = float(ms.item()) / 1e3 / args.steps
@@ -199,12 +245,13 @@ def bench_main(args, rank, world, local_rank, dist, bench):
         line = {
             "metric": bench.METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64 (Goldilocks, integer pipes)", "data": "synthetic", "config": bench.config_dict(args.workload, world),
+            "dtype": "u64", "data": "synthetic", "config": bench.config_dict(args.workload, world),
             "rows_per_s": (1 << n_bits) / sec, "all_to_all_bytes_per_gpu": a2a, "gpu_launches": int(launches.item()), "clocks": clocks,
             "root": root,
-            "e2e": None, "cpu_baseline": None,
-            "roofline": {"kernel": "merkle_leaf_kernel (per-rank share): Poseidon-GL", "bound": "int",
-                         "note": "per-kernel roofline is reported by the N=1 run; N>1 adds one NCCL all-to-all of "
+            "e2e": e2e, "cpu_baseline": None,
+            "roofline": {"kernel": "merkle_leaf_kernel (per-rank share)", "bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None,
+                         "traffic": None,
+                         "note": "per-kernel roofline is reported by the N=1 run (same kernels on 1/N of the rows); N>1 adds one NCCL all-to-all of "
                                  f"{a2a >> 20} MiB per GPU between the LDE and the hashing"},
         }
         print(json.dumps(line), flush=True)

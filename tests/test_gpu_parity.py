@@ -379,3 +379,73 @@ def test_sharded_commit_two_gpus():
         assert np.array_equal(root, nodes[-4:])
     stitched = assemble_nodes([r[2] for r in res], res[0][3], (1 << (n_bits + blow)) // world, world, C.merkle_nnodes)
     assert np.array_equal(stitched, nodes)
+
+
+# ---------------------------------------------------------------- full-size properties (sizes the oracle cannot sweep)
+def _fadd(a, b):
+    """elementwise (a + b) mod p on canonical uint64 arrays"""
+    s = a.astype(object) + b.astype(object)
+    return np.array([int(x) % P for x in s], dtype=np.uint64) if a.size < 1 << 12 else _fadd_np(a, b)
+
+
+def _fadd_np(a, b):
+    with np.errstate(over="ignore"):
+        s = a + b
+        wrapped = s < a                                   # 2^64 = 2^32 - 1 (mod p)
+        s = np.where(wrapped, s + np.uint64(0xFFFFFFFF), s)
+        return np.where(s >= np.uint64(P), s - np.uint64(P), s)
+
+
+def test_ntt_roundtrip_and_linearity_large(ctx):
+    """2^20 rows x 8 cols (three passes 7/7/6): INTT(NTT(x)) == x and NTT(a + b) == NTT(a) + NTT(b)."""
+    bits, npols = 20, 8
+    a, b = rnd_field(51, npols << bits), rnd_field(52, npols << bits)
+    fa, fb, fs, back = (np.empty_like(a) for _ in range(4))
+    ctx.ntt(a, npols, bits, fa)
+    ctx.ntt(b, npols, bits, fb)
+    ctx.ntt(_fadd_np(a, b), npols, bits, fs)
+    assert np.array_equal(fs, _fadd_np(fa, fb))
+    ctx.ntt(fa, npols, bits, back, inverse=True)
+    assert np.array_equal(back, a)
+    assert int(fa.max()) < P and int(back.max()) < P      # canonical outputs
+
+
+def test_lde_decimation_and_linearity_large(ctx):
+    """2^19 rows x 16 cols: every 2nd / 4th row of the blowup-2 / blowup-4 extension is the blowup-1 extension (the same
+    coset 7<w_N>), and the extension is linear.  Exercises the fused middle kernel with B = 1, 2, 4 on three-pass plans."""
+    bits, npols = 19, 16
+    a, b = rnd_field(61, npols << bits), rnd_field(62, npols << bits)
+    e1 = np.empty(npols << bits, dtype=np.uint64)
+    e2 = np.empty(npols << (bits + 1), dtype=np.uint64)
+    e4 = np.empty(npols << (bits + 2), dtype=np.uint64)
+    ctx.lde(a, npols, bits, e1, bits)
+    ctx.lde(a, npols, bits, e2, bits + 1)
+    ctx.lde(a, npols, bits, e4, bits + 2)
+    assert np.array_equal(e2.reshape(-1, npols)[0::2].reshape(-1), e1)
+    assert np.array_equal(e4.reshape(-1, npols)[0::4].reshape(-1), e1)
+    assert np.array_equal(e4.reshape(-1, npols)[0::2].reshape(-1), e2)
+    eb, es = np.empty_like(e2), np.empty_like(e2)
+    ctx.lde(b, npols, bits, eb, bits + 1)
+    ctx.lde(_fadd_np(a, b), npols, bits, es, bits + 1)
+    assert np.array_equal(es, _fadd_np(e2, eb))
+
+
+def test_cfg2_commit_root_vs_oracle(ctx):
+    """BASELINE config 2 at full size (2^20 rows x 64 cols, blowup 2): device-resident commit root, the host-buffer
+    pipelined commit and the C oracle agree; random openings verify against the root."""
+    bits, npols = 20, 64
+    src = rnd_field(71, npols << bits)
+    tree, root = ctx.commit(src, npols, bits, bits + 1)
+    ext = C.lde(src, npols, bits, bits + 1)
+    nodes = C.merkelize(ext, npols, 1 << (bits + 1))
+    assert np.array_equal(root, nodes[-4:])
+    _, nodes_pipe, root_pipe = ctx.extend_and_merkelize(src, npols, bits, bits + 1, want_dst=False)
+    assert np.array_equal(nodes_pipe, nodes) and np.array_equal(root_pipe, root)
+    import pil2_stark_js_b200 as m
+    MH = m.buildMerkleHash(False, ctx)
+    idxs = [0, 1, (1 << (bits + 1)) - 1, 123456, 1 << bits]
+    rows, sibs = tree.group_proofs(idxs)
+    for q, idx in enumerate(idxs):
+        assert np.array_equal(rows[q], ext[idx * npols:(idx + 1) * npols])
+        assert MH.verifyGroupProof([int(x) for x in root], [[int(x) for x in s] for s in sibs[q]], idx, [int(x) for x in rows[q]])
+    tree.free()
