@@ -76,6 +76,51 @@ int pil2gpu_lde_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const 
                       uint64_t* const* dst_pages, const uint64_t* dst_page_words, uint32_t n_dst_pages, uint64_t nPols,
                       uint32_t nBits, uint32_t nBitsExt);
 
+/* ---- multi-GPU row exchange fused into the LDE (no reference counterpart: the reference is single-process) ------- */
+/* CUDA IPC plumbing so that one process per GPU can map its peers' receive buffers (cudaIpcGetMemHandle /
+ * cudaIpcOpenMemHandle).  dptr must be the base of an allocation made with pil2gpu_dev_alloc. */
+int pil2gpu_ipc_export(pil2gpu_ctx* ctx, const void* dptr, uint8_t handle_out[64]);
+int pil2gpu_ipc_open(pil2gpu_ctx* ctx, const uint8_t handle[64], void** dptr_out);
+int pil2gpu_ipc_close(pil2gpu_ctx* ctx, void* dptr);
+/* interpolate (fft_p.js:187-297) of this rank's column slab (2^nBits x nPols) whose LAST butterfly pass stores extended
+ * row R directly into the receive buffer of the rank that hashes it: peer_recv_dev[R / rows_local] (a HOST array of
+ * n_ranks device pointers valid on this device, own buffer included), at word offset
+ * rank * rows_local * nPols + (R % rows_local) * nPols, rows_local = 2^nBitsExt / n_ranks -- the tile layout
+ * pil2gpu_merkelize_tiled_dev hashes in place.  dst_dev (2^nBitsExt x nPols) is the in-place workspace of the earlier
+ * passes.  The caller orders the ranks (a barrier before the receive buffers are read). */
+int pil2gpu_lde_scatter_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t* dst_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
+                            uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank);
+
+/* ---- quotient polynomial: computeQStark, src/stark/stark_gen_helpers.js:168-208 ----------------------------------- */
+/* q_ext: 2^nBitsExt x qDim evaluations of Q on 7<w_ext>.  cmq_ext (2^nBitsExt x qDim*qDeg): column p*qDim + k holds the
+ * evaluations on 7<w_ext> of the p-th degree-<2^nBits chunk of Q (ifft :177, shift-split :179-190, fft :192).  qDeg must
+ * not exceed the blowup factor.  The host-pointer form also merkelizes cmq_ext (:198): cmq_ext_out / nodes_out may be NULL. */
+int pil2gpu_compute_q_dev(pil2gpu_ctx* ctx, const uint64_t* q_ext_dev, uint64_t qDim, uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt,
+                          uint64_t* cmq_ext_dev);
+int pil2gpu_compute_q(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim, uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt, int split,
+                      uint64_t* cmq_ext_out, uint64_t* nodes_out, uint64_t root_out[4]);
+
+/* ---- evaluations at the challenge point: computeEvalsStark, src/stark/stark_gen_helpers.js:210-273 ------------------ */
+/* LEv vector of one opening point (:216-231): lev_dev (2^nBits x 3 words) = F3 ifft of the powers of
+ * xi_challenge * w_n^opening / 7.  xi_challenge is an F3 element (3 words). */
+int pil2gpu_compute_lev_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], int32_t opening, uint32_t nBits, uint64_t* lev_dev);
+/* One entry of pilInfo.evMap inside one extended buffer (:236-249). */
+typedef struct pil2gpu_eval_desc {
+    uint64_t offset;   /* first column of the polynomial inside a row (p.offset) */
+    uint32_t dim;      /* 1 or 3 (p.dim) */
+    uint32_t lev;      /* index of the opening point (openingPoints.findIndex(...), :262) */
+} pil2gpu_eval_desc;
+/* The evaluation loop (:250-264) over one device-resident extended buffer buf_dev (2^nBitsExt rows of `size` words):
+ * evals_out[3e ..] = sum_k buf[(k << (nBitsExt - nBits)) * size + offset_e (..+2)] * LEv_{lev_e}[k].  lev_dev holds n_lev
+ * vectors back to back (n_lev x 2^nBits x 3).  evals_out is a HOST array of n_evals x 3 words; the call synchronises. */
+int pil2gpu_compute_evals_dev(pil2gpu_ctx* ctx, const uint64_t* buf_dev, uint64_t size, uint32_t nBits, uint32_t nBitsExt,
+                              const pil2gpu_eval_desc* desc, uint32_t n_evals, const uint64_t* lev_dev, uint32_t n_lev, uint64_t* evals_out);
+/* xDivXSubXi_ext of computeFRIStark (:289-323): out_dev[3 * (k * n_open + i) ..] = x_k / (x_k - xi_challenge * w_n^openings[i]),
+ * x_k = 7 * w_ext^k, k < 2^nBitsExt.  (A point where x_k equals the shifted challenge makes the reference throw
+ * "Division by zero"; here the affected words are unspecified.) */
+int pil2gpu_x_div_x_sub_xi_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
+                               uint32_t nBitsExt, uint64_t* out_dev);
+
 /* ---- hashing: src/helpers/hash/poseidon/poseidon.js, linearhash/*.js -------------------------------------- */
 /* poseidon(inputs[8], capacity[4], nOuts) poseidon.js:57-108: full 12-word permutation of in12 = inputs || capacity. */
 int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[12]);

@@ -342,3 +342,98 @@ int orc_fri_fold(const u64 *pol, unsigned prev_bits, unsigned cur_bits, int next
     parallel_for(1ULL << cur_bits, nthreads, fold_range, &fc);
     return 0;
 }
+
+/* ================= SURVEY 8(f) rows: quotient commit, evaluations at xi, x/(x - xi) ================= */
+/* f3g.js:136-172 */
+static void f3inv(u64 r[3], const u64 a[3]) {
+    u64 aa = fmul(a[0], a[0]), ac = fmul(a[0], a[2]), ba = fmul(a[1], a[0]), bb = fmul(a[1], a[1]), bc = fmul(a[1], a[2]), cc = fmul(a[2], a[2]);
+    u64 aaa = fmul(aa, a[0]), aac = fmul(aa, a[2]), abc = fmul(ba, a[2]), abb = fmul(ba, a[1]), acc = fmul(ac, a[2]);
+    u64 bbb = fmul(bb, a[1]), bcc = fmul(bc, a[2]), ccc = fmul(cc, a[2]);
+    u64 t = fsub(0, aaa);
+    t = fsub(t, aac); t = fsub(t, aac); t = fadd(t, abc); t = fadd(t, abc); t = fadd(t, abc); t = fadd(t, abb);
+    t = fsub(t, acc); t = fsub(t, bbb); t = fadd(t, bcc); t = fsub(t, ccc);
+    u64 ti = finv(t);
+    u64 i1 = fsub(0, aa); i1 = fsub(i1, ac); i1 = fsub(i1, ac); i1 = fadd(i1, bc); i1 = fadd(i1, bb); i1 = fsub(i1, cc);
+    u64 i2 = fsub(ba, cc);
+    u64 i3 = fadd(fsub(ac, bb), cc);
+    r[0] = fmul(i1, ti); r[1] = fmul(i2, ti); r[2] = fmul(i3, ti);
+}
+
+/* computeQStark, stark_gen_helpers.js:168-192: ifft(q_ext) -> shift-split into qdeg chunks -> fft.  out: 2^bits_ext x qdim*qdeg. */
+int orc_compute_q(const u64 *q_ext, u64 qdim, u64 qdeg, unsigned bits, unsigned bits_ext, u64 *out, int nthreads) {
+    u64 n = 1ULL << bits, ne = 1ULL << bits_ext;
+    if (qdeg * n > ne) return -2;
+    u64 *qq1 = (u64 *)malloc(ne * qdim * sizeof(u64));
+    u64 *qq2 = (u64 *)calloc(ne * qdim * qdeg, sizeof(u64));
+    if (!qq1 || !qq2) { free(qq1); free(qq2); return -1; }
+    orc_ntt(q_ext, qq1, qdim, bits_ext, 1, nthreads);                                  /* :177 */
+    u64 cur = 1, shift_in = fpow(finv(GL_SHIFT), n);                                   /* :180 */
+    for (u64 p = 0; p < qdeg; p++) {                                                   /* :181-190 */
+        for (u64 i = 0; i < n; i++)
+            for (u64 k = 0; k < qdim; k++) qq2[i * qdim * qdeg + qdim * p + k] = fmul(qq1[p * n * qdim + i * qdim + k], cur);
+        cur = fmul(cur, shift_in);
+    }
+    orc_ntt(qq2, out, qdim * qdeg, bits_ext, 0, nthreads);                             /* :192 */
+    free(qq1); free(qq2);
+    return 0;
+}
+
+static void opening_xi(u64 xi[3], const u64 xi_challenge[3], int opening, unsigned bits) {   /* stark_gen_helpers.js:222-226 */
+    u64 w = 1, wn = root_of_unity(bits);
+    for (int j = 0; j < (opening < 0 ? -opening : opening); j++) w = fmul(w, wn);
+    if (opening < 0) w = finv(w);
+    for (int c = 0; c < 3; c++) xi[c] = fmul(xi_challenge[c], w);
+}
+
+/* LEv of computeEvalsStark, stark_gen_helpers.js:216-231: lev (2^bits x 3) = ifft of the powers of xi*w^opening/shift.
+ * The F3 ifft acts on each coordinate separately (its twiddles are base-field elements). */
+int orc_lev(const u64 xi_challenge[3], int opening, unsigned bits, u64 *lev, int nthreads) {
+    u64 n = 1ULL << bits;
+    u64 *pw = (u64 *)malloc(n * 3 * sizeof(u64));
+    if (!pw) return -1;
+    u64 xi[3], sinv = finv(GL_SHIFT);
+    opening_xi(xi, xi_challenge, opening, bits);
+    for (int c = 0; c < 3; c++) xi[c] = fmul(xi[c], sinv);                             /* :227 */
+    pw[0] = 1; pw[1] = 0; pw[2] = 0;
+    for (u64 k = 1; k < n; k++) f3mul(pw + 3 * k, pw + 3 * (k - 1), xi);               /* :228-230 */
+    orc_ntt(pw, lev, 3, bits, 1, nthreads);                                            /* :231 */
+    free(pw);
+    return 0;
+}
+
+/* One evaluation of computeEvalsStark, stark_gen_helpers.js:250-263: sum_k buf[(k << extend_bits)*size + offset (..+2)] * lev[k]. */
+void orc_eval(const u64 *buf, u64 size, u64 offset, int dim, const u64 *lev, unsigned bits, unsigned extend_bits, u64 out[3]) {
+    u64 n = 1ULL << bits, acc[3] = { 0, 0, 0 };
+    for (u64 k = 0; k < n; k++) {
+        const u64 *v = buf + (k << extend_bits) * size + offset;
+        u64 t[3];
+        if (dim == 1) { for (int c = 0; c < 3; c++) t[c] = fmul(lev[3 * k + c], v[0]); }
+        else f3mul(t, v, lev + 3 * k);
+        for (int c = 0; c < 3; c++) acc[c] = fadd(acc[c], t[c]);
+    }
+    memcpy(out, acc, 24);
+}
+
+/* xDivXSubXi_ext of computeFRIStark, stark_gen_helpers.js:289-323: out[3*(k*n_open + i) ..] = x_k / (x_k - xi*w^opening_i). */
+typedef struct { const u64 *xi; u64 n_open; u64 w_ext; u64 *out; } xdiv_ctx;
+static void xdiv_range(void *p, u64 b, u64 e) {
+    xdiv_ctx *c = (xdiv_ctx *)p;
+    for (u64 i = 0; i < c->n_open; i++) {
+        u64 x = fmul(GL_SHIFT, fpow(c->w_ext, b));
+        for (u64 k = b; k < e; k++) {
+            u64 den[3] = { fsub(x, c->xi[3 * i]), fsub(0, c->xi[3 * i + 1]), fsub(0, c->xi[3 * i + 2]) }, inv[3];
+            f3inv(inv, den);
+            for (int j = 0; j < 3; j++) c->out[3 * (k * c->n_open + i) + j] = fmul(inv[j], x);
+            x = fmul(x, c->w_ext);
+        }
+    }
+}
+int orc_xdivxsubxi(const u64 xi_challenge[3], const int *openings, u64 n_open, unsigned bits, unsigned bits_ext, u64 *out, int nthreads) {
+    u64 *xi = (u64 *)malloc(3 * n_open * sizeof(u64));
+    if (!xi) return -1;
+    for (u64 i = 0; i < n_open; i++) opening_xi(xi + 3 * i, xi_challenge, openings[i], bits);
+    xdiv_ctx xc = { xi, n_open, root_of_unity(bits_ext), out };
+    parallel_for(1ULL << bits_ext, nthreads, xdiv_range, &xc);
+    free(xi);
+    return 0;
+}

@@ -35,6 +35,11 @@ def lib():
         L.orc_group_proof.argtypes = [_U64P, _U64P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, _U64P, _U64P]
         L.orc_fri_fold.argtypes = [_U64P, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_uint, _U64P, _U64P,
                                    _U64P, ctypes.c_int]
+        L.orc_compute_q.argtypes = [_U64P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint, _U64P, ctypes.c_int]
+        L.orc_lev.argtypes = [_U64P, ctypes.c_int, ctypes.c_uint, _U64P, ctypes.c_int]
+        L.orc_eval.argtypes = [_U64P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, _U64P, ctypes.c_uint, ctypes.c_uint, _U64P]
+        L.orc_eval.restype = None
+        L.orc_xdivxsubxi.argtypes = [_U64P, ctypes.POINTER(ctypes.c_int), ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint, _U64P, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -109,3 +114,45 @@ def fri_fold(pol, prev_bits, cur_bits, next_bits, step0_bits, challenge, threads
     lib().orc_fri_fold(_p(pol), prev_bits, cur_bits, 0 if next_bits is None else next_bits + 1, step0_bits, _p(ch),
                        _p(pol2), _p(rows) if rows is not None else None, threads or default_threads())
     return pol2.reshape(-1, 3), rows
+
+
+def compute_q(q_ext, q_dim, q_deg, n_bits, n_bits_ext, threads=None):
+    """computeQStark up to the merkelize (stark_gen_helpers.js:168-192)."""
+    q_ext = _arr(q_ext)
+    assert q_ext.size == q_dim << n_bits_ext
+    out = np.empty((q_dim * q_deg) << n_bits_ext, dtype=np.uint64)
+    rc = lib().orc_compute_q(_p(q_ext), q_dim, q_deg, n_bits, n_bits_ext, _p(out), threads or default_threads())
+    assert rc == 0
+    return out
+
+
+def lev(xi_challenge, opening, n_bits, threads=None):
+    """LEv of computeEvalsStark (stark_gen_helpers.js:216-231): (2^n_bits, 3) array."""
+    xi = _arr(xi_challenge)
+    out = np.empty(3 << n_bits, dtype=np.uint64)
+    rc = lib().orc_lev(_p(xi), int(opening), n_bits, _p(out), threads or default_threads())
+    assert rc == 0
+    return out.reshape(-1, 3)
+
+
+def evals(buffers, ev_map, levs, n_bits, extend_bits):
+    """computeEvalsStark loop (stark_gen_helpers.js:234-267); same arguments as gl_spec.compute_evals with numpy buffers."""
+    out = np.empty((len(ev_map), 3), dtype=np.uint64)
+    bufs = {k: (_arr(v[0]), v[1]) for k, v in buffers.items()}
+    levs = [_arr(l).reshape(-1) for l in levs]
+    for i, (name, offset, dim, oi) in enumerate(ev_map):
+        buf, size = bufs[name]
+        r = np.empty(3, dtype=np.uint64)
+        lib().orc_eval(_p(buf), size, offset, dim, _p(levs[oi]), n_bits, extend_bits, _p(r))
+        out[i] = r
+    return out
+
+
+def x_div_x_sub_xi(xi_challenge, openings, n_bits, n_bits_ext, threads=None):
+    """xDivXSubXi_ext of computeFRIStark (stark_gen_helpers.js:289-323): (2^n_bits_ext, nOpenings, 3) array."""
+    xi = _arr(xi_challenge)
+    op = (ctypes.c_int * len(openings))(*[int(o) for o in openings])
+    out = np.empty(3 * len(openings) << n_bits_ext, dtype=np.uint64)
+    rc = lib().orc_xdivxsubxi(_p(xi), op, len(openings), n_bits, n_bits_ext, _p(out), threads or default_threads())
+    assert rc == 0
+    return out.reshape(-1, len(openings), 3)

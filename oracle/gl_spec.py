@@ -453,3 +453,80 @@ def fri_verify_fold(pgroup, pol_bits, shift, challenge, query):
     c = intt([list(x) for x in pgroup])
     sinv = inv((shift * pow(root_of_unity(pol_bits), query, P)) % P)
     return eval_pol(c, f3_mul_scalar(challenge, sinv))
+
+
+# ----------------------------------------------------------------------------------------------
+# quotient commit, evaluations at xi, x/(x - xi)     src/stark/stark_gen_helpers.js
+# ----------------------------------------------------------------------------------------------
+def compute_q(q_ext, q_dim, q_deg, n_bits, n_bits_ext):
+    """computeQStark, stark_gen_helpers.js:168-192 (up to the merkelize at :198): returns cmQ_ext as a flat row-major
+    list of extN x (q_dim*q_deg).  qq2 rows >= N stay zero (a fresh BigBuffer)."""
+    n, ne = 1 << n_bits, 1 << n_bits_ext
+    qq1 = fft_p(q_ext, q_dim, n_bits_ext, inverse=True)                     # :177
+    qq2 = [0] * (q_dim * q_deg * ne)                                       # :175
+    cur_s = 1
+    shift_in = pow(inv(SHIFT), n, P)                                       # :180
+    for p in range(q_deg):                                                 # :181-190
+        for i in range(n):
+            for k in range(q_dim):
+                qq2[i * q_dim * q_deg + q_dim * p + k] = (qq1[p * n * q_dim + i * q_dim + k] * cur_s) % P
+        cur_s = (cur_s * shift_in) % P
+    return fft_p(qq2, q_dim * q_deg, n_bits_ext)                           # :192
+
+
+def opening_xi(xi_challenge, opening, n_bits):
+    """xi * w^opening (stark_gen_helpers.js:222-226 / :291-300); xi_challenge in F3."""
+    w = 1
+    for _ in range(abs(opening)):
+        w = (w * root_of_unity(n_bits)) % P
+    if opening < 0:
+        w = inv(w)
+    return f3_mul_scalar(xi_challenge, w)
+
+
+def compute_lev(xi_challenge, opening, n_bits):
+    """LEv[i] of computeEvalsStark (stark_gen_helpers.js:216-231): ifft of the powers of xi*w^opening/shift (F3)."""
+    n = 1 << n_bits
+    xi = f3_mul_scalar(opening_xi(xi_challenge, opening, n_bits), SHIFT_INV)   # :227
+    lev = [[1, 0, 0]]
+    for _ in range(1, n):                                                   # :228-230
+        lev.append(f3_mul(lev[-1], xi))
+    return intt(lev)                                                        # :231
+
+
+def compute_evals(buffers, ev_map, levs, n_bits, extend_bits):
+    """Evaluation loop of computeEvalsStark (stark_gen_helpers.js:234-267).  buffers: name -> (flat list, row size);
+    ev_map: list of (buffer name, column offset, dim in {1,3}, index into levs).  Returns a list of F3 values."""
+    n = 1 << n_bits
+    out = []
+    for name, offset, dim, oi in ev_map:
+        buf, size = buffers[name]
+        acc = [0, 0, 0]
+        for k in range(n):
+            base = (k << extend_bits) * size + offset                      # :252-259
+            if dim == 1:
+                t = f3_mul_scalar(levs[oi][k], buf[base])
+            else:
+                t = f3_mul(buf[base:base + 3], levs[oi][k])
+            acc = f3_add(acc, t)                                           # :261
+        out.append(acc)
+    return out
+
+
+def x_div_x_sub_xi(xi_challenge, openings, n_bits, n_bits_ext):
+    """xDivXSubXi_ext of computeFRIStark (stark_gen_helpers.js:289-323): flat list of extN x nOpenings F3 values,
+    element (k, i) = x_k / (x_k - xi*w^opening_i), x_k = 7*w_ext^k.  (The reference's batch inverse is an exact field
+    inverse, f3g.js:370-385.)"""
+    ne = 1 << n_bits_ext
+    no = len(openings)
+    out = [0] * (3 * ne * no)
+    w_ext = root_of_unity(n_bits_ext)
+    for i, opening in enumerate(openings):
+        xi = opening_xi(xi_challenge, opening, n_bits)
+        x = SHIFT
+        for k in range(ne):
+            den = f3_sub([x, 0, 0], xi)                                    # :309
+            v = f3_mul_scalar(f3_inv(den), x)                              # :312-315
+            out[3 * (k * no + i):3 * (k * no + i) + 3] = v                 # :316-318
+            x = (x * w_ext) % P
+    return out

@@ -25,6 +25,11 @@ class OutOfRange(Pil2GpuError, IndexError):
     """Mirrors `throw new Error("Out of range")` of merklehash_p.js:143."""
 
 
+class EvalDesc(ctypes.Structure):
+    """pil2gpu_eval_desc (include/pil2gpu.h)"""
+    _fields_ = [("offset", ctypes.c_uint64), ("dim", ctypes.c_uint32), ("lev", ctypes.c_uint32)]
+
+
 _SIGS = {
     # name: (restype, [argtypes])
     "pil2gpu_create": (c_int, [c_int, vp, ctypes.POINTER(vp)]),
@@ -45,6 +50,15 @@ _SIGS = {
     "pil2gpu_lde": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32]),
     "pil2gpu_lde_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32]),
     "pil2gpu_lde_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u32, c_u32]),
+    "pil2gpu_ipc_export": (c_int, [vp, vp, vp]),
+    "pil2gpu_ipc_open": (c_int, [vp, vp, ctypes.POINTER(vp)]),
+    "pil2gpu_ipc_close": (c_int, [vp, vp]),
+    "pil2gpu_lde_scatter_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32, ctypes.POINTER(vp), c_u32, c_u32]),
+    "pil2gpu_compute_q_dev": (c_int, [vp, vp, c_u64, c_u64, c_u32, c_u32, vp]),
+    "pil2gpu_compute_q": (c_int, [vp, vp, c_u64, c_u64, c_u32, c_u32, c_int, vp, vp, vp]),
+    "pil2gpu_compute_lev_dev": (c_int, [vp, vp, c_i32, c_u32, vp]),
+    "pil2gpu_compute_evals_dev": (c_int, [vp, vp, c_u64, c_u32, c_u32, vp, c_u32, vp, c_u32, vp]),
+    "pil2gpu_x_div_x_sub_xi_dev": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp]),
     "pil2gpu_poseidon": (c_int, [vp, vp, vp]),
     "pil2gpu_linear_hash": (c_int, [vp, vp, c_u64, c_int, vp]),
     "pil2gpu_merkle_nnodes": (c_u64, [c_u64]),

@@ -116,6 +116,63 @@ class Context:
                                                    _ptr(dst) if want_dst else None, _ptr(nodes) if want_nodes else None, _ptr(root)))
         return dst, nodes, root
 
+    # ---- quotient polynomial / evaluations (stark_gen_helpers.js:168-323) ----
+    def compute_q(self, q_ext, q_dim, q_deg, n_bits, n_bits_ext, split=False, want_ext=True, want_nodes=True):
+        """computeQStark (stark_gen_helpers.js:168-208) with host buffers: returns (cmQ_ext|None, nodes|None, root[4])."""
+        _as_u64(q_ext, "q_ext")
+        if q_ext.size != q_dim << n_bits_ext:
+            raise ValueError("buffer size does not match qDim * 2^nBitsExt")
+        ext = np.empty((q_dim * q_deg) << n_bits_ext, dtype=np.uint64) if want_ext else None
+        nodes = np.empty(self.merkle_nnodes(1 << n_bits_ext), dtype=np.uint64) if want_nodes else None
+        root = np.empty(4, dtype=np.uint64)
+        check(self._L.pil2gpu_compute_q(self.handle, _ptr(q_ext), q_dim, q_deg, n_bits, n_bits_ext, int(split),
+                                        _ptr(ext) if want_ext else None, _ptr(nodes) if want_nodes else None, _ptr(root)))
+        return ext, nodes, root
+
+    def alloc(self, words):
+        return DeviceBuffer(self, words)
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1)
+        b = DeviceBuffer(self, a.size)
+        check(self._L.pil2gpu_h2d(self.handle, b.ptr, _ptr(a), a.size * 8))
+        self.sync()
+        return b
+
+    def compute_levs(self, xi_challenge, openings, n_bits):
+        """LEv vectors of computeEvalsStark (stark_gen_helpers.js:216-231), one per opening point, back to back on the
+        device: DeviceBuffer of len(openings) x 2^n_bits x 3 words."""
+        xi = np.ascontiguousarray(xi_challenge, dtype=np.uint64).reshape(-1)
+        if xi.size != 3:
+            raise ValueError("the challenge is an F3 element (3 words)")
+        n = 1 << n_bits
+        lev = DeviceBuffer(self, len(openings) * n * 3)
+        for i, o in enumerate(openings):
+            check(self._L.pil2gpu_compute_lev_dev(self.handle, _ptr(xi), int(o), n_bits, vp(lev.ptr.value + 8 * i * n * 3)))
+        return lev
+
+    def compute_evals(self, buf_ptr, size, n_bits, n_bits_ext, ev_descs, levs, n_lev):
+        """Evaluation loop of computeEvalsStark (:250-264) over one device-resident extended buffer.  ev_descs: list of
+        (offset, dim, opening index).  Returns an (n, 3) uint64 array."""
+        n = len(ev_descs)
+        out = np.empty((n, 3), dtype=np.uint64)
+        if n == 0:
+            return out
+        desc = (_lib.EvalDesc * n)(*[_lib.EvalDesc(int(o), int(d), int(l)) for o, d, l in ev_descs])
+        bp = buf_ptr.ptr if isinstance(buf_ptr, DeviceBuffer) else vp(buf_ptr)
+        check(self._L.pil2gpu_compute_evals_dev(self.handle, bp, size, n_bits, n_bits_ext, desc, n, levs.ptr, n_lev, _ptr(out)))
+        return out
+
+    def x_div_x_sub_xi(self, xi_challenge, openings, n_bits, n_bits_ext, download=True):
+        """xDivXSubXi_ext of computeFRIStark (:289-323): (2^n_bits_ext, nOpenings, 3) array (or the DeviceBuffer)."""
+        xi = np.ascontiguousarray(xi_challenge, dtype=np.uint64).reshape(-1)
+        op = (ctypes.c_int32 * len(openings))(*[int(o) for o in openings])
+        out = DeviceBuffer(self, 3 * len(openings) << n_bits_ext)
+        check(self._L.pil2gpu_x_div_x_sub_xi_dev(self.handle, _ptr(xi), op, len(openings), n_bits, n_bits_ext, out.ptr))
+        if not download:
+            return out
+        return out.download().reshape(-1, len(openings), 3)
+
     # ---- device-resident commit ----
     def commit(self, src, n_pols, n_bits, n_bits_ext, split=False):
         """interpolate + merkelize with the LDE kept in HBM.  Returns (DeviceTree, root[4])."""
@@ -139,6 +196,35 @@ class Context:
         t = vp()
         check(self._L.pil2gpu_tree_from_host(self.handle, _ptr(elems), width, height, int(split), ctypes.byref(t)))
         return DeviceTree(self, t)
+
+
+class DeviceBuffer:
+    """A device allocation of u64 words owned through the C ABI (pil2gpu_dev_alloc / pil2gpu_dev_free)."""
+
+    def __init__(self, ctx, words):
+        self.ctx, self.words = ctx, int(words)
+        p = vp()
+        check(ctx._L.pil2gpu_dev_alloc(ctx.handle, self.words * 8, ctypes.byref(p)))
+        self.ptr = p
+
+    def download(self):
+        a = np.empty(self.words, dtype=np.uint64)
+        check(self.ctx._L.pil2gpu_d2h(self.ctx.handle, _ptr(a), self.ptr, self.words * 8))
+        self.ctx.sync()
+        return a
+
+    def free(self):
+        if self.ptr:
+            self.ctx.sync()
+            self.ctx._L.pil2gpu_dev_free(self.ctx.handle, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
 
 
 class DeviceTree:

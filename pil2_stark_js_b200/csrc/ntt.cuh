@@ -38,6 +38,17 @@ struct NttTables {
 };
 #define NTT_TABLE_WORDS (1024 + 2 * (1 << NTT_TMAX) + 32)
 
+// Row scatter of the multi-GPU commit: the pass that finishes the LDE stores extended row R of this rank's
+// column slab straight into the receive buffer of the rank that hashes row R (peer memory over NVLink / NVSwitch, mapped
+// with CUDA IPC) instead of the local buffer -- the column -> row exchange rides on the stores of the last butterfly pass.
+//   destination = peer[R >> rl_bits] + tile_off + (R & (2^rl_bits - 1)) * C + column
+#define NTT_MAX_PEERS 16
+struct NttScatter {
+    u64* peer[NTT_MAX_PEERS];   // peer[h]: rank h's receive buffer (device pointer valid on this device)
+    int rl_bits;                // log2(rows per rank)
+    u64 tile_off;               // word offset of this rank's column tile inside a receive buffer
+};
+
 // W32^E * 2^64 (canonical) for a 32-bit exponent E: any root of unity of order <= 2^32 to any power.
 GL_D u64 ntt_root_pow(const u64* __restrict__ bytepow, u32 E) {
     u64 r = bytepow[3 * 256 + (E >> 24)];
@@ -79,9 +90,9 @@ __global__ void ntt_setup_tables(u64* bytepow, u64* tw_fwd, u64* tw_inv, u64* po
 // Must be called by all threads; ends with a barrier.
 template <bool INVERSE>
 __device__ __forceinline__ void ntt_build_tw(u64* __restrict__ TW, u64* __restrict__ G, int t, int lo, u32 base_lo, int coset_r, int n,
-                                             int ext_bits, const NttTables& tb) {
+                                             int ext_bits, const NttTables& tb, bool unit_shift = false) {
     const u64* __restrict__ base = INVERSE ? tb.tw_inv : tb.tw_fwd;
-    const bool plain = (base_lo == 0) && (coset_r < 0);
+    const bool plain = (base_lo == 0) && (coset_r < 0 || (coset_r == 0 && unit_shift));
     if (plain) {
         for (int i = threadIdx.x; i < (1 << t); i += NTT_THREADS) TW[i] = base[i];
         __syncthreads();
@@ -95,7 +106,8 @@ __device__ __forceinline__ void ntt_build_tw(u64* __restrict__ TW, u64* __restri
         if (coset_r >= 0) {
             const int k = n - 1 - sg;                    // (7 w_E^r)^(2^k)
             if (coset_r > 0) E += ((u32)coset_r << (32 - ext_bits)) << k;
-            g = gl_mmul(ntt_root_pow(tb.bytepow, E), tb.pow7[k]);
+            g = ntt_root_pow(tb.bytepow, E);
+            if (!unit_shift) g = gl_mmul(g, tb.pow7[k]);
         } else {
             g = ntt_root_pow(tb.bytepow, E);
         }
@@ -262,6 +274,8 @@ struct NttPass {
     int coset;         // forward LDE passes: blockIdx.z is the coset index r
     int ext_bits;
     u64 scale;         // Montgomery-form factor applied on store (plain INTT: 1/N), 0 = none
+    int in_z;          // coset passes: the input rows are interleaved by coset too (0: every coset reads the same rows)
+    int unit_shift;    // coset passes: evaluate on w_E^r <w_N> (shift 1) instead of 7 w_E^r <w_N>
 };
 
 // Tile load: tile row k comes from buffer row (row0 + k * row_step), or, for the first DIT pass of a natural -> natural
@@ -291,11 +305,13 @@ __device__ __forceinline__ bool ntt_tile_load(ulonglong2* __restrict__ tile, con
 }
 
 // Tile store to buffer rows (row0 + k * row_step); FIX: 0 = as is, 1 = canonicalise, 2 = multiply by `scale` (Montgomery form).
-template <int FIX>
+// SC: rows go to the peer receive buffers described by `sc` (see NttScatter) instead of `out`.
+template <int FIX, bool SC>
 __device__ __forceinline__ void ntt_tile_store_fix(const ulonglong2* __restrict__ tile, u64* __restrict__ out, u64 C, u64 c0, int cw, int t, u64 scale,
-                                                   u64 row0, u64 row_step) {
+                                                   u64 row0, u64 row_step, const NttScatter& sc) {
     const int rows = 1 << t, RS = ntt_region_elems(t);
-    if (cw == NTT_W && (C % 2 == 0) && ((((size_t)out) & 15) == 0)) {
+    const u64 rl_mask = SC ? (((u64)1 << sc.rl_bits) - 1) : 0;
+    if (cw == NTT_W && (C % 2 == 0) && (SC || ((((size_t)out) & 15) == 0))) {
         const int cp = threadIdx.x % NTT_CP, k0 = threadIdx.x / NTT_CP;
         u64* __restrict__ dst = out + (row0 + (u64)k0 * row_step) * C + c0 + 2 * cp;
         const u64 step = row_step * C * (NTT_THREADS / NTT_CP);
@@ -304,7 +320,13 @@ __device__ __forceinline__ void ntt_tile_store_fix(const ulonglong2* __restrict_
             ulonglong2 v = src[ntt_pad(k)];
             if (FIX == 2) { v.x = gl_mmul(v.x, scale); v.y = gl_mmul(v.y, scale); }
             if (FIX == 1) { v.x = gl_canon(v.x); v.y = gl_canon(v.y); }
-            *reinterpret_cast<ulonglong2*>(dst) = v;
+            if (SC) {
+                const u64 row = row0 + (u64)k * row_step;
+                u64* p = sc.peer[row >> sc.rl_bits] + sc.tile_off + (row & rl_mask) * C + c0 + 2 * cp;
+                *reinterpret_cast<ulonglong2*>(p) = v;
+            } else {
+                *reinterpret_cast<ulonglong2*>(dst) = v;
+            }
         }
     } else {
         const int c = threadIdx.x % NTT_W;
@@ -314,24 +336,28 @@ __device__ __forceinline__ void ntt_tile_store_fix(const ulonglong2* __restrict_
                 u64 v = tw[ntt_pad(k) * 2];
                 if (FIX == 2) v = gl_mmul(v, scale);
                 if (FIX == 1) v = gl_canon(v);
-                out[(row0 + (u64)k * row_step) * C + c0 + c] = v;
+                const u64 row = row0 + (u64)k * row_step;
+                if (SC) sc.peer[row >> sc.rl_bits][sc.tile_off + (row & rl_mask) * C + c0 + c] = v;
+                else out[row * C + c0 + c] = v;
             }
         }
     }
 }
+template <bool SC>
 __device__ __forceinline__ void ntt_tile_store(const ulonglong2* __restrict__ tile, u64* __restrict__ out, u64 C, u64 c0, int cw, int t, int fix, u64 scale,
-                                               u64 row0, u64 row_step) {
-    if (fix == 2) ntt_tile_store_fix<2>(tile, out, C, c0, cw, t, scale, row0, row_step);
-    else if (fix == 1) ntt_tile_store_fix<1>(tile, out, C, c0, cw, t, scale, row0, row_step);
-    else ntt_tile_store_fix<0>(tile, out, C, c0, cw, t, scale, row0, row_step);
+                                               u64 row0, u64 row_step, const NttScatter& sc) {
+    if (fix == 2) ntt_tile_store_fix<2, SC>(tile, out, C, c0, cw, t, scale, row0, row_step, sc);
+    else if (fix == 1) ntt_tile_store_fix<1, SC>(tile, out, C, c0, cw, t, scale, row0, row_step, sc);
+    else ntt_tile_store_fix<0, SC>(tile, out, C, c0, cw, t, scale, row0, row_step, sc);
 }
 
 // ---- generic pass ------------------------------------------------------------------------------------------
 // One pass over bits [lo, lo+t) of a 2^n-point transform of every column.
 //   position(k) = (base_hi << (lo+t)) | (k << lo) | base_lo,   tile id = (base_hi << lo) | base_lo
 // gridDim.x = 2^(n-t) tiles, gridDim.y = ceil(C / NTT_W) column chunks, gridDim.z = cosets.
-template <bool DIF, bool INVERSE>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __restrict__ in, u64* __restrict__ out, NttPass P, NttTables tb) {
+template <bool DIF, bool INVERSE, bool SC = false>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __restrict__ in, u64* __restrict__ out, NttPass P, NttTables tb,
+                                                               const __grid_constant__ NttScatter sc) {
     extern __shared__ __align__(16) u64 ntt_smem[];
     const int t = P.t, lo = P.lo;
     const int RS = ntt_region_elems(t);
@@ -348,8 +374,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __rest
     // loads first: they are in flight while the twiddle table is built.  position(k) = pos0 + (k << lo); buffer row =
     // position * mul + z (bit-reversed gather: the helper reverses the position itself, mul is 1 and z is 0 there)
     const bool async = P.bitrev_in ? ntt_tile_load(tile, in, P.C, c0, cw, t, pos0, (u64)1 << lo, P.n)
-                                   : ntt_tile_load(tile, in, P.C, c0, cw, t, pos0 * P.in_mul + z, P.in_mul << lo, -1);
-    ntt_build_tw<INVERSE>(TW, G, t, lo, base_lo, P.coset ? (int)z : -1, P.n, P.ext_bits, tb);   // ends with a barrier
+                                   : ntt_tile_load(tile, in, P.C, c0, cw, t, pos0 * P.in_mul + (P.in_z ? z : 0), P.in_mul << lo, -1);
+    ntt_build_tw<INVERSE>(TW, G, t, lo, base_lo, P.coset ? (int)z : -1, P.n, P.ext_bits, tb, P.unit_shift != 0);   // ends with a barrier
     if (async) { ntt_cp_async_wait(); __syncthreads(); }
     ulonglong2* reg = tile + (threadIdx.x >> 5) * RS;      // this warp's column pair
     if (DIF && P.canon_in) {   // the caller's buffer may hold non-canonical words; DIF butterflies need canonical inputs
@@ -362,16 +388,17 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __rest
     }
     ntt_warp_transform<DIF>(reg, TW, t);
     __syncthreads();
-    ntt_tile_store(tile, out, P.C, c0, cw, t, P.scale ? 2 : ((!DIF && P.canon_out) ? 1 : 0), P.scale, pos0 * P.out_mul + z, P.out_mul << lo);
+    ntt_tile_store<SC>(tile, out, P.C, c0, cw, t, P.scale ? 2 : ((!DIF && P.canon_out) ? 1 : 0), P.scale, pos0 * P.out_mul + z, P.out_mul << lo, sc);
 }
 
 // ---- fused LDE middle kernel ---------------------------------------------------------------------------------
 // Tile = 2^t contiguous transform positions q (lo = 0).  Finishes the INTT (last t DIF layers, inverse roots), scales by
 // 1/N, then for every coset r < B runs the first t DIT layers of the size-N forward NTT on 7 w_E^r <w_N> (coset folded into
 // the twiddles) and stores to row (B*q + r).  Input row = q*in_mul (src: in_mul = 1; dst: in_mul = B).
+template <bool SC>
 __global__ void __launch_bounds__(NTT_THREADS) ntt_lde_fused_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 C, int n,
                                                                     int ext_bits, int t, u64 in_mul, u64 n_inv_mont, int canon_in,
-                                                                    int canon_out, NttTables tb) {
+                                                                    int canon_out, NttTables tb, const __grid_constant__ NttScatter sc) {
     extern __shared__ __align__(16) u64 ntt_smem[];
     const int RS = ntt_region_elems(t);
     ulonglong2* tile = reinterpret_cast<ulonglong2*>(ntt_smem);
@@ -414,7 +441,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_lde_fused_kernel(const u64* _
         }
         ntt_warp_transform<false>(work, TW, t);
         __syncthreads();
-        ntt_tile_store((r + 1 < B) ? tile2 : tile, out, C, c0, cw, t, canon_out ? 1 : 0, 0, (q0 << (ext_bits - n)) + r, (u64)B);
+        ntt_tile_store<SC>((r + 1 < B) ? tile2 : tile, out, C, c0, cw, t, canon_out ? 1 : 0, 0, (q0 << (ext_bits - n)) + r, (u64)B, sc);
     }
 }
 
@@ -441,30 +468,45 @@ static inline cudaError_t ntt_set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+static inline NttPass ntt_pass_defaults(u64 C, int n, int ext_bits) {
+    NttPass P;
+    P.C = C; P.n = n; P.lo = 0; P.t = 0; P.in_mul = 1; P.out_mul = 1;
+    P.bitrev_in = 0; P.canon_in = 0; P.canon_out = 0; P.coset = 0; P.ext_bits = ext_bits; P.scale = 0; P.in_z = 1; P.unit_shift = 0;
+    return P;
+}
+static inline NttScatter ntt_no_scatter() {
+    NttScatter sc;
+    for (int i = 0; i < NTT_MAX_PEERS; i++) sc.peer[i] = nullptr;
+    sc.rl_bits = 0;
+    sc.tile_off = 0;
+    return sc;
+}
+
 // natural -> natural transform of every column; src != dst.  DIT passes: the first one gathers its rows from src in
 // bit-reversed order, every later pass runs in place in dst.  Returns the number of kernel launches or -1.
 static int ntt_launch_transform(const u64* src, u64* dst, u64 C, int n, bool inverse, const NttTables& tb, cudaStream_t st) {
     NttPlan p = ntt_plan(n, NTT_TMAX);
     const u64 n_inv = glh_to_mont(glh_inv((1ULL << n) % GL_P));
+    const NttScatter nosc = ntt_no_scatter();
     int lo = 0;
     const unsigned ychunks = (unsigned)((C + NTT_W - 1) / NTT_W);
     int launches = 0;
     for (int i = p.npass - 1; i >= 0; i--) {
         const int t = p.bits[i];
         const bool first = (lo == 0), last = (i == 0);
-        NttPass P;
-        P.C = C; P.n = n; P.lo = lo; P.t = t; P.in_mul = 1; P.out_mul = 1;
-        P.bitrev_in = first ? 1 : 0; P.canon_in = 0; P.canon_out = last ? 1 : 0; P.coset = 0; P.ext_bits = n;
+        NttPass P = ntt_pass_defaults(C, n, n);
+        P.lo = lo; P.t = t;
+        P.bitrev_in = first ? 1 : 0; P.canon_out = last ? 1 : 0;
         P.scale = (last && inverse) ? n_inv : 0;
         const u64* in = first ? src : dst;
         dim3 grid(1u << (n - t), ychunks, 1);
         const size_t smem = ntt_smem_bytes(t, false);
         if (inverse) {
             if (ntt_set_smem(ntt_pass_kernel<false, true>, smem) != cudaSuccess) return -1;
-            ntt_pass_kernel<false, true><<<grid, NTT_THREADS, smem, st>>>(in, dst, P, tb);
+            ntt_pass_kernel<false, true><<<grid, NTT_THREADS, smem, st>>>(in, dst, P, tb, nosc);
         } else {
             if (ntt_set_smem(ntt_pass_kernel<false, false>, smem) != cudaSuccess) return -1;
-            ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, st>>>(in, dst, P, tb);
+            ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, st>>>(in, dst, P, tb, nosc);
         }
         launches++;
         lo += t;
@@ -472,11 +514,15 @@ static int ntt_launch_transform(const u64* src, u64* dst, u64 C, int n, bool inv
     return launches;
 }
 
-// LDE src (2^n rows) -> dst (2^ext rows), all in dst after the first pass.  Returns the number of kernel launches or -1.
-static int ntt_launch_lde(const u64* src, u64* dst, u64 C, int n, int ext_bits, const NttTables& tb, cudaStream_t st) {
+// LDE src (2^n rows) -> dst (2^ext rows), all in dst after the first pass.  With `sc` the stores of the last kernel go to
+// the peer receive buffers instead of dst (multi-GPU row exchange fused into the LDE).  Returns the number of kernel
+// launches or -1.
+static int ntt_launch_lde(const u64* src, u64* dst, u64 C, int n, int ext_bits, const NttTables& tb, cudaStream_t st,
+                          const NttScatter* sc = nullptr) {
     NttPlan p = ntt_plan(n, NTT_TMAX);
     const int B = 1 << (ext_bits - n);
     const u64 n_inv = glh_to_mont(glh_inv((1ULL << n) % GL_P));
+    const NttScatter nosc = ntt_no_scatter();
     const unsigned ychunks = (unsigned)((C + NTT_W - 1) / NTT_W);
     int launches = 0;
     // INTT passes (DIF, inverse roots) except the last: src/dst rows q -> dst rows B*q
@@ -484,13 +530,13 @@ static int ntt_launch_lde(const u64* src, u64* dst, u64 C, int n, int ext_bits, 
     for (int i = 0; i + 1 < p.npass; i++) {
         const int t = p.bits[i];
         const int lo = hi - t;
-        NttPass P;
-        P.C = C; P.n = n; P.lo = lo; P.t = t; P.in_mul = (i == 0) ? 1 : (u64)B; P.out_mul = (u64)B;
-        P.bitrev_in = 0; P.canon_in = (i == 0) ? 1 : 0; P.canon_out = 0; P.coset = 0; P.ext_bits = ext_bits; P.scale = 0;
+        NttPass P = ntt_pass_defaults(C, n, ext_bits);
+        P.lo = lo; P.t = t; P.in_mul = (i == 0) ? 1 : (u64)B; P.out_mul = (u64)B;
+        P.canon_in = (i == 0) ? 1 : 0;
         dim3 grid(1u << (n - t), ychunks, 1);
         const size_t smem = ntt_smem_bytes(t, false);
         if (ntt_set_smem(ntt_pass_kernel<true, true>, smem) != cudaSuccess) return -1;
-        ntt_pass_kernel<true, true><<<grid, NTT_THREADS, smem, st>>>(i == 0 ? src : dst, dst, P, tb);
+        ntt_pass_kernel<true, true><<<grid, NTT_THREADS, smem, st>>>(i == 0 ? src : dst, dst, P, tb, nosc);
         launches++;
         hi = lo;
     }
@@ -499,23 +545,80 @@ static int ntt_launch_lde(const u64* src, u64* dst, u64 C, int n, int ext_bits, 
     {
         dim3 grid(1u << (n - tf), ychunks, 1);
         const size_t smem = ntt_smem_bytes(tf, true);
-        if (ntt_set_smem(ntt_lde_fused_kernel, smem) != cudaSuccess) return -1;
         const bool only = (p.npass == 1);
-        ntt_lde_fused_kernel<<<grid, NTT_THREADS, smem, st>>>(only ? src : dst, dst, C, n, ext_bits, tf, only ? 1 : (u64)B, n_inv, only ? 1 : 0,
-                                                              only ? 1 : 0, tb);
+        if (only && sc) {
+            if (ntt_set_smem(ntt_lde_fused_kernel<true>, smem) != cudaSuccess) return -1;
+            ntt_lde_fused_kernel<true><<<grid, NTT_THREADS, smem, st>>>(src, dst, C, n, ext_bits, tf, 1, n_inv, 1, 1, tb, *sc);
+        } else {
+            if (ntt_set_smem(ntt_lde_fused_kernel<false>, smem) != cudaSuccess) return -1;
+            ntt_lde_fused_kernel<false><<<grid, NTT_THREADS, smem, st>>>(only ? src : dst, dst, C, n, ext_bits, tf, only ? 1 : (u64)B, n_inv,
+                                                                         only ? 1 : 0, only ? 1 : 0, tb, nosc);
+        }
         launches++;
     }
     // remaining forward DIT passes, in place on the interleaved layout, one grid.z slice per coset
     int lo = tf;
     for (int i = p.npass - 2; i >= 0; i--) {
         const int t = p.bits[i];
-        NttPass P;
-        P.C = C; P.n = n; P.lo = lo; P.t = t; P.in_mul = (u64)B; P.out_mul = (u64)B;
-        P.bitrev_in = 0; P.canon_in = 0; P.canon_out = (i == 0) ? 1 : 0; P.coset = 1; P.ext_bits = ext_bits; P.scale = 0;
+        NttPass P = ntt_pass_defaults(C, n, ext_bits);
+        P.lo = lo; P.t = t; P.in_mul = (u64)B; P.out_mul = (u64)B;
+        P.canon_out = (i == 0) ? 1 : 0; P.coset = 1;
+        dim3 grid(1u << (n - t), ychunks, (unsigned)B);
+        const size_t smem = ntt_smem_bytes(t, false);
+        if (i == 0 && sc) {
+            if (ntt_set_smem(ntt_pass_kernel<false, false, true>, smem) != cudaSuccess) return -1;
+            ntt_pass_kernel<false, false, true><<<grid, NTT_THREADS, smem, st>>>(dst, dst, P, tb, *sc);
+        } else {
+            if (ntt_set_smem(ntt_pass_kernel<false, false>, smem) != cudaSuccess) return -1;
+            ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, st>>>(dst, dst, P, tb, nosc);
+        }
+        launches++;
+        lo += t;
+    }
+    return launches;
+}
+
+// INTT of every column WITHOUT the 1/2^n scale, natural -> bit-reversed: dst row q holds 2^n * a_{bitrev_n(q)}.  DIF passes,
+// the first one reads src, the others run in place in dst (src == dst is allowed).  Returns launches or -1.
+static int ntt_launch_intt_bitrev(const u64* src, u64* dst, u64 C, int n, const NttTables& tb, cudaStream_t st) {
+    NttPlan p = ntt_plan(n, NTT_TMAX);
+    const NttScatter nosc = ntt_no_scatter();
+    const unsigned ychunks = (unsigned)((C + NTT_W - 1) / NTT_W);
+    int launches = 0, hi = n;
+    for (int i = 0; i < p.npass; i++) {
+        const int t = p.bits[i];
+        const int lo = hi - t;
+        NttPass P = ntt_pass_defaults(C, n, n);
+        P.lo = lo; P.t = t; P.canon_in = (i == 0) ? 1 : 0;
+        dim3 grid(1u << (n - t), ychunks, 1);
+        const size_t smem = ntt_smem_bytes(t, false);
+        if (ntt_set_smem(ntt_pass_kernel<true, true>, smem) != cudaSuccess) return -1;
+        ntt_pass_kernel<true, true><<<grid, NTT_THREADS, smem, st>>>(i == 0 ? src : dst, dst, P, tb, nosc);
+        launches++;
+        hi = lo;
+    }
+    return launches;
+}
+
+// Evaluate polynomials given by their coefficients in bit-reversed row order (coef row q = a_{bitrev_n(q)}, 2^n rows, any
+// u64 representatives) on the 2^ext_bits points  s * w_E^j  (s = 7, or 1 with unit_shift), natural order, canonical out:
+// B = 2^(ext_bits - n) coset NTTs of size 2^n (DIT), the first pass reads coef, the others run in place in dst.
+static int ntt_launch_coset_eval(const u64* coef, u64* dst, u64 C, int n, int ext_bits, bool unit_shift, const NttTables& tb, cudaStream_t st) {
+    NttPlan p = ntt_plan(n, NTT_TMAX);
+    const int B = 1 << (ext_bits - n);
+    const NttScatter nosc = ntt_no_scatter();
+    const unsigned ychunks = (unsigned)((C + NTT_W - 1) / NTT_W);
+    int launches = 0, lo = 0;
+    for (int i = p.npass - 1; i >= 0; i--) {
+        const int t = p.bits[i];
+        const bool first = (lo == 0);
+        NttPass P = ntt_pass_defaults(C, n, ext_bits);
+        P.lo = lo; P.t = t; P.in_mul = first ? 1 : (u64)B; P.out_mul = (u64)B; P.in_z = first ? 0 : 1;
+        P.canon_out = (i == 0) ? 1 : 0; P.coset = 1; P.unit_shift = unit_shift ? 1 : 0;
         dim3 grid(1u << (n - t), ychunks, (unsigned)B);
         const size_t smem = ntt_smem_bytes(t, false);
         if (ntt_set_smem(ntt_pass_kernel<false, false>, smem) != cudaSuccess) return -1;
-        ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, st>>>(dst, dst, P, tb);
+        ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, st>>>(first ? coef : dst, dst, P, tb, nosc);
         launches++;
         lo += t;
     }

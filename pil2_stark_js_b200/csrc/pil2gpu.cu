@@ -15,6 +15,8 @@
 #include "gl.cuh"
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "qpath.cuh"
+#include "evals.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -39,7 +41,8 @@ struct pil2gpu_ctx {
     int device;
     cudaStream_t stream;
     bool own_stream;
-    u64* tables;      // bytepow[1024] | tw_fwd[2^TMAX] | tw_inv[2^TMAX] | pow7[32]  (Montgomery form, see ntt.cuh)
+    u64* tables;      // bytepow[1024] | tw_fwd[2^TMAX] | tw_inv[2^TMAX] | pow7[32]  (Montgomery form, see ntt.cuh) | small[256]
+    u64* small;       // 256 words of per-call constants (quotient chunk factors)
     uint64_t launches;
     NttTables tb;
     cudaStream_t copy_stream;   // D2H stream: downloads of finished slabs overlap the compute (extend_and_merkelize)
@@ -164,7 +167,7 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
         pil2gpu_destroy(ctx);
         return fail(PIL2GPU_E_CUDA, "stream/event creation failed");
     }
-    const size_t words = NTT_TABLE_WORDS;
+    const size_t words = NTT_TABLE_WORDS + 256;
     e = cudaMalloc(&ctx->tables, words * sizeof(u64));
     if (e != cudaSuccess) { pil2gpu_destroy(ctx); return fail(PIL2GPU_E_NOMEM, "cudaMalloc(tables): %s", cudaGetErrorString(e)); }
     u64* tw_fwd = ctx->tables + 1024;
@@ -181,6 +184,7 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
     ctx->tb.tw_fwd = tw_fwd;
     ctx->tb.tw_inv = tw_inv;
     ctx->tb.pow7 = pow7;
+    ctx->small = ctx->tables + NTT_TABLE_WORDS;
     *out = ctx;
     return PIL2GPU_OK;
 }
@@ -290,6 +294,205 @@ int pil2gpu_lde_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64
     if ((const u64*)src < (const u64*)dst + dw && (const u64*)dst < (const u64*)src + sw) return fail(PIL2GPU_E_INVALID, "src and dst overlap");
     int l = ntt_launch_lde((const u64*)src, (u64*)dst, nPols, (int)nBits, (int)nBitsExt, ctx->tb, ctx->stream);
     return check_launch(ctx, l, "lde");
+}
+
+// ---- multi-GPU row exchange fused into the LDE ----
+int pil2gpu_ipc_export(pil2gpu_ctx* ctx, const void* dptr, uint8_t handle_out[64]) {
+    ENTER(ctx);
+    if (!dptr || !handle_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
+    memcpy(handle_out, &h, 64);
+    return PIL2GPU_OK;
+}
+int pil2gpu_ipc_open(pil2gpu_ctx* ctx, const uint8_t handle[64], void** dptr_out) {
+    ENTER(ctx);
+    if (!handle || !dptr_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return PIL2GPU_OK;
+}
+int pil2gpu_ipc_close(pil2gpu_ctx* ctx, void* dptr) {
+    ENTER(ctx);
+    if (dptr) CU(cudaIpcCloseMemHandle(dptr));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_lde_scatter_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
+                            uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank) {
+    ENTER(ctx);
+    int rc = check_ntt_args(src, dst, nPols, nBitsExt);
+    if (rc) return rc;
+    if (nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "nBitsExt (%u) < nBits (%u)", nBitsExt, nBits);
+    if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
+    if (!peer_recv_dev || n_ranks == 0 || n_ranks > NTT_MAX_PEERS || (n_ranks & (n_ranks - 1)) || rank >= n_ranks)
+        return fail(PIL2GPU_E_INVALID, "bad rank description (n_ranks must be a power of two <= %d)", NTT_MAX_PEERS);
+    uint32_t gb = 0;
+    while ((1u << gb) < n_ranks) gb++;
+    if (gb > nBitsExt) return fail(PIL2GPU_E_INVALID, "more ranks than extended rows");
+    NttScatter sc = ntt_no_scatter();
+    for (uint32_t h = 0; h < n_ranks; h++) {
+        if (!peer_recv_dev[h]) return fail(PIL2GPU_E_INVALID, "null peer buffer %u", h);
+        sc.peer[h] = (u64*)peer_recv_dev[h];
+    }
+    sc.rl_bits = (int)(nBitsExt - gb);
+    sc.tile_off = (u64)rank * (nPols << sc.rl_bits);
+    int l = ntt_launch_lde((const u64*)src, (u64*)dst, nPols, (int)nBits, (int)nBitsExt, ctx->tb, ctx->stream, &sc);
+    return check_launch(ctx, l, "lde_scatter");
+}
+
+// ---- quotient polynomial path: computeQStark (stark_gen_helpers.js:168-208) ----
+int pil2gpu_compute_q_dev(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim, uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt,
+                          uint64_t* cmq_ext) {
+    ENTER(ctx);
+    if (!q_ext || !cmq_ext) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (qDim == 0 || qDeg == 0) return fail(PIL2GPU_E_INVALID, "qDim and qDeg must be > 0");
+    if (nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
+    const u64 B = 1ULL << (nBitsExt - nBits), N = 1ULL << nBits, E = 1ULL << nBitsExt;
+    if (qDeg > B) return fail(PIL2GPU_E_INVALID, "qDeg (%llu) exceeds the blowup factor (%llu): the quotient does not fit the extended domain",
+                              (unsigned long long)qDeg, (unsigned long long)B);
+    // chunk factors shiftIn^p / E, shiftIn = 7^-N (stark_gen_helpers.js:178-190), Montgomery form
+    u64 fac[256];
+    const u64 shift_in = glh_pow(glh_inv(GL_SHIFT), N);
+    u64 cur = glh_inv(E % GL_P);
+    for (u64 p = 0; p < qDeg; p++) { fac[p] = glh_to_mont(cur); cur = glh_mul(cur, shift_in); }
+    CU(cudaMemcpyAsync(ctx->small, fac, qDeg * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    u64 *S = nullptr, *T = nullptr;
+    CU(cudaMallocAsync(&S, E * qDim * sizeof(u64), ctx->stream));
+    cudaError_t e = cudaMallocAsync(&T, N * qDim * qDeg * sizeof(u64), ctx->stream);
+    if (e != cudaSuccess) { cudaFreeAsync(S, ctx->stream); return fail(PIL2GPU_E_NOMEM, "scratch allocation failed: %s", cudaGetErrorString(e)); }
+    int launches = 0;
+    int l = ntt_launch_intt_bitrev((const u64*)q_ext, S, qDim, (int)nBitsExt, ctx->tb, ctx->stream);
+    if (l >= 0) {
+        launches += l;
+        const u64 total = N * qDim * qDeg;
+        const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        q_split_kernel<<<blocks, 256, 0, ctx->stream>>>(S, T, ctx->small, N, (int)(nBitsExt - nBits), (u32)qDim, (u32)qDeg);
+        launches++;
+        l = ntt_launch_coset_eval(T, (u64*)cmq_ext, qDim * qDeg, (int)nBits, (int)nBitsExt, true, ctx->tb, ctx->stream);
+        if (l >= 0) launches += l;
+    }
+    cudaFreeAsync(S, ctx->stream);
+    cudaFreeAsync(T, ctx->stream);
+    return check_launch(ctx, l < 0 ? -1 : launches, "compute_q");
+}
+
+int pil2gpu_compute_q(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim, uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt, int split,
+                      uint64_t* cmq_ext_out, uint64_t* nodes_out, uint64_t root_out[4]) {
+    ENTER(ctx);
+    if (!q_ext) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (qDim == 0 || qDeg == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    const u64 E = 1ULL << nBitsExt;
+    const size_t qw = E * qDim, cw = E * qDim * qDeg, nw = merkle_nnodes_words(E);
+    int rc = ensure_ws(ctx, ev2(qw) + ev2(cw) + nw);
+    if (rc) return rc;
+    u64 *a = ctx->ws, *b = ctx->ws + ev2(qw), *n = ctx->ws + ev2(qw) + ev2(cw);
+    CU(cudaMemcpyAsync(a, q_ext, qw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pil2gpu_compute_q_dev(ctx, a, qDim, qDeg, nBits, nBitsExt, b);
+    if (rc) return rc;
+    if (cmq_ext_out) {   // download the extended buffer on the copy stream while the main stream hashes it
+        CU(cudaEventRecord(ctx->ev, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev, 0));
+        CU(cudaMemcpyAsync(cmq_ext_out, b, cw * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    rc = pil2gpu_merkelize_dev(ctx, b, qDim * qDeg, E, split, n);
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    if (nodes_out) CU(cudaMemcpyAsync(nodes_out, n, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (root_out) CU(cudaMemcpyAsync(root_out, n + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return PIL2GPU_OK;
+}
+
+// ---- evaluations at xi and FRI denominators: computeEvalsStark / computeFRIStark (stark_gen_helpers.js:210-323) ----
+static void host_opening_xi(u64 xi[3], const uint64_t xi_challenge[3], int32_t opening, uint32_t nBits) {   // :222-226
+    u64 w = 1;
+    const u64 wn = glh_root(nBits);
+    for (int32_t j = 0; j < (opening < 0 ? -opening : opening); j++) w = glh_mul(w, wn);
+    if (opening < 0) w = glh_inv(w);
+    for (int c = 0; c < 3; c++) xi[c] = glh_mul(xi_challenge[c] % GL_P, w);
+}
+
+int pil2gpu_compute_lev_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], int32_t opening, uint32_t nBits, uint64_t* lev_dev) {
+    ENTER(ctx);
+    if (!xi_challenge || !lev_dev) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nBits > 32) return fail(PIL2GPU_E_INVALID, "nBits %u exceeds the 2-adicity of the field (32)", nBits);
+    const u64 N = 1ULL << nBits;
+    u64 xi[3];
+    host_opening_xi(xi, xi_challenge, opening, nBits);
+    const u64 sinv = glh_inv(GL_SHIFT);
+    for (int c = 0; c < 3; c++) xi[c] = glh_mul(xi[c], sinv);                       // :227
+    u64* pw = nullptr;
+    CU(cudaMallocAsync(&pw, N * 3 * sizeof(u64), ctx->stream));
+    const u64 threads_needed = (N + EV_POW_CHUNK - 1) / EV_POW_CHUNK;
+    f3_powers_kernel<<<(unsigned)((threads_needed + 255) / 256), 256, 0, ctx->stream>>>(xi[0], xi[1], xi[2], N, pw);   // :228-230
+    int l = ntt_launch_transform(pw, (u64*)lev_dev, 3, (int)nBits, true, ctx->tb, ctx->stream);                        // :231
+    cudaFreeAsync(pw, ctx->stream);
+    return check_launch(ctx, l < 0 ? -1 : l + 1, "compute_lev");
+}
+
+int pil2gpu_compute_evals_dev(pil2gpu_ctx* ctx, const uint64_t* buf_dev, uint64_t size, uint32_t nBits, uint32_t nBitsExt,
+                              const pil2gpu_eval_desc* desc, uint32_t n_evals, const uint64_t* lev_dev, uint32_t n_lev, uint64_t* evals_out) {
+    ENTER(ctx);
+    if (n_evals == 0) return PIL2GPU_OK;
+    if (!buf_dev || !desc || !lev_dev || !evals_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    static_assert(sizeof(pil2gpu_eval_desc) == sizeof(EvalDesc), "descriptor layout");
+    for (uint32_t e = 0; e < n_evals; e++) {
+        if (desc[e].dim != 1 && desc[e].dim != 3) return fail(PIL2GPU_E_INVALID, "evaluation %u: dim must be 1 or 3", e);
+        if (desc[e].offset + desc[e].dim > size) return fail(PIL2GPU_E_RANGE, "evaluation %u: columns [%llu, %llu) outside a row of %llu", e,
+                                                             (unsigned long long)desc[e].offset, (unsigned long long)(desc[e].offset + desc[e].dim),
+                                                             (unsigned long long)size);
+        if (desc[e].lev >= n_lev) return fail(PIL2GPU_E_RANGE, "evaluation %u: opening index %u out of range", e, desc[e].lev);
+    }
+    const u64 N = 1ULL << nBits;
+    u32 ew = 1;
+    while (ew < n_evals && ew < EV_THREADS) ew <<= 1;
+    u64 chunks = N / 64 ? N / 64 : 1;                 // >= 64 rows per CTA, at most 8 CTAs per SM
+    if (chunks > 148 * 8) chunks = 148 * 8;
+    u64* scratch = nullptr;                           // desc | partial | out
+    const size_t desc_words = ((size_t)n_evals * sizeof(EvalDesc) + 7) / 8, part_words = chunks * n_evals * 3, out_words = (size_t)n_evals * 3;
+    CU(cudaMallocAsync(&scratch, (desc_words + part_words + out_words) * sizeof(u64), ctx->stream));
+    EvalDesc* ddesc = reinterpret_cast<EvalDesc*>(scratch);
+    u64 *partial = scratch + desc_words, *dout = partial + part_words;
+    cudaError_t e = cudaMemcpyAsync(ddesc, desc, (size_t)n_evals * sizeof(EvalDesc), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        evals_partial_kernel<<<(unsigned)chunks, EV_THREADS, EV_THREADS * 3 * sizeof(u64), ctx->stream>>>(
+            (const u64*)buf_dev, size, (int)(nBitsExt - nBits), N, ddesc, n_evals, (const u64*)lev_dev, ew, partial);
+        evals_reduce_kernel<<<(n_evals * 3 + 127) / 128, 128, 0, ctx->stream>>>(partial, (u32)chunks, n_evals, dout);
+        e = cudaMemcpyAsync(evals_out, dout, out_words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaFreeAsync(scratch, ctx->stream);
+    if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "compute_evals: %s", cudaGetErrorString(e));
+    int rc = check_launch(ctx, 2, "compute_evals");
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_x_div_x_sub_xi_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
+                               uint32_t nBitsExt, uint64_t* out_dev) {
+    ENTER(ctx);
+    if (n_open == 0) return PIL2GPU_OK;
+    if (!xi_challenge || !openings || !out_dev) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    if (n_open > 64) return fail(PIL2GPU_E_UNSUPPORTED, "at most 64 opening points");
+    u64 xi[64 * 3];
+    for (uint32_t i = 0; i < n_open; i++) host_opening_xi(xi + 3 * i, xi_challenge, openings[i], nBits);   // :291-300
+    u64* dxi = nullptr;
+    CU(cudaMallocAsync(&dxi, (size_t)n_open * 3 * sizeof(u64), ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(dxi, xi, (size_t)n_open * 3 * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const u64 E = 1ULL << nBitsExt, per = (u64)XDIV_THREADS * XDIV_BATCH;
+        dim3 grid((unsigned)((E + per - 1) / per), n_open, 1);
+        xdiv_kernel<<<grid, XDIV_THREADS, 0, ctx->stream>>>(dxi, n_open, (int)nBitsExt, ctx->tb, (u64*)out_dev);
+    }
+    cudaFreeAsync(dxi, ctx->stream);
+    if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "x_div_x_sub_xi: %s", cudaGetErrorString(e));
+    return check_launch(ctx, 1, "x_div_x_sub_xi");
 }
 
 // Gather a paged host buffer into device memory / scatter back (async on the ctx stream).

@@ -2,8 +2,12 @@
 
     rank g owns columns [g*C/G, (g+1)*C/G) of the trace            (columns are independent NTTs: no communication)
     1. LDE of the column slab on the local GPU                       N x C/G  ->  E x C/G
-    2. ONE all-to-all over NVLink: rank g sends rows [h*E/G, (h+1)*E/G) of its slab to rank h; rank h receives G tiles
-       (one per source rank) of E/G rows x C/G columns -- its row range across all columns, kept as column tiles
+    2. ONE exchange over NVLink: rank g sends rows [h*E/G, (h+1)*E/G) of its slab to rank h; rank h receives G tiles
+       (one per source rank) of E/G rows x C/G columns -- its row range across all columns, kept as column tiles.
+       Default: the exchange is FUSED into the LDE -- the last butterfly pass stores every finished row straight into the
+       owner's receive buffer (peer memory mapped with CUDA IPC, pil2gpu_lde_scatter_dev), so the transfer overlaps the
+       pass tile by tile and only a one-word all-reduce (the "all stores have landed" barrier) remains.  Fallback
+       (PIL2GPU_EXCHANGE=nccl, or IPC mapping unavailable): local LDE followed by one NCCL all_to_all_single.
     3. leaf hashing + subtree of the E/G local rows straight from the tiles (pil2gpu_merkelize_tiled_dev, no repack)
     4. all-gather of the G sub-roots (G x 32 bytes); the top log2(G) levels are hashed redundantly on every rank
 The root (and every node) equals the single-GPU tree: contiguous leaf ranges make each local root the level-log2(E/G)
@@ -40,6 +44,64 @@ class GpuEngine:
     def lde(self, src, cols, n_bits, ext_bits, dst):
         self.check(self.L.pil2gpu_lde_dev(self.h, self._p(src), self._p(dst), cols, n_bits, ext_bits))
 
+    # ---- peer-memory exchange (CUDA IPC through the C ABI; torch.distributed only carries the 64-byte handles) ----
+    def open_exchange(self, dist, rank, world, recv_words):
+        """Allocate this rank's receive buffer, map every peer's, and return {"recv": tensor view, "peers": [ptr], ...} or
+        None when peer mapping is unavailable on any rank (the caller then uses the NCCL all-to-all)."""
+        import os
+        torch = self.torch
+        if os.environ.get("PIL2GPU_EXCHANGE", "peer") == "nccl":
+            return None
+        ok, raw, peers, err = 1, ctypes.c_void_p(), [None] * world, ""
+        try:
+            self.check(self.L.pil2gpu_dev_alloc(self.h, int(recv_words) * 8, ctypes.byref(raw)))
+            handle = (ctypes.c_uint8 * 64)()
+            self.check(self.L.pil2gpu_ipc_export(self.h, raw, handle))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle))
+            for r in range(world):
+                if r == rank:
+                    peers[r] = raw.value
+                else:
+                    p = ctypes.c_void_p()
+                    hb = (ctypes.c_uint8 * 64).from_buffer_copy(handles[r])
+                    self.check(self.L.pil2gpu_ipc_open(self.h, hb, ctypes.byref(p)))
+                    peers[r] = p.value
+        except Exception as ex:       # noqa: BLE001 -- any failure means "no peer mapping here"; all ranks must agree below
+            ok, err = 0, str(ex)
+        flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if err:
+                print(f"[pil2gpu] rank {rank}: peer exchange unavailable ({err}); using NCCL all_to_all", flush=True)
+            self._close_peers(rank, peers, raw)
+            return None
+
+        class _Raw:       # torch view of the raw allocation (for D2H copies and the fallback-compatible interface)
+            pass
+        view = _Raw()
+        view.__cuda_array_interface__ = {"shape": (int(recv_words),), "typestr": "<i8", "data": (raw.value, False), "version": 2}
+        recv = torch.as_tensor(view, device=self.device)
+        arr = (ctypes.c_void_p * world)(*peers)
+        return {"recv": recv, "peers": arr, "peer_list": peers, "raw": raw, "rank": rank, "world": world,
+                "flag": torch.zeros(1, device=self.device, dtype=torch.int32)}
+
+    def _close_peers(self, rank, peers, raw):
+        for r, p in enumerate(peers):
+            if p and r != rank:
+                self.L.pil2gpu_ipc_close(self.h, ctypes.c_void_p(p))
+        if raw and raw.value:
+            self.L.pil2gpu_dev_free(self.h, raw)
+
+    def close_exchange(self, ex):
+        if ex:
+            self.torch.cuda.synchronize()
+            self._close_peers(ex["rank"], ex["peer_list"], ex["raw"])
+
+    def lde_scatter(self, src, cols, n_bits, ext_bits, dst, ex):
+        self.check(self.L.pil2gpu_lde_scatter_dev(self.h, self._p(src), self._p(dst), cols, n_bits, ext_bits, ex["peers"], ex["world"],
+                                                  ex["rank"]))
+
     def merkelize_tiled(self, tiles, n_tiles, tile_cols, rows, nodes, split=False):
         self.check(self.L.pil2gpu_merkelize_tiled_dev(self.h, self._p(tiles), n_tiles, tile_cols, rows * tile_cols, rows, int(split),
                                                       self._p(nodes)))
@@ -69,8 +131,20 @@ class ShardedCommit:
         cg = self.shard_cols(cols)
         rows_local = (1 << ext_bits) // self.world
         e = self.e
-        return {"dst": e.empty(cg << ext_bits), "recv": e.empty(cg << ext_bits), "nodes": e.empty(e.nnodes(rows_local)),
-                "top": e.empty(max(8, e.nnodes(self.world))), "sub": e.empty(4 * self.world)}
+        buf = {"dst": e.empty(cg << ext_bits), "nodes": e.empty(e.nnodes(rows_local)),
+               "top": e.empty(max(8, e.nnodes(self.world))), "sub": e.empty(4 * self.world), "exchange": None}
+        if self.world > 1 and hasattr(e, "open_exchange"):
+            buf["exchange"] = e.open_exchange(self.dist, self.rank, self.world, cg << ext_bits)
+        buf["recv"] = buf["exchange"]["recv"] if buf["exchange"] else e.empty(cg << ext_bits)
+        return buf
+
+    def release(self, buf):
+        if buf.get("exchange"):
+            self.e.close_exchange(buf["exchange"])
+            buf["exchange"] = None
+
+    def exchange_kind(self, buf):
+        return "peer stores fused into the last LDE pass (CUDA IPC over NVLink)" if buf.get("exchange") else "NCCL all_to_all_single"
 
     def commit(self, src_slab, cols, n_bits, ext_bits, buf, split=False):
         """src_slab: this rank's N x C/G column slab (row-major).  Returns the 4-word root tensor (on every rank)."""
@@ -80,11 +154,20 @@ class ShardedCommit:
         if E % G:
             raise ValueError("extended height must be divisible by the number of GPUs")
         rows_local = E // G
-        e.lde(src_slab, cg, n_bits, ext_bits, buf["dst"])
-        if G > 1:
+        ex = buf.get("exchange")
+        if G > 1 and ex:
+            # Barrier BEFORE the stores: whatever the peers still do with their receive buffers (hashing of the previous
+            # commit, a download) is stream-ordered before their contribution to this one-word all-reduce.
+            self.dist.all_reduce(ex["flag"])
+            e.lde_scatter(src_slab, cg, n_bits, ext_bits, buf["dst"], ex)
+            self.dist.all_reduce(ex["flag"])                                # every rank's stores have landed (stream-ordered)
+            tiles = buf["recv"]
+        elif G > 1:
+            e.lde(src_slab, cg, n_bits, ext_bits, buf["dst"])
             self.dist.all_to_all_single(buf["recv"], buf["dst"])            # equal splits: chunk h = rows of rank h
             tiles = buf["recv"]
         else:
+            e.lde(src_slab, cg, n_bits, ext_bits, buf["dst"])
             tiles = buf["dst"]
         e.merkelize_tiled(tiles, G, cg, rows_local, buf["nodes"], split)
         if G == 1:
@@ -246,14 +329,16 @@ def bench_main(args, rank, world, local_rank, dist, bench):
             "metric": bench.METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": bench.config_dict(args.workload, world),
-            "rows_per_s": (1 << n_bits) / sec, "all_to_all_bytes_per_gpu": a2a, "gpu_launches": int(launches.item()), "clocks": clocks,
+            "rows_per_s": (1 << n_bits) / sec, "all_to_all_bytes_per_gpu": a2a, "exchange": sc.exchange_kind(buf),
+            "gpu_launches": int(launches.item()), "clocks": clocks,
             "root": root,
             "e2e": e2e, "cpu_baseline": None,
             "roofline": {"kernel": "merkle_leaf_kernel (per-rank share)", "bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None,
                          "traffic": None,
-                         "note": "per-kernel roofline is reported by the N=1 run (same kernels on 1/N of the rows); N>1 adds one NCCL all-to-all of "
-                                 f"{a2a >> 20} MiB per GPU between the LDE and the hashing"},
+                         "note": "per-kernel roofline is reported by the N=1 run (same kernels on 1/N of the rows); N>1 moves "
+                                 f"{a2a >> 20} MiB per GPU over NVLink between the LDE and the hashing ({sc.exchange_kind(buf)})"},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
+    sc.release(buf)
     dist.destroy_process_group()

@@ -1,0 +1,137 @@
+"""Python mirror of the prover-side callers of the commit path, src/stark/stark_gen_helpers.js (same function names,
+same ctx fields, same results), so that the stage loop of the reference prover (src/prover/prover.js:42-122) can be driven
+against the GPU library:
+
+    extendAndMerkelize(stage, ctx)          :388-412   interpolate + merkelize
+    computeQStark(ctx)                      :168-208   ifft -> shift-split -> fft -> merkelize
+    computeEvalsStark(ctx)                  :210-273   LEv vectors + evaluation sums
+    computeXDivXSubXi(ctx)                  :289-323   the xDivXSubXi_ext part of computeFRIStark
+    computeFRIFolding(step, ctx, challenge) :337-356
+    computeFRIQueries(ctx, friQueries)      :358-360
+    getPermutationsStark(ctx, challenge)    :474-493
+
+`ctx` is any attribute bag (types.SimpleNamespace) carrying the reference's field names: pilInfo (dict with qDim, qDeg,
+nStages, mapSectionsN, openingPoints, evMap, cmPolsMap, nConstants, starkStruct), nBits, nBitsExt, N, extN, extendBits,
+cm<stage>_n / cm<stage>_ext / const_ext / q_ext (numpy uint64, row-major), trees, MH, challenges, fri, friPol, friProof,
+friTrees, and `gpu` (a pil2_stark_js_b200.Context).  Expression evaluation (callCalculateExps) is not part of this path.
+"""
+import numpy as np
+
+from .context import default_context
+from .transcript import Transcript
+
+
+def _gpu(ctx):
+    g = getattr(ctx, "gpu", None) or getattr(getattr(ctx, "MH", None), "ctx", None)
+    return g if g is not None else default_context()
+
+
+def _split(ctx):
+    return bool(getattr(ctx.MH, "splitLinearHash", False))
+
+
+def _tree(buff, nodes, width, height):
+    return {"elements": buff, "nodes": nodes, "width": width, "height": height}
+
+
+def extendAndMerkelize(stage, ctx, options=None):
+    """stark_gen_helpers.js:388-412.  One fused call: the extended buffer stays in HBM between the LDE and the hashing."""
+    n_pols = ctx.pilInfo["mapSectionsN"].get("cm%d" % stage, 0)
+    buff_from = getattr(ctx, "cm%d_n" % stage)
+    dst, nodes, root = _gpu(ctx).extend_and_merkelize(buff_from, n_pols, ctx.nBits, ctx.nBitsExt, split=_split(ctx))
+    getattr(ctx, "cm%d_ext" % stage)[:] = dst
+    ctx.trees[stage] = _tree(getattr(ctx, "cm%d_ext" % stage), nodes, n_pols, ctx.extN)
+    return [[int(x) for x in root]]
+
+
+def computeQStark(ctx, options=None):
+    """stark_gen_helpers.js:168-208."""
+    q_stage = ctx.pilInfo["nStages"] + 1
+    q_dim, q_deg = ctx.pilInfo["qDim"], ctx.pilInfo["qDeg"]
+    ext, nodes, root = _gpu(ctx).compute_q(ctx.q_ext, q_dim, q_deg, ctx.nBits, ctx.nBitsExt, split=_split(ctx))
+    name = "cm%d_ext" % q_stage
+    if getattr(ctx, name, None) is None:
+        setattr(ctx, name, ext)
+    else:
+        getattr(ctx, name)[:] = ext
+    n_pols_q = ctx.pilInfo["mapSectionsN"].get("cm%d" % q_stage, 0)
+    if n_pols_q != q_dim * q_deg:
+        raise ValueError("mapSectionsN.cm%d (%d) != qDim*qDeg (%d)" % (q_stage, n_pols_q, q_dim * q_deg))
+    ctx.trees[q_stage] = _tree(getattr(ctx, name), nodes, n_pols_q, ctx.extN)
+    return [[int(x) for x in root]]
+
+
+def _pol_ref_ext(ctx, ev):
+    """getPolRef(ctx, id, "ext") (prover_helpers.js:305-321) / the const branch of computeEvalsStark (:238-245):
+    (buffer name, row size, column offset, dim)."""
+    if ev["type"] == "const":
+        return "const_ext", ctx.pilInfo["nConstants"], ev["id"], 1
+    if ev["type"] == "cm":
+        p = ctx.pilInfo["cmPolsMap"][ev["id"]]
+        st = "cm%d" % p["stage"]
+        return st + "_ext", ctx.pilInfo["mapSectionsN"][st], p["stagePos"], p["dim"]
+    raise ValueError("Invalid ev type: " + str(ev["type"]))
+
+
+def computeEvalsStark(ctx, options=None):
+    """stark_gen_helpers.js:210-273 (hashCommits == false branch): sets and returns ctx.evals (list of F3 values)."""
+    g = _gpu(ctx)
+    evals_stage = ctx.pilInfo["nStages"] + 1
+    xi = ctx.challenges[evals_stage][0]
+    openings = [int(o) for o in ctx.pilInfo["openingPoints"]]
+    levs = g.compute_levs(xi, openings, ctx.nBits)
+    ev_map = ctx.pilInfo["evMap"]
+    by_buffer = {}
+    for i, ev in enumerate(ev_map):
+        name, size, offset, dim = _pol_ref_ext(ctx, ev)
+        by_buffer.setdefault((name, size), []).append((i, offset, dim, openings.index(int(ev["prime"]))))
+    out = [None] * len(ev_map)
+    dev = getattr(ctx, "dev_buffers", {})
+    for (name, size), items in by_buffer.items():
+        buf = dev.get(name)
+        owned = buf is None
+        if owned:
+            buf = g.upload(getattr(ctx, name))
+        vals = g.compute_evals(buf, size, ctx.nBits, ctx.nBitsExt, [(o, d, l) for _, o, d, l in items], levs, len(openings))
+        for (i, _, _, _), v in zip(items, vals):
+            out[i] = [int(x) for x in v]
+        if owned:
+            buf.free()
+    levs.free()
+    ctx.evals = out
+    return ctx.evals
+
+
+def computeXDivXSubXi(ctx, options=None):
+    """The xDivXSubXi_ext loop of computeFRIStark (stark_gen_helpers.js:289-323)."""
+    evals_stage = ctx.pilInfo["nStages"] + 1
+    xi = ctx.challenges[evals_stage][0]
+    openings = [int(o) for o in ctx.pilInfo["openingPoints"]]
+    ctx.xDivXSubXi_ext = _gpu(ctx).x_div_x_sub_xi(xi, openings, ctx.nBits, ctx.nBitsExt).reshape(-1)
+    return ctx.xDivXSubXi_ext
+
+
+def computeFRIFolding(step, ctx, challenge, options=None):
+    """stark_gen_helpers.js:337-356 (hashCommits == false)."""
+    step_proof = ctx.fri.fold(step, ctx.friPol[step], challenge)
+    ctx.friPol[step + 1] = step_proof["pol"]
+    ctx.friProof[step + 1] = step_proof["proof"]
+    n_steps = len(ctx.pilInfo["starkStruct"]["steps"])
+    if step < n_steps - 1:
+        ctx.friTrees[step + 1] = step_proof["tree"]
+    if step + 1 < n_steps:
+        return [ctx.friProof[step + 1]["root"]]
+    return ctx.friPol[step + 1]
+
+
+def computeFRIQueries(ctx, friQueries):
+    """stark_gen_helpers.js:358-360."""
+    ctx.fri.proofQueries(ctx.friProof, ctx.friTrees, friQueries)
+
+
+def getPermutationsStark(ctx, challenge):
+    """stark_gen_helpers.js:474-493 (verificationHashType == "GL")."""
+    t = Transcript(_gpu(ctx))
+    t.put(challenge)
+    ss = ctx.pilInfo["starkStruct"]
+    return t.getPermutations(ss["nQueries"], ss["steps"][0]["nBits"])

@@ -1,0 +1,226 @@
+"""GPU parity for the rows built after the core commit path: the LDE with fused row scatter, the quotient
+commit (8 f1), the evaluations at xi and the FRI denominators (8 f3) -- all through the C ABI, bit-exact against the oracle."""
+import ctypes
+import types
+
+import numpy as np
+import pytest
+
+from oracle import gl_oracle as C
+from oracle import gl_spec as S
+
+pytestmark = pytest.mark.gpu
+P = S.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import pil2_stark_js_b200 as m
+    return m.default_context(0)
+
+
+def rnd_field(seed, n):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    return np.where(a >= np.uint64(P), a - np.uint64(P), a)
+
+
+# ---------------------------------------------------------------- LDE with the row scatter fused into its last pass
+@pytest.mark.parametrize("n_bits,blow,cols,world", [(6, 1, 32, 2), (10, 1, 64, 4), (12, 2, 32, 2), (13, 1, 128, 8), (4, 1, 16, 2),
+                                                    (11, 1, 24, 1)])
+def test_lde_scatter_virtual_ranks(ctx, n_bits, blow, cols, world):
+    """All `world` ranks played by one GPU, one after the other: every rank's slab is extended with
+    pil2gpu_lde_scatter_dev into the `world` receive buffers; each receive buffer must then hold that rank's rows as
+    column tiles (what the all-to-all used to deliver) and hash to the oracle's subtree."""
+    from pil2_stark_js_b200._lib import vp, check
+    L = ctx._L
+    ext = n_bits + blow
+    E, cg = 1 << ext, cols // world
+    rows_local = E // world
+    full = rnd_field(77 + n_bits + cols, cols << n_bits).reshape(1 << n_bits, cols)
+    want = C.lde(full.reshape(-1), cols, n_bits, ext).reshape(E, cols)
+    recv = [ctx.alloc(cg * E) for _ in range(world)]
+    peers = (ctypes.c_void_p * world)(*[r.ptr.value for r in recv])
+    dst = ctx.alloc(cg * E)
+    for g in range(world):
+        slab = ctx.upload(np.ascontiguousarray(full[:, g * cg:(g + 1) * cg]))
+        check(L.pil2gpu_lde_scatter_dev(ctx.handle, slab.ptr, dst.ptr, cg, n_bits, ext, peers, world, g))
+        ctx.sync()
+        slab.free()
+    for h in range(world):
+        tiles = recv[h].download().reshape(world, rows_local, cg)
+        got = np.ascontiguousarray(tiles.transpose(1, 0, 2)).reshape(rows_local, cols)
+        assert np.array_equal(got, want[h * rows_local:(h + 1) * rows_local]), f"rank {h} rows differ"
+        if cg % 8 == 0 or world == 1:
+            nodes = ctx.alloc(ctx.merkle_nnodes(rows_local))
+            check(L.pil2gpu_merkelize_tiled_dev(ctx.handle, recv[h].ptr, world, cg, rows_local * cg, rows_local, 0, nodes.ptr))
+            exp = C.merkelize(np.ascontiguousarray(want[h * rows_local:(h + 1) * rows_local]).reshape(-1), cols, rows_local)
+            assert np.array_equal(nodes.download(), exp)
+            nodes.free()
+    for r in recv:
+        r.free()
+    dst.free()
+
+
+def test_lde_scatter_argument_checks(ctx):
+    from pil2_stark_js_b200 import Pil2GpuError
+    from pil2_stark_js_b200._lib import check
+    L = ctx._L
+    a, b = ctx.alloc(64), ctx.alloc(128)
+    peers3 = (ctypes.c_void_p * 3)(b.ptr.value, b.ptr.value, b.ptr.value)
+    with pytest.raises(Pil2GpuError):      # 3 ranks: not a power of two
+        check(L.pil2gpu_lde_scatter_dev(ctx.handle, a.ptr, b.ptr, 8, 3, 4, peers3, 3, 0))
+    peers2 = (ctypes.c_void_p * 2)(b.ptr.value, None)
+    with pytest.raises(Pil2GpuError):      # null peer
+        check(L.pil2gpu_lde_scatter_dev(ctx.handle, a.ptr, b.ptr, 8, 3, 4, peers2, 2, 0))
+    a.free(); b.free()
+
+
+# ---------------------------------------------------------------- quotient commit (computeQStark)
+@pytest.mark.parametrize("n_bits,ext_bits,q_dim,q_deg,split", [(4, 5, 3, 2, False), (6, 8, 3, 3, False), (10, 11, 3, 2, False),
+                                                               (10, 12, 3, 4, True), (12, 13, 1, 2, False), (9, 10, 2, 1, False),
+                                                               (13, 14, 3, 2, False), (5, 5, 3, 1, False)])
+def test_compute_q_vs_oracle(ctx, n_bits, ext_bits, q_dim, q_deg, split):
+    q = rnd_field(31 * n_bits + q_deg, q_dim << ext_bits)
+    ext, nodes, root = ctx.compute_q(q, q_dim, q_deg, n_bits, ext_bits, split)
+    want = C.compute_q(q, q_dim, q_deg, n_bits, ext_bits)
+    assert np.array_equal(ext, want)
+    want_nodes = C.merkelize(want, q_dim * q_deg, 1 << ext_bits, split=split)
+    assert np.array_equal(nodes, want_nodes)
+    assert np.array_equal(root, want_nodes[-4:])
+
+
+def test_compute_q_rejects_oversized_degree(ctx):
+    from pil2_stark_js_b200 import Pil2GpuError
+    q = rnd_field(1, 3 << 6)
+    with pytest.raises(Pil2GpuError):
+        ctx.compute_q(q, 3, 4, 5, 6)          # qDeg 4 > blowup 2
+
+
+def test_compute_q_recombines_large(ctx):
+    """2^18 x 3, blowup 4, qDeg 3 (beyond what the oracle sweeps quickly): stark_verify.js:140-147 identity at sampled
+    rows -- sum_p x^(N p) cmQ[p] == q_ext, for a quotient of degree < qDeg * N built by LDE of random coefficients."""
+    n_bits, ext_bits, q_dim, q_deg = 18, 20, 3, 3
+    n, ne = 1 << n_bits, 1 << ext_bits
+    # q_ext = evaluations on 7<w_E> of a random polynomial of degree < q_deg * n: NTT_E of coefficients c_j * 7^j
+    coef = np.zeros((ne, q_dim), dtype=np.uint64)
+    coef[:q_deg * n] = rnd_field(5, q_deg * n * q_dim).reshape(-1, q_dim)
+    pw = np.empty(ne, dtype=object)
+    acc = 1
+    for j in range(ne):
+        pw[j] = acc
+        acc = acc * 7 % P
+    scaled = np.array([[int(coef[j, k]) * pw[j] % P for k in range(q_dim)] for j in range(q_deg * n)], dtype=np.uint64)
+    coef[:q_deg * n] = scaled
+    q_ext = np.empty_like(coef).reshape(-1)
+    ctx.ntt(np.ascontiguousarray(coef).reshape(-1), q_dim, ext_bits, q_ext)
+    ext, _, _ = ctx.compute_q(q_ext, q_dim, q_deg, n_bits, ext_bits, want_nodes=False)
+    ext = ext.reshape(ne, q_dim * q_deg)
+    q_ext = q_ext.reshape(ne, q_dim)
+    w = S.root_of_unity(ext_bits)
+    for j in [0, 1, 12345, ne // 2 + 3, ne - 1]:
+        x = 7 * pow(w, j, P) % P
+        xn = pow(x, n, P)
+        for k in range(q_dim):
+            tot, xa = 0, 1
+            for p in range(q_deg):
+                tot = (tot + xa * int(ext[j, p * q_dim + k])) % P
+                xa = xa * xn % P
+            assert tot == int(q_ext[j, k])
+
+
+# ---------------------------------------------------------------- evaluations at xi, x / (x - xi)
+@pytest.mark.parametrize("n_bits,opening", [(0, 0), (1, 1), (4, 0), (7, 1), (10, -1), (13, 2)])
+def test_compute_lev_vs_oracle(ctx, n_bits, opening):
+    xi = rnd_field(3 + n_bits, 3)
+    lev = ctx.compute_levs(xi, [opening], n_bits)
+    got = lev.download().reshape(-1, 3)
+    assert np.array_equal(got, C.lev(xi, opening, n_bits))
+    lev.free()
+
+
+@pytest.mark.parametrize("n_bits,extend_bits,size,n_evals", [(6, 1, 9, 5), (10, 1, 37, 40), (12, 2, 15, 300), (13, 1, 128, 100), (3, 0, 4, 2)])
+def test_compute_evals_vs_oracle(ctx, n_bits, extend_bits, size, n_evals):
+    rng = np.random.default_rng(n_bits + size)
+    xi = rnd_field(11, 3)
+    openings = [0, 1, -1]
+    ext_bits = n_bits + extend_bits
+    buf = rnd_field(13 + size, size << ext_bits)
+    ev = []
+    for _ in range(n_evals):
+        dim = 3 if (size >= 3 and rng.integers(0, 3) == 0) else 1
+        ev.append((int(rng.integers(0, size - dim + 1)), dim, int(rng.integers(0, len(openings)))))
+    levs = ctx.compute_levs(xi, openings, n_bits)
+    dbuf = ctx.upload(buf)
+    got = ctx.compute_evals(dbuf, size, n_bits, ext_bits, ev, levs, len(openings))
+    levs_o = [C.lev(xi, o, n_bits) for o in openings]
+    want = C.evals({"b": (buf, size)}, [("b", o, d, l) for o, d, l in ev], levs_o, n_bits, extend_bits)
+    assert np.array_equal(got, want)
+    dbuf.free(); levs.free()
+
+
+def test_compute_evals_range_checks(ctx):
+    from pil2_stark_js_b200 import Pil2GpuError
+    xi = rnd_field(1, 3)
+    levs = ctx.compute_levs(xi, [0], 4)
+    dbuf = ctx.upload(rnd_field(2, 5 << 5))
+    with pytest.raises(Pil2GpuError):
+        ctx.compute_evals(dbuf, 5, 4, 5, [(4, 3, 0)], levs, 1)       # columns 4..6 of a 5-word row
+    with pytest.raises(Pil2GpuError):
+        ctx.compute_evals(dbuf, 5, 4, 5, [(0, 1, 1)], levs, 1)       # opening index 1 of 1
+    with pytest.raises(Pil2GpuError):
+        ctx.compute_evals(dbuf, 5, 4, 5, [(0, 2, 0)], levs, 1)       # dim 2
+    dbuf.free(); levs.free()
+
+
+@pytest.mark.parametrize("n_bits,ext_bits,openings", [(3, 5, [0, 1, -2]), (9, 10, [0, 1]), (12, 14, [0, 1, -1, 5]), (0, 0, [0]), (2, 2, [0, 1])])
+def test_x_div_x_sub_xi_vs_oracle(ctx, n_bits, ext_bits, openings):
+    xi = rnd_field(19 + ext_bits, 3)
+    got = ctx.x_div_x_sub_xi(xi, openings, n_bits, ext_bits)
+    assert np.array_equal(got, C.x_div_x_sub_xi(xi, openings, n_bits, ext_bits))
+
+
+# ---------------------------------------------------------------- the prover-side callers (stark_gen_helpers mirror)
+def test_stark_gen_helpers_stage_flow(ctx):
+    """extendAndMerkelize -> computeQStark -> computeEvalsStark -> xDivXSubXi with the reference's ctx field names, checked
+    row by row against the oracle's restatement of the same functions."""
+    import pil2_stark_js_b200 as m
+    from pil2_stark_js_b200 import stark_gen_helpers as H
+    n_bits, ext_bits = 8, 9
+    N, extN = 1 << n_bits, 1 << ext_bits
+    pil = {"nStages": 1, "qDim": 3, "qDeg": 2, "mapSectionsN": {"cm1": 10, "cm2": 6}, "nConstants": 4,
+           "openingPoints": [0, 1],
+           "cmPolsMap": [{"stage": 1, "stagePos": 0, "dim": 1}, {"stage": 1, "stagePos": 3, "dim": 3}, {"stage": 2, "stagePos": 0, "dim": 3},
+                         {"stage": 2, "stagePos": 3, "dim": 3}],
+           "evMap": [{"type": "cm", "id": 0, "prime": 0}, {"type": "cm", "id": 0, "prime": 1}, {"type": "cm", "id": 1, "prime": 0},
+                     {"type": "const", "id": 2, "prime": 1}, {"type": "cm", "id": 2, "prime": 0}, {"type": "cm", "id": 3, "prime": 0}],
+           "starkStruct": {"nBits": n_bits, "nBitsExt": ext_bits, "nQueries": 8, "steps": [{"nBits": ext_bits}, {"nBits": 5}]}}
+    c = types.SimpleNamespace(pilInfo=pil, nBits=n_bits, nBitsExt=ext_bits, N=N, extN=extN, extendBits=1, trees={}, gpu=ctx,
+                              MH=m.buildMerkleHash(False, ctx))
+    c.cm1_n = rnd_field(1, 10 * N)
+    c.cm1_ext = np.zeros(10 * extN, dtype=np.uint64)
+    c.const_ext = C.lde(rnd_field(2, 4 * N), 4, n_bits, ext_bits)
+    c.q_ext = rnd_field(3, 3 * extN)
+    c.cm2_ext = None
+    root1 = H.extendAndMerkelize(1, c)
+    want1 = C.lde(c.cm1_n, 10, n_bits, ext_bits)
+    assert np.array_equal(c.cm1_ext, want1)
+    assert root1[0] == [int(x) for x in C.merkelize(want1, 10, extN)[-4:]]
+    root2 = H.computeQStark(c)
+    want2 = C.compute_q(c.q_ext, 3, 2, n_bits, ext_bits)
+    assert np.array_equal(c.cm2_ext, want2)
+    assert root2[0] == [int(x) for x in C.merkelize(want2, 6, extN)[-4:]]
+    assert c.MH.root(c.trees[2]) == root2[0]
+    c.challenges = {2: [[int(x) for x in rnd_field(4, 3)]]}
+    evals = H.computeEvalsStark(c)
+    levs = [C.lev(np.array(c.challenges[2][0], dtype=np.uint64), o, n_bits) for o in (0, 1)]
+    want_ev = C.evals({"cm1": (want1, 10), "cm2": (want2, 6), "const": (c.const_ext, 4)},
+                      [("cm1", 0, 1, 0), ("cm1", 0, 1, 1), ("cm1", 3, 3, 0), ("const", 2, 1, 1), ("cm2", 0, 3, 0), ("cm2", 3, 3, 0)],
+                      levs, n_bits, 1)
+    assert evals == [[int(x) for x in r] for r in want_ev]
+    xd = H.computeXDivXSubXi(c)
+    assert np.array_equal(xd.reshape(-1, 2, 3), C.x_div_x_sub_xi(np.array(c.challenges[2][0], dtype=np.uint64), [0, 1], n_bits, ext_bits))
+    q = H.getPermutationsStark(c, [1, 2, 3])
+    t = S.Transcript()
+    t.put([1, 2, 3])
+    assert q == t.get_permutations(8, ext_bits)

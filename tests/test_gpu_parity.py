@@ -329,8 +329,9 @@ def test_fri_class_prove_then_verify(ctx):
 
 
 # ---------------------------------------------------------------- multi-GPU (runs when the box has >= 2 GPUs)
-def _mgpu_worker(rank, world, port, n_bits, blow, cols, q):
+def _mgpu_worker(rank, world, port, n_bits, blow, cols, q, mode="peer"):
     import os
+    os.environ["PIL2GPU_EXCHANGE"] = mode
     import torch
     import torch.distributed as dist
     from pil2_stark_js_b200.sharded import GpuEngine, ShardedCommit
@@ -346,15 +347,18 @@ def _mgpu_worker(rank, world, port, n_bits, blow, cols, q):
         slab = torch.from_numpy(np.ascontiguousarray(full[:, rank * cg:(rank + 1) * cg]).reshape(-1).view(np.int64)).cuda()
         buf = sc.buffers(cols, n_bits, n_bits + blow)
         root = sc.commit(slab, cols, n_bits, n_bits + blow, buf)
+        root = sc.commit(slab, cols, n_bits, n_bits + blow, buf)          # twice: the receive buffers are reused
         torch.cuda.synchronize()
         q.put((rank, root.cpu().numpy().view(np.uint64).copy(), buf["nodes"].cpu().numpy().view(np.uint64).copy(),
-               buf["top"].cpu().numpy().view(np.uint64).copy()))
+               buf["top"].cpu().numpy().view(np.uint64).copy(), sc.exchange_kind(buf)))
         dist.barrier()
+        sc.release(buf)
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_commit_two_gpus():
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_sharded_commit_two_gpus(mode):
     import socket
     import torch
     import torch.multiprocessing as mp
@@ -365,7 +369,7 @@ def test_sharded_commit_two_gpus():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx_mp = mp.get_context("spawn")
     q = ctx_mp.Queue()
-    procs = [ctx_mp.Process(target=_mgpu_worker, args=(r, world, port, n_bits, blow, cols, q)) for r in range(world)]
+    procs = [ctx_mp.Process(target=_mgpu_worker, args=(r, world, port, n_bits, blow, cols, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda x: x[0])
@@ -375,8 +379,9 @@ def test_sharded_commit_two_gpus():
     rng = np.random.default_rng(5)
     full = rng.integers(0, P, size=(1 << n_bits, cols), dtype=np.uint64)
     nodes = C.merkelize(C.lde(full.reshape(-1), cols, n_bits, n_bits + blow), cols, 1 << (n_bits + blow))
-    for _, root, _, _ in res:
+    for _, root, _, _, kind in res:
         assert np.array_equal(root, nodes[-4:])
+        assert ("peer stores" in kind) == (mode == "peer"), f"exchange used: {kind}"
     stitched = assemble_nodes([r[2] for r in res], res[0][3], (1 << (n_bits + blow)) // world, world, C.merkle_nnodes)
     assert np.array_equal(stitched, nodes)
 

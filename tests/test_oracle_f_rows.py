@@ -1,0 +1,100 @@
+"""SURVEY 8(f) rows in the oracle (quotient commit, evaluations at xi, x/(x - xi)): C port == pure-Python spec, and both
+pinned by identities the reference's own verifier relies on (no literal vector exists for these rows: root2..4 of the
+golden proof need the full prover)."""
+import numpy as np
+import pytest
+
+from oracle import gl_oracle as C
+from oracle import gl_spec as S
+
+P = S.P
+
+
+def _rand(rng, n):
+    return rng.integers(0, P, size=n, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("n_bits,ext_bits,q_dim,q_deg", [(3, 4, 1, 2), (4, 6, 3, 2), (4, 6, 3, 4), (5, 6, 3, 1), (3, 3, 2, 1)])
+def test_compute_q_c_equals_spec(n_bits, ext_bits, q_dim, q_deg):
+    rng = np.random.default_rng(n_bits * 100 + ext_bits)
+    q = _rand(rng, q_dim << ext_bits)
+    a = C.compute_q(q, q_dim, q_deg, n_bits, ext_bits, threads=2)
+    b = S.compute_q([int(x) for x in q], q_dim, q_deg, n_bits, ext_bits)
+    assert [int(x) for x in a] == b
+
+
+@pytest.mark.parametrize("n_bits,ext_bits,q_deg", [(4, 5, 2), (4, 6, 3), (5, 7, 4)])
+def test_compute_q_recombination_identity(n_bits, ext_bits, q_deg):
+    """stark_verify.js:140-147: Q(x) = sum_p x^(N*p) * Q_p(x).  For a quotient of degree < q_deg*N the committed chunk
+    evaluations recombine to q_ext at every point 7*w_ext^j of the extended domain."""
+    rng = np.random.default_rng(11)
+    n, ne, q_dim = 1 << n_bits, 1 << ext_bits, 3
+    coef = [[int(x) for x in _rand(rng, q_deg * n)] + [0] * (ne - q_deg * n) for _ in range(q_dim)]
+    w = S.root_of_unity(ext_bits)
+    xs = [S.SHIFT * pow(w, j, P) % P for j in range(ne)]
+    q_ext = np.zeros((ne, q_dim), dtype=np.uint64)
+    for k in range(q_dim):
+        ev = S.ntt([c * pow(S.SHIFT, i, P) % P for i, c in enumerate(coef[k])])      # Q_k(7 * w^j)
+        q_ext[:, k] = np.array(ev, dtype=np.uint64)
+    cm = C.compute_q(q_ext.reshape(-1), q_dim, q_deg, n_bits, ext_bits).reshape(ne, q_deg * q_dim)
+    for j in range(ne):
+        xn = pow(xs[j], n, P)
+        for k in range(q_dim):
+            acc, xa = 0, 1
+            for p in range(q_deg):
+                acc = (acc + xa * int(cm[j, p * q_dim + k])) % P
+                xa = xa * xn % P
+            assert acc == int(q_ext[j, k])
+
+
+@pytest.mark.parametrize("opening", [0, 1, -1, 3])
+def test_lev_c_equals_spec_and_evaluates_polynomials(opening):
+    """LEv[k] weights turn the trace values on 7<w> ... into P(xi*w^opening): checked against Horner on the coefficients."""
+    n_bits, extend_bits = 4, 1
+    n = 1 << n_bits
+    rng = np.random.default_rng(5)
+    xi = [int(x) for x in _rand(rng, 3)]
+    lev_c = C.lev(np.array(xi, dtype=np.uint64), opening, n_bits, threads=1)
+    lev_s = S.compute_lev(xi, opening, n_bits)
+    assert [list(map(int, r)) for r in lev_c] == lev_s
+    # a random base-field column and a random F3 column, committed as LDE rows (blowup 2): the values at rows k << extend_bits
+    # are P(7 * w_n^k)
+    size = 5
+    cols = _rand(rng, n * size).reshape(n, size)
+    ext = C.lde(cols.reshape(-1), size, n_bits, n_bits + extend_bits)
+    evm = [("cm", 0, 1, 0), ("cm", 2, 3, 0)]
+    got = C.evals({"cm": (ext, size)}, evm, [lev_c], n_bits, extend_bits)
+    exp = S.compute_evals({"cm": ([int(x) for x in ext], size)}, evm, [lev_s], n_bits, extend_bits)
+    assert [list(map(int, r)) for r in got] == exp
+    z = S.opening_xi(xi, opening, n_bits)
+    # Horner on the interpolated coefficients: P(z) with P(w^k) = cols[k]
+    for (_, off, dim, _), e in zip(evm, exp):
+        for c in range(dim):
+            coeffs = S.intt([int(v) for v in cols[:, off + c]])
+            val = S.eval_pol([[a, 0, 0] for a in coeffs], z)
+            if dim == 1:
+                assert val == e
+            else:
+                # F3 column (a, b, c) = a + b*x + c*x^2 over the base-field polynomials
+                pass
+    coeffs = [S.intt([int(v) for v in cols[:, 2 + c]]) for c in range(3)]
+    vals = [S.eval_pol([[a, 0, 0] for a in coeffs[c]], z) for c in range(3)]
+    comb = S.f3_add(S.f3_add(vals[0], S.f3_mul(vals[1], [0, 1, 0])), S.f3_mul(vals[2], [0, 0, 1]))
+    assert comb == exp[1]
+
+
+def test_x_div_x_sub_xi_c_equals_spec_and_definition():
+    n_bits, ext_bits = 3, 5
+    rng = np.random.default_rng(9)
+    xi = [int(x) for x in _rand(rng, 3)]
+    openings = [0, 1, -2]
+    got = C.x_div_x_sub_xi(np.array(xi, dtype=np.uint64), openings, n_bits, ext_bits, threads=3)
+    exp = S.x_div_x_sub_xi(xi, openings, n_bits, ext_bits)
+    assert [int(v) for v in got.reshape(-1)] == exp
+    w = S.root_of_unity(ext_bits)
+    for i, o in enumerate(openings):
+        z = S.opening_xi(xi, o, n_bits)
+        for k in (0, 1, 7, 31):
+            x = S.SHIFT * pow(w, k, P) % P
+            v = [int(t) for t in got[k, i]]
+            assert S.f3_mul(v, S.f3_sub([x, 0, 0], z)) == [x, 0, 0]          # v * (x - xi) == x

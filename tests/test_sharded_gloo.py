@@ -37,18 +37,46 @@ class OracleEngine:
         self._u(nodes)[:C.merkle_nnodes(height)] = C.merkelize(d, 4, height, threads=1)   # width 4 = passthrough leaves
 
 
-def _worker(rank, world, port, n_bits, blow, cols, split, q):
+class PeerOracleEngine(OracleEngine):
+    """Stand-in for the fused peer-store exchange: `lde_scatter` delivers the rows to their owners itself (here through a
+    gloo all-to-all), so the test covers the branch of ShardedCommit.commit that skips all_to_all_single and relies on the
+    two one-word all-reduces for ordering."""
+
+    def __init__(self, dist_mod):
+        self.dist = dist_mod
+        self.scatter_calls = 0
+
+    def open_exchange(self, dist_mod, rank, world, recv_words):
+        return {"recv": self.empty(recv_words), "rank": rank, "world": world, "flag": torch.zeros(1, dtype=torch.int32)}
+
+    def close_exchange(self, ex):
+        ex["closed"] = True
+
+    def lde_scatter(self, src, cols, n_bits, ext_bits, dst, ex):
+        self.lde(src, cols, n_bits, ext_bits, dst)
+        self.dist.all_to_all_single(ex["recv"], dst)
+        self.scatter_calls += 1
+
+
+def _worker(rank, world, port, n_bits, blow, cols, split, q, peer=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         rng = np.random.default_rng(5)
         full = rng.integers(0, 0xFFFFFFFF00000001, size=(1 << n_bits, cols), dtype=np.uint64)
-        sc = ShardedCommit(OracleEngine(), dist, rank, world)
+        eng = PeerOracleEngine(dist) if peer else OracleEngine()
+        sc = ShardedCommit(eng, dist, rank, world)
         cg = sc.shard_cols(cols)
         slab = torch.from_numpy(np.ascontiguousarray(full[:, rank * cg:(rank + 1) * cg]).reshape(-1).view(np.int64))
         buf = sc.buffers(cols, n_bits, n_bits + blow)
         root = sc.commit(slab, cols, n_bits, n_bits + blow, buf, split)
+        if peer:
+            assert eng.scatter_calls == 1 and "peer stores" in sc.exchange_kind(buf)
+            root = sc.commit(slab, cols, n_bits, n_bits + blow, buf, split)      # buffers are reusable
+            sc.release(buf)
+        else:
+            assert "NCCL" in sc.exchange_kind(buf)
         q.put((rank, root.numpy().view(np.uint64).copy(), buf["nodes"].numpy().view(np.uint64).copy(),
                buf["top"].numpy().view(np.uint64).copy()))
         dist.barrier()
@@ -64,13 +92,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,split", [(2, False), (4, False), (2, True)])
-def test_sharded_commit_matches_single_process(world, split):
+@pytest.mark.parametrize("world,split,peer", [(2, False, False), (4, False, False), (2, True, False), (2, False, True), (4, False, True)])
+def test_sharded_commit_matches_single_process(world, split, peer):
     n_bits, blow, cols = 6, 1, 32
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_bits, blow, cols, split, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_bits, blow, cols, split, q, peer)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
