@@ -39,8 +39,8 @@ typedef struct pil2gpu_ctx pil2gpu_ctx;
 typedef struct pil2gpu_tree pil2gpu_tree;   /* device-resident {elements, nodes, width, height} */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
-/* stream: a cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream) or NULL to let the ctx
- * create its own non-blocking stream.  Replaces the per-call workerpool.pool()/terminate() of fft_p.js:121,175
+/* stream: a cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream; pass cudaStreamLegacy = 0x1 for
+ * the default stream, whose handle is 0) or NULL to let the ctx create its own non-blocking stream.  Replaces the per-call workerpool.pool()/terminate() of fft_p.js:121,175
  * and merklehash_p.js:53,105 (no threads are left alive between calls; the ctx only owns twiddle tables). */
 int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out);
 void pil2gpu_destroy(pil2gpu_ctx* ctx);
@@ -82,14 +82,20 @@ int pil2gpu_lde_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const 
 int pil2gpu_ipc_export(pil2gpu_ctx* ctx, const void* dptr, uint8_t handle_out[64]);
 int pil2gpu_ipc_open(pil2gpu_ctx* ctx, const uint8_t handle[64], void** dptr_out);
 int pil2gpu_ipc_close(pil2gpu_ctx* ctx, void* dptr);
-/* interpolate (fft_p.js:187-297) of this rank's column slab (2^nBits x nPols) whose LAST butterfly pass stores extended
+/* interpolate (fft_p.js:187-297) of a column slab (2^nBits x nPols) of this rank whose LAST butterfly pass stores extended
  * row R directly into the receive buffer of the rank that hashes it: peer_recv_dev[R / rows_local] (a HOST array of
  * n_ranks device pointers valid on this device, own buffer included), at word offset
- * rank * rows_local * nPols + (R % rows_local) * nPols, rows_local = 2^nBitsExt / n_ranks -- the tile layout
- * pil2gpu_merkelize_tiled_dev hashes in place.  dst_dev (2^nBitsExt x nPols) is the in-place workspace of the earlier
- * passes.  The caller orders the ranks (a barrier before the receive buffers are read). */
+ *     rank * rows_local * tile_cols + (R % rows_local) * tile_cols + col_off + column,   rows_local = 2^nBitsExt / n_ranks
+ * -- the tile layout pil2gpu_merkelize_tiled_dev hashes in place (tile_cols = columns this rank contributes in total,
+ * 0 = nPols; col_off = first column of this slab inside the tile).  dst_dev (2^nBitsExt x nPols) is the in-place workspace
+ * of the earlier passes.  The caller orders the ranks (a barrier before the receive buffers are read or rewritten). */
 int pil2gpu_lde_scatter_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t* dst_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
-                            uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank);
+                            uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank, uint64_t tile_cols, uint64_t col_off);
+/* Same with the slab in HOST memory (row pitch src_pitch_cols words, pinned for full speed): uploads and transforms it
+ * in sub-slabs of 32 columns so that the PCIe upload overlaps the LDE and the peer stores.  Asynchronous: returns once
+ * the work is enqueued on the ctx stream. */
+int pil2gpu_lde_scatter(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t src_pitch_cols, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
+                        uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank);
 
 /* ---- quotient polynomial: computeQStark, src/stark/stark_gen_helpers.js:168-208 ----------------------------------- */
 /* q_ext: 2^nBitsExt x qDim evaluations of Q on 7<w_ext>.  cmq_ext (2^nBitsExt x qDim*qDeg): column p*qDim + k holds the

@@ -53,7 +53,8 @@ _SIGS = {
     "pil2gpu_ipc_export": (c_int, [vp, vp, vp]),
     "pil2gpu_ipc_open": (c_int, [vp, vp, ctypes.POINTER(vp)]),
     "pil2gpu_ipc_close": (c_int, [vp, vp]),
-    "pil2gpu_lde_scatter_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32, ctypes.POINTER(vp), c_u32, c_u32]),
+    "pil2gpu_lde_scatter_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32, ctypes.POINTER(vp), c_u32, c_u32, c_u64, c_u64]),
+    "pil2gpu_lde_scatter": (c_int, [vp, vp, c_u64, c_u64, c_u32, c_u32, ctypes.POINTER(vp), c_u32, c_u32]),
     "pil2gpu_compute_q_dev": (c_int, [vp, vp, c_u64, c_u64, c_u32, c_u32, vp]),
     "pil2gpu_compute_q": (c_int, [vp, vp, c_u64, c_u64, c_u32, c_u32, c_int, vp, vp, vp]),
     "pil2gpu_compute_lev_dev": (c_int, [vp, vp, c_i32, c_u32, vp]),

@@ -41,12 +41,14 @@ struct NttTables {
 // Row scatter of the multi-GPU commit: the pass that finishes the LDE stores extended row R of this rank's
 // column slab straight into the receive buffer of the rank that hashes row R (peer memory over NVLink / NVSwitch, mapped
 // with CUDA IPC) instead of the local buffer -- the column -> row exchange rides on the stores of the last butterfly pass.
-//   destination = peer[R >> rl_bits] + tile_off + (R & (2^rl_bits - 1)) * C + column
+//   destination = peer[R >> rl_bits] + tile_off + (R & (2^rl_bits - 1)) * out_C + col_off + column
 #define NTT_MAX_PEERS 16
 struct NttScatter {
     u64* peer[NTT_MAX_PEERS];   // peer[h]: rank h's receive buffer (device pointer valid on this device)
     int rl_bits;                // log2(rows per rank)
     u64 tile_off;               // word offset of this rank's column tile inside a receive buffer
+    u64 out_C;                  // columns of that tile (>= the columns of the slab being transformed)
+    u64 col_off;                // first column of the slab inside the tile
 };
 
 // W32^E * 2^64 (canonical) for a 32-bit exponent E: any root of unity of order <= 2^32 to any power.
@@ -311,7 +313,7 @@ __device__ __forceinline__ void ntt_tile_store_fix(const ulonglong2* __restrict_
                                                    u64 row0, u64 row_step, const NttScatter& sc) {
     const int rows = 1 << t, RS = ntt_region_elems(t);
     const u64 rl_mask = SC ? (((u64)1 << sc.rl_bits) - 1) : 0;
-    if (cw == NTT_W && (C % 2 == 0) && (SC || ((((size_t)out) & 15) == 0))) {
+    if (cw == NTT_W && (C % 2 == 0) && (SC ? (((sc.out_C | sc.col_off) & 1) == 0) : ((((size_t)out) & 15) == 0))) {
         const int cp = threadIdx.x % NTT_CP, k0 = threadIdx.x / NTT_CP;
         u64* __restrict__ dst = out + (row0 + (u64)k0 * row_step) * C + c0 + 2 * cp;
         const u64 step = row_step * C * (NTT_THREADS / NTT_CP);
@@ -322,7 +324,7 @@ __device__ __forceinline__ void ntt_tile_store_fix(const ulonglong2* __restrict_
             if (FIX == 1) { v.x = gl_canon(v.x); v.y = gl_canon(v.y); }
             if (SC) {
                 const u64 row = row0 + (u64)k * row_step;
-                u64* p = sc.peer[row >> sc.rl_bits] + sc.tile_off + (row & rl_mask) * C + c0 + 2 * cp;
+                u64* p = sc.peer[row >> sc.rl_bits] + sc.tile_off + (row & rl_mask) * sc.out_C + sc.col_off + c0 + 2 * cp;
                 *reinterpret_cast<ulonglong2*>(p) = v;
             } else {
                 *reinterpret_cast<ulonglong2*>(dst) = v;
@@ -337,7 +339,7 @@ __device__ __forceinline__ void ntt_tile_store_fix(const ulonglong2* __restrict_
                 if (FIX == 2) v = gl_mmul(v, scale);
                 if (FIX == 1) v = gl_canon(v);
                 const u64 row = row0 + (u64)k * row_step;
-                if (SC) sc.peer[row >> sc.rl_bits][sc.tile_off + (row & rl_mask) * C + c0 + c] = v;
+                if (SC) sc.peer[row >> sc.rl_bits][sc.tile_off + (row & rl_mask) * sc.out_C + sc.col_off + c0 + c] = v;
                 else out[row * C + c0 + c] = v;
             }
         }
@@ -479,6 +481,8 @@ static inline NttScatter ntt_no_scatter() {
     for (int i = 0; i < NTT_MAX_PEERS; i++) sc.peer[i] = nullptr;
     sc.rl_bits = 0;
     sc.tile_off = 0;
+    sc.out_C = 0;
+    sc.col_off = 0;
     return sc;
 }
 

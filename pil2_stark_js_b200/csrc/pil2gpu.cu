@@ -60,6 +60,17 @@ struct pil2gpu_tree {
     bool own_elems, own_nodes;
 };
 
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    ~EventPool() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    bool timing = false;
+    cudaError_t make(cudaEvent_t* out) {
+        cudaError_t e = cudaEventCreateWithFlags(out, timing ? cudaEventDefault : cudaEventDisableTiming);
+        if (e == cudaSuccess) ev.push_back(*out);
+        return e;
+    }
+};
+
 struct DeviceGuard {
     int prev;
     bool ok;
@@ -320,27 +331,82 @@ int pil2gpu_ipc_close(pil2gpu_ctx* ctx, void* dptr) {
     return PIL2GPU_OK;
 }
 
-int pil2gpu_lde_scatter_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
-                            uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank) {
-    ENTER(ctx);
-    int rc = check_ntt_args(src, dst, nPols, nBitsExt);
-    if (rc) return rc;
-    if (nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "nBitsExt (%u) < nBits (%u)", nBitsExt, nBits);
-    if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
+static int make_scatter(NttScatter& sc, uint64_t nPols, uint32_t nBitsExt, uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank,
+                        uint64_t tile_cols, uint64_t col_off) {
     if (!peer_recv_dev || n_ranks == 0 || n_ranks > NTT_MAX_PEERS || (n_ranks & (n_ranks - 1)) || rank >= n_ranks)
         return fail(PIL2GPU_E_INVALID, "bad rank description (n_ranks must be a power of two <= %d)", NTT_MAX_PEERS);
+    if (col_off + nPols > tile_cols) return fail(PIL2GPU_E_INVALID, "slab columns [%llu, %llu) outside a tile of %llu columns",
+                                                 (unsigned long long)col_off, (unsigned long long)(col_off + nPols), (unsigned long long)tile_cols);
     uint32_t gb = 0;
     while ((1u << gb) < n_ranks) gb++;
     if (gb > nBitsExt) return fail(PIL2GPU_E_INVALID, "more ranks than extended rows");
-    NttScatter sc = ntt_no_scatter();
+    sc = ntt_no_scatter();
     for (uint32_t h = 0; h < n_ranks; h++) {
         if (!peer_recv_dev[h]) return fail(PIL2GPU_E_INVALID, "null peer buffer %u", h);
         sc.peer[h] = (u64*)peer_recv_dev[h];
     }
     sc.rl_bits = (int)(nBitsExt - gb);
-    sc.tile_off = (u64)rank * (nPols << sc.rl_bits);
+    sc.tile_off = (u64)rank * (tile_cols << sc.rl_bits);
+    sc.out_C = tile_cols;
+    sc.col_off = col_off;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_lde_scatter_dev(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
+                            uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank, uint64_t tile_cols, uint64_t col_off) {
+    ENTER(ctx);
+    int rc = check_ntt_args(src, dst, nPols, nBitsExt);
+    if (rc) return rc;
+    if (nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "nBitsExt (%u) < nBits (%u)", nBitsExt, nBits);
+    if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
+    NttScatter sc;
+    rc = make_scatter(sc, nPols, nBitsExt, peer_recv_dev, n_ranks, rank, tile_cols ? tile_cols : nPols, col_off);
+    if (rc) return rc;
     int l = ntt_launch_lde((const u64*)src, (u64*)dst, nPols, (int)nBits, (int)nBitsExt, ctx->tb, ctx->stream, &sc);
     return check_launch(ctx, l, "lde_scatter");
+}
+
+// Host-source form: the slab is cut into sub-slabs of PIPE columns; the upload of sub-slab s+1 (in_stream) overlaps the
+// LDE + peer stores of sub-slab s (ctx stream).  Returns once everything is enqueued; the work is complete when the ctx
+// stream is (pil2gpu_sync, or a collective ordered after it).
+int pil2gpu_lde_scatter(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t src_pitch_cols, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
+                        uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank) {
+    ENTER(ctx);
+    if (!src) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits || src_pitch_cols < nPols) return fail(PIL2GPU_E_INVALID, "bad LDE shape");
+    if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
+    const u64 N = 1ULL << nBits, E = 1ULL << nBitsExt;
+    const u64 cs = (nPols % 32 == 0 && nPols > 32) ? 32 : ((nPols % 16 == 0 && nPols > 16) ? 16 : nPols);
+    const u64 nslabs = nPols / cs;
+    int rc = ensure_ws(ctx, 2 * N * cs + 2 * E * cs);
+    if (rc) return rc;
+    u64* sbuf[2] = {ctx->ws, ctx->ws + N * cs};
+    u64* dbuf[2] = {ctx->ws + 2 * N * cs, ctx->ws + 2 * N * cs + E * cs};
+    EventPool pool;
+    std::vector<cudaEvent_t> ev_in(nslabs), ev_done(nslabs);
+    for (u64 s = 0; s < nslabs; s++) { CU(pool.make(&ev_in[s])); CU(pool.make(&ev_done[s])); }
+    cudaEvent_t ev_start;
+    CU(pool.make(&ev_start));
+    CU(cudaEventRecord(ev_start, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->in_stream, ev_start, 0));
+    for (u64 s = 0; s < nslabs; s++) {
+        const int b = (int)(s & 1);
+        if (s >= 2) CU(cudaStreamWaitEvent(ctx->in_stream, ev_done[s - 2], 0));      // sbuf[b] is free again
+        CU(cudaMemcpy2DAsync(sbuf[b], cs * 8, src + s * cs, src_pitch_cols * 8, cs * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
+        CU(cudaEventRecord(ev_in[s], ctx->in_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
+        NttScatter sc;
+        rc = make_scatter(sc, cs, nBitsExt, peer_recv_dev, n_ranks, rank, nPols, s * cs);
+        if (rc) break;
+        int l = ntt_launch_lde(sbuf[b], dbuf[b], cs, (int)nBits, (int)nBitsExt, ctx->tb, ctx->stream, &sc);
+        rc = check_launch(ctx, l, "lde_scatter");
+        if (rc) break;
+        CU(cudaEventRecord(ev_done[s], ctx->stream));
+    }
+    // the events may be destroyed while still pending (CUDA keeps them alive until they complete); the in_stream must not
+    // be left with work that outlives the workspace on the error path
+    if (rc) { cudaStreamSynchronize(ctx->in_stream); cudaStreamSynchronize(ctx->stream); }
+    return rc;
 }
 
 // ---- quotient polynomial path: computeQStark (stark_gen_helpers.js:168-208) ----
@@ -516,6 +582,7 @@ static int dev_to_pages(pil2gpu_ctx* ctx, const u64* dev, uint64_t* const* pages
     if (off != expect) return fail(PIL2GPU_E_INVALID, "pages hold %zu words, expected %zu", off, expect);
     return PIL2GPU_OK;
 }
+
 
 struct DevBuf {   // RAII device allocation for the host-pointer entry points
     u64* p = nullptr;
@@ -775,28 +842,28 @@ int pil2gpu_commit(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32
 //     H2D of slab s+1   |   LDE + sponge absorption of slab s   |   D2H of the extended slab s-1
 // so the call costs max(PCIe down, PCIe up, compute) instead of their sum.  Strided 2D copies of >= 256-byte row
 // segments run at the full PCIe rate (measured 55.6 / 57.2 GB/s up / down, 98.7 GB/s both ways: tools/probe/pcie_probe.cu).
-struct EventPool {
-    std::vector<cudaEvent_t> ev;
-    ~EventPool() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
-    bool timing = false;
-    cudaError_t make(cudaEvent_t* out) {
-        cudaError_t e = cudaEventCreateWithFlags(out, timing ? cudaEventDefault : cudaEventDisableTiming);
-        if (e == cudaSuccess) ev.push_back(*out);
-        return e;
-    }
-};
 
 static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, uint64_t cs,
                                           uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]) {
     const u64 N = 1ULL << nBits, E = 1ULL << nBitsExt;
     const size_t nw = merkle_nnodes_words(E);
-    const u64 nslabs = nPols / cs;
+    // Slab widths.  The download is the longest leg, and a strided device->host copy only reaches the full PCIe rate with
+    // row segments of >= 512 bytes (measured: 256-byte segments 44-50 GB/s, 512-byte segments 57 GB/s), so wide traces use
+    // 64-column slabs -- after two 32-column ones that get the first download going early.
+    std::vector<u64> col0, width;
+    const bool wide = dst_out && cs == 32 && nPols % 64 == 0 && nPols >= 256;
+    for (u64 c = 0; c < nPols;) {
+        const u64 w = (wide && c >= 64) ? 64 : cs;
+        col0.push_back(c); width.push_back(w);
+        c += w;
+    }
+    const u64 nslabs = col0.size(), wmax = wide ? 64 : cs;
     // workspace: the whole trace (so the upload runs ahead at full rate and then leaves PCIe to the download, which is the
     // longer of the two), two extended slabs, the sponge states and the nodes
-    int wrc = ensure_ws(ctx, N * nPols + 2 * E * cs + 4 * E + nw);
+    int wrc = ensure_ws(ctx, N * nPols + 2 * E * wmax + 4 * E + nw);
     if (wrc) return wrc;
-    struct { u64* p; } sall = {ctx->ws}, dbuf[2] = {{ctx->ws + N * nPols}, {ctx->ws + N * nPols + E * cs}}, state = {ctx->ws + N * nPols + 2 * E * cs},
-                       nodes = {ctx->ws + N * nPols + 2 * E * cs + 4 * E};
+    struct { u64* p; } sall = {ctx->ws}, dbuf[2] = {{ctx->ws + N * nPols}, {ctx->ws + N * nPols + E * wmax}}, state = {ctx->ws + N * nPols + 2 * E * wmax},
+                       nodes = {ctx->ws + N * nPols + 2 * E * wmax + 4 * E};
     EventPool pool;
     const bool trace = getenv("PIL2GPU_TRACE") != nullptr;   // diagnostic: print the slab timeline after the call
     pool.timing = trace;
@@ -811,20 +878,21 @@ static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const uint64_t* src,
     int rc = PIL2GPU_OK;
     for (u64 s = 0; s < nslabs && rc == PIL2GPU_OK; s++) {
         const int b = (int)(s & 1);
-        u64* sslab = sall.p + s * N * cs;
-        CU(cudaMemcpy2DAsync(sslab, cs * 8, src + s * cs, nPols * 8, cs * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
+        const u64 w = width[s];
+        u64* sslab = sall.p + N * col0[s];
+        CU(cudaMemcpy2DAsync(sslab, w * 8, src + col0[s], nPols * 8, w * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
         CU(cudaEventRecord(ev_in[s], ctx->in_stream));
         CU(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
         if (s >= 2 && dst_out) CU(cudaStreamWaitEvent(ctx->stream, ev_out[s - 2], 0));   // dbuf[b] was downloaded
-        rc = pil2gpu_lde_dev(ctx, sslab, dbuf[b].p, cs, nBits, nBitsExt);
+        rc = pil2gpu_lde_dev(ctx, sslab, dbuf[b].p, w, nBits, nBitsExt);
         if (rc) break;
         CU(cudaEventRecord(ev_lde[s], ctx->stream));
         if (dst_out) {
             CU(cudaStreamWaitEvent(ctx->copy_stream, ev_lde[s], 0));
-            CU(cudaMemcpy2DAsync(dst_out + s * cs, nPols * 8, dbuf[b].p, cs * 8, cs * 8, E, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CU(cudaMemcpy2DAsync(dst_out + col0[s], nPols * 8, dbuf[b].p, w * 8, w * 8, E, cudaMemcpyDeviceToHost, ctx->copy_stream));
             CU(cudaEventRecord(ev_out[s], ctx->copy_stream));
         }
-        merkle_absorb_kernel<<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(dbuf[b].p, cs, E, state.p, s == 0, s + 1 == nslabs, nodes.p);
+        merkle_absorb_kernel<<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(dbuf[b].p, w, E, state.p, s == 0, s + 1 == nslabs, nodes.p);
         rc = check_launch(ctx, 1, "absorb");
         if (trace) CU(cudaEventRecord(ev_abs[s], ctx->stream));
     }
@@ -844,7 +912,8 @@ static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const uint64_t* src,
             float a = 0, b = 0, c = 0, d = 0;
             cudaEventElapsedTime(&a, ev_start, ev_in[s]); cudaEventElapsedTime(&b, ev_start, ev_lde[s]); cudaEventElapsedTime(&c, ev_start, ev_abs[s]);
             if (dst_out) cudaEventElapsedTime(&d, ev_start, ev_out[s]);
-            fprintf(stderr, "[pil2gpu] slab %llu: h2d done %.1f ms, lde done %.1f, absorb done %.1f, d2h done %.1f\n", (unsigned long long)s, a, b, c, d);
+            fprintf(stderr, "[pil2gpu] slab %llu (%llu cols): h2d done %.1f ms, lde done %.1f, absorb done %.1f, d2h done %.1f\n", (unsigned long long)s,
+                    (unsigned long long)width[s], a, b, c, d);
         }
     }
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)

@@ -28,7 +28,10 @@ class GpuEngine:
         from . import _lib
         self.torch, self.L, self.check = torch, _lib.load(), _lib.check
         h = ctypes.c_void_p()
-        self.check(self.L.pil2gpu_create(device_index, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), ctypes.byref(h)))
+        # The library must enqueue on the stream torch.distributed orders its collectives against.  torch reports the
+        # default stream as handle 0, which pil2gpu_create reads as "make your own stream": pass cudaStreamLegacy (0x1).
+        stream = torch.cuda.current_stream().cuda_stream or 1
+        self.check(self.L.pil2gpu_create(device_index, ctypes.c_void_p(stream), ctypes.byref(h)))
         self.h = h
         self.device = torch.device("cuda", device_index)
 
@@ -100,7 +103,12 @@ class GpuEngine:
 
     def lde_scatter(self, src, cols, n_bits, ext_bits, dst, ex):
         self.check(self.L.pil2gpu_lde_scatter_dev(self.h, self._p(src), self._p(dst), cols, n_bits, ext_bits, ex["peers"], ex["world"],
-                                                  ex["rank"]))
+                                                  ex["rank"], 0, 0))
+
+    def lde_scatter_host(self, src_host, cols, n_bits, ext_bits, ex):
+        """Pinned host slab -> peers: upload in sub-slabs overlapped with the LDE + peer stores (asynchronous)."""
+        self.check(self.L.pil2gpu_lde_scatter(self.h, ctypes.c_void_p(src_host.data_ptr()), cols, cols, n_bits, ext_bits, ex["peers"],
+                                              ex["world"], ex["rank"]))
 
     def merkelize_tiled(self, tiles, n_tiles, tile_cols, rows, nodes, split=False):
         self.check(self.L.pil2gpu_merkelize_tiled_dev(self.h, self._p(tiles), n_tiles, tile_cols, rows * tile_cols, rows, int(split),
@@ -147,28 +155,40 @@ class ShardedCommit:
         return "peer stores fused into the last LDE pass (CUDA IPC over NVLink)" if buf.get("exchange") else "NCCL all_to_all_single"
 
     def commit(self, src_slab, cols, n_bits, ext_bits, buf, split=False):
-        """src_slab: this rank's N x C/G column slab (row-major).  Returns the 4-word root tensor (on every rank)."""
+        """src_slab: this rank's N x C/G column slab (row-major, on the device).  Returns the 4-word root tensor (on every rank)."""
+        tiles = self.extend_exchange(src_slab, cols, n_bits, ext_bits, buf)
+        return self.hash_and_root(tiles, cols, ext_bits, buf, split)
+
+    def extend_exchange(self, src_slab, cols, n_bits, ext_bits, buf, host_src=False):
+        """LDE of the local column slab + the column -> row exchange.  Returns the tensor holding this rank's rows as G column
+        tiles.  host_src: src_slab is a pinned HOST tensor, uploaded in sub-slabs overlapped with the LDE (peer exchange only)."""
         G, e = self.world, self.e
         cg = self.shard_cols(cols)
-        E = 1 << ext_bits
-        if E % G:
+        if (1 << ext_bits) % G:
             raise ValueError("extended height must be divisible by the number of GPUs")
-        rows_local = E // G
         ex = buf.get("exchange")
+        if host_src and not (G > 1 and ex):
+            raise ValueError("host-source extension needs the peer exchange")
         if G > 1 and ex:
             # Barrier BEFORE the stores: whatever the peers still do with their receive buffers (hashing of the previous
             # commit, a download) is stream-ordered before their contribution to this one-word all-reduce.
             self.dist.all_reduce(ex["flag"])
-            e.lde_scatter(src_slab, cg, n_bits, ext_bits, buf["dst"], ex)
+            if host_src:
+                e.lde_scatter_host(src_slab, cg, n_bits, ext_bits, ex)
+            else:
+                e.lde_scatter(src_slab, cg, n_bits, ext_bits, buf["dst"], ex)
             self.dist.all_reduce(ex["flag"])                                # every rank's stores have landed (stream-ordered)
-            tiles = buf["recv"]
-        elif G > 1:
-            e.lde(src_slab, cg, n_bits, ext_bits, buf["dst"])
+            return buf["recv"]
+        e.lde(src_slab, cg, n_bits, ext_bits, buf["dst"])
+        if G > 1:
             self.dist.all_to_all_single(buf["recv"], buf["dst"])            # equal splits: chunk h = rows of rank h
-            tiles = buf["recv"]
-        else:
-            e.lde(src_slab, cg, n_bits, ext_bits, buf["dst"])
-            tiles = buf["dst"]
+            return buf["recv"]
+        return buf["dst"]
+
+    def hash_and_root(self, tiles, cols, ext_bits, buf, split=False):
+        G, e = self.world, self.e
+        cg = self.shard_cols(cols)
+        rows_local = (1 << ext_bits) // G
         e.merkelize_tiled(tiles, G, cg, rows_local, buf["nodes"], split)
         if G == 1:
             return buf["nodes"][-4:]
@@ -291,10 +311,22 @@ def bench_main(args, rank, world, local_rank, dist, bench):
             fri_host["pol0"].copy_(fri["pol"][0])
         torch.cuda.synchronize()
 
+        copy_stream = torch.cuda.Stream()
+        peer = buf.get("exchange") is not None
+
         def e2e_step():
-            src.copy_(src_host, non_blocking=True)
-            root = sc.commit(src, cols, n_bits, ext_bits, buf)
-            out_host.copy_(ext_dev, non_blocking=True)
+            if peer:
+                # pinned slab -> sub-slab uploads overlapped with the LDE + peer stores; then the download of this rank's
+                # extended rows (copy stream) overlaps their hashing
+                tiles = sc.extend_exchange(src_host, cols, n_bits, ext_bits, buf, host_src=True)
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    out_host.copy_(tiles, non_blocking=True)
+                root = sc.hash_and_root(tiles, cols, ext_bits, buf)
+            else:
+                src.copy_(src_host, non_blocking=True)
+                root = sc.commit(src, cols, n_bits, ext_bits, buf)
+                out_host.copy_(ext_dev, non_blocking=True)
             nodes_host.copy_(buf["nodes"], non_blocking=True)
             if rank == 0:
                 fri["pol"][0].copy_(fri_host["pol0"], non_blocking=True)
@@ -318,8 +350,10 @@ def bench_main(args, rank, world, local_rank, dist, bench):
         d2h = 8 * (cols << ext_bits) + 8 * world * buf["nodes"].numel() + 32
         d2h += 8 * sum(3 << b for b in steps) + 8 * sum(3 << steps[s] for s in range(len(steps) - 1)) + 8 * sum(eng.nnodes(1 << steps[s + 1]) for s in range(len(steps) - 1))
         e2e = {"value": float(dt.item()), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "call": "per rank: pinned host slab -> device, ShardedCommit.commit, extended rows + nodes -> pinned host; rank 0 also the FRI chain "
-                       "(polynomial up, layers down)"}
+               "call": ("per rank: pinned host slab -> pil2gpu_lde_scatter (sub-slab uploads overlapped with the LDE + peer stores) -> hashing "
+                        "overlapped with the download of the extended rows; nodes -> pinned host" if peer else
+                        "per rank: pinned host slab -> device, ShardedCommit.commit, extended rows + nodes -> pinned host") +
+                       "; rank 0 also the FRI chain (polynomial up, layers down)"}
     if rank == 0:
         clocks = sampler.stop()
         sec = float(ms.item()) / 1e3 / args.steps

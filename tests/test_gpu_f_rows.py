@@ -44,7 +44,7 @@ def test_lde_scatter_virtual_ranks(ctx, n_bits, blow, cols, world):
     dst = ctx.alloc(cg * E)
     for g in range(world):
         slab = ctx.upload(np.ascontiguousarray(full[:, g * cg:(g + 1) * cg]))
-        check(L.pil2gpu_lde_scatter_dev(ctx.handle, slab.ptr, dst.ptr, cg, n_bits, ext, peers, world, g))
+        check(L.pil2gpu_lde_scatter_dev(ctx.handle, slab.ptr, dst.ptr, cg, n_bits, ext, peers, world, g, 0, 0))
         ctx.sync()
         slab.free()
     for h in range(world):
@@ -69,10 +69,12 @@ def test_lde_scatter_argument_checks(ctx):
     a, b = ctx.alloc(64), ctx.alloc(128)
     peers3 = (ctypes.c_void_p * 3)(b.ptr.value, b.ptr.value, b.ptr.value)
     with pytest.raises(Pil2GpuError):      # 3 ranks: not a power of two
-        check(L.pil2gpu_lde_scatter_dev(ctx.handle, a.ptr, b.ptr, 8, 3, 4, peers3, 3, 0))
+        check(L.pil2gpu_lde_scatter_dev(ctx.handle, a.ptr, b.ptr, 8, 3, 4, peers3, 3, 0, 0, 0))
     peers2 = (ctypes.c_void_p * 2)(b.ptr.value, None)
     with pytest.raises(Pil2GpuError):      # null peer
-        check(L.pil2gpu_lde_scatter_dev(ctx.handle, a.ptr, b.ptr, 8, 3, 4, peers2, 2, 0))
+        check(L.pil2gpu_lde_scatter_dev(ctx.handle, a.ptr, b.ptr, 8, 3, 4, peers2, 2, 0, 0, 0))
+    with pytest.raises(Pil2GpuError):      # slab columns outside the tile
+        check(L.pil2gpu_lde_scatter_dev(ctx.handle, a.ptr, b.ptr, 8, 3, 4, (ctypes.c_void_p * 1)(b.ptr.value), 1, 0, 8, 4))
     a.free(); b.free()
 
 
@@ -224,3 +226,27 @@ def test_stark_gen_helpers_stage_flow(ctx):
     t = S.Transcript()
     t.put([1, 2, 3])
     assert q == t.get_permutations(8, ext_bits)
+
+
+@pytest.mark.parametrize("n_bits,blow,cols,world", [(10, 1, 128, 2), (12, 1, 256, 4), (9, 2, 64, 2), (8, 1, 48, 2)])
+def test_lde_scatter_from_host_virtual_ranks(ctx, n_bits, blow, cols, world):
+    """pil2gpu_lde_scatter: every virtual rank pulls its column slab straight out of the full-width HOST buffer (row pitch =
+    all columns) in sub-slabs; the receive buffers must equal the oracle's rows, tile by tile."""
+    from pil2_stark_js_b200._lib import check
+    L = ctx._L
+    ext = n_bits + blow
+    E, cg = 1 << ext, cols // world
+    rows_local = E // world
+    full = rnd_field(123 + cols, cols << n_bits).reshape(1 << n_bits, cols)
+    want = C.lde(full.reshape(-1), cols, n_bits, ext).reshape(E, cols)
+    recv = [ctx.alloc(cg * E) for _ in range(world)]
+    peers = (ctypes.c_void_p * world)(*[r.ptr.value for r in recv])
+    for g in range(world):
+        check(L.pil2gpu_lde_scatter(ctx.handle, ctypes.c_void_p(full.ctypes.data + 8 * g * cg), cols, cg, n_bits, ext, peers, world, g))
+    ctx.sync()
+    for h in range(world):
+        tiles = recv[h].download().reshape(world, rows_local, cg)
+        got = np.ascontiguousarray(tiles.transpose(1, 0, 2)).reshape(rows_local, cols)
+        assert np.array_equal(got, want[h * rows_local:(h + 1) * rows_local]), f"rank {h} rows differ"
+    for r in recv:
+        r.free()

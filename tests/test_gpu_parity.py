@@ -26,10 +26,11 @@ def rnd_field(seed, n):
 
 # ---------------------------------------------------------------- extendAndMerkelize (host buffers, slab pipeline)
 @pytest.mark.parametrize("bits,ext,npols,split", [(12, 13, 64, False), (12, 14, 80, False), (13, 14, 128, False), (12, 13, 96, True),
-                                                   (12, 13, 48, False), (5, 6, 64, False), (12, 12, 64, False)])
+                                                   (12, 13, 48, False), (5, 6, 64, False), (12, 12, 64, False), (12, 13, 256, False), (12, 13, 320, False)])
 def test_extend_and_merkelize_vs_oracle(ctx, bits, ext, npols, split):
-    """stark_gen_helpers.js:388-412 = interpolate + merkelize.  Shapes 1-3 and 7 take the column-slab pipeline
-    (npols % 16 == 0, >= 4 slabs, standard hash); the others fall back to the whole-buffer path."""
+    """stark_gen_helpers.js:388-412 = interpolate + merkelize.  Shapes 1-3 and 7-9 take the column-slab pipeline
+    (npols % 16 == 0, >= 4 slabs, standard hash; the last two with mixed 32/64-column slabs); the others fall back to the
+    whole-buffer path."""
     src = rnd_field(1000 + bits * 7 + npols, npols << bits)
     dst, nodes, root = ctx.extend_and_merkelize(src, npols, bits, ext, split)
     want_dst = C.lde(src, npols, bits, ext)
