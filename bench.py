@@ -365,6 +365,57 @@ def run_ours(args, rank, world, local_rank):
                     "note": "integer-pipe bound as well: %.3g butterflies at the measured register-only butterfly rate is the floor"
                             % (3 * cols * (1 << n_bits) * n_bits / 2)}
 
+    # ---- rows next to the commit: quotient commit, evaluations at xi, FRI denominators -- device-resident, timed
+    # with CUDA events like the phases above; GB/s are ALGORITHMIC bytes over the measured time ----
+    extras = None
+    if not args.no_extras:
+        from pil2_stark_js_b200._lib import EvalDesc
+        q_dim, q_deg = 3, 1 << blow
+        q_ext = g.dev(q_dim << ext_bits)
+        cmq = g.dev((q_dim * q_deg) << ext_bits)
+        q_nodes = g.dev(g.nnodes(1 << ext_bits))
+        check(L.pil2gpu_synth_dev(g.h, g.ptr(q_ext), q_dim << ext_bits, seed + 9, 0))
+
+        def phase_q():
+            check(L.pil2gpu_compute_q_dev(g.h, g.ptr(q_ext), q_dim, q_deg, n_bits, ext_bits, g.ptr(cmq)))
+            check(L.pil2gpu_merkelize_dev(g.h, g.ptr(cmq), q_dim * q_deg, 1 << ext_bits, 0, g.ptr(q_nodes)))
+        openings = [0, 1]
+        xi = np.ascontiguousarray(splitmix_field(seed + 10, 0, 3))
+        lev = g.dev(len(openings) * (3 << n_bits))
+
+        def phase_lev():
+            for i, o in enumerate(openings):
+                check(L.pil2gpu_compute_lev_dev(g.h, npp(xi), o, n_bits, g.ptr(lev, i * (3 << n_bits))))
+        n_ev = 2 * cols
+        desc = (EvalDesc * n_ev)(*[EvalDesc(c, 1, o) for o in range(2) for c in range(cols)])
+        ev_out = np.empty(3 * n_ev, dtype=np.uint64)
+
+        def phase_evals():
+            check(L.pil2gpu_compute_evals_dev(g.h, g.ptr(dst), cols, n_bits, ext_bits, desc, n_ev, g.ptr(lev), len(openings), npp(ev_out)))
+        xd = g.dev(3 * len(openings) << ext_bits)
+        op_arr = (ctypes.c_int32 * len(openings))(*openings)
+
+        def phase_xdiv():
+            check(L.pil2gpu_x_div_x_sub_xi_dev(g.h, npp(xi), op_arr, len(openings), n_bits, ext_bits, g.ptr(xd)))
+        for f in (phase_q, phase_lev, phase_evals, phase_xdiv):
+            f()
+        t_q, t_lev, t_ev, t_xd = (time_phase(f, reps) for f in (phase_q, phase_lev, phase_evals, phase_xdiv))
+        Ew, Nw = 1 << ext_bits, 1 << n_bits
+        q_bytes = 8 * Ew * q_dim * (1 + q_deg) + 8 * Ew * q_dim * q_deg + 64 * Ew
+        ev_bytes = 8 * Nw * cols + 24 * Nw * len(openings)
+        xd_bytes = 24 * Ew * len(openings)
+        extras = {
+            "q_commit": {"s": t_q, "shape": f"qDim {q_dim}, qDeg {q_deg}, 2^{ext_bits} rows (INTT + split + {q_deg} coset NTTs + merkelize)",
+                         "algorithmic_bytes": q_bytes, "GBps": q_bytes / t_q / 1e9, "frac_hbm": q_bytes / t_q / 1e9 / hbm_peak},
+            "lev": {"s": t_lev, "shape": f"{len(openings)} openings x 2^{n_bits} F3 (powers + INTT)"},
+            "evals": {"s": t_ev, "shape": f"{n_ev} evaluations over the 2^{n_bits} base rows of the {cols}-column extended buffer",
+                      "algorithmic_bytes": ev_bytes, "GBps": ev_bytes / t_ev / 1e9, "frac_hbm": ev_bytes / t_ev / 1e9 / hbm_peak,
+                      "mulmod_per_s": 3.0 * n_ev * Nw / t_ev},
+            "x_div_x_sub_xi": {"s": t_xd, "shape": f"{len(openings)} openings x 2^{ext_bits} points", "algorithmic_bytes": xd_bytes,
+                               "GBps": xd_bytes / t_xd / 1e9, "frac_hbm": xd_bytes / t_xd / 1e9 / hbm_peak},
+        }
+        del q_ext, cmq, q_nodes, lev, xd
+
     # ---- e2e: the same commit through the host-buffer entry points (pinned host memory) ----
     e2e = None
     if not args.no_e2e:
@@ -383,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": sec_per_commit * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": config_dict(args.workload, 1),
         "rows_per_s": (1 << n_bits) / sec_per_commit, "phases_s": {"lde": t_lde, "merkle": t_mk, "merkle_leaf": t_leaf, "fri": t_fri},
-        "roofline": roofline, "roofline_lde": roofline_lde, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "roofline_lde": roofline_lde, "cpu_baseline": cpu, "e2e": e2e, "next_rows": extras, "gpu_launches": launches,
         "clocks": clocks, "root": root_dev,
     }
     print(json.dumps(line), flush=True)
@@ -469,6 +520,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -186,6 +186,10 @@ int pil2gpu_tree_root(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t root_out
  * siblings_out[(q*depth + level)*4 ..] = sibling at each level.  Any idx >= height -> PIL2GPU_E_RANGE ("Out of range"). */
 int pil2gpu_tree_group_proofs(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uint64_t* idxs, uint32_t n_idx, uint64_t* rows_out,
                               uint64_t* siblings_out);
+/* Same with device-resident indices and outputs (asynchronous, no range check: an index >= height marks a slot that
+ * belongs to another rank and is zero-filled, so that the per-rank results of a sharded tree combine with one sum-reduce). */
+int pil2gpu_tree_group_proofs_dev(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uint64_t* idxs_dev, uint32_t n_idx, uint64_t* rows_out_dev,
+                                  uint64_t* siblings_out_dev);
 /* Copy back to the host layout of the reference tree object {elements, nodes}; either pointer may be NULL. */
 int pil2gpu_tree_download(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t* elems_out, uint64_t* nodes_out);
 void pil2gpu_tree_free(pil2gpu_ctx* ctx, pil2gpu_tree* t);
@@ -195,7 +199,8 @@ void pil2gpu_tree_free(pil2gpu_ctx* ctx, pil2gpu_tree* t);
  * step0Bits = steps[0].nBits (fixes the coset shift, fri.js:31-36).  nextBits >= 0: also produce the transposed rows
  * (getTransposedBuffer fri.js:187-202; rows_out: 2^nextBits x 3*2^(curBits-nextBits) words) and their Merkle nodes
  * (nodes_out: pil2gpu_merkle_nnodes(2^nextBits) words); nextBits < 0 is the last step (rows_out/nodes_out ignored).
- * Step 0 (identity fold, fri.js:48-49, followed by the first layer commit :63-71) is prevBits == curBits. */
+ * Step 0 (identity fold, fri.js:48-49, followed by the first layer commit :63-71) is prevBits == curBits.
+ * The _dev form accepts nodes_out_dev == NULL with nextBits >= 0: rows only, the caller hashes them (sharded layer trees). */
 int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
                      const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out);
 int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol_dev, uint32_t prevBits, uint32_t curBits, int32_t nextBits,

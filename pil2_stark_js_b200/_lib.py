@@ -82,6 +82,7 @@ _SIGS = {
     "pil2gpu_tree_nodes_dev": (vp, [vp]),
     "pil2gpu_tree_root": (c_int, [vp, vp, vp]),
     "pil2gpu_tree_group_proofs": (c_int, [vp, vp, vp, c_u32, vp, vp]),
+    "pil2gpu_tree_group_proofs_dev": (c_int, [vp, vp, vp, c_u32, vp, vp]),
     "pil2gpu_tree_download": (c_int, [vp, vp, vp, vp]),
     "pil2gpu_tree_free": (None, [vp, vp]),
     "pil2gpu_tree_wrap_dev": (c_int, [vp, vp, vp, c_u64, c_u64, ctypes.POINTER(vp)]),

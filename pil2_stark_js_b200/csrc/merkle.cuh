@@ -279,6 +279,11 @@ __global__ void merkle_group_proof_kernel(RowTiles t, const u64* __restrict__ no
                                           const u64* __restrict__ idxs, int depth, u64* __restrict__ rows_out, u64* __restrict__ sib_out) {
     const u64 q = blockIdx.x;
     u64 idx = idxs[q];
+    if (idx >= height) {   // "not mine" marker of the multi-GPU gather (host entry points reject out-of-range indices): zero fill
+        for (u64 i = threadIdx.x; i < width; i += blockDim.x) rows_out[q * width + i] = 0;
+        for (u64 i = threadIdx.x; i < (u64)depth * 4; i += blockDim.x) sib_out[q * depth * 4 + i] = 0;
+        return;
+    }
     for (u64 i = threadIdx.x; i < width; i += blockDim.x) rows_out[q * width + i] = *tiles_ptr(t, idx, i);
     if (threadIdx.x < 4) {
         u64 off = 0, n = height * 4;

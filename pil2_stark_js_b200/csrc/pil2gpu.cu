@@ -1049,6 +1049,18 @@ int pil2gpu_tree_group_proofs(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uin
     return PIL2GPU_OK;
 }
 
+int pil2gpu_tree_group_proofs_dev(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uint64_t* idxs_dev, uint32_t n_idx, uint64_t* rows_out_dev,
+                                  uint64_t* siblings_out_dev) {
+    ENTER(ctx);
+    if (!t || !idxs_dev || !rows_out_dev || !siblings_out_dev) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (!t->elems) return fail(PIL2GPU_E_INVALID, "tree has no device-resident elements");
+    if (n_idx == 0) return PIL2GPU_OK;
+    RowTiles rt = {t->elems, t->tile_cols ? t->tile_cols : 1, t->tile_stride};
+    merkle_group_proof_kernel<<<n_idx, 128, 0, ctx->stream>>>(rt, t->nodes, t->width, t->height, (const u64*)idxs_dev, merkle_depth(t->height),
+                                                              (u64*)rows_out_dev, (u64*)siblings_out_dev);
+    return check_launch(ctx, 1, "group_proofs_dev");
+}
+
 int pil2gpu_tree_download(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t* elems_out, uint64_t* nodes_out) {
     ENTER(ctx);
     if (!t) return fail(PIL2GPU_E_INVALID, "null tree");
@@ -1067,7 +1079,7 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
     ENTER(ctx);
     if (!pol || !pol_out || !challenge) return fail(PIL2GPU_E_INVALID, "null argument");
     if (curBits > prevBits || prevBits > step0Bits || step0Bits > 32) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
-    if (nextBits >= 0 && ((uint32_t)nextBits > curBits || !rows_out || !nodes_out)) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
+    if (nextBits >= 0 && ((uint32_t)nextBits > curBits || !rows_out)) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
     if (prevBits - curBits > FRI_MAX_FOLD_BITS) return fail(PIL2GPU_E_UNSUPPORTED, "fold by 2^%u not supported (max 2^%d)", prevBits - curBits, FRI_MAX_FOLD_BITS);
     FriParams P;
     P.prev_bits = (int)prevBits;
@@ -1082,11 +1094,11 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
     const u64 gs = nextBits >= 0 ? (1ULL << (curBits - nextBits)) : 1;
     // The in-kernel leaf hash runs on FRI_ROWS_PER_CTA threads of each CTA: worth it only for small layers, where it saves
     // a launch; big layers (the first FRI tree has 2^20 leaves at cfg3) go through the full-width leaf kernel instead.
-    P.fuse_leaf_hash = (nextBits >= 0) && (!split || 3 * gs <= 4) && (gs * 3 * 8 * FRI_ROWS_PER_CTA <= 160 * 1024) && nextBits <= 12;
+    P.fuse_leaf_hash = (nextBits >= 0) && nodes_out && (!split || 3 * gs <= 4) && (gs * 3 * 8 * FRI_ROWS_PER_CTA <= 160 * 1024) && nextBits <= 12;
     int l = fri_launch_fold((const u64*)pol, (u64*)pol_out, (u64*)rows_out, (u64*)nodes_out, P, ctx->tb, ctx->stream);
     int rc = check_launch(ctx, l, "fri_fold");
     if (rc) return rc;
-    if (nextBits >= 0) {
+    if (nextBits >= 0 && nodes_out) {
         const u64 height = 1ULL << nextBits;
         if (P.fuse_leaf_hash) {
             l = merkle_launch_tree((u64*)nodes_out, height, ctx->stream);

@@ -117,8 +117,70 @@ class GpuEngine:
     def tree_from_digests(self, nodes, height):
         self.check(self.L.pil2gpu_merkle_tree_from_digests_dev(self.h, self._p(nodes), height))
 
+    def merkelize(self, elems, width, height, nodes):
+        self.check(self.L.pil2gpu_merkelize_dev(self.h, self._p(elems), width, height, 0, self._p(nodes)))
+
+    def group_proofs(self, tiles, n_tiles, tile_cols, rows, nodes, idxs, n_idx, rows_out, sib_out):
+        """getGroupProof (merklehash_p.js:142-168) for n_idx device-resident leaf indices of a (tiled) device tree; an index
+        >= rows marks a slot owned by another rank and is zero-filled."""
+        t = ctypes.c_void_p()
+        self.check(self.L.pil2gpu_tree_wrap_tiled_dev(self.h, self._p(tiles), n_tiles, tile_cols, rows * tile_cols, self._p(nodes), rows,
+                                                      ctypes.byref(t)))
+        try:
+            self.check(self.L.pil2gpu_tree_group_proofs_dev(self.h, t, self._p(idxs), n_idx, self._p(rows_out), self._p(sib_out)))
+        finally:
+            self.L.pil2gpu_tree_free(None, t)       # a wrapper: owns nothing on the device
+
     def launches(self):
         return int(self.L.pil2gpu_launch_count(self.h))
+
+
+class ShardedTree:
+    """A Merkle tree whose leaves are spread over the ranks in contiguous ranges: rank h holds rows [h*R, (h+1)*R) (as
+    n_tiles column tiles), the subtree over them (`nodes`, reference layout of a height-R tree) and -- like every rank --
+    the gathered sub-roots (`sub`) with the levels above them (`top`, reference layout of a height-G tree)."""
+
+    def __init__(self, engine, dist, rank, world, tiles, n_tiles, tile_cols, rows_local, nodes, sub, top):
+        self.e, self.dist, self.rank, self.world = engine, dist, rank, world
+        self.tiles, self.n_tiles, self.tile_cols, self.rows_local = tiles, n_tiles, tile_cols, rows_local
+        self.nodes, self.sub, self.top = nodes, sub, top
+        self.width = n_tiles * tile_cols
+
+    def reduce_to_root(self):
+        """Sub-root all-gather + the top log2(G) levels (hashed redundantly on every rank).  Returns the 4-word root tensor."""
+        G, e = self.world, self.e
+        if G == 1:
+            return self.nodes[-4:]
+        nn = e.nnodes(self.rows_local)
+        self.dist.all_gather_into_tensor(self.sub, self.nodes[nn - 4:nn].contiguous())
+        self.top[:4 * G].copy_(self.sub)
+        e.tree_from_digests(self.top, G)
+        nt = e.nnodes(G)
+        return self.top[nt - 4:nt]
+
+    def open(self, queries):
+        """getGroupProof for global leaf indices `queries` (int64 tensor on the engine's device, identical on every rank):
+        every rank gathers the rows it owns, one sum all-reduce combines them (the other ranks contribute zeros), and the
+        top-level siblings come from the replicated top tree.  Returns (rows [Q, width], siblings [Q, depth, 4]) on every rank."""
+        e, G, R = self.e, self.world, self.rows_local
+        Q = int(queries.numel())
+        dl = max(R.bit_length() - 1, 0)
+        local = queries - self.rank * R
+        idx = local.clone()
+        idx[(local < 0) | (local >= R)] = -1                              # 0xFFFF...: "not mine"
+        rows_out, sib_local = e.empty(Q * self.width), e.empty(max(1, Q * dl * 4))
+        e.group_proofs(self.tiles, self.n_tiles, self.tile_cols, R, self.nodes, idx, Q, rows_out, sib_local)
+        sib_local = sib_local[:Q * dl * 4].view(Q, dl, 4)
+        if G == 1:
+            return rows_out.view(Q, self.width), sib_local
+        self.dist.all_reduce(rows_out)
+        self.dist.all_reduce(sib_local)
+        dt = G.bit_length() - 1
+        owners = (queries // R).contiguous()
+        sub_rows, sib_top = e.empty(Q * 4), e.empty(Q * dt * 4)
+        e.group_proofs(self.sub, 1, 4, G, self.top, owners, Q, sub_rows, sib_top)
+        import torch
+        return rows_out.view(Q, self.width), torch.cat([sib_local, sib_top.view(Q, dt, 4)], dim=1)
 
 
 class ShardedCommit:
@@ -190,15 +252,18 @@ class ShardedCommit:
         cg = self.shard_cols(cols)
         rows_local = (1 << ext_bits) // G
         e.merkelize_tiled(tiles, G, cg, rows_local, buf["nodes"], split)
-        if G == 1:
-            return buf["nodes"][-4:]
-        nn = e.nnodes(rows_local)
-        local_root = buf["nodes"][nn - 4:nn]
-        self.dist.all_gather_into_tensor(buf["sub"], local_root.contiguous())
-        buf["top"][:4 * G].copy_(buf["sub"])
-        e.tree_from_digests(buf["top"], G)
-        nt = e.nnodes(G)
-        return buf["top"][nt - 4:nt]
+        buf["tree"] = ShardedTree(e, self.dist, self.rank, G, tiles, G, cg, rows_local, buf["nodes"], buf["sub"], buf["top"])
+        return buf["tree"].reduce_to_root()
+
+    def commit_rows(self, rows, width, height, nodes, sub, top):
+        """Layer tree over rows every rank already holds in full (FRI layers, fri.js:63-71): rank h hashes leaves
+        [h*height/G, (h+1)*height/G) and the sub-roots are gathered.  Returns (ShardedTree, root tensor)."""
+        G, e = self.world, self.e
+        cnt = height // G
+        mine = rows[self.rank * cnt * width:(self.rank + 1) * cnt * width]
+        e.merkelize(mine, width, cnt, nodes)
+        t = ShardedTree(e, self.dist, self.rank, G, mine, 1, width, cnt, nodes, sub, top)
+        return t, t.reduce_to_root()
 
 
 def assemble_nodes(local_nodes_per_rank, top_nodes, rows_local, world, nnodes_fn):
@@ -244,33 +309,73 @@ def bench_main(args, rank, world, local_rank, dist, bench):
     src = eng.empty(cg << n_bits)
     check(L.pil2gpu_synth2d_dev(eng.h, vp(src.data_ptr()), 1 << n_bits, cg, cols, rank * cg, seed))
     buf = sc.buffers(cols, n_bits, ext_bits)
-    # FRI chain + queries run on rank 0 (layers shrink 16x per step; the chain is ~2% of the commit)
+    # FRI chain: every rank holds the FRI polynomial; the first layer tree (2^steps[1] leaves, ~3/4 of the
+    # chain's hashing) is hashed sharded like the trace tree, the layers below it (16x smaller each) run on rank 0.
     steps = bench.fri_steps(ext_bits)
-    fri = None
+    nl = len(steps) - 1                                   # layer trees
+    w0, h0 = 3 << (steps[0] - steps[1]), 1 << steps[1]
+    shard_l0 = nl >= 1 and h0 // world >= 2
+    fri = {"pol0": eng.empty(3 << steps[0]), "rows0": eng.empty(3 << steps[0]),
+           "chal": [np.ascontiguousarray(bench.splitmix_field(seed + 2 + s, 0, 3)) for s in range(len(steps))]}
+    check(L.pil2gpu_synth_dev(eng.h, vp(fri["pol0"].data_ptr()), 3 << steps[0], seed + 1, 0))
+    if shard_l0:
+        fri["nodes0"], fri["sub0"], fri["top0"] = eng.empty(eng.nnodes(h0 // world)), eng.empty(4 * world), eng.empty(max(8, eng.nnodes(world)))
+    elif rank == 0:
+        fri["nodes0"] = eng.empty(eng.nnodes(h0))
     if rank == 0:
-        fri = {"pol": [eng.empty(3 << b) for b in steps], "rows": [eng.empty(3 << steps[s]) for s in range(len(steps) - 1)],
-               "nodes": [eng.empty(eng.nnodes(1 << steps[s + 1])) for s in range(len(steps) - 1)],
-               "chal": [np.ascontiguousarray(bench.splitmix_field(seed + 2 + s, 0, 3)) for s in range(len(steps))]}
-        check(L.pil2gpu_synth_dev(eng.h, vp(fri["pol"][0].data_ptr()), 3 << steps[0], seed + 1, 0))
+        fri["pol"] = [fri["pol0"]] + [eng.empty(3 << b) for b in steps[1:]]
+        fri["rows"] = [fri["rows0"]] + [eng.empty(3 << steps[s]) for s in range(1, nl)]
+        fri["nodes"] = [fri.get("nodes0")] + [eng.empty(eng.nnodes(1 << steps[s + 1])) for s in range(1, nl)]
     npp = lambda a: vp(a.ctypes.data)
     P = lambda t: vp(t.data_ptr())
+    rng = np.random.default_rng(7)
+    queries_np = rng.integers(0, 1 << ext_bits, size=bench.N_QUERIES, dtype=np.int64)
+    queries = torch.from_numpy(queries_np).to(eng.device)
+    lower = []                                            # rank 0: (tree handle, host outputs) of the unsharded layer trees
+    if rank == 0:
+        for s in range(0 if not shard_l0 else 1, nl):
+            t = vp()
+            gsz = 3 << (steps[s] - steps[s + 1])
+            check(L.pil2gpu_tree_wrap_dev(eng.h, P(fri["rows"][s]), P(fri["nodes"][s]), gsz, 1 << steps[s + 1], ctypes.byref(t)))
+            lower.append((t, steps[s + 1], np.empty(bench.N_QUERIES * gsz, dtype=np.uint64),
+                          np.empty(bench.N_QUERIES * max(1, steps[s + 1]) * 4, dtype=np.uint64)))
+    opened = {}
 
     def fri_chain():
         f = fri
-        check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol"][0]), steps[0], steps[0], steps[1], steps[0], npp(f["chal"][0]), 0, P(f["pol"][0]),
-                                     P(f["rows"][0]), P(f["nodes"][0])))
-        for s in range(1, len(steps)):
-            last = s == len(steps) - 1
-            check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol"][s - 1]), steps[s - 1], steps[s], -1 if last else steps[s + 1], steps[0],
-                                         npp(f["chal"][s]), 0, P(f["pol"][s]), None if last else P(f["rows"][s]),
-                                         None if last else P(f["nodes"][s])))
+        # step 0: identity fold (fri.js:48-49) = transposed rows of the first layer, then its tree
+        if shard_l0:
+            check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol0"]), steps[0], steps[0], steps[1], steps[0], npp(f["chal"][0]), 0, P(f["pol0"]),
+                                         P(f["rows0"]), None))
+            f["tree0"], f["root0"] = sc.commit_rows(f["rows0"], w0, h0, f["nodes0"], f["sub0"], f["top0"])
+        elif rank == 0:
+            check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol0"]), steps[0], steps[0], steps[1], steps[0], npp(f["chal"][0]), 0, P(f["pol0"]),
+                                         P(f["rows0"]), P(f["nodes0"])))
+        if rank == 0:
+            for s in range(1, len(steps)):
+                last = s == len(steps) - 1
+                check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol"][s - 1]), steps[s - 1], steps[s], -1 if last else steps[s + 1], steps[0],
+                                             npp(f["chal"][s]), 0, P(f["pol"][s]), None if last else P(f["rows"][s]),
+                                             None if last else P(f["nodes"][s])))
+
+    def open_queries():
+        # proofQueries (fri.js:83-105): the trace tree and the first FRI layer are opened where their rows live (one
+        # sum all-reduce each); the small lower layers are opened on rank 0
+        opened["main"] = buf["tree"].open(queries)
+        if shard_l0:
+            opened["fri0"] = fri["tree0"].open(queries % h0)
+        if rank == 0:
+            q = queries_np.astype(np.uint64)
+            for t, bits, r_out, s_out in lower:
+                qq = np.ascontiguousarray(q % np.uint64(1 << bits))
+                check(L.pil2gpu_tree_group_proofs(eng.h, t, npp(qq), bench.N_QUERIES, npp(r_out), npp(s_out)))
 
     root_host = torch.empty(4, dtype=torch.int64, pin_memory=True)
 
     def step():
         root = sc.commit(src, cols, n_bits, ext_bits, buf)
-        if rank == 0:
-            fri_chain()
+        fri_chain()
+        open_queries()
         root_host.copy_(root, non_blocking=True)
 
     for _ in range(args.warmup):
@@ -304,37 +409,64 @@ def bench_main(args, rank, world, local_rank, dist, bench):
         src_host.copy_(src)
         ext_dev = buf["recv"] if world > 1 else buf["dst"]
         out_host, nodes_host = pin(ext_dev), pin(buf["nodes"])
-        fri_host = None
+        # FRI: the polynomial goes up on every rank (each hashes its share of the first layer); rank 0 brings the layers down,
+        # every rank its share of the first layer's nodes
+        fri_host = {"pol0": pin(fri["pol0"])}
+        fri_host["pol0"].copy_(fri["pol0"])
+        fri_down = []
+        if shard_l0:
+            fri_down.append(fri["nodes0"])
         if rank == 0:
-            fri_host = {"pol0": pin(fri["pol"][0]), "pol": [pin(t) for t in fri["pol"]], "rows": [pin(t) for t in fri["rows"]],
-                        "nodes": [pin(t) for t in fri["nodes"]]}
-            fri_host["pol0"].copy_(fri["pol"][0])
+            fri_down += fri["pol"] + fri["rows"] + [t for t in fri["nodes"] if t is not None and not (shard_l0 and t is fri.get("nodes0"))]
+        fri_host["down"] = [pin(t) for t in fri_down]
         torch.cuda.synchronize()
 
         copy_stream = torch.cuda.Stream()
         peer = buf.get("exchange") is not None
 
+        import os
+        trace = os.environ.get("PIL2GPU_TRACE") is not None
+        marks = []
+
+        def mark(name, stream=None):
+            if trace:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream or torch.cuda.current_stream())
+                marks.append((name, ev))
+
         def e2e_step():
+            del marks[:]
+            mark("start")
             if peer:
                 # pinned slab -> sub-slab uploads overlapped with the LDE + peer stores; then the download of this rank's
                 # extended rows (copy stream) overlaps their hashing
                 tiles = sc.extend_exchange(src_host, cols, n_bits, ext_bits, buf, host_src=True)
+                mark("lde+exchange")
                 copy_stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(copy_stream):
                     out_host.copy_(tiles, non_blocking=True)
+                    mark("rows down (copy stream)", copy_stream)
                 root = sc.hash_and_root(tiles, cols, ext_bits, buf)
+                mark("hash+root")
             else:
                 src.copy_(src_host, non_blocking=True)
                 root = sc.commit(src, cols, n_bits, ext_bits, buf)
+                mark("commit")
                 out_host.copy_(ext_dev, non_blocking=True)
+                mark("rows down")
             nodes_host.copy_(buf["nodes"], non_blocking=True)
-            if rank == 0:
-                fri["pol"][0].copy_(fri_host["pol0"], non_blocking=True)
-                fri_chain()
-                for d, h in zip(fri["pol"] + fri["rows"] + fri["nodes"], fri_host["pol"] + fri_host["rows"] + fri_host["nodes"]):
-                    h.copy_(d, non_blocking=True)
+            mark("nodes down")
+            if shard_l0 or rank == 0:
+                fri["pol0"].copy_(fri_host["pol0"], non_blocking=True)
+            fri_chain()
+            mark("fri")
+            for d, h in zip(fri_down, fri_host["down"]):
+                h.copy_(d, non_blocking=True)
             root_host.copy_(root, non_blocking=True)
+            mark("fri down")
             torch.cuda.synchronize()
+            if trace:
+                print(f"[pil2gpu] rank {rank} e2e: " + ", ".join(f"{n} {marks[0][1].elapsed_time(ev):.1f} ms" for n, ev in marks[1:]), flush=True)
 
         e2e_step()
         n_e2e = max(1, min(args.steps, 3))
@@ -346,14 +478,16 @@ def bench_main(args, rank, world, local_rank, dist, bench):
         dist.barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = 8 * (cols << n_bits) + 8 * (3 << steps[0])
+        h2d = 8 * (cols << n_bits) + 8 * (3 << steps[0]) * (world if shard_l0 else 1)
         d2h = 8 * (cols << ext_bits) + 8 * world * buf["nodes"].numel() + 32
-        d2h += 8 * sum(3 << b for b in steps) + 8 * sum(3 << steps[s] for s in range(len(steps) - 1)) + 8 * sum(eng.nnodes(1 << steps[s + 1]) for s in range(len(steps) - 1))
+        d2h += 8 * sum(3 << b for b in steps) + 8 * sum(3 << steps[s] for s in range(len(steps) - 1))
+        d2h += 8 * sum(eng.nnodes(1 << steps[s + 1]) for s in range(1, len(steps) - 1))
+        d2h += 8 * (world * eng.nnodes(h0 // world) if shard_l0 else eng.nnodes(h0))
         e2e = {"value": float(dt.item()), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
                "call": ("per rank: pinned host slab -> pil2gpu_lde_scatter (sub-slab uploads overlapped with the LDE + peer stores) -> hashing "
                         "overlapped with the download of the extended rows; nodes -> pinned host" if peer else
                         "per rank: pinned host slab -> device, ShardedCommit.commit, extended rows + nodes -> pinned host") +
-                       "; rank 0 also the FRI chain (polynomial up, layers down)"}
+                       "; FRI polynomial up on every rank, first layer tree sharded, layers down from rank 0"}
     if rank == 0:
         clocks = sampler.stop()
         sec = float(ms.item()) / 1e3 / args.steps
@@ -364,6 +498,8 @@ def bench_main(args, rank, world, local_rank, dist, bench):
             "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": bench.config_dict(args.workload, world),
             "rows_per_s": (1 << n_bits) / sec, "all_to_all_bytes_per_gpu": a2a, "exchange": sc.exchange_kind(buf),
+            "fri": ("first layer tree hashed on all ranks, lower layers on rank 0" if shard_l0 else "rank 0") + f"; {bench.N_QUERIES} queries "
+                   "opened on the owning ranks and combined with one all-reduce per tree",
             "gpu_launches": int(launches.item()), "clocks": clocks,
             "root": root,
             "e2e": e2e, "cpu_baseline": None,

@@ -349,9 +349,18 @@ def _mgpu_worker(rank, world, port, n_bits, blow, cols, q, mode="peer"):
         buf = sc.buffers(cols, n_bits, n_bits + blow)
         root = sc.commit(slab, cols, n_bits, n_bits + blow, buf)
         root = sc.commit(slab, cols, n_bits, n_bits + blow, buf)          # twice: the receive buffers are reused
+        E = 1 << (n_bits + blow)
+        qs = [0, 1, E - 1, E // world, E // world - 1, 1234 % E]
+        rows_q, sib_q = buf["tree"].open(torch.tensor(qs, dtype=torch.int64, device="cuda"))
+        lw, lh = 48, 1 << (n_bits - 2)
+        layer_np = np.random.default_rng(9).integers(0, P, size=lw * lh, dtype=np.uint64)
+        layer = torch.from_numpy(layer_np.view(np.int64)).cuda()
+        eng = sc.e
+        lt, lroot = sc.commit_rows(layer, lw, lh, eng.empty(eng.nnodes(lh // world)), eng.empty(4 * world), eng.empty(max(8, eng.nnodes(world))))
+        lrows, lsib = lt.open(torch.tensor([0, lh - 1, lh // 2 + 1], dtype=torch.int64, device="cuda"))
         torch.cuda.synchronize()
-        q.put((rank, root.cpu().numpy().view(np.uint64).copy(), buf["nodes"].cpu().numpy().view(np.uint64).copy(),
-               buf["top"].cpu().numpy().view(np.uint64).copy(), sc.exchange_kind(buf)))
+        u = lambda t: t.cpu().numpy().view(np.uint64).copy()
+        q.put((rank, u(root), u(buf["nodes"]), u(buf["top"]), sc.exchange_kind(buf), (qs, u(rows_q), u(sib_q), layer_np, u(lroot), u(lrows), u(lsib))))
         dist.barrier()
         sc.release(buf)
     finally:
@@ -379,12 +388,55 @@ def test_sharded_commit_two_gpus(mode):
         assert p.exitcode == 0
     rng = np.random.default_rng(5)
     full = rng.integers(0, P, size=(1 << n_bits, cols), dtype=np.uint64)
-    nodes = C.merkelize(C.lde(full.reshape(-1), cols, n_bits, n_bits + blow), cols, 1 << (n_bits + blow))
-    for _, root, _, _, kind in res:
+    ext = C.lde(full.reshape(-1), cols, n_bits, n_bits + blow)
+    nodes = C.merkelize(ext, cols, 1 << (n_bits + blow))
+    for _, root, _, _, kind, extra in res:
         assert np.array_equal(root, nodes[-4:])
         assert ("peer stores" in kind) == (mode == "peer"), f"exchange used: {kind}"
+        qs, rows_q, sib_q, layer, lroot, lrows, lsib = extra          # sharded proofQueries + a sharded layer tree
+        for k, qi in enumerate(qs):
+            r, sb = C.group_proof(ext, nodes, cols, 1 << (n_bits + blow), qi)
+            assert np.array_equal(rows_q[k], r) and np.array_equal(sib_q[k].reshape(-1), np.asarray(sb, dtype=np.uint64).reshape(-1))
+        lw, lh = 48, 1 << (n_bits - 2)
+        lnodes = C.merkelize(layer, lw, lh)
+        assert np.array_equal(lroot, lnodes[-4:])
+        for k, qi in enumerate([0, lh - 1, lh // 2 + 1]):
+            r, sb = C.group_proof(layer, lnodes, lw, lh, qi)
+            assert np.array_equal(lrows[k], r) and np.array_equal(lsib[k].reshape(-1), np.asarray(sb, dtype=np.uint64).reshape(-1))
     stitched = assemble_nodes([r[2] for r in res], res[0][3], (1 << (n_bits + blow)) // world, world, C.merkle_nnodes)
     assert np.array_equal(stitched, nodes)
+
+
+def test_group_proofs_dev_and_rows_only_fold(ctx):
+    """pil2gpu_tree_group_proofs_dev (device indices, "not mine" slots zero-filled) and pil2gpu_fri_fold_dev with
+    nodes_out == NULL (rows only): the single-GPU pieces of the sharded query / FRI-layer path."""
+    import ctypes
+    from pil2_stark_js_b200._lib import vp, check
+    L = ctx._L
+    w, h = 24, 512
+    elems = rnd_field(4, w * h)
+    tree = ctx.tree_from_host(elems, w, h)
+    nodes = C.merkelize(elems, w, h)
+    idx = np.array([3, 0xFFFFFFFFFFFFFFFF, 511, 700], dtype=np.uint64)
+    d_idx, d_rows, d_sib = ctx.upload(idx), ctx.alloc(4 * w), ctx.alloc(4 * 9 * 4)
+    check(L.pil2gpu_tree_group_proofs_dev(ctx.handle, tree._h, d_idx.ptr, 4, d_rows.ptr, d_sib.ptr))
+    rows, sib = d_rows.download().reshape(4, w), d_sib.download().reshape(4, 9, 4)
+    for k, i in enumerate(idx):
+        if i >= h:
+            assert not rows[k].any() and not sib[k].any()
+        else:
+            r, sb = C.group_proof(elems, nodes, w, h, int(i))
+            assert np.array_equal(rows[k], r) and np.array_equal(sib[k].reshape(-1), np.asarray(sb, dtype=np.uint64).reshape(-1))
+    # rows-only fold: step 0 of a chain 2^10 -> 2^6
+    pol = rnd_field(8, 3 << 10)
+    ch = np.array([3, 5, 7], dtype=np.uint64)
+    d_pol, d_rows2 = ctx.upload(pol), ctx.alloc(3 << 10)
+    check(L.pil2gpu_fri_fold_dev(ctx.handle, d_pol.ptr, 10, 10, 6, 10, vp(ch.ctypes.data), 0, d_pol.ptr, d_rows2.ptr, None))
+    want = np.ascontiguousarray(pol.reshape(16, 64, 3).transpose(1, 0, 2)).reshape(-1)
+    assert np.array_equal(d_rows2.download(), want)
+    assert np.array_equal(d_pol.download(), pol)
+    for b in (d_idx, d_rows, d_sib, d_pol, d_rows2):
+        b.free()
 
 
 # ---------------------------------------------------------------- full-size properties (sizes the oracle cannot sweep)

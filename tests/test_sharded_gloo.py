@@ -32,6 +32,26 @@ class OracleEngine:
         full = np.ascontiguousarray(t.transpose(1, 0, 2)).reshape(-1)
         self._u(nodes)[:] = C.merkelize(full, n_tiles * tile_cols, rows, split, threads=1)
 
+    def merkelize(self, elems, width, height, nodes):
+        self._u(nodes)[:C.merkle_nnodes(height)] = C.merkelize(self._u(elems)[:width * height].copy(), width, height, threads=1)
+
+    def group_proofs(self, tiles, n_tiles, tile_cols, rows, nodes, idxs, n_idx, rows_out, sib_out):
+        width = n_tiles * tile_cols
+        t = self._u(tiles)[:n_tiles * rows * tile_cols].reshape(n_tiles, rows, tile_cols)
+        full = np.ascontiguousarray(t.transpose(1, 0, 2)).reshape(-1)
+        depth = max(rows.bit_length() - 1, 0)
+        ro, so = self._u(rows_out), self._u(sib_out)
+        nd = self._u(nodes)[:C.merkle_nnodes(rows)].copy()
+        for q in range(n_idx):
+            i = int(self._u(idxs)[q])
+            if i >= rows:
+                ro[q * width:(q + 1) * width] = 0
+                so[q * depth * 4:(q + 1) * depth * 4] = 0
+            else:
+                r, sb = C.group_proof(full, nd, width, rows, i)
+                ro[q * width:(q + 1) * width] = r
+                so[q * depth * 4:(q + 1) * depth * 4] = np.asarray(sb, dtype=np.uint64).reshape(-1)
+
     def tree_from_digests(self, nodes, height):
         d = self._u(nodes)[:4 * height].copy()
         self._u(nodes)[:C.merkle_nnodes(height)] = C.merkelize(d, 4, height, threads=1)   # width 4 = passthrough leaves
@@ -71,6 +91,16 @@ def _worker(rank, world, port, n_bits, blow, cols, split, q, peer=False):
         slab = torch.from_numpy(np.ascontiguousarray(full[:, rank * cg:(rank + 1) * cg]).reshape(-1).view(np.int64))
         buf = sc.buffers(cols, n_bits, n_bits + blow)
         root = sc.commit(slab, cols, n_bits, n_bits + blow, buf, split)
+        # proofQueries over the sharded tree: rows + siblings of the full-height tree, on every rank
+        qs = [0, 1, (1 << (n_bits + blow)) - 1, (1 << (n_bits + blow)) // world, 37 % (1 << (n_bits + blow)), 5]
+        rows_q, sib_q = buf["tree"].open(torch.tensor(qs, dtype=torch.int64))
+        # a layer tree over rows every rank holds in full (FRI layers)
+        lw, lh = 6, 1 << (n_bits - 1)
+        layer = torch.from_numpy(rng.integers(0, 0xFFFFFFFF00000001, size=lw * lh, dtype=np.uint64).view(np.int64))
+        lt, lroot = sc.commit_rows(layer, lw, lh, eng.empty(eng.nnodes(lh // world)), eng.empty(4 * world), eng.empty(max(8, eng.nnodes(world))))
+        lrows, lsib = lt.open(torch.tensor([0, lh - 1, lh // 2], dtype=torch.int64))
+        extra = (qs, rows_q.numpy().view(np.uint64).copy(), sib_q.numpy().view(np.uint64).copy(), layer.numpy().view(np.uint64).copy(),
+                 lroot.numpy().view(np.uint64).copy(), lrows.numpy().view(np.uint64).copy(), lsib.numpy().view(np.uint64).copy())
         if peer:
             assert eng.scatter_calls == 1 and "peer stores" in sc.exchange_kind(buf)
             root = sc.commit(slab, cols, n_bits, n_bits + blow, buf, split)      # buffers are reusable
@@ -78,7 +108,7 @@ def _worker(rank, world, port, n_bits, blow, cols, split, q, peer=False):
         else:
             assert "NCCL" in sc.exchange_kind(buf)
         q.put((rank, root.numpy().view(np.uint64).copy(), buf["nodes"].numpy().view(np.uint64).copy(),
-               buf["top"].numpy().view(np.uint64).copy()))
+               buf["top"].numpy().view(np.uint64).copy(), extra))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -109,8 +139,20 @@ def test_sharded_commit_matches_single_process(world, split, peer):
     full = rng.integers(0, 0xFFFFFFFF00000001, size=(1 << n_bits, cols), dtype=np.uint64)
     ext = C.lde(full.reshape(-1), cols, n_bits, n_bits + blow)
     nodes = C.merkelize(ext, cols, 1 << (n_bits + blow), split)
-    for _, root, _, _ in res:
+    E = 1 << (n_bits + blow)
+    for _, root, _, _, extra in res:
         assert np.array_equal(root, nodes[-4:])
+        qs, rows_q, sib_q, layer, lroot, lrows, lsib = extra
+        for k, qi in enumerate(qs):
+            r, sb = C.group_proof(ext, nodes, cols, E, qi)
+            assert np.array_equal(rows_q[k], r) and np.array_equal(sib_q[k].reshape(-1), np.asarray(sb, dtype=np.uint64).reshape(-1)), f"query {qi}"
+        if not split:
+            lw, lh = 6, 1 << (n_bits - 1)
+            lnodes = C.merkelize(layer, lw, lh)
+            assert np.array_equal(lroot, lnodes[-4:])
+            for k, qi in enumerate([0, lh - 1, lh // 2]):
+                r, sb = C.group_proof(layer, lnodes, lw, lh, qi)
+                assert np.array_equal(lrows[k], r) and np.array_equal(lsib[k].reshape(-1), np.asarray(sb, dtype=np.uint64).reshape(-1))
     rows_local = (1 << (n_bits + blow)) // world
     stitched = assemble_nodes([r[2] for r in res], res[0][3], rows_local, world, C.merkle_nnodes)
     assert np.array_equal(stitched, nodes)

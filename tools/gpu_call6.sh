@@ -1,0 +1,15 @@
+#!/bin/bash
+set -x
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/c6_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/c6_pytest.log
+tail -25 gpurun_out/c6_pytest.log
+NG=2
+for mode in peer; do
+  PIL2GPU_EXCHANGE=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
+     bench.py --gpus $NG --steps 5 --warmup 3 > gpurun_out/c6_bench_${NG}_$mode.json 2> gpurun_out/c6_bench_${NG}_$mode.err
+  echo "bench $mode exit $?"
+  tail -5 gpurun_out/c6_bench_${NG}_$mode.err
+  grep '^{' gpurun_out/c6_bench_${NG}_$mode.json | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print(d["n_gpus"], d["value"], d["e2e"]["value"], d["exchange"], d["root"], d["gpu_launches"])'
+done
