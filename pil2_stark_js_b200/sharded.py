@@ -466,7 +466,8 @@ def bench_main(args, rank, world, local_rank, dist, bench):
             mark("fri down")
             torch.cuda.synchronize()
             if trace:
-                print(f"[pil2gpu] rank {rank} e2e: " + ", ".join(f"{n} {marks[0][1].elapsed_time(ev):.1f} ms" for n, ev in marks[1:]), flush=True)
+                import sys as _sys
+                print(f"[pil2gpu] rank {rank} e2e: " + ", ".join(f"{n} {marks[0][1].elapsed_time(ev):.1f} ms" for n, ev in marks[1:]), file=_sys.stderr, flush=True)
 
         e2e_step()
         n_e2e = max(1, min(args.steps, 3))
