@@ -3,7 +3,7 @@
  *
  * Drop-in boundary for the three JavaScript modules of pil2-stark-js that make up the STARK commit phase.  Every
  * entry point names the reference interface it replaces (paths relative to the reference repo root); the N-API
- * addon (napi/pil2gpu_addon.cc), the JS shims (js/*.js) and the Python mirror (pil2_stark_js_b200/) all bind
+ * addon (napi/pil2gpu_addon.cc), the JS shims (js/ *.js) and the Python mirror (pil2_stark_js_b200/) all bind
  * exactly these symbols.
  *
  * Conventions
@@ -121,13 +121,20 @@ typedef struct pil2gpu_eval_desc {
  * vectors back to back (n_lev x 2^nBits x 3).  evals_out is a HOST array of n_evals x 3 words; the call synchronises. */
 int pil2gpu_compute_evals_dev(pil2gpu_ctx* ctx, const uint64_t* buf_dev, uint64_t size, uint32_t nBits, uint32_t nBitsExt,
                               const pil2gpu_eval_desc* desc, uint32_t n_evals, const uint64_t* lev_dev, uint32_t n_lev, uint64_t* evals_out);
+/* Host-buffer form of the whole of computeEvalsStark's arithmetic for one extended buffer `buf` (2^nBitsExt rows of `size`
+ * words, host): builds the LEv vectors of all opening points and uploads only the 2^nBits rows the loop reads (:252-259). */
+int pil2gpu_compute_evals(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
+                          uint32_t nBitsExt, const uint64_t* buf, uint64_t size, const pil2gpu_eval_desc* desc, uint32_t n_evals,
+                          uint64_t* evals_out);
 /* xDivXSubXi_ext of computeFRIStark (:289-323): out_dev[3 * (k * n_open + i) ..] = x_k / (x_k - xi_challenge * w_n^openings[i]),
  * x_k = 7 * w_ext^k, k < 2^nBitsExt.  (A point where x_k equals the shifted challenge makes the reference throw
  * "Division by zero"; here the affected words are unspecified.) */
 int pil2gpu_x_div_x_sub_xi_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
                                uint32_t nBitsExt, uint64_t* out_dev);
+int pil2gpu_x_div_x_sub_xi(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
+                           uint32_t nBitsExt, uint64_t* out);
 
-/* ---- hashing: src/helpers/hash/poseidon/poseidon.js, linearhash/*.js -------------------------------------- */
+/* ---- hashing: src/helpers/hash/poseidon/poseidon.js, linearhash/ *.js -------------------------------------- */
 /* poseidon(inputs[8], capacity[4], nOuts) poseidon.js:57-108: full 12-word permutation of in12 = inputs || capacity. */
 int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[12]);
 /* LinearHash.hash linearhash.js:8-42 (split == 0) / LinearHashGPU.hash linearhash_gpu.js:31-67 (split != 0). */

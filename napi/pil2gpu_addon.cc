@@ -116,6 +116,57 @@ static napi_value FriFold(napi_env env, napi_callback_info info) {
     return nullptr;
 }
 
+// ---- prover-side callers (src/stark/stark_gen_helpers.js) ----
+// extendAndMerkelize(ctx, src, nPols, nBits, nBitsExt, split, dst, nodes) -> root BigUint64Array(4)   (:388-412; flat typed arrays)
+static napi_value ExtendAndMerkelize(napi_env env, napi_callback_info info) {
+    size_t argc = 8; napi_value a[8]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    uint64_t *src, *dst = nullptr, *nodes = nullptr, root[4]; size_t l;
+    if (!get_u64_array(env, a[1], &src, &l)) { napi_throw_type_error(env, nullptr, "expected BigUint64Array"); return nullptr; }
+    get_u64_array(env, a[6], &dst, &l);      // null: keep the extended buffer off the host
+    get_u64_array(env, a[7], &nodes, &l);
+    if (pil2gpu_extend_and_merkelize(get_ctx(env, a[0]), src, u64_of(env, a[2]), u32_of(env, a[3]), u32_of(env, a[4]), i32_of(env, a[5]), dst, nodes,
+                                     root)) return fail(env);
+    return make_u64_array(env, root, 4);
+}
+// computeQ(ctx, qExt, qDim, qDeg, nBits, nBitsExt, split, cmqExt, nodes) -> root   (computeQStark :168-208)
+static napi_value ComputeQ(napi_env env, napi_callback_info info) {
+    size_t argc = 9; napi_value a[9]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    uint64_t *q, *ext = nullptr, *nodes = nullptr, root[4]; size_t l;
+    if (!get_u64_array(env, a[1], &q, &l)) { napi_throw_type_error(env, nullptr, "expected BigUint64Array"); return nullptr; }
+    get_u64_array(env, a[7], &ext, &l);
+    get_u64_array(env, a[8], &nodes, &l);
+    if (pil2gpu_compute_q(get_ctx(env, a[0]), q, u64_of(env, a[2]), u64_of(env, a[3]), u32_of(env, a[4]), u32_of(env, a[5]), i32_of(env, a[6]), ext,
+                          nodes, root)) return fail(env);
+    return make_u64_array(env, root, 4);
+}
+// computeEvals(ctx, xi(3), openings Int32Array, nBits, nBitsExt, buf, size, descs BigUint64Array(2*n: offset, dim | lev << 32)) -> BigUint64Array(3n)
+static napi_value ComputeEvals(napi_env env, napi_callback_info info) {
+    size_t argc = 8; napi_value a[8]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    uint64_t *xi, *buf, *d; size_t l, nd; int32_t* op; size_t nop; napi_typedarray_type ty; napi_value ab; size_t off;
+    if (!get_u64_array(env, a[1], &xi, &l) || l != 3 || !get_u64_array(env, a[5], &buf, &l) || !get_u64_array(env, a[7], &d, &nd) ||
+        napi_get_typedarray_info(env, a[2], &ty, &nop, (void**)&op, &ab, &off) != napi_ok || ty != napi_int32_array) {
+        napi_throw_type_error(env, nullptr, "bad argument types"); return nullptr;
+    }
+    const uint32_t n = (uint32_t)(nd / 2);
+    std::vector<pil2gpu_eval_desc> desc(n);
+    for (uint32_t i = 0; i < n; i++) { desc[i].offset = d[2 * i]; desc[i].dim = (uint32_t)d[2 * i + 1]; desc[i].lev = (uint32_t)(d[2 * i + 1] >> 32); }
+    std::vector<uint64_t> out((size_t)3 * n);
+    if (pil2gpu_compute_evals(get_ctx(env, a[0]), xi, op, (uint32_t)nop, u32_of(env, a[3]), u32_of(env, a[4]), buf, u64_of(env, a[6]), desc.data(), n,
+                              out.data())) return fail(env);
+    return make_u64_array(env, out.data(), out.size());
+}
+// xDivXSubXi(ctx, xi(3), openings Int32Array, nBits, nBitsExt, out)   (computeFRIStark :289-323)
+static napi_value XDivXSubXi(napi_env env, napi_callback_info info) {
+    size_t argc = 6; napi_value a[6]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    uint64_t *xi, *out; size_t l; int32_t* op; size_t nop; napi_typedarray_type ty; napi_value ab; size_t off;
+    if (!get_u64_array(env, a[1], &xi, &l) || l != 3 || !get_u64_array(env, a[5], &out, &l) ||
+        napi_get_typedarray_info(env, a[2], &ty, &nop, (void**)&op, &ab, &off) != napi_ok || ty != napi_int32_array) {
+        napi_throw_type_error(env, nullptr, "bad argument types"); return nullptr;
+    }
+    if (pil2gpu_x_div_x_sub_xi(get_ctx(env, a[0]), xi, op, (uint32_t)nop, u32_of(env, a[3]), u32_of(env, a[4]), out)) return fail(env);
+    return nullptr;
+}
+
 static napi_value Init(napi_env env, napi_value exports) {
     const napi_property_descriptor props[] = {
         {"create", nullptr, Create, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -126,6 +177,10 @@ static napi_value Init(napi_env env, napi_value exports) {
         {"poseidon", nullptr, Poseidon, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"linearHash", nullptr, LinearHash, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"friFold", nullptr, FriFold, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"extendAndMerkelize", nullptr, ExtendAndMerkelize, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"computeQ", nullptr, ComputeQ, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"computeEvals", nullptr, ComputeEvals, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"xDivXSubXi", nullptr, XDivXSubXi, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
     return exports;

@@ -60,6 +60,8 @@ _SIGS = {
     "pil2gpu_compute_lev_dev": (c_int, [vp, vp, c_i32, c_u32, vp]),
     "pil2gpu_compute_evals_dev": (c_int, [vp, vp, c_u64, c_u32, c_u32, vp, c_u32, vp, c_u32, vp]),
     "pil2gpu_x_div_x_sub_xi_dev": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp]),
+    "pil2gpu_compute_evals": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp, c_u64, vp, c_u32, vp]),
+    "pil2gpu_x_div_x_sub_xi": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp]),
     "pil2gpu_poseidon": (c_int, [vp, vp, vp]),
     "pil2gpu_linear_hash": (c_int, [vp, vp, c_u64, c_int, vp]),
     "pil2gpu_merkle_nnodes": (c_u64, [c_u64]),

@@ -163,6 +163,29 @@ class Context:
         check(self._L.pil2gpu_compute_evals_dev(self.handle, bp, size, n_bits, n_bits_ext, desc, n, levs.ptr, n_lev, _ptr(out)))
         return out
 
+    def compute_evals_host(self, xi_challenge, openings, n_bits, n_bits_ext, buf, size, ev_descs):
+        """computeEvalsStark's arithmetic (:216-267) for one HOST extended buffer: LEv vectors + evaluation sums; only the
+        2^n_bits rows the loop reads are uploaded.  ev_descs: list of (offset, dim, opening index).  Returns (n, 3) uint64."""
+        _as_u64(buf, "buffer")
+        if buf.size != size << n_bits_ext:
+            raise ValueError("buffer size does not match size * 2^nBitsExt")
+        xi = np.ascontiguousarray(xi_challenge, dtype=np.uint64).reshape(-1)
+        n = len(ev_descs)
+        out = np.empty((n, 3), dtype=np.uint64)
+        if n == 0:
+            return out
+        op = (ctypes.c_int32 * len(openings))(*[int(o) for o in openings])
+        desc = (_lib.EvalDesc * n)(*[_lib.EvalDesc(int(o), int(d), int(l)) for o, d, l in ev_descs])
+        check(self._L.pil2gpu_compute_evals(self.handle, _ptr(xi), op, len(openings), n_bits, n_bits_ext, _ptr(buf), size, desc, n, _ptr(out)))
+        return out
+
+    def x_div_x_sub_xi_host(self, xi_challenge, openings, n_bits, n_bits_ext):
+        xi = np.ascontiguousarray(xi_challenge, dtype=np.uint64).reshape(-1)
+        op = (ctypes.c_int32 * len(openings))(*[int(o) for o in openings])
+        out = np.empty(3 * len(openings) << n_bits_ext, dtype=np.uint64)
+        check(self._L.pil2gpu_x_div_x_sub_xi(self.handle, _ptr(xi), op, len(openings), n_bits, n_bits_ext, _ptr(out)))
+        return out.reshape(-1, len(openings), 3)
+
     def x_div_x_sub_xi(self, xi_challenge, openings, n_bits, n_bits_ext, download=True):
         """xDivXSubXi_ext of computeFRIStark (:289-323): (2^n_bits_ext, nOpenings, 3) array (or the DeviceBuffer)."""
         xi = np.ascontiguousarray(xi_challenge, dtype=np.uint64).reshape(-1)

@@ -561,6 +561,43 @@ int pil2gpu_x_div_x_sub_xi_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3],
     return check_launch(ctx, 1, "x_div_x_sub_xi");
 }
 
+// Host-buffer forms (what the JS shims call): only the 2^nBits base rows of the extended buffer travel over PCIe.
+int pil2gpu_compute_evals(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
+                          uint32_t nBitsExt, const uint64_t* buf, uint64_t size, const pil2gpu_eval_desc* desc, uint32_t n_evals,
+                          uint64_t* evals_out) {
+    ENTER(ctx);
+    if (n_evals == 0) return PIL2GPU_OK;
+    if (!xi_challenge || !openings || !buf || !desc || !evals_out || n_open == 0) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nBitsExt > 32 || nBitsExt < nBits || size == 0) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    const u64 N = 1ULL << nBits;
+    int rc = ensure_ws(ctx, ev2(N * size) + (size_t)n_open * N * 3);
+    if (rc) return rc;
+    u64 *rows = ctx->ws, *lev = ctx->ws + ev2(N * size);
+    // rows k << extendBits of the extended buffer, compacted (stark_gen_helpers.js:252-259 reads nothing else)
+    CU(cudaMemcpy2DAsync(rows, size * 8, buf, (size << (nBitsExt - nBits)) * 8, size * 8, N, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t i = 0; i < n_open; i++) {
+        rc = pil2gpu_compute_lev_dev(ctx, xi_challenge, openings[i], nBits, lev + (size_t)i * N * 3);
+        if (rc) return rc;
+    }
+    return pil2gpu_compute_evals_dev(ctx, rows, size, nBits, nBits, desc, n_evals, lev, n_open, evals_out);
+}
+
+int pil2gpu_x_div_x_sub_xi(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
+                           uint32_t nBitsExt, uint64_t* out) {
+    ENTER(ctx);
+    if (n_open == 0) return PIL2GPU_OK;
+    if (!out) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nBitsExt > 32) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    const size_t words = ((size_t)3 * n_open) << nBitsExt;
+    int rc = ensure_ws(ctx, words);
+    if (rc) return rc;
+    rc = pil2gpu_x_div_x_sub_xi_dev(ctx, xi_challenge, openings, n_open, nBits, nBitsExt, ctx->ws);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, ctx->ws, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
 // Gather a paged host buffer into device memory / scatter back (async on the ctx stream).
 static int pages_to_dev(pil2gpu_ctx* ctx, u64* dev, const uint64_t* const* pages, const uint64_t* page_words, uint32_t n_pages, size_t expect) {
     size_t off = 0;

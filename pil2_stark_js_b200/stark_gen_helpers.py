@@ -79,25 +79,24 @@ def computeEvalsStark(ctx, options=None):
     evals_stage = ctx.pilInfo["nStages"] + 1
     xi = ctx.challenges[evals_stage][0]
     openings = [int(o) for o in ctx.pilInfo["openingPoints"]]
-    levs = g.compute_levs(xi, openings, ctx.nBits)
     ev_map = ctx.pilInfo["evMap"]
     by_buffer = {}
     for i, ev in enumerate(ev_map):
         name, size, offset, dim = _pol_ref_ext(ctx, ev)
         by_buffer.setdefault((name, size), []).append((i, offset, dim, openings.index(int(ev["prime"]))))
     out = [None] * len(ev_map)
-    dev = getattr(ctx, "dev_buffers", {})
+    dev = getattr(ctx, "dev_buffers", {})          # optional: name -> DeviceBuffer of extended buffers already in HBM
+    levs = g.compute_levs(xi, openings, ctx.nBits) if any(name in dev for name, _ in by_buffer) else None
     for (name, size), items in by_buffer.items():
-        buf = dev.get(name)
-        owned = buf is None
-        if owned:
-            buf = g.upload(getattr(ctx, name))
-        vals = g.compute_evals(buf, size, ctx.nBits, ctx.nBitsExt, [(o, d, l) for _, o, d, l in items], levs, len(openings))
+        descs = [(o, d, l) for _, o, d, l in items]
+        if name in dev:
+            vals = g.compute_evals(dev[name], size, ctx.nBits, ctx.nBitsExt, descs, levs, len(openings))
+        else:
+            vals = g.compute_evals_host(xi, openings, ctx.nBits, ctx.nBitsExt, getattr(ctx, name), size, descs)
         for (i, _, _, _), v in zip(items, vals):
             out[i] = [int(x) for x in v]
-        if owned:
-            buf.free()
-    levs.free()
+    if levs is not None:
+        levs.free()
     ctx.evals = out
     return ctx.evals
 
@@ -107,7 +106,7 @@ def computeXDivXSubXi(ctx, options=None):
     evals_stage = ctx.pilInfo["nStages"] + 1
     xi = ctx.challenges[evals_stage][0]
     openings = [int(o) for o in ctx.pilInfo["openingPoints"]]
-    ctx.xDivXSubXi_ext = _gpu(ctx).x_div_x_sub_xi(xi, openings, ctx.nBits, ctx.nBitsExt).reshape(-1)
+    ctx.xDivXSubXi_ext = _gpu(ctx).x_div_x_sub_xi_host(xi, openings, ctx.nBits, ctx.nBitsExt).reshape(-1)
     return ctx.xDivXSubXi_ext
 
 

@@ -56,3 +56,25 @@ def test_product_does_not_import_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         txt = f.read_text()
         assert "oracle" not in txt.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_addon_type_checks():
+    """include/pil2gpu.h must compile as C (the boundary is a C ABI), and the N-API addon must type-check against it
+    (Node.js is absent from this image: tests/stubs/node_api.h declares the N-API functions the addon uses)."""
+    import subprocess
+    hdr = ROOT / "include" / "pil2gpu.h"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", str(hdr)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", str(ROOT / "tests" / "stubs"),
+                        str(ROOT / "napi" / "pil2gpu_addon.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_js_shims_bind_only_exported_addon_functions():
+    """Every addon.<name> used by js/*.js is registered by the addon's Init table."""
+    addon_src = (ROOT / "napi" / "pil2gpu_addon.cc").read_text()
+    registered = set(re.findall(r'\{"([A-Za-z0-9]+)", nullptr,', addon_src))
+    used = set()
+    for f in (ROOT / "js").glob("*.js"):
+        used |= set(re.findall(r"\baddon\.([A-Za-z0-9]+)\(", f.read_text()))
+    assert used and used <= registered, f"js uses unregistered addon functions: {sorted(used - registered)}"
