@@ -454,12 +454,14 @@ def bench_main(args, rank, world, local_rank, dist, bench):
                 mark("commit")
                 out_host.copy_(ext_dev, non_blocking=True)
                 mark("rows down")
-            nodes_host.copy_(buf["nodes"], non_blocking=True)
-            mark("nodes down")
+            # the FRI chain first: its kernels overlap the row download, whereas a device->host copy issued here would queue
+            # behind those 32/G GiB on the copy engine and hold the chain back
             if shard_l0 or rank == 0:
                 fri["pol0"].copy_(fri_host["pol0"], non_blocking=True)
             fri_chain()
             mark("fri")
+            nodes_host.copy_(buf["nodes"], non_blocking=True)
+            mark("nodes down")
             for d, h in zip(fri_down, fri_host["down"]):
                 h.copy_(d, non_blocking=True)
             root_host.copy_(root, non_blocking=True)

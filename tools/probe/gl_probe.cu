@@ -8,6 +8,7 @@
 #include "poseidon_mont.cuh"
 #include "poseidon_fp64.cuh"
 #include "poseidon_z.cuh"
+#include "poseidon_lr.cuh"
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
@@ -22,6 +23,7 @@ __device__ __forceinline__ void permute_mont_var(u64 x[12]) {
     if (VAR == 1) poseidon_permute_lanes64(x);
     if (VAR == 2) poseidon_permute_fp64(x);
     if (VAR == 3) poseidon_permute_mont_z(x);
+    if (VAR == 4) poseidon_permute_mont_lr(x);
 }
 
 template <int VAR>
@@ -139,10 +141,11 @@ int main() {
         for (int lazy = 0; lazy < 2; lazy++) {
             k_check<0><<<blocks, threads>>>(o0, 777 + lazy, lazy); CK(cudaDeviceSynchronize());
             CK(cudaMemcpy(h0, o0, n * 96, cudaMemcpyDeviceToHost));
-            for (int var = 1; var <= 3; var++) {
+            for (int var = 1; var <= 4; var++) {
                 if (var == 1) k_check<1><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 if (var == 2) k_check<2><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 if (var == 3) k_check<3><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 4) k_check<4><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 CK(cudaDeviceSynchronize());
                 CK(cudaMemcpy(h1, o1, n * 96, cudaMemcpyDeviceToHost));
                 long bad = 0;
@@ -151,8 +154,8 @@ int main() {
             }
         }
     }
-    const char* pn[4] = {"shipped (mont, 3 limbs)", "64-bit lanes", "FP64-pipe MDS", "3 limbs, adds forced to IADD3"};
-    for (int var = 0; var < 4; var++) {
+    const char* pn[5] = {"shipped (mont, 3 limbs)", "64-bit lanes", "FP64-pipe MDS", "3 limbs, adds forced to IADD3", "limb-resident partial rounds"};
+    for (int var = 0; var < 5; var++) {
         float best = 1e30f; int iters = 64;
         for (int rep = 0; rep < 3; rep++) {
             CK(cudaEventRecord(e0));
@@ -160,6 +163,7 @@ int main() {
             if (var == 1) k_chain<1><<<blocks, threads>>>(o0, iters);
             if (var == 2) k_chain<2><<<blocks, threads>>>(o0, iters);
             if (var == 3) k_chain<3><<<blocks, threads>>>(o0, iters);
+            if (var == 4) k_chain<4><<<blocks, threads>>>(o0, iters);
             CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
         }
