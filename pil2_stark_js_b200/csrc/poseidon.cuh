@@ -34,7 +34,8 @@ GL_D u64 poseidon_sbox(u64 x) {
 //     (k_lo - k_hi)/2 = [2,-4,16,1,-1,-1]                            (negacyclic 6)
 // so one MDS on a vector of small integers is ~76 shift-adds, which ptxas spreads over the alu pipe (IADD3/LEA) and the
 // fmaheavy pipe (IMAD.IADD / IMAD with a power-of-two immediate).  Each state word is cut into three limbs of 22/22/20
-// bits; limb sums stay below 264 * 2^22 + 2^22 < 2^31, so plain wrap-around u32 arithmetic is exact.  The round constant of
+// bits (up to 2^23 after a limb-form re-normalisation, poseidon_renorm); limb sums stay below 264 * 2^23 + 2^22 < 2^32, so plain
+// wrap-around u32 arithmetic is exact.  The round constant of
 // the NEXT round rides on the last butterfly as the third operand of an IADD3.
 // Alternatives measured on B200 (tools/probe/gl_probe.cu, Gperm/s): this 1.26; two 64-bit lanes with carries 1.20; adds
 // forced onto the fmaheavy pipe 1.20; the same CRT on the FP64 pipe (exact, DFMA/DADD) 1.22; previous non-Montgomery 1.11.
@@ -82,7 +83,7 @@ GL_D void poseidon_mds_limb(u32 y[12], const u32 x[12], const u32* __restrict__ 
     y[0] += 8 * x[0];
 }
 
-// limbs -> field element: Y0 + Y1*2^22 + Y2*2^44 (Y < 2^32 each) mod p, with 2^64 = EPS.  3 IMAD.WIDE + 5 ALU.
+// limbs -> field element: Y0 + Y1*2^22 + Y2*2^44 (any u32 limbs) mod p, with 2^64 = EPS.  3 IMAD.WIDE + 5 ALU.
 GL_D u64 poseidon_join(u32 Y0, u32 Y1, u32 Y2) {
     const u64 v = (u64)Y1 * (1u << 22) + Y0;             // < 2^55
     const u64 w = (u64)Y2 * (1u << 12);                  // Y2 * 2^44 = w * 2^32, w < 2^44
@@ -103,44 +104,65 @@ GL_D u64 poseidon_join(u32 Y0, u32 Y1, u32 Y2) {
     return ((u64)r1 << 32) | r0;
 }
 
-// MDS over the whole state + limb-wise addition of the NEXT round's constants (rc_limbs: [lane][limb]).
-GL_D void poseidon_mds(u64 x[12], const u32* __restrict__ rc_limbs) {
-    u32 a[12], b[12], c[12];
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-        const u32 lo = (u32)x[j], hi = (u32)(x[j] >> 32);
-        a[j] = lo & 0x3FFFFFu;
-        b[j] = __funnelshift_r(lo, hi, 22) & 0x3FFFFFu;
-        c[j] = hi >> 12;
-    }
-    u32 ya[12], yb[12], yc[12];
-    poseidon_mds_limb(ya, a, rc_limbs);
-    poseidon_mds_limb(yb, b, rc_limbs + 1);
-    poseidon_mds_limb(yc, c, rc_limbs + 2);
-#pragma unroll
-    for (int i = 0; i < 12; i++) x[i] = poseidon_join(ya[i], yb[i], yc[i]);
+// u64 -> limbs (22/22/20 bits).  4 ALU.
+GL_D void poseidon_split(u64 x, u32& a, u32& b, u32& c) {
+    const u32 lo = (u32)x, hi = (u32)(x >> 32);
+    a = lo & 0x3FFFFFu;
+    b = __funnelshift_r(lo, hi, 22) & 0x3FFFFFu;
+    c = hi >> 12;
 }
 
-// Montgomery-form constants of round r+1 pre-split into limbs, added after the MDS of round r (row 29 = 0): one code
-// path for all rounds.
+// Carry re-normalisation of a lane that stays in limb form across a partial round: MDS outputs (Y0 < 2^31, Y1 < 2^32 - 2^10,
+// Y2 < 2^31) -> limbs of the same value + 2^12 (mod p) with a in (0, 2^22 + 2^12], b < 2^23, c < 2^20, small enough for the
+// next MDS to stay below 2^32 per limb (264 * 2^23 + 2^22 < 2^32).  The top carry folds with 2^64 = 2^32 - 1: + top * 2^10 on
+// limb b, - top on limb a; the + 2^12 keeps limb a positive and its image under the MDS is already taken out of the round
+// constants (POSEIDON_RC_LIMBS_PARTIAL).  8 ALU-pipe instructions, against join (3 IMAD.WIDE + 5) + split (4).
+GL_D void poseidon_renorm(u32 Y0, u32 Y1, u32 Y2, u32& a, u32& b, u32& c) {
+    const u32 t1 = Y1 + (Y0 >> 22);
+    const u32 t2 = Y2 + (t1 >> 22);
+    const u32 top = t2 >> 20;
+    a = (Y0 & 0x3FFFFFu) - top + 4096u;
+    b = (t1 & 0x3FFFFFu) + (top << 10);
+    c = t2 & 0xFFFFFu;
+}
+
+// Montgomery-form constants of round r+1 pre-split into limbs, added after the MDS of round r (row 29 = 0), and the
+// bias-compensated rows used after the MDS of the partial rounds 4..25 (see poseidon_renorm).
 __constant__ u32 POSEIDON_RC_LIMBS[30 * 36] = {
 #include "poseidon_rc_limbs.inc"
 };
+__constant__ u32 POSEIDON_RC_LIMBS_PARTIAL[22 * 36] = {
+#include "poseidon_rc_limbs_partial.inc"
+};
 
-// Permutation of a MONTGOMERY-FORM state (x * 2^64 mod p, any 64-bit representative in and out).  A single 30-iteration
-// loop keeps one copy of the S-box layer and one copy of the MDS in the instruction cache.
+// Permutation of a MONTGOMERY-FORM state (x * 2^64 mod p, any 64-bit representative in and out).
+// The state crosses every round boundary as three limb planes -- the form the MDS works on.  A full round joins every lane
+// back to a u64 for the S-box and splits it again; a partial round does that for lane 0 only and re-normalises the other 11
+// lanes in limb form (measured, tools/probe: 1.260 -> 1.288 Gperm/s).  One 30-iteration loop keeps a single copy of the
+// S-box layer and of the MDS in the instruction cache.
 GL_D void poseidon_permute_mont(u64 x[12]) {
+    u32 ya[12], yb[12], yc[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) x[i] = gl_addc(x[i], POSEIDON_RC0[i]);
+    for (int i = 0; i < 12; i++) poseidon_split(gl_addc(x[i], POSEIDON_RC0[i]), ya[i], yb[i], yc[i]);
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
-        x[0] = poseidon_sbox(x[0]);
-        if (r < 4 || r >= 26) {
+        u32 a[12], b[12], c[12];
+        const bool full = (r < 4 || r >= 26);
+        poseidon_split(poseidon_sbox(poseidon_join(ya[0], yb[0], yc[0])), a[0], b[0], c[0]);
+        if (full) {
 #pragma unroll
-            for (int i = 1; i < 12; i++) x[i] = poseidon_sbox(x[i]);
+            for (int i = 1; i < 12; i++) poseidon_split(poseidon_sbox(poseidon_join(ya[i], yb[i], yc[i])), a[i], b[i], c[i]);
+        } else {
+#pragma unroll
+            for (int i = 1; i < 12; i++) poseidon_renorm(ya[i], yb[i], yc[i], a[i], b[i], c[i]);
         }
-        poseidon_mds(x, POSEIDON_RC_LIMBS + r * 36);
+        const u32* __restrict__ rc = full ? (POSEIDON_RC_LIMBS + r * 36) : (POSEIDON_RC_LIMBS_PARTIAL + (r - 4) * 36);
+        poseidon_mds_limb(ya, a, rc);
+        poseidon_mds_limb(yb, b, rc + 1);
+        poseidon_mds_limb(yc, c, rc + 2);
     }
+#pragma unroll
+    for (int i = 0; i < 12; i++) x[i] = poseidon_join(ya[i], yb[i], yc[i]);
 }
 
 // Permutation of a plain state; output canonical.  (Test hook / transcript: hashing kernels stay in Montgomery form.)

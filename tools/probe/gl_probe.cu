@@ -16,14 +16,14 @@ __device__ __forceinline__ u64 splitmix(u64 z) {
     z += 0x9E3779B97F4A7C15ULL; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31);
 }
 
-// VAR: 0 shipped, 1 64-bit lanes, 2 FP64-pipe MDS, 3 shipped with two-input adds forced to IADD3
+// VAR: 0 shipped, 1 64-bit lanes, 2 FP64-pipe MDS, 3 u64-state loop with two-input adds forced to IADD3, 4 previous shipped loop (u64 state)
 template <int VAR>
 __device__ __forceinline__ void permute_mont_var(u64 x[12]) {
     if (VAR == 0) poseidon_permute_mont(x);
     if (VAR == 1) poseidon_permute_lanes64(x);
     if (VAR == 2) poseidon_permute_fp64(x);
     if (VAR == 3) poseidon_permute_mont_z(x);
-    if (VAR == 4) poseidon_permute_mont_lr(x);
+    if (VAR == 4) poseidon_permute_mont_u64state(x);
 }
 
 template <int VAR>
@@ -154,7 +154,8 @@ int main() {
             }
         }
     }
-    const char* pn[5] = {"shipped (mont, 3 limbs)", "64-bit lanes", "FP64-pipe MDS", "3 limbs, adds forced to IADD3", "limb-resident partial rounds"};
+    const char* pn[5] = {"shipped (limb-resident partial rounds)", "64-bit lanes", "FP64-pipe MDS", "u64 state, adds forced to IADD3",
+                         "u64 state at every round (previous)"};
     for (int var = 0; var < 5; var++) {
         float best = 1e30f; int iters = 64;
         for (int rep = 0; rep < 3; rep++) {
