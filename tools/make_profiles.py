@@ -16,14 +16,15 @@ ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 names = [r[ki].split("(")[0].replace("void ", "") for r in data]
 t = [float(r[vi].replace(",", "")) for r in data]
 open(os.path.join(P, f"{rnd}_launches_cfg3.csv"), "w").write(open(src).read())
-starts = [i for i, n in enumerate(names) if n == "ntt_pass_kernel<1, 1>" and (i == 0 or names[i - 1] != "ntt_pass_kernel<1, 1>")]
+is_first = lambda n: n.startswith("ntt_pass_kernel<1, 1")          # first kernel of every LDE (DIF pass with inverse roots)
+starts = [i for i, n in enumerate(names) if is_first(n) and (i == 0 or not is_first(names[i - 1]))]
 s, e = starts[1], starts[2]          # warm-up step, TIMED step, then the per-phase re-runs
 agg = collections.OrderedDict()
 for n, x in zip(names[s:e], t[s:e]):
     a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += x
 tot = sum(a[1] for a in agg.values())
 plain = json.loads(open(os.path.join(G, f"{rnd}_plain_cfg3.log")).read().strip().splitlines()[-1])
-out = [f"# {rnd} - launch list of `python bench.py --workload cfg3 --steps 1 --warmup 1 --no-e2e --no-cpu` (1xB200)", "",
+out = [f"# {rnd} - launch list of `python bench.py --workload cfg3 --steps 1 --warmup 1 --no-e2e --no-cpu --no-extras` (1xB200)", "",
        f"Source: `profiles/{rnd}_launches_cfg3.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none`; per-launch times are",
        f"serialised and cold-cache: compare shares, not absolutes). Window = the timed step (launches {s}..{e - 1} of {len(data)}).", "",
        "| kernel | launches | total ms | share |", "|---|---|---|---|"]
@@ -71,6 +72,9 @@ table(f"{rnd}_prof_cfg3.ncu-rep", f"{rnd} - ncu --set full, cfg3 (2^23 x 256, bl
 table(f"{rnd}_prof_ntt_slab.ncu-rep", f"{rnd} - ncu --set full, one 32-column slab of cfg3 (pass structure 8/8/7)", f"{rnd}_ncu_ntt_slab.md")
 table(f"{rnd}_prof_leaf_cfg2.ncu-rep", f"{rnd} - ncu --set full, merkle_leaf_kernel at cfg2 (2^21 rows x 64 cols)", f"{rnd}_ncu_leaf_cfg2.md", "cfg2")
 if traffic:
-    json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    tp = os.path.join(P, "traffic.json")
+    old = json.load(open(tp)) if os.path.exists(tp) else {}
+    old.update(traffic)
+    json.dump(old, open(tp, "w"), indent=1)
 print(open(os.path.join(P, f"{rnd}_launches_cfg3.md")).read())
 print(json.dumps(traffic))
