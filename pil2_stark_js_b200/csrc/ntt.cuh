@@ -29,6 +29,12 @@
 #define NTT_W 16        // columns per tile (128 contiguous bytes per row segment)
 #define NTT_TMAX 9      // max log2(rows) per tile: 2^9 * 16 * 8 B = 64 KiB (+ twiddles) -> 3 CTAs / SM
 #define NTT_THREADS 256
+#ifndef NTT_PASS_MIN_CTAS
+#define NTT_PASS_MIN_CTAS 5
+#endif
+#ifndef NTT_FUSED_MIN_CTAS
+#define NTT_FUSED_MIN_CTAS 5
+#endif
 
 struct NttTables {
     const u64* bytepow;   // [4][256]: W32^(b << (8k)) * 2^64
@@ -358,7 +364,7 @@ __device__ __forceinline__ void ntt_tile_store(const ulonglong2* __restrict__ ti
 //   position(k) = (base_hi << (lo+t)) | (k << lo) | base_lo,   tile id = (base_hi << lo) | base_lo
 // gridDim.x = 2^(n-t) tiles, gridDim.y = ceil(C / NTT_W) column chunks, gridDim.z = cosets.
 template <bool DIF, bool INVERSE, bool SC = false>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __restrict__ in, u64* __restrict__ out, NttPass P, NttTables tb,
+__global__ void __launch_bounds__(NTT_THREADS, NTT_PASS_MIN_CTAS) ntt_pass_kernel(const u64* __restrict__ in, u64* __restrict__ out, NttPass P, NttTables tb,
                                                                const __grid_constant__ NttScatter sc) {
     extern __shared__ __align__(16) u64 ntt_smem[];
     const int t = P.t, lo = P.lo;
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const u64* __rest
 // 1/N, then for every coset r < B runs the first t DIT layers of the size-N forward NTT on 7 w_E^r <w_N> (coset folded into
 // the twiddles) and stores to row (B*q + r).  Input row = q*in_mul (src: in_mul = 1; dst: in_mul = B).
 template <bool SC>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_lde_fused_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 C, int n,
+__global__ void __launch_bounds__(NTT_THREADS, NTT_FUSED_MIN_CTAS) ntt_lde_fused_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 C, int n,
                                                                     int ext_bits, int t, u64 in_mul, u64 n_inv_mont, int canon_in,
                                                                     int canon_out, NttTables tb, const __grid_constant__ NttScatter sc) {
     extern __shared__ __align__(16) u64 ntt_smem[];
