@@ -184,6 +184,10 @@ int pil2gpu_bench_int_pipes(pil2gpu_ctx* ctx, double* mulmod_per_s, double* imad
 
 /* Wrap / build trees over existing data.  tree_from_host uploads elements and merkelizes them on the device. */
 int pil2gpu_tree_from_host(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, pil2gpu_tree** tree_out);
+/* A tree whose nodes are already known -- readFromFile (merklehash_p.js:249-278), the const tree of a setup -- goes to the
+ * device without re-hashing: allocate, then fill elements (which = 0) and nodes (which = 1) piecewise from host chunks. */
+int pil2gpu_tree_alloc(pil2gpu_ctx* ctx, uint64_t width, uint64_t height, pil2gpu_tree** tree_out);
+int pil2gpu_tree_fill(pil2gpu_ctx* ctx, pil2gpu_tree* t, int which, uint64_t offset_words, const uint64_t* src, uint64_t n_words);
 int pil2gpu_tree_width(const pil2gpu_tree* t, uint64_t* width, uint64_t* height);
 const uint64_t* pil2gpu_tree_elements_dev(const pil2gpu_tree* t);
 const uint64_t* pil2gpu_tree_nodes_dev(const pil2gpu_tree* t);

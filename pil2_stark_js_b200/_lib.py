@@ -79,6 +79,8 @@ _SIGS = {
     "pil2gpu_synth_dev": (c_int, [vp, vp, c_u64, c_u64, c_u64]),
     "pil2gpu_bench_int_pipes": (c_int, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "pil2gpu_tree_from_host": (c_int, [vp, vp, c_u64, c_u64, c_int, ctypes.POINTER(vp)]),
+    "pil2gpu_tree_alloc": (c_int, [vp, c_u64, c_u64, ctypes.POINTER(vp)]),
+    "pil2gpu_tree_fill": (c_int, [vp, vp, c_int, c_u64, vp, c_u64]),
     "pil2gpu_tree_width": (c_int, [vp, u64p, u64p]),
     "pil2gpu_tree_elements_dev": (vp, [vp]),
     "pil2gpu_tree_nodes_dev": (vp, [vp]),

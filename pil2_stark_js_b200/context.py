@@ -214,6 +214,12 @@ class Context:
                                          _ptr(root)))
         return DeviceTree(self, t), root
 
+    def tree_alloc(self, width, height):
+        """Empty device tree to be filled from a file (DeviceTree.fill)."""
+        t = vp()
+        check(self._L.pil2gpu_tree_alloc(self.handle, width, height, ctypes.byref(t)))
+        return DeviceTree(self, t)
+
     def tree_from_host(self, elems, width, height, split=False):
         _as_u64(elems, "buff")
         t = vp()
@@ -275,6 +281,11 @@ class DeviceTree:
         check(self.ctx._L.pil2gpu_tree_group_proofs(self.ctx.handle, self._h, _ptr(ia) if len(idxs) else None, len(idxs), _ptr(rows),
                                                     _ptr(sib)))
         return rows, sib
+
+    def fill(self, which, offset_words, chunk):
+        """Copy a host chunk into the elements (which = 0) or the nodes (which = 1) at a word offset."""
+        a = np.ascontiguousarray(chunk, dtype=np.uint64).reshape(-1)
+        check(self.ctx._L.pil2gpu_tree_fill(self.ctx.handle, self._h, int(which), int(offset_words), _ptr(a) if a.size else None, a.size))
 
     def download(self, elements=True, nodes=True):
         e = np.empty(self.width * self.height, dtype=np.uint64) if elements else None

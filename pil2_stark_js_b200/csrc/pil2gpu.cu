@@ -1062,6 +1062,38 @@ int pil2gpu_tree_from_host(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t wid
     return PIL2GPU_OK;
 }
 
+// A tree whose nodes are already known (read back from a const-tree file, merklehash_p.js:249-278): device allocation only.
+// The caller fills it piecewise with pil2gpu_tree_fill (so that a 30+ GiB file can stream through a small host buffer).
+int pil2gpu_tree_alloc(pil2gpu_ctx* ctx, uint64_t width, uint64_t height, pil2gpu_tree** tree_out) {
+    ENTER(ctx);
+    if (!tree_out || height == 0) return fail(PIL2GPU_E_INVALID, "bad tree description");
+    pil2gpu_tree* t = new_tree();
+    if (!t) return fail(PIL2GPU_E_NOMEM, "out of host memory");
+    t->width = width;
+    t->tile_cols = width ? width : 1;
+    t->height = height;
+    t->own_elems = t->own_nodes = true;
+    cudaError_t e = cudaMalloc(&t->elems, (width * height ? width * height : 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&t->nodes, merkle_nnodes_words(height) * 8);
+    if (e != cudaSuccess) { pil2gpu_tree_free(ctx, t); return fail(PIL2GPU_E_NOMEM, "device allocation failed: %s", cudaGetErrorString(e)); }
+    *tree_out = t;
+    return PIL2GPU_OK;
+}
+// which: 0 = elements, 1 = nodes; copies n_words host words to word offset `offset` of that array (synchronous).
+int pil2gpu_tree_fill(pil2gpu_ctx* ctx, pil2gpu_tree* t, int which, uint64_t offset, const uint64_t* src, uint64_t n_words) {
+    ENTER(ctx);
+    if (!t || (!src && n_words)) return fail(PIL2GPU_E_INVALID, "null argument");
+    const u64 cap = which == 0 ? t->width * t->height : merkle_nnodes_words(t->height);
+    if (which != 0 && which != 1) return fail(PIL2GPU_E_INVALID, "which must be 0 (elements) or 1 (nodes)");
+    if (offset > cap || n_words > cap - offset) return fail(PIL2GPU_E_RANGE, "fill of %llu words at %llu exceeds %llu", (unsigned long long)n_words,
+                                                            (unsigned long long)offset, (unsigned long long)cap);
+    if (n_words == 0) return PIL2GPU_OK;
+    u64* dst = (which == 0 ? t->elems : t->nodes) + offset;
+    CU(cudaMemcpyAsync(dst, src, n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
 int pil2gpu_tree_group_proofs(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uint64_t* idxs, uint32_t n_idx, uint64_t* rows_out,
                               uint64_t* siblings_out) {
     ENTER(ctx);

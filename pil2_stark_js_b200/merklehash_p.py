@@ -5,7 +5,7 @@ tree = {"elements": buff (the caller's array, aliased like the reference), "node
 import numpy as np
 
 from ._lib import OutOfRange, E_RANGE
-from .context import default_context
+from .context import default_context, DeviceTree
 
 P = 0xFFFFFFFF00000001
 
@@ -31,10 +31,16 @@ class MerkleHash:
 
     def getElement(self, tree, idx, subIdx):
         """merklehash_p.js:136-139."""
+        if isinstance(tree, DeviceTree):
+            return int(tree.group_proofs([idx])[0][0][subIdx])
         return int(tree["elements"][tree["width"] * idx + subIdx])
 
     def getGroupProof(self, tree, idx):
-        """merklehash_p.js:142-168: [row values, [4-word sibling per level]]."""
+        """merklehash_p.js:142-168: [row values, [4-word sibling per level]].  `tree` is the reference's tree object (host
+        arrays) or a DeviceTree (rows and siblings gathered on the GPU, only the proof crosses PCIe)."""
+        if isinstance(tree, DeviceTree):
+            rows, sib = tree.group_proofs([idx])            # raises OutOfRange like merklehash_p.js:143
+            return [[int(x) for x in rows[0]], [[int(x) for x in s] for s in sib[0]]]
         if idx < 0 or idx >= tree["height"]:
             raise OutOfRange(E_RANGE, "Out of range")
         w = tree["width"]
@@ -74,6 +80,8 @@ class MerkleHash:
 
     def root(self, tree):
         """merklehash_p.js:224-226."""
+        if isinstance(tree, DeviceTree):
+            return [int(x) for x in tree.root()]
         return [int(x) for x in tree["nodes"][-4:]]
 
     def writeToFile(self, tree, fileName):
@@ -82,6 +90,25 @@ class MerkleHash:
             np.array([tree["width"], tree["height"]], dtype="<u8").tofile(f)
             np.ascontiguousarray(tree["elements"], dtype="<u8").tofile(f)
             np.ascontiguousarray(tree["nodes"], dtype="<u8").tofile(f)
+
+    def readFromFileToDevice(self, fileName, chunk_words=1 << 25):
+        """readFromFile (merklehash_p.js:249-278) straight into a device-resident tree: the file streams through one host
+        chunk (the reference reads in 2^25-element chunks too, :262-276), nothing is re-hashed, and proofQueries over the
+        result only move the opened rows and siblings back (getGroupProof / root accept the returned DeviceTree)."""
+        with open(fileName, "rb") as f:
+            width, height = (int(x) for x in np.fromfile(f, dtype="<u8", count=2))
+            tree = self.ctx.tree_alloc(width, height)
+            for which, total in ((0, width * height), (1, self._getNNodes(height * 4))):
+                off = 0
+                while off < total:
+                    n = min(chunk_words, total - off)
+                    chunk = np.fromfile(f, dtype="<u8", count=n)
+                    if chunk.size != n:
+                        tree.free()
+                        raise ValueError("const tree file is truncated")
+                    tree.fill(which, off, chunk)
+                    off += n
+        return tree
 
     def readFromFile(self, fileName):
         """merklehash_p.js:249-278."""

@@ -250,3 +250,40 @@ def test_lde_scatter_from_host_virtual_ranks(ctx, n_bits, blow, cols, world):
         assert np.array_equal(got, want[h * rows_local:(h + 1) * rows_local]), f"rank {h} rows differ"
     for r in recv:
         r.free()
+
+
+# ---------------------------------------------------------------- const tree files -> device-resident trees
+def test_const_tree_file_to_device(ctx, tmp_path):
+    """buildConstTree (stark_buildConstTree.js:17-33) -> writeToFile -> readFromFileToDevice / `.cnts` with tree_to_device:
+    root and group proofs from the device handle equal the host tree's, and "Out of range" still throws."""
+    import pil2_stark_js_b200 as m
+    from pil2_stark_js_b200 import stark_consts_file as CF
+    n_bits, ext_bits, n_consts = 9, 10, 9
+    MH = m.buildMerkleHash(False, ctx)
+    const_n = rnd_field(3, n_consts << n_bits)
+    const_ext = np.empty(n_consts << ext_bits, dtype=np.uint64)
+    m.interpolate(const_n, n_consts, n_bits, const_ext, ext_bits, ctx=ctx)
+    tree = MH.merkelize(const_ext, n_consts, 1 << ext_bits)
+    assert np.array_equal(tree["nodes"], C.merkelize(C.lde(const_n, n_consts, n_bits, ext_bits), n_consts, 1 << ext_bits))
+    fn = tmp_path / "const.tree"
+    MH.writeToFile(tree, fn)
+    dev = MH.readFromFileToDevice(fn, chunk_words=1000)            # several chunks per array
+    assert MH.root(dev) == MH.root(tree)
+    for idx in (0, 1, 513, (1 << ext_bits) - 1):
+        assert MH.getGroupProof(dev, idx) == MH.getGroupProof(tree, idx)
+        assert MH.verifyGroupProof(MH.root(dev), MH.getGroupProof(dev, idx)[1], idx, MH.getGroupProof(dev, idx)[0])
+    assert MH.getElement(dev, 7, 3) == MH.getElement(tree, 7, 3)
+    with pytest.raises(m.OutOfRange):
+        MH.getGroupProof(dev, 1 << ext_bits)
+    w = S.root_of_unity(n_bits)
+    consts = {"fixedPolsEvals": const_n, "constTree": tree, "x_n": np.array([pow(w, i, P) for i in range(1 << n_bits)], dtype=np.uint64),
+              "x_ext": np.array([7 * pow(S.root_of_unity(ext_bits), i, P) % P for i in range(1 << ext_bits)], dtype=np.uint64)}
+    fn2 = tmp_path / "setup.cnts"
+    CF.writePilStarkConstsFile(consts, fn2)
+    back = CF.readPilStarkConstsFile(fn2, ctx=ctx, tree_to_device=True)
+    assert np.array_equal(back["fixedPolsEvals"], const_n) and np.array_equal(back["x_ext"], consts["x_ext"])
+    assert MH.root(back["constTree"]) == MH.root(tree)
+    assert MH.getGroupProof(back["constTree"], 77) == MH.getGroupProof(tree, 77)
+    e, n = back["constTree"].download()
+    assert np.array_equal(e, const_ext) and np.array_equal(n, tree["nodes"])
+    dev.free(); back["constTree"].free()
