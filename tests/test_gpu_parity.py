@@ -240,7 +240,7 @@ def test_golden_fri_fold_links(ctx, golden):
 
 # ---------------------------------------------------------------- FRI vs oracle
 @pytest.mark.parametrize("split", [False, True])
-@pytest.mark.parametrize("steps", [[9, 5, 2], [12, 8, 4, 2], [10, 5, 0], [8, 7, 3], [6, 6, 2]])
+@pytest.mark.parametrize("steps", [[9, 5, 2], [12, 8, 4, 2], [10, 5, 0], [8, 7, 3], [6, 6, 2], [13, 7, 1], [14, 9, 4]])
 def test_fri_chain_vs_oracle(ctx, steps, split):
     pol = rnd_field(sum(steps), 3 << steps[0]).reshape(-1, 3)
     rng = random.Random(7)
