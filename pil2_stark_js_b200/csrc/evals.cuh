@@ -43,6 +43,30 @@ struct EvalDesc {      // one entry of pilInfo.evMap restricted to one buffer (s
 };
 #define EV_THREADS 256
 
+// 160-bit accumulator for sums of 128-bit products: the modular reduction is paid once per thread, not once per product
+// (a thread adds at most 2^32 products of < 2^128).
+struct Acc160 {
+    u64 lo, hi;
+    u32 top;
+};
+GL_D void acc_mad(Acc160& a, u64 x, u64 y) {          // a += x * y
+    const u64 pl = x * y, ph = __umul64hi(x, y);
+    a.lo += pl;
+    const u64 c0 = a.lo < pl;
+    a.hi += ph;
+    const u64 c1 = a.hi < ph;
+    a.hi += c0;
+    a.top += (u32)(c1 + (a.hi < c0));
+}
+GL_D void acc_add(Acc160& a, u64 x) {                 // a += x
+    a.lo += x;
+    const u64 c0 = a.lo < x;
+    a.hi += c0;
+    a.top += (u32)(a.hi < c0);
+}
+// top * 2^128 + hi * 2^64 + lo  mod p  (2^128 = -2^32 mod p; top * 2^32 <= p - 1 is canonical)
+GL_D u64 acc_reduce(const Acc160& a) { return gl_sub(gl_reduce128(a.hi, a.lo), (u64)a.top << 32); }
+
 // partial[(chunk * n_evals + e) * 3 ..] = sum over the chunk's rows k of buf[(k << eb) * size + offset] * lev[k]
 // blockDim.x = EV_THREADS = ew * rw: thread (r, e) takes rows r, r + rw, ... of the chunk for evaluation e (+ ew, ...).
 __global__ void __launch_bounds__(EV_THREADS) evals_partial_kernel(const u64* __restrict__ buf, u64 size, int eb, u64 n, const EvalDesc* __restrict__ desc,
@@ -59,14 +83,25 @@ __global__ void __launch_bounds__(EV_THREADS) evals_partial_kernel(const u64* __
         if (e < n_evals) {
             const EvalDesc d = desc[e];
             const u64* __restrict__ lv = lev + (u64)d.lev * n * 3;
-            for (u64 k = kb + r; k < ke; k += rw) {
-                const u64* __restrict__ v = buf + (k << eb) * size + d.offset;
-                const gl3 l = {{lv[3 * k], lv[3 * k + 1], lv[3 * k + 2]}};
-                gl3 t;
-                if (d.dim == 1) t = gl3_scale(l, v[0]);
-                else t = gl3_mul(gl3{{v[0], v[1], v[2]}}, l);
-                acc = gl3_add(acc, t);
+            Acc160 s0 = {0, 0, 0}, s1 = {0, 0, 0}, s2 = {0, 0, 0};
+            if (d.dim == 1) {
+#pragma unroll 4
+                for (u64 k = kb + r; k < ke; k += rw) {
+                    const u64 v = buf[(k << eb) * size + d.offset];
+                    acc_mad(s0, v, lv[3 * k]);
+                    acc_mad(s1, v, lv[3 * k + 1]);
+                    acc_mad(s2, v, lv[3 * k + 2]);
+                }
+            } else {
+                for (u64 k = kb + r; k < ke; k += rw) {
+                    const u64* __restrict__ v = buf + (k << eb) * size + d.offset;
+                    const gl3 t = gl3_mul(gl3{{v[0], v[1], v[2]}}, gl3{{lv[3 * k], lv[3 * k + 1], lv[3 * k + 2]}});
+                    acc_add(s0, t.c[0]);
+                    acc_add(s1, t.c[1]);
+                    acc_add(s2, t.c[2]);
+                }
             }
+            acc = gl3{{acc_reduce(s0), acc_reduce(s1), acc_reduce(s2)}};
         }
         ev_sm[(r * ew + e_lane) * 3 + 0] = acc.c[0];
         ev_sm[(r * ew + e_lane) * 3 + 1] = acc.c[1];
@@ -88,6 +123,194 @@ __global__ void evals_reduce_kernel(const u64* __restrict__ partial, u32 chunks,
     u64 acc = 0;
     for (u32 ch = 0; ch < chunks; ch++) acc = gl_add(acc, partial[(u64)ch * n_evals * 3 + i]);
     out[i] = gl_canon(acc);
+}
+
+// ---- evaluations as a byte-limb GEMM on the tensor cores ---------------------------------------------------------------
+// evals[col][o][c] = sum_k V[k][col] * LEv_o[k][c] is a dense contraction over the 2^nBits rows: (size x N) . (N x 3*nOpen).
+// Both factors are cut into their 8 byte limbs -- which is how they already sit in memory -- and the limb products are summed
+// exactly by IMMA (mma.sync m16n8k32, u8 x u8 -> s32):
+//     D[m][n] = sum_k A[m][k] * B[k][n],   m = (o*3 + c)*8 + b'  (byte b' of LEv_o[k][c]),   n = byte b of V[k][col]
+// One n8 tile is one trace column, one half m16 tile is one (opening, coordinate) pair.  A K-chunk is at most 2^15 rows so
+// that the s32 accumulators cannot overflow (2^15 * 255^2 < 2^31); at the end of a chunk every 8 x 8 block of limb sums is
+// recombined, sum_{b,b'} D * 2^(8(b+b')) mod p, with one warp reduction, and written as a field element.  What is left is
+// HBM-bound: the base rows of the buffer are read once, whatever the number of evaluations.
+// LEv arrives pre-transposed by lev_bytes_kernel as LT[kstep][m][32 bytes of k], so an A fragment is one 32-bit load; the V
+// tile (32 rows x 32 columns) is staged in shared memory with cp.async and byte-transposed 4 x 4 with PRMT.
+#define EVM_THREADS 256
+#define EVM_COLS 32              // columns per CTA (4 per warp)
+#define EVM_KSTEP 32
+#define EVM_PITCH 264            // bytes per staged row (256 + 8: rows 4 apart land 8 banks apart)
+#define EVM_MAX_CHUNK 32768
+#define EVM_STAGES 4             // cp.async ring: 3 K-steps (24 KiB per CTA) in flight hide the DRAM latency
+
+// LT[(kstep * M + m) * 32 + (k % 32)] = byte (m % 8) of lev[(m / 24) * n * 3 + k * 3 + (m / 8) % 3]; rows m >= 24 * n_lev are zero.
+__global__ void lev_bytes_kernel(const u64* __restrict__ lev, u64 n, u32 n_lev, u32 M, unsigned char* __restrict__ LT) {
+    // one thread per 4 output bytes (k % 32 = 4q .. 4q+3 of one m): consecutive threads write consecutive words
+    const u64 total = ((n + EVM_KSTEP - 1) / EVM_KSTEP) * M * (EVM_KSTEP / 4), stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const u32 q = (u32)(i % (EVM_KSTEP / 4));
+        const u64 rest = i / (EVM_KSTEP / 4);
+        const u32 m = (u32)(rest % M);
+        const u64 ks = rest / M;
+        u32 w = 0;
+        if (m < 24 * n_lev) {
+            const u32 o = m / 24, c = (m / 8) % 3, b = m % 8;
+            const u64* __restrict__ src = lev + (u64)o * n * 3 + c;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const u64 k = ks * EVM_KSTEP + 4 * q + j;
+                if (k < n) w |= (u32)((src[k * 3] >> (8 * b)) & 0xFF) << (8 * j);
+            }
+        }
+        reinterpret_cast<u32*>(LT)[i] = w;
+    }
+}
+
+GL_D void evm_mma(int (&d)[4], const u32 (&a)[4], u32 b0, u32 b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+GL_D void evm_cp8(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+
+// grid = (column groups, K-chunks).  partial[(chunk * size + col) * (3 * n_lev) + oc] = sum over the chunk's rows (field element).
+template <int MT>
+__global__ void __launch_bounds__(EVM_THREADS) evals_mma_kernel(const u64* __restrict__ buf, u64 size, int eb, u64 n, u64 rows_per_chunk,
+                                                                const unsigned char* __restrict__ LT, u32 n_lev, u64* __restrict__ partial) {
+    __shared__ __align__(16) unsigned char Vs[EVM_STAGES][EVM_KSTEP * EVM_PITCH];
+    __shared__ u64 pow8[16];                                  // 2^(8d) mod p, d < 15
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    const u64 col0 = (u64)blockIdx.x * EVM_COLS;
+    const u64 kb = (u64)blockIdx.y * rows_per_chunk;
+    const u64 ke = kb + rows_per_chunk < n ? kb + rows_per_chunk : n;
+    const u32 M = MT * 16;
+    if (threadIdx.x < 16) {
+        u64 v = 1;
+        for (int i = 0; i < (int)threadIdx.x; i++) v = gl_canon(gl_mul(v, 256));
+        pow8[threadIdx.x] = v;
+    }
+    int acc[MT][4][4];
+#pragma unroll
+    for (int i = 0; i < MT; i++)
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][t][j] = 0;
+
+    const u64 nsteps = (ke > kb) ? (ke - kb + EVM_KSTEP - 1) / EVM_KSTEP : 0;
+    // stage loader: 32 rows x 32 columns of 8 bytes = 1024 copies, 4 per thread; always commits a group (possibly empty) so that
+    // the wait_group arithmetic below is uniform
+    auto stage = [&](u64 step) {
+        if (step < nsteps) {
+            const int sbuf = (int)(step % EVM_STAGES);
+            const u64 k0 = kb + step * EVM_KSTEP;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int idx = threadIdx.x + q * EVM_THREADS;
+                const int r = idx >> 5, c = idx & 31;
+                unsigned char* dst = &Vs[sbuf][r * EVM_PITCH + c * 8];
+                const u64 k = k0 + r;
+                if (k < ke && col0 + c < size) evm_cp8(dst, buf + (k << eb) * size + col0 + c);
+                else *reinterpret_cast<u64*>(dst) = 0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // A fragments of one K-step: LT[kstep][m][k]
+    auto load_a = [&](u32 (&a)[MT][4], u64 step) {
+        const unsigned char* __restrict__ lt = LT + ((kb / EVM_KSTEP + step) * M) * EVM_KSTEP;
+#pragma unroll
+        for (int i = 0; i < MT; i++) {
+            const unsigned char* p0 = lt + (i * 16 + gid) * EVM_KSTEP + tig * 4;
+            a[i][0] = *reinterpret_cast<const u32*>(p0);
+            a[i][1] = *reinterpret_cast<const u32*>(p0 + 8 * EVM_KSTEP);
+            a[i][2] = *reinterpret_cast<const u32*>(p0 + 16);
+            a[i][3] = *reinterpret_cast<const u32*>(p0 + 8 * EVM_KSTEP + 16);
+        }
+    };
+#pragma unroll
+    for (int st = 0; st < EVM_STAGES - 1; st++) stage(st);
+    const u32 sel = (u32)(gid & 3) | ((4u + (gid & 3)) << 4);          // PRMT: byte q of x, byte q of y
+    u32 a[MT][4], an[MT][4];
+    if (nsteps) load_a(a, 0);
+    for (u64 s = 0; s < nsteps; s++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(EVM_STAGES - 2) : "memory");     // the group of step s has landed
+        __syncthreads();                                     // ... for every thread; and everyone is done with step s - 1
+        stage(s + EVM_STAGES - 1);                           // refills the buffer step s - 1 used
+        if (s + 1 < nsteps) load_a(an, s + 1);
+        const int cur = (int)(s % EVM_STAGES);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            // B fragment of column (warp*4 + t): byte gid of rows tig*4 .. +3 (b0) and +16 (b1)
+            const unsigned char* vb = &Vs[cur][(tig * 4) * EVM_PITCH + (warp * 4 + t) * 8 + (gid & 4)];
+            u32 w[8];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                w[j] = *reinterpret_cast<const u32*>(vb + j * EVM_PITCH);
+                w[4 + j] = *reinterpret_cast<const u32*>(vb + (16 + j) * EVM_PITCH);
+            }
+            const u32 b0 = __byte_perm(__byte_perm(w[0], w[1], sel), __byte_perm(w[2], w[3], sel), 0x5410);
+            const u32 b1 = __byte_perm(__byte_perm(w[4], w[5], sel), __byte_perm(w[6], w[7], sel), 0x5410);
+#pragma unroll
+            for (int i = 0; i < MT; i++) evm_mma(acc[i][t], a[i], b0, b1);
+        }
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) a[i][j] = an[i][j];
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                         // pow8 visible even when the chunk is empty
+    // recombination: (i, half) -> oc = 2i + half; lane holds limb sums (b' = gid; b = 2 tig, 2 tig + 1)
+    const u32 n_oc = 3 * n_lev;
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const u32 oc = 2 * i + half;
+            if (oc >= n_oc) continue;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const u64 v0 = (u64)(u32)acc[i][t][2 * half], v1 = (u64)(u32)acc[i][t][2 * half + 1];
+                u64 f = gl_add(gl_mul(v0, pow8[gid + 2 * tig]), gl_mul(v1, pow8[gid + 2 * tig + 1]));
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) f = gl_add(f, __shfl_xor_sync(0xFFFFFFFFu, f, off));
+                const u64 col = col0 + warp * 4 + t;
+                if (lane == 0 && col < size) partial[((u64)blockIdx.y * size + col) * n_oc + oc] = gl_canon(f);
+            }
+        }
+    }
+}
+
+// out[e] from the dense per-chunk results: dim 1 -> (o, c) of the column; dim 3 -> R(col) + x R(col+1) + x^2 R(col+2) in F3, with
+// x (r0, r1, r2) = (r2, r0 + r2, r1).
+__global__ void evals_gather_kernel(const u64* __restrict__ partial, u32 chunks, u64 size, u32 n_lev, const EvalDesc* __restrict__ desc, u32 n_evals,
+                                    u64* __restrict__ out) {
+    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_evals) return;
+    const EvalDesc d = desc[e];
+    const u32 n_oc = 3 * n_lev;
+    gl3 r[3];
+    for (u32 j = 0; j < d.dim; j++) {
+        gl3 a = {{0, 0, 0}};
+        for (u32 ch = 0; ch < chunks; ch++) {
+            const u64* p = partial + ((u64)ch * size + d.offset + j) * n_oc + 3 * d.lev;
+            a = gl3_add(a, gl3{{p[0], p[1], p[2]}});
+        }
+        r[j] = a;
+    }
+    gl3 v = r[0];
+    if (d.dim == 3) {
+        const gl3 x1 = {{r[1].c[2], gl_add(r[1].c[0], r[1].c[2]), r[1].c[1]}};                    // x * r1
+        const gl3 t2 = {{r[2].c[2], gl_add(r[2].c[0], r[2].c[2]), r[2].c[1]}};                    // x * r2
+        const gl3 x2 = {{t2.c[2], gl_add(t2.c[0], t2.c[2]), t2.c[1]}};                            // x^2 * r2
+        v = gl3_add(gl3_add(v, x1), x2);
+    }
+    v = gl3_canon(v);
+    out[3 * e] = v.c[0]; out[3 * e + 1] = v.c[1]; out[3 * e + 2] = v.c[2];
 }
 
 // ---- x / (x - xi) over the extended domain ----------------------------------------------------------------------------

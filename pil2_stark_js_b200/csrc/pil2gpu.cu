@@ -48,6 +48,9 @@ struct pil2gpu_ctx {
     cudaStream_t copy_stream;   // D2H stream: downloads of finished slabs overlap the compute (extend_and_merkelize)
     cudaStream_t in_stream;     // H2D stream: uploads of the next slab overlap the compute
     cudaEvent_t ev;
+    cudaMemPool_t pool;         // stream-ordered scratch (cudaMallocFromPoolAsync); keeps what it frees (release threshold = max):
+                                // with the default threshold of 0 every synchronisation hands the scratch back to the driver and the
+                                // next call pays for mapping hundreds of MiB again (measured: 2x on the quotient commit)
     u64* ws;                    // grow-only device workspace of the host-pointer entry points (cudaMalloc/cudaFree of tens of GiB
     size_t ws_words;            // per call cost ~0.3 s at cfg3); released by pil2gpu_destroy / pil2gpu_release_workspace
 };
@@ -161,6 +164,7 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
     ctx->ev = nullptr;
     ctx->ws = nullptr;
     ctx->ws_words = 0;
+    ctx->pool = nullptr;
     ctx->tables = nullptr;
     ctx->stream = nullptr;
     ctx->own_stream = false;
@@ -177,6 +181,19 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming) != cudaSuccess) {
         pil2gpu_destroy(ctx);
         return fail(PIL2GPU_E_CUDA, "stream/event creation failed");
+    }
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        unsigned long long keep = ~0ULL;
+        if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess ||
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
+            pil2gpu_destroy(ctx);
+            return fail(PIL2GPU_E_CUDA, "memory pool creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
     }
     const size_t words = NTT_TABLE_WORDS + 256;
     e = cudaMalloc(&ctx->tables, words * sizeof(u64));
@@ -209,6 +226,7 @@ void pil2gpu_destroy(pil2gpu_ctx* ctx) {
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->tables) cudaFree(ctx->tables);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(ctx->pool); }
     delete ctx;
 }
 
@@ -234,6 +252,8 @@ static int ensure_ws(pil2gpu_ctx* ctx, size_t words) {
 }
 int pil2gpu_release_workspace(pil2gpu_ctx* ctx) {
     ENTER(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pool) CU(cudaMemPoolTrimTo(ctx->pool, 0));
     if (ctx->ws) {
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaFree(ctx->ws));
@@ -427,8 +447,8 @@ int pil2gpu_compute_q_dev(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim
     for (u64 p = 0; p < qDeg; p++) { fac[p] = glh_to_mont(cur); cur = glh_mul(cur, shift_in); }
     CU(cudaMemcpyAsync(ctx->small, fac, qDeg * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
     u64 *S = nullptr, *T = nullptr;
-    CU(cudaMallocAsync(&S, E * qDim * sizeof(u64), ctx->stream));
-    cudaError_t e = cudaMallocAsync(&T, N * qDim * qDeg * sizeof(u64), ctx->stream);
+    CU(cudaMallocFromPoolAsync(&S, E * qDim * sizeof(u64), ctx->pool, ctx->stream));
+    cudaError_t e = cudaMallocFromPoolAsync(&T, N * qDim * qDeg * sizeof(u64), ctx->pool, ctx->stream);
     if (e != cudaSuccess) { cudaFreeAsync(S, ctx->stream); return fail(PIL2GPU_E_NOMEM, "scratch allocation failed: %s", cudaGetErrorString(e)); }
     int launches = 0;
     int l = ntt_launch_intt_bitrev((const u64*)q_ext, S, qDim, (int)nBitsExt, ctx->tb, ctx->stream);
@@ -492,7 +512,7 @@ int pil2gpu_compute_lev_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], in
     const u64 sinv = glh_inv(GL_SHIFT);
     for (int c = 0; c < 3; c++) xi[c] = glh_mul(xi[c], sinv);                       // :227
     u64* pw = nullptr;
-    CU(cudaMallocAsync(&pw, N * 3 * sizeof(u64), ctx->stream));
+    CU(cudaMallocFromPoolAsync(&pw, N * 3 * sizeof(u64), ctx->pool, ctx->stream));
     const u64 threads_needed = (N + EV_POW_CHUNK - 1) / EV_POW_CHUNK;
     f3_powers_kernel<<<(unsigned)((threads_needed + 255) / 256), 256, 0, ctx->stream>>>(xi[0], xi[1], xi[2], N, pw);   // :228-230
     int l = ntt_launch_transform(pw, (u64*)lev_dev, 3, (int)nBits, true, ctx->tb, ctx->stream);                        // :231
@@ -515,19 +535,57 @@ int pil2gpu_compute_evals_dev(pil2gpu_ctx* ctx, const uint64_t* buf_dev, uint64_
         if (desc[e].lev >= n_lev) return fail(PIL2GPU_E_RANGE, "evaluation %u: opening index %u out of range", e, desc[e].lev);
     }
     const u64 N = 1ULL << nBits;
+    const int eb = (int)(nBitsExt - nBits);
+    // Tensor-core path (evals.cuh: byte-limb GEMM): the base rows are read once for all evaluations.  PIL2GPU_EVALS=scalar forces
+    // the per-evaluation kernel (kept for small inputs and as the cross-check in the tests).
+    const char* mode = getenv("PIL2GPU_EVALS");
+    const bool use_mma = nBits >= 10 && n_lev <= 4 && !(mode && strcmp(mode, "scalar") == 0);
+    if (use_mma) {
+        const u32 n_oc = 3 * n_lev, MT = (24 * n_lev + 15) / 16, M = MT * 16;
+        u64 rpc = (N / 64) & ~(u64)(EVM_KSTEP - 1);
+        if (rpc < EVM_KSTEP) rpc = EVM_KSTEP;
+        if (rpc > EVM_MAX_CHUNK) rpc = EVM_MAX_CHUNK;
+        const u64 chunks = (N + rpc - 1) / rpc;
+        const size_t lt_words = (N * M + 7) / 8, desc_words = ((size_t)n_evals * sizeof(EvalDesc) + 7) / 8,
+                     part_words = chunks * size * n_oc, out_words = (size_t)n_evals * 3;
+        u64* scratch = nullptr;
+        CU(cudaMallocFromPoolAsync(&scratch, (lt_words + desc_words + part_words + out_words) * sizeof(u64), ctx->pool, ctx->stream));
+        unsigned char* LT = reinterpret_cast<unsigned char*>(scratch);
+        EvalDesc* ddesc = reinterpret_cast<EvalDesc*>(scratch + lt_words);
+        u64 *partial = scratch + lt_words + desc_words, *dout = partial + part_words;
+        cudaError_t e = cudaMemcpyAsync(ddesc, desc, (size_t)n_evals * sizeof(EvalDesc), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            lev_bytes_kernel<<<148 * 8, 256, 0, ctx->stream>>>((const u64*)lev_dev, N, n_lev, M, LT);
+            dim3 grid((unsigned)((size + EVM_COLS - 1) / EVM_COLS), (unsigned)chunks, 1);
+            switch (MT) {
+                case 2: evals_mma_kernel<2><<<grid, EVM_THREADS, 0, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, LT, n_lev, partial); break;
+                case 3: evals_mma_kernel<3><<<grid, EVM_THREADS, 0, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, LT, n_lev, partial); break;
+                case 5: evals_mma_kernel<5><<<grid, EVM_THREADS, 0, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, LT, n_lev, partial); break;
+                default: evals_mma_kernel<6><<<grid, EVM_THREADS, 0, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, LT, n_lev, partial); break;
+            }
+            evals_gather_kernel<<<(n_evals + 127) / 128, 128, 0, ctx->stream>>>(partial, (u32)chunks, size, n_lev, ddesc, n_evals, dout);
+            e = cudaMemcpyAsync(evals_out, dout, out_words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        cudaFreeAsync(scratch, ctx->stream);
+        if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "compute_evals: %s", cudaGetErrorString(e));
+        int rc = check_launch(ctx, 3, "compute_evals");
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        return PIL2GPU_OK;
+    }
     u32 ew = 1;
     while (ew < n_evals && ew < EV_THREADS) ew <<= 1;
     u64 chunks = N / 64 ? N / 64 : 1;                 // >= 64 rows per CTA, at most 8 CTAs per SM
     if (chunks > 148 * 8) chunks = 148 * 8;
     u64* scratch = nullptr;                           // desc | partial | out
     const size_t desc_words = ((size_t)n_evals * sizeof(EvalDesc) + 7) / 8, part_words = chunks * n_evals * 3, out_words = (size_t)n_evals * 3;
-    CU(cudaMallocAsync(&scratch, (desc_words + part_words + out_words) * sizeof(u64), ctx->stream));
+    CU(cudaMallocFromPoolAsync(&scratch, (desc_words + part_words + out_words) * sizeof(u64), ctx->pool, ctx->stream));
     EvalDesc* ddesc = reinterpret_cast<EvalDesc*>(scratch);
     u64 *partial = scratch + desc_words, *dout = partial + part_words;
     cudaError_t e = cudaMemcpyAsync(ddesc, desc, (size_t)n_evals * sizeof(EvalDesc), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         evals_partial_kernel<<<(unsigned)chunks, EV_THREADS, EV_THREADS * 3 * sizeof(u64), ctx->stream>>>(
-            (const u64*)buf_dev, size, (int)(nBitsExt - nBits), N, ddesc, n_evals, (const u64*)lev_dev, ew, partial);
+            (const u64*)buf_dev, size, eb, N, ddesc, n_evals, (const u64*)lev_dev, ew, partial);
         evals_reduce_kernel<<<(n_evals * 3 + 127) / 128, 128, 0, ctx->stream>>>(partial, (u32)chunks, n_evals, dout);
         e = cudaMemcpyAsync(evals_out, dout, out_words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
     }
@@ -549,7 +607,7 @@ int pil2gpu_x_div_x_sub_xi_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3],
     u64 xi[64 * 3];
     for (uint32_t i = 0; i < n_open; i++) host_opening_xi(xi + 3 * i, xi_challenge, openings[i], nBits);   // :291-300
     u64* dxi = nullptr;
-    CU(cudaMallocAsync(&dxi, (size_t)n_open * 3 * sizeof(u64), ctx->stream));
+    CU(cudaMallocFromPoolAsync(&dxi, (size_t)n_open * 3 * sizeof(u64), ctx->pool, ctx->stream));
     cudaError_t e = cudaMemcpyAsync(dxi, xi, (size_t)n_open * 3 * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         const u64 E = 1ULL << nBitsExt, per = (u64)XDIV_THREADS * XDIV_BATCH;
@@ -694,7 +752,7 @@ int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[1
 static int merkelize_tiles(pil2gpu_ctx* ctx, RowTiles t, uint64_t width, uint64_t height, int split, uint64_t* nodes) {
     u64* scratch = nullptr;
     const u64 sw = (split && width > 4) ? merkle_split_scratch_words(width, height) : 0;
-    if (sw) CU(cudaMallocAsync(&scratch, sw * sizeof(u64), ctx->stream));
+    if (sw) CU(cudaMallocFromPoolAsync(&scratch, sw * sizeof(u64), ctx->pool, ctx->stream));
     int l = merkle_launch(t, width, height, split, (u64*)nodes, scratch, ctx->stream);
     if (scratch) CU(cudaFreeAsync(scratch, ctx->stream));
     return check_launch(ctx, l, "merkelize");

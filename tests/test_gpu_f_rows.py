@@ -141,13 +141,21 @@ def test_compute_lev_vs_oracle(ctx, n_bits, opening):
     lev.free()
 
 
-@pytest.mark.parametrize("n_bits,extend_bits,size,n_evals", [(6, 1, 9, 5), (10, 1, 37, 40), (12, 2, 15, 300), (13, 1, 128, 100), (3, 0, 4, 2)])
-def test_compute_evals_vs_oracle(ctx, n_bits, extend_bits, size, n_evals):
+@pytest.mark.parametrize("mode", ["mma", "scalar"])
+@pytest.mark.parametrize("n_bits,extend_bits,size,n_evals,openings", [
+    (6, 1, 9, 5, [0, 1, -1]), (10, 1, 37, 40, [0, 1, -1]), (12, 2, 15, 300, [0, 1, -1]), (13, 1, 128, 100, [0, 1]), (3, 0, 4, 2, [0, 1, -1]),
+    (11, 1, 64, 64, [0]), (10, 0, 33, 50, [0, 1, -1, 2]), (15, 1, 8, 30, [0, 1]), (12, 1, 2, 4, [0, 1, 2, 3, 4])])
+def test_compute_evals_vs_oracle(ctx, monkeypatch, mode, n_bits, extend_bits, size, n_evals, openings):
+    """Evaluation sums through the tensor-core byte-limb GEMM (n_bits >= 10, <= 4 openings) and through the per-evaluation
+    kernel (PIL2GPU_EVALS=scalar; also what small inputs and > 4 openings use): both bit-exact against the oracle."""
+    if mode == "scalar":
+        monkeypatch.setenv("PIL2GPU_EVALS", "scalar")
     rng = np.random.default_rng(n_bits + size)
     xi = rnd_field(11, 3)
-    openings = [0, 1, -1]
     ext_bits = n_bits + extend_bits
     buf = rnd_field(13 + size, size << ext_bits)
+    if size >= 3:
+        buf[:3] = [P - 1, P - 1, 0xFFFFFFFF]                 # extreme limbs in the first row
     ev = []
     for _ in range(n_evals):
         dim = 3 if (size >= 3 and rng.integers(0, 3) == 0) else 1
@@ -159,6 +167,25 @@ def test_compute_evals_vs_oracle(ctx, n_bits, extend_bits, size, n_evals):
     want = C.evals({"b": (buf, size)}, [("b", o, d, l) for o, d, l in ev], levs_o, n_bits, extend_bits)
     assert np.array_equal(got, want)
     dbuf.free(); levs.free()
+
+
+def test_compute_evals_mma_saturated_limbs(ctx):
+    """All-0xFF bytes in both factors over a full 2^15-row chunk: the s32 limb accumulators reach 2^15 * 255^2 = 2130706432 < 2^31."""
+    n_bits, size = 15, 32
+    n = 1 << n_bits
+    buf = np.full(size * n, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)          # non-canonical on purpose: interpreted mod p
+    lev = np.full(3 * n, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    dlev, dbuf = ctx.upload(lev), ctx.upload(buf)
+    got = ctx.compute_evals(dbuf, size, n_bits, n_bits, [(0, 1, 0), (7, 3, 0)], dlev, 1)
+    v = (2**64 - 1) % P
+    s = n * v * v % P
+    assert [int(x) for x in got[0]] == [s, s, s]
+    r = [s, s, s]
+    x1 = [r[2], (r[0] + r[2]) % P, r[1]]
+    x2t = [r[2], (r[0] + r[2]) % P, r[1]]
+    x2 = [x2t[2], (x2t[0] + x2t[2]) % P, x2t[1]]
+    assert [int(x) for x in got[1]] == [(r[i] + x1[i] + x2[i]) % P for i in range(3)]
+    dlev.free(); dbuf.free()
 
 
 def test_compute_evals_range_checks(ctx):
