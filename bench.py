@@ -427,14 +427,25 @@ def run_ours(args, rank, world, local_rank):
 
         def phase_xdiv():
             check(L.pil2gpu_x_div_x_sub_xi_dev(g.h, npp(xi), op_arr, len(openings), n_bits, ext_bits, g.ptr(xd)))
-        for f in (phase_q, phase_lev, phase_evals, phase_xdiv):
+        from pil2_stark_js_b200._lib import FriTerm
+        fterms = (FriTerm * n_ev)(*[FriTerm(dst.data_ptr(), cols, c, 1, o) for o in openings for c in range(cols)])
+        f_ext = g.dev(3 << ext_bits)
+        vf = [np.ascontiguousarray(splitmix_field(seed + 11 + i, 0, 3)) for i in range(2)]
+
+        def phase_fripol():
+            check(L.pil2gpu_fri_pol_dev(g.h, fterms, n_ev, npp(ev_out), op_arr, len(openings), g.ptr(xd), npp(vf[0]), npp(vf[1]), ext_bits,
+                                        g.ptr(f_ext)))
+        for f in (phase_q, phase_lev, phase_evals, phase_xdiv, phase_fripol):
             f()
-        t_q, t_lev, t_ev, t_xd = (time_phase(f, reps) for f in (phase_q, phase_lev, phase_evals, phase_xdiv))
+        t_q, t_lev, t_ev, t_xd, t_fp = (time_phase(f, reps) for f in (phase_q, phase_lev, phase_evals, phase_xdiv, phase_fripol))
         Ew, Nw = 1 << ext_bits, 1 << n_bits
         q_bytes = 8 * Ew * q_dim * (1 + q_deg) + 8 * Ew * q_dim * q_deg + 64 * Ew
         ev_bytes = 8 * Nw * cols + 24 * Nw * len(openings)
         xd_bytes = 24 * Ew * len(openings)
+        fp_bytes = 8 * Ew * cols + 24 * Ew * len(openings) + 24 * Ew
         extras = {
+            "fri_pol": {"s": t_fp, "shape": f"{n_ev} evMap terms over the 2^{ext_bits} rows of the {cols}-column extended buffer (friExp -> f_ext)",
+                        "algorithmic_bytes": fp_bytes, "GBps": fp_bytes / t_fp / 1e9, "frac_hbm": fp_bytes / t_fp / 1e9 / hbm_peak},
             "q_commit": {"s": t_q, "shape": f"qDim {q_dim}, qDeg {q_deg}, 2^{ext_bits} rows (INTT + split + {q_deg} coset NTTs + merkelize)",
                          "algorithmic_bytes": q_bytes, "GBps": q_bytes / t_q / 1e9, "frac_hbm": q_bytes / t_q / 1e9 / hbm_peak},
             "lev": {"s": t_lev, "shape": f"{len(openings)} openings x 2^{n_bits} F3 (powers + INTT)"},
@@ -444,7 +455,7 @@ def run_ours(args, rank, world, local_rank):
             "x_div_x_sub_xi": {"s": t_xd, "shape": f"{len(openings)} openings x 2^{ext_bits} points", "algorithmic_bytes": xd_bytes,
                                "GBps": xd_bytes / t_xd / 1e9, "frac_hbm": xd_bytes / t_xd / 1e9 / hbm_peak},
         }
-        del q_ext, cmq, q_nodes, lev, xd
+        del q_ext, cmq, q_nodes, lev, xd, f_ext
 
     # ---- e2e: the same commit through the host-buffer entry points (pinned host memory) ----
     e2e = None

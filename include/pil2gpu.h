@@ -134,6 +134,25 @@ int pil2gpu_x_div_x_sub_xi_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3],
 int pil2gpu_x_div_x_sub_xi(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
                            uint32_t nBitsExt, uint64_t* out);
 
+/* ---- FRI polynomial: computeFRIStark after the xDivXSubXi table, src/stark/stark_gen_helpers.js:325-334 ------------- */
+/* One entry of pilInfo.evMap, in evMap order (the Horner order of friPolinomial.js:26-40 depends on it): the polynomial's
+ * extended buffer on the device (2^nBitsExt rows of `size` words), its first column, dim 1 or 3, and the opening (prime). */
+typedef struct pil2gpu_fri_term {
+    const uint64_t* buf_dev;
+    uint64_t size;
+    uint64_t offset;
+    uint32_t dim;
+    int32_t prime;
+} pil2gpu_fri_term;
+/* f_dev[3k ..] = friExp at row k (src/pil_info/helpers/polynomials/friPolinomial.js:26-56, what callCalculateExps evaluates into
+ * f_ext): per opening o the Horner combination in vf2 of (p_i(x_k) - evals[i]) over the evMap entries opened at o, times
+ * xDivXSubXi_ext[k][index of o], combined across the openings by Horner in vf1 in the order JavaScript enumerates the keys of
+ * friExps.  evals: HOST array n_terms x 3 (ctx.evals); xdiv_dev: 2^nBitsExt x n_open x 3 on the device; at most 4 distinct
+ * openings, rows of at most 4096 columns.  Asynchronous on the ctx stream. */
+int pil2gpu_fri_pol_dev(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_t n_terms, const uint64_t* evals, const int32_t* openings,
+                        uint32_t n_open, const uint64_t* xdiv_dev, const uint64_t vf1[3], const uint64_t vf2[3], uint32_t nBitsExt,
+                        uint64_t* f_dev);
+
 /* ---- hashing: src/helpers/hash/poseidon/poseidon.js, linearhash/ *.js -------------------------------------- */
 /* poseidon(inputs[8], capacity[4], nOuts) poseidon.js:57-108: full 12-word permutation of in12 = inputs || capacity. */
 int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[12]);

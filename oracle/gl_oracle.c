@@ -437,3 +437,38 @@ int orc_xdivxsubxi(const u64 xi_challenge[3], const int *openings, u64 n_open, u
     free(xi);
     return 0;
 }
+
+/* FRI polynomial f_ext: friExp of src/pil_info/helpers/polynomials/friPolinomial.js:26-56 evaluated on every row of the extended
+ * domain (computeFRIStark, stark_gen_helpers.js:325).  Terms are given in evMap order; group[i] = position of the term's opening
+ * in the enumeration order of friExps' keys, xidx[g] = column of that opening in xDivXSubXi_ext. */
+typedef struct { const u64 *const *bufs; const u64 *sizes, *offsets; const int *dims, *group; u64 n_terms; const u64 *evals;
+                 const int *xidx; int n_groups; u64 n_open; const u64 *xdiv, *vf1, *vf2; u64 *out; } fripol_ctx;
+static void fripol_range(void *p, u64 b, u64 e) {
+    fripol_ctx *c = (fripol_ctx *)p;
+    for (u64 k = b; k < e; k++) {
+        u64 g[64][3]; int used[64] = { 0 };
+        for (u64 i = 0; i < c->n_terms; i++) {
+            const u64 *v = c->bufs[i] + k * c->sizes[i] + c->offsets[i];
+            u64 t[3] = { v[0], c->dims[i] == 3 ? v[1] : 0, c->dims[i] == 3 ? v[2] : 0 };
+            for (int j = 0; j < 3; j++) t[j] = fsub(t[j], c->evals[3 * i + j]);
+            int gi = c->group[i];
+            if (used[gi]) { u64 m[3]; f3mul(m, g[gi], c->vf2); for (int j = 0; j < 3; j++) g[gi][j] = fadd(m[j], t[j]); }
+            else { memcpy(g[gi], t, 24); used[gi] = 1; }
+        }
+        u64 acc[3] = { 0, 0, 0 };
+        for (int gi = 0; gi < c->n_groups; gi++) {
+            u64 f[3]; f3mul(f, g[gi], c->xdiv + 3 * (k * c->n_open + c->xidx[gi]));
+            if (gi == 0) memcpy(acc, f, 24);
+            else { u64 m[3]; f3mul(m, c->vf1, acc); for (int j = 0; j < 3; j++) acc[j] = fadd(m[j], f[j]); }
+        }
+        memcpy(c->out + 3 * k, acc, 24);
+    }
+}
+int orc_fri_pol(const u64 *const *bufs, const u64 *sizes, const u64 *offsets, const int *dims, const int *group, u64 n_terms, const u64 *evals,
+                const int *xidx, int n_groups, u64 n_open, const u64 *xdiv, const u64 vf1[3], const u64 vf2[3], unsigned bits_ext, u64 *out,
+                int nthreads) {
+    if (n_groups > 64) return -2;
+    fripol_ctx fc = { bufs, sizes, offsets, dims, group, n_terms, evals, xidx, n_groups, n_open, xdiv, vf1, vf2, out };
+    parallel_for(1ULL << bits_ext, nthreads, fripol_range, &fc);
+    return 0;
+}

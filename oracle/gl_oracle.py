@@ -40,6 +40,9 @@ def lib():
         L.orc_eval.argtypes = [_U64P, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, _U64P, ctypes.c_uint, ctypes.c_uint, _U64P]
         L.orc_eval.restype = None
         L.orc_xdivxsubxi.argtypes = [_U64P, ctypes.POINTER(ctypes.c_int), ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint, _U64P, ctypes.c_int]
+        L.orc_fri_pol.argtypes = [ctypes.POINTER(_U64P), _U64P, _U64P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_uint64,
+                                  _U64P, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_uint64, _U64P, _U64P, _U64P, ctypes.c_uint, _U64P,
+                                  ctypes.c_int]
         _lib = L
     return _lib
 
@@ -156,3 +159,29 @@ def x_div_x_sub_xi(xi_challenge, openings, n_bits, n_bits_ext, threads=None):
     rc = lib().orc_xdivxsubxi(_p(xi), op, len(openings), n_bits, n_bits_ext, _p(out), threads or default_threads())
     assert rc == 0
     return out.reshape(-1, len(openings), 3)
+
+
+def fri_polynomial(buffers, ev_map, evals_, openings, xdiv, vf1, vf2, n_bits_ext, threads=None):
+    """f_ext of computeFRIStark (friPolinomial.js:26-56 evaluated per row); same arguments as gl_spec.fri_polynomial with numpy
+    buffers.  Returns a (2^n_bits_ext, 3) array."""
+    from .gl_spec import js_object_key_order
+    bufs = {k: (_arr(v[0]), int(v[1])) for k, v in buffers.items()}
+    first_use = []
+    for _, _, _, prime in ev_map:
+        if prime not in first_use:
+            first_use.append(prime)
+    order = js_object_key_order(first_use)
+    n = len(ev_map)
+    ptrs = (_U64P * n)(*[_p(bufs[name][0]) for name, _, _, _ in ev_map])
+    sizes = np.array([bufs[name][1] for name, _, _, _ in ev_map], dtype=np.uint64)
+    offs = np.array([o for _, o, _, _ in ev_map], dtype=np.uint64)
+    dims = (ctypes.c_int * n)(*[int(d) for _, _, d, _ in ev_map])
+    group = (ctypes.c_int * n)(*[order.index(pr) for _, _, _, pr in ev_map])
+    xidx = (ctypes.c_int * len(order))(*[list(openings).index(o) for o in order])
+    ev = _arr(np.asarray(evals_, dtype=np.uint64).reshape(-1))
+    xd, a, b = _arr(np.asarray(xdiv).reshape(-1)), _arr(vf1), _arr(vf2)
+    out = np.empty(3 << n_bits_ext, dtype=np.uint64)
+    rc = lib().orc_fri_pol(ptrs, _p(sizes), _p(offs), dims, group, n, _p(ev), xidx, len(order), len(openings), _p(xd), _p(a), _p(b), n_bits_ext,
+                           _p(out), threads or default_threads())
+    assert rc == 0
+    return out.reshape(-1, 3)

@@ -530,3 +530,42 @@ def x_div_x_sub_xi(xi_challenge, openings, n_bits, n_bits_ext):
             out[3 * (k * no + i):3 * (k * no + i) + 3] = v                 # :316-318
             x = (x * w_ext) % P
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# FRI polynomial: the fixed-form expression friExp             src/pil_info/helpers/polynomials/friPolinomial.js
+# ----------------------------------------------------------------------------------------------
+def js_object_key_order(keys):
+    """Order in which JavaScript enumerates the own keys of `friExps` (friPolinomial.js:44): canonical non-negative integer
+    keys ascending first, then the remaining (negative) keys in insertion order.  `keys` = primes in order of first use."""
+    ints = sorted(k for k in keys if k >= 0)
+    return ints + [k for k in keys if k < 0]
+
+
+def fri_polynomial(buffers, ev_map, evals, openings, xdiv, vf1, vf2, n_bits_ext):
+    """Row-by-row evaluation of friExp (friPolinomial.js:26-56) as callCalculateExps(..., "ext") does for computeFRIStark
+    (stark_gen_helpers.js:325): buffers: name -> (flat list, row size); ev_map: list of (buffer name, column offset, dim, prime);
+    evals: list of F3 (ctx.evals); xdiv: flat xDivXSubXi_ext; vf1, vf2 in F3.  Returns the 2^n_bits_ext F3 values of f_ext."""
+    ne = 1 << n_bits_ext
+    no = len(openings)
+    first_use = []
+    for _, _, _, prime in ev_map:
+        if prime not in first_use:
+            first_use.append(prime)
+    order = js_object_key_order(first_use)
+    out = []
+    for k in range(ne):
+        fri_exps = {}
+        for i, (name, offset, dim, prime) in enumerate(ev_map):
+            buf, size = buffers[name]
+            base = k * size + offset
+            e = [buf[base], 0, 0] if dim == 1 else list(buf[base:base + 3])
+            term = f3_sub(e, evals[i])                                              # E.sub(e, E.eval(i, 3))          :36,38
+            fri_exps[prime] = f3_add(f3_mul(fri_exps[prime], vf2), term) if prime in fri_exps else term
+        acc = None
+        for opening in order:                                                       # :44-53
+            idx = openings.index(opening)
+            f = f3_mul(fri_exps[opening], xdiv[3 * (k * no + idx):3 * (k * no + idx) + 3])
+            acc = f3_add(f3_mul(vf1, acc), f) if acc is not None else f
+        out.append(acc)
+    return out

@@ -30,6 +30,12 @@ class EvalDesc(ctypes.Structure):
     _fields_ = [("offset", ctypes.c_uint64), ("dim", ctypes.c_uint32), ("lev", ctypes.c_uint32)]
 
 
+class FriTerm(ctypes.Structure):
+    """pil2gpu_fri_term (include/pil2gpu.h)"""
+    _fields_ = [("buf_dev", ctypes.c_void_p), ("size", ctypes.c_uint64), ("offset", ctypes.c_uint64), ("dim", ctypes.c_uint32),
+                ("prime", ctypes.c_int32)]
+
+
 _SIGS = {
     # name: (restype, [argtypes])
     "pil2gpu_create": (c_int, [c_int, vp, ctypes.POINTER(vp)]),
@@ -62,6 +68,7 @@ _SIGS = {
     "pil2gpu_x_div_x_sub_xi_dev": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp]),
     "pil2gpu_compute_evals": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp, c_u64, vp, c_u32, vp]),
     "pil2gpu_x_div_x_sub_xi": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp]),
+    "pil2gpu_fri_pol_dev": (c_int, [vp, vp, c_u32, vp, vp, c_u32, vp, vp, vp, c_u32, vp]),
     "pil2gpu_poseidon": (c_int, [vp, vp, vp]),
     "pil2gpu_linear_hash": (c_int, [vp, vp, c_u64, c_int, vp]),
     "pil2gpu_merkle_nnodes": (c_u64, [c_u64]),

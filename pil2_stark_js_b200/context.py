@@ -196,6 +196,28 @@ class Context:
             return out
         return out.download().reshape(-1, len(openings), 3)
 
+    def fri_pol(self, terms, evals, openings, xdiv, vf1, vf2, n_bits_ext, download=True):
+        """f_ext of computeFRIStark (stark_gen_helpers.js:325-334; friPolinomial.js:26-56).  terms: evMap in order as
+        (DeviceBuffer | device pointer, row size, column offset, dim, prime); evals: (n, 3) array-like (ctx.evals); xdiv: the
+        DeviceBuffer from x_div_x_sub_xi(download=False).  Returns the (2^n_bits_ext, 3) array (or the DeviceBuffer)."""
+        n = len(terms)
+        arr = (_lib.FriTerm * n)()
+        for i, (buf, size, offset, dim, prime) in enumerate(terms):
+            ptr = buf.ptr.value if isinstance(buf, DeviceBuffer) else int(buf)
+            arr[i] = _lib.FriTerm(ptr, int(size), int(offset), int(dim), int(prime))
+        ev = np.ascontiguousarray(np.asarray(evals, dtype=np.uint64).reshape(-1))
+        if ev.size != 3 * n:
+            raise ValueError("evals must hold one F3 value per evMap entry")
+        op = (ctypes.c_int32 * len(openings))(*[int(o) for o in openings])
+        a, b = (np.ascontiguousarray(v, dtype=np.uint64).reshape(-1) for v in (vf1, vf2))
+        out = DeviceBuffer(self, 3 << n_bits_ext)
+        check(self._L.pil2gpu_fri_pol_dev(self.handle, arr, n, _ptr(ev), op, len(openings), xdiv.ptr, _ptr(a), _ptr(b), n_bits_ext, out.ptr))
+        if not download:
+            return out
+        res = out.download().reshape(-1, 3)
+        out.free()
+        return res
+
     # ---- device-resident commit ----
     def commit(self, src, n_pols, n_bits, n_bits_ext, split=False):
         """interpolate + merkelize with the LDE kept in HBM.  Returns (DeviceTree, root[4])."""

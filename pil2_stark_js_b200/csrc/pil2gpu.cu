@@ -2,6 +2,7 @@
 // interfaces each entry point replaces).  Unity build: the kernels live in the .cuh files included below.
 // There is deliberately no CPU implementation behind any entry point: every failure to reach the GPU is an error.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +18,7 @@
 #include "ntt.cuh"
 #include "qpath.cuh"
 #include "evals.cuh"
+#include "fripol.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -654,6 +656,138 @@ int pil2gpu_x_div_x_sub_xi(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], con
     CU(cudaMemcpyAsync(out, ctx->ws, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return PIL2GPU_OK;
+}
+
+// ---- FRI polynomial: computeFRIStark after the xDivXSubXi table (stark_gen_helpers.js:325-334; friPolinomial.js:26-56) ----
+int pil2gpu_fri_pol_dev(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_t n_terms, const uint64_t* evals, const int32_t* openings,
+                        uint32_t n_open, const uint64_t* xdiv_dev, const uint64_t vf1[3], const uint64_t vf2[3], uint32_t nBitsExt, uint64_t* f_dev) {
+    ENTER(ctx);
+    if (!terms || !evals || !openings || !xdiv_dev || !vf1 || !vf2 || !f_dev || n_terms == 0 || n_open == 0)
+        return fail(PIL2GPU_E_INVALID, "null or empty argument");
+    if (nBitsExt > 32) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    const u64 E = 1ULL << nBitsExt;
+    // enumeration order of friExps' keys (friPolinomial.js:44): non-negative primes ascending, then the negative ones as first used
+    std::vector<int32_t> first_use, order;
+    for (uint32_t i = 0; i < n_terms; i++) {
+        if (terms[i].dim != 1 && terms[i].dim != 3) return fail(PIL2GPU_E_INVALID, "term %u: dim must be 1 or 3", i);
+        if (!terms[i].buf_dev || terms[i].offset + terms[i].dim > terms[i].size) return fail(PIL2GPU_E_RANGE, "term %u: columns outside its buffer", i);
+        if (terms[i].size * 8 > 32768) return fail(PIL2GPU_E_UNSUPPORTED, "term %u: rows wider than 4096 columns", i);
+        bool seen = false;
+        for (int32_t p : first_use) seen |= (p == terms[i].prime);
+        if (!seen) first_use.push_back(terms[i].prime);
+    }
+    for (int32_t p : first_use) if (p >= 0) order.push_back(p);
+    for (size_t a = 0; a < order.size(); a++) for (size_t b = a + 1; b < order.size(); b++) if (order[b] < order[a]) std::swap(order[a], order[b]);
+    for (int32_t p : first_use) if (p < 0) order.push_back(p);
+    const int n_groups = (int)order.size();
+    if (n_groups > 4) return fail(PIL2GPU_E_UNSUPPORTED, "more than 4 distinct opening points in the evaluation map");
+    FriPolFinish fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.n_groups = n_groups;
+    fin.n_open = (int)n_open;
+    std::vector<int> group(n_terms), count(n_groups, 0), rank(n_terms);
+    for (int g = 0; g < n_groups; g++) {
+        fin.xidx[g] = -1;
+        for (uint32_t o = 0; o < n_open; o++) if (openings[o] == order[g]) { fin.xidx[g] = (int)o; break; }
+        if (fin.xidx[g] < 0) return fail(PIL2GPU_E_INVALID, "opening %d of the evaluation map is not in openingPoints", order[g]);
+    }
+    for (uint32_t i = 0; i < n_terms; i++) {
+        for (int g = 0; g < n_groups; g++) if (order[g] == terms[i].prime) group[i] = g;
+        rank[i] = count[group[i]]++;
+    }
+    const h3 one = {{1, 0, 0}}, v1 = {{vf1[0] % GL_P, vf1[1] % GL_P, vf1[2] % GL_P}}, v2 = {{vf2[0] % GL_P, vf2[1] % GL_P, vf2[2] % GL_P}};
+    int max_count = 0;
+    for (int g = 0; g < n_groups; g++) max_count = count[g] > max_count ? count[g] : max_count;
+    std::vector<h3> pow2(max_count > 0 ? max_count : 1, one);
+    for (int k = 1; k < max_count; k++) pow2[k] = h3_mul(pow2[k - 1], v2);
+    std::vector<h3> w(n_terms);
+    h3 cg[4] = {{{0, 0, 0}}, {{0, 0, 0}}, {{0, 0, 0}}, {{0, 0, 0}}};
+    for (uint32_t i = 0; i < n_terms; i++) {
+        w[i] = pow2[count[group[i]] - 1 - rank[i]];                                    // Horner in vf2 (:33-39)
+        const h3 ev = {{evals[3 * i] % GL_P, evals[3 * i + 1] % GL_P, evals[3 * i + 2] % GL_P}};
+        cg[group[i]] = h3_add(cg[group[i]], h3_mul(w[i], ev));
+    }
+    h3 ug = one;
+    for (int g = n_groups - 1; g >= 0; g--) {                                          // Horner in vf1 (:48-52)
+        for (int c = 0; c < 3; c++) { fin.u[g][c] = ug.c[c]; fin.c[g][c] = cg[g].c[c]; }
+        ug = h3_mul(ug, v1);
+    }
+    const int NT = 3 * n_groups;
+    // distinct buffers
+    struct BufRef { const uint64_t* p; uint64_t size; };
+    std::vector<BufRef> bufs;
+    for (uint32_t i = 0; i < n_terms; i++) {
+        bool seen = false;
+        for (const BufRef& b : bufs) seen |= (b.p == terms[i].buf_dev && b.size == terms[i].size);
+        if (!seen) bufs.push_back(BufRef{terms[i].buf_dev, terms[i].size});
+    }
+    u64* S = nullptr;
+    CU(cudaMallocFromPoolAsync(&S, E * NT * sizeof(u64), ctx->pool, ctx->stream));
+    int launches = 0;
+    cudaError_t e = cudaSuccess;
+    std::vector<uint2*> bfs;
+    for (size_t bi = 0; bi < bufs.size() && e == cudaSuccess; bi++) {
+        const u64 size = bufs[bi].size;
+        const u32 dsteps = (u32)((size * 8 + 63) / 64);
+        std::vector<h3> W((size_t)size * n_groups, h3{{0, 0, 0}});                     // W[col][g]: coefficient of column col in S_g
+        for (uint32_t i = 0; i < n_terms; i++) {
+            if (terms[i].buf_dev != bufs[bi].p || terms[i].size != size) continue;
+            h3 t = w[i];
+            for (uint32_t j = 0; j < terms[i].dim; j++) {                              // F3 column (a, b, c) = a + b x + c x^2
+                h3& dst = W[(size_t)(terms[i].offset + j) * n_groups + group[i]];
+                dst = h3_add(dst, t);
+                t = h3_mulx(t);
+            }
+        }
+        // byte limbs of W'[(col, b)][oc] = W[col][oc] * 2^(8b), in fragment order (see fripol.cuh)
+        const size_t K = (size_t)dsteps * 64;
+        std::vector<unsigned char> Wb(K * NT * 8, 0);
+        for (u64 col = 0; col < size; col++)
+            for (int oc = 0; oc < NT; oc++) {
+                u64 v = W[(size_t)col * n_groups + oc / 3].c[oc % 3];
+                for (int b = 0; b < 8; b++) {
+                    for (int bp = 0; bp < 8; bp++) Wb[((size_t)col * 8 + b) * NT * 8 + oc * 8 + bp] = (unsigned char)(v >> (8 * bp));
+                    v = glh_mul(v, 256);
+                }
+            }
+        std::vector<uint2> BF((size_t)dsteps * 2 * NT * 32);
+        for (u32 j = 0; j < dsteps; j++)
+            for (int h = 0; h < 2; h++)
+                for (int nt = 0; nt < NT; nt++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int gid = lane >> 2, tig = lane & 3;
+                        u32 b0 = 0, b1 = 0;
+                        for (int i = 0; i < 4; i++) {
+                            const size_t P0 = (size_t)j * 64 + 16 * tig + 8 * h + i;
+                            b0 |= (u32)Wb[P0 * NT * 8 + nt * 8 + gid] << (8 * i);
+                            b1 |= (u32)Wb[(P0 + 4) * NT * 8 + nt * 8 + gid] << (8 * i);
+                        }
+                        BF[((size_t)(2 * j + h) * NT + nt) * 32 + lane] = make_uint2(b0, b1);
+                    }
+        uint2* dBF = nullptr;
+        e = cudaMallocFromPoolAsync(&dBF, BF.size() * sizeof(uint2), ctx->pool, ctx->stream);
+        if (e != cudaSuccess) break;
+        bfs.push_back(dBF);
+        e = cudaMemcpyAsync(dBF, BF.data(), BF.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream);   // pageable source: staged before return
+        if (e != cudaSuccess) break;
+        const unsigned blocks = (unsigned)((E + FP_WARPS * 32 - 1) / (FP_WARPS * 32));
+        const int accum = bi > 0;
+        switch (NT) {
+            case 3: fripol_mma_kernel<3><<<blocks, FP_WARPS * 32, 0, ctx->stream>>>((const u64*)bufs[bi].p, size, E, dBF, dsteps, S, accum); break;
+            case 6: fripol_mma_kernel<6><<<blocks, FP_WARPS * 32, 0, ctx->stream>>>((const u64*)bufs[bi].p, size, E, dBF, dsteps, S, accum); break;
+            case 9: fripol_mma_kernel<9><<<blocks, FP_WARPS * 32, 0, ctx->stream>>>((const u64*)bufs[bi].p, size, E, dBF, dsteps, S, accum); break;
+            default: fripol_mma_kernel<12><<<blocks, FP_WARPS * 32, 0, ctx->stream>>>((const u64*)bufs[bi].p, size, E, dBF, dsteps, S, accum); break;
+        }
+        launches++;
+    }
+    if (e == cudaSuccess) {
+        fripol_finish_kernel<<<(unsigned)((E + 255) / 256), 256, 0, ctx->stream>>>(S, (const u64*)xdiv_dev, fin, E, (u64*)f_dev);
+        launches++;
+    }
+    for (uint2* b : bfs) cudaFreeAsync(b, ctx->stream);
+    cudaFreeAsync(S, ctx->stream);
+    if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "fri_pol: %s", cudaGetErrorString(e));
+    return check_launch(ctx, launches, "fri_pol");
 }
 
 // Gather a paged host buffer into device memory / scatter back (async on the ctx stream).

@@ -6,6 +6,7 @@ against the GPU library:
     computeQStark(ctx)                      :168-208   ifft -> shift-split -> fft -> merkelize
     computeEvalsStark(ctx)                  :210-273   LEv vectors + evaluation sums
     computeXDivXSubXi(ctx)                  :289-323   the xDivXSubXi_ext part of computeFRIStark
+    computeFRIPol(ctx)                      :325-334   friExp over the extended domain -> f_ext, friPol[0]
     computeFRIFolding(step, ctx, challenge) :337-356
     computeFRIQueries(ctx, friQueries)      :358-360
     getPermutationsStark(ctx, challenge)    :474-493
@@ -108,6 +109,35 @@ def computeXDivXSubXi(ctx, options=None):
     openings = [int(o) for o in ctx.pilInfo["openingPoints"]]
     ctx.xDivXSubXi_ext = _gpu(ctx).x_div_x_sub_xi_host(xi, openings, ctx.nBits, ctx.nBitsExt).reshape(-1)
     return ctx.xDivXSubXi_ext
+
+
+def computeFRIPol(ctx, options=None):
+    """The rest of computeFRIStark (stark_gen_helpers.js:325-334): evaluates friExp (friPolinomial.js:26-56) over the extended
+    domain into ctx.f_ext and ctx.friPol[0].  Needs ctx.evals, ctx.challenges[nStages + 3] = [vf1, vf2] and the extended buffers."""
+    g = _gpu(ctx)
+    stage = ctx.pilInfo["nStages"] + 3
+    vf1, vf2 = ctx.challenges[stage][0], ctx.challenges[stage][1]
+    xi = ctx.challenges[ctx.pilInfo["nStages"] + 1][0]
+    openings = [int(o) for o in ctx.pilInfo["openingPoints"]]
+    dev = dict(getattr(ctx, "dev_buffers", {}))
+    owned = []
+    terms = []
+    for ev in ctx.pilInfo["evMap"]:
+        name, size, offset, dim = _pol_ref_ext(ctx, ev)
+        if name not in dev:
+            dev[name] = g.upload(getattr(ctx, name))
+            owned.append(dev[name])
+        terms.append((dev[name], size, offset, dim, int(ev["prime"])))
+    xdiv = g.x_div_x_sub_xi(xi, openings, ctx.nBits, ctx.nBitsExt, download=False)
+    f = g.fri_pol(terms, ctx.evals, openings, xdiv, vf1, vf2, ctx.nBitsExt)
+    xdiv.free()
+    for b in owned:
+        b.free()
+    ctx.f_ext = f.reshape(-1)
+    if not hasattr(ctx, "friPol") or ctx.friPol is None:
+        ctx.friPol = {}
+    ctx.friPol[0] = f
+    return f
 
 
 def computeFRIFolding(step, ctx, challenge, options=None):

@@ -253,6 +253,21 @@ def test_stark_gen_helpers_stage_flow(ctx):
     t = S.Transcript()
     t.put([1, 2, 3])
     assert q == t.get_permutations(8, ext_bits)
+    # FRI polynomial from the honest evaluations, then the FRI chain on it: the final polynomial passes the degree check of
+    # fri.js:158-171 only because f_ext really is of degree < N -- commit, evaluations, xDivXSubXi and friExp all have to agree
+    c.challenges[4] = [[int(x) for x in rnd_field(5, 3)], [int(x) for x in rnd_field(6, 3)]]
+    f = H.computeFRIPol(c)
+    ev_map_o = [("cm1", 0, 1, 0), ("cm1", 0, 1, 1), ("cm1", 3, 3, 0), ("const", 2, 1, 1), ("cm2", 0, 3, 0), ("cm2", 3, 3, 0)]
+    want_f = C.fri_polynomial({"cm1": (want1, 10), "cm2": (want2, 6), "const": (c.const_ext, 4)}, ev_map_o, np.array(evals, dtype=np.uint64), [0, 1],
+                              xd, np.array(c.challenges[4][0], dtype=np.uint64), np.array(c.challenges[4][1], dtype=np.uint64), ext_bits)
+    assert np.array_equal(f, want_f)
+    c.fri = m.FRI(pil["starkStruct"], c.MH)
+    c.friPol, c.friProof, c.friTrees = {0: f}, {0: {}}, {}
+    H.computeFRIFolding(0, c, [0, 0, 0])
+    last = H.computeFRIFolding(1, c, [int(x) for x in rnd_field(7, 3)])
+    coeffs = S.intt([[int(v) for v in e] for e in np.asarray(last).reshape(-1, 3)])
+    max_deg = 1 << (5 - (ext_bits - n_bits))
+    assert all(cf == [0, 0, 0] for cf in coeffs[max_deg:]) and any(cf != [0, 0, 0] for cf in coeffs[:max_deg])
 
 
 @pytest.mark.parametrize("n_bits,blow,cols,world", [(10, 1, 128, 2), (12, 1, 256, 4), (9, 2, 64, 2), (8, 1, 48, 2)])
@@ -314,3 +329,62 @@ def test_const_tree_file_to_device(ctx, tmp_path):
     e, n = back["constTree"].download()
     assert np.array_equal(e, const_ext) and np.array_equal(n, tree["nodes"])
     dev.free(); back["constTree"].free()
+
+
+# ---------------------------------------------------------------- FRI polynomial (friExp over the extended domain)
+@pytest.mark.parametrize("n_bits,ext_bits,openings,sizes,n_terms", [
+    (4, 6, [0, 1], (4, 5), 6), (8, 9, [0, 1, -1], (37, 6), 40), (10, 11, [0, 1], (256, 12), 300), (6, 8, [0], (3, 3), 4),
+    (9, 10, [0, 1, -1, 2], (64, 9), 100), (11, 12, [1, -1, 0], (130, 16), 200)])
+def test_fri_pol_vs_oracle(ctx, n_bits, ext_bits, openings, sizes, n_terms):
+    rng = np.random.default_rng(n_bits * 31 + n_terms)
+    ne = 1 << ext_bits
+    bufs = {"a": (rnd_field(1 + n_terms, sizes[0] * ne), sizes[0]), "b": (rnd_field(2 + n_terms, sizes[1] * ne), sizes[1])}
+    bufs["a"][0][:3] = [P - 1, 0, 0xFFFFFFFF]
+    ev_map = []
+    for _ in range(n_terms):
+        name = "a" if rng.integers(0, 3) else "b"
+        size = bufs[name][1]
+        dim = 3 if (size >= 3 and rng.integers(0, 4) == 0) else 1
+        ev_map.append((name, int(rng.integers(0, size - dim + 1)), dim, int(openings[rng.integers(0, len(openings))])))
+    evals = rnd_field(5, 3 * n_terms).reshape(-1, 3)
+    xi = rnd_field(6, 3)
+    vf1, vf2 = rnd_field(7, 3), rnd_field(8, 3)
+    xdiv_h = C.x_div_x_sub_xi(xi, openings, n_bits, ext_bits)
+    want = C.fri_polynomial(bufs, ev_map, evals, openings, xdiv_h, vf1, vf2, ext_bits)
+    dev = {k: ctx.upload(v[0]) for k, v in bufs.items()}
+    xdiv = ctx.x_div_x_sub_xi(xi, openings, n_bits, ext_bits, download=False)
+    assert np.array_equal(xdiv.download().reshape(xdiv_h.shape), xdiv_h)
+    terms = [(dev[name], bufs[name][1], off, dim, prime) for name, off, dim, prime in ev_map]
+    got = ctx.fri_pol(terms, evals, openings, xdiv, vf1, vf2, ext_bits)
+    assert np.array_equal(got, want)
+    for b in list(dev.values()) + [xdiv]:
+        b.free()
+
+
+def test_fri_pol_low_degree_large(ctx):
+    """2^14 rows, blowup 4, 96 columns: honest evaluations (computed by the evaluation kernels) make f_ext a polynomial of degree
+    < N -- INTT on the GPU, coefficients above N vanish after undoing the coset shift is not even needed (zero stays zero)."""
+    n_bits, ext_bits, size = 14, 16, 96
+    n, ne = 1 << n_bits, 1 << ext_bits
+    openings = [0, 1]
+    trace = rnd_field(40, size * n)
+    ext = np.empty(size * ne, dtype=np.uint64)
+    ctx.lde(trace, size, n_bits, ext, ext_bits)
+    xi, vf1, vf2 = rnd_field(41, 3), rnd_field(42, 3), rnd_field(43, 3)
+    ev_map = [(c, 1, o) for o in (0, 1) for c in range(0, size, 2)] + [(5, 3, 0)]
+    dext = ctx.upload(ext)
+    levs = ctx.compute_levs(xi, openings, n_bits)
+    evals = ctx.compute_evals(dext, size, n_bits, ext_bits, [(c, d, openings.index(o)) for c, d, o in ev_map], levs, 2)
+    xdiv = ctx.x_div_x_sub_xi(xi, openings, n_bits, ext_bits, download=False)
+    f = ctx.fri_pol([(dext, size, c, d, o) for c, d, o in ev_map], evals, openings, xdiv, vf1, vf2, ext_bits)
+    coef = np.empty(3 * ne, dtype=np.uint64)
+    ctx.ntt(np.ascontiguousarray(f).reshape(-1), 3, ext_bits, coef, inverse=True)
+    coef = coef.reshape(ne, 3)
+    assert not coef[n:].any(), "f_ext is not of degree < N"
+    assert coef[:n].any()
+    evals[3, 1] ^= np.uint64(1)                                  # one wrong evaluation: no longer a polynomial of degree < N
+    f2 = ctx.fri_pol([(dext, size, c, d, o) for c, d, o in ev_map], evals, openings, xdiv, vf1, vf2, ext_bits)
+    ctx.ntt(np.ascontiguousarray(f2).reshape(-1), 3, ext_bits, coef.reshape(-1), inverse=True)
+    assert coef.reshape(ne, 3)[n:].any()
+    for b in (dext, levs, xdiv):
+        b.free()

@@ -92,3 +92,51 @@ def test_x_div_x_sub_xi_c_equals_spec_and_definition():
             x = S.SHIFT * pow(w, k, P) % P
             v = [int(t) for t in got[k, i]]
             assert S.f3_mul(v, S.f3_sub([x, 0, 0], z)) == [x, 0, 0]          # v * (x - xi) == x
+
+
+def _fri_pol_case(rng, n_bits, ext_bits, openings, ev_primes):
+    """A consistent opening instance: random low-degree columns (one base-field buffer, one with an F3 column), their
+    evaluations at xi*w^prime, the xDivXSubXi table and two random combination challenges."""
+    n, ne = 1 << n_bits, 1 << ext_bits
+    size_a, size_b = 4, 5
+    a_n, b_n = _rand(rng, n * size_a), _rand(rng, n * size_b)
+    a_ext, b_ext = C.lde(a_n, size_a, n_bits, ext_bits), C.lde(b_n, size_b, n_bits, ext_bits)
+    xi = [int(x) for x in _rand(rng, 3)]
+    ev_map = []
+    cols = [("a", 0, 1), ("a", 3, 1), ("b", 1, 3), ("b", 0, 1), ("a", 1, 1), ("b", 4, 1)]
+    for (name, off, dim), prime in zip(cols, ev_primes):
+        ev_map.append((name, off, dim, prime))
+    levs = {o: C.lev(np.array(xi, dtype=np.uint64), o, n_bits) for o in set(ev_primes)}
+    evals = []
+    for name, off, dim, prime in ev_map:
+        buf, size = (a_ext, size_a) if name == "a" else (b_ext, size_b)
+        evals.append([int(x) for x in C.evals({"x": (buf, size)}, [("x", off, dim, 0)], [levs[prime]], n_bits, ext_bits - n_bits)[0]])
+    xdiv = C.x_div_x_sub_xi(np.array(xi, dtype=np.uint64), openings, n_bits, ext_bits)
+    vf1, vf2 = [int(x) for x in _rand(rng, 3)], [int(x) for x in _rand(rng, 3)]
+    return {"a": (a_ext, size_a), "b": (b_ext, size_b)}, ev_map, evals, xdiv, vf1, vf2
+
+
+@pytest.mark.parametrize("openings,primes", [([0, 1], [0, 1, 0, 1, 0, 0]), ([0, 1, -1], [1, -1, 0, 0, -1, 1]), ([0], [0] * 6)])
+def test_fri_polynomial_c_equals_spec_and_is_low_degree(openings, primes):
+    """C port == spec, JS key-order quirk included ([1, -1, 0] enumerates as 0, 1, -1), and the soundness identity the whole FRI
+    stage rests on: with honest evaluations every (p_i(x) - ev_i) * x / (x - xi w^o) is a polynomial, so f_ext interpolates to
+    degree < N -- its coefficients above N vanish."""
+    n_bits, ext_bits = 4, 6
+    rng = np.random.default_rng(len(openings))
+    buffers, ev_map, evals, xdiv, vf1, vf2 = _fri_pol_case(rng, n_bits, ext_bits, openings, primes)
+    got = C.fri_polynomial(buffers, ev_map, evals, openings, xdiv, np.array(vf1, dtype=np.uint64), np.array(vf2, dtype=np.uint64), ext_bits,
+                           threads=2)
+    spec_bufs = {k: ([int(x) for x in v[0]], v[1]) for k, v in buffers.items()}
+    want = S.fri_polynomial(spec_bufs, ev_map, evals, openings, [int(x) for x in xdiv.reshape(-1)], vf1, vf2, ext_bits)
+    assert [list(map(int, r)) for r in got] == want
+    assert S.js_object_key_order([1, -1, 0]) == [0, 1, -1]
+    # coefficients of f on the coset 7<w_ext>: INTT, then undo the shift; degree < N (+ the x factor keeps it <= N - 1 + 1 - 1)
+    coeffs = S.intt([list(map(int, r)) for r in got])
+    n = 1 << n_bits
+    assert all(c == [0, 0, 0] for c in coeffs[n:]), "f_ext is not of degree < N"
+    # and a wrong evaluation breaks it
+    bad = [list(e) for e in evals]
+    bad[2][0] = (bad[2][0] + 1) % P
+    f_bad = C.fri_polynomial(buffers, ev_map, bad, openings, xdiv, np.array(vf1, dtype=np.uint64), np.array(vf2, dtype=np.uint64), ext_bits)
+    coeffs_bad = S.intt([list(map(int, r)) for r in f_bad])
+    assert any(c != [0, 0, 0] for c in coeffs_bad[n:])
