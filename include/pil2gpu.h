@@ -153,6 +153,13 @@ int pil2gpu_fri_pol_dev(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_
                         uint32_t n_open, const uint64_t* xdiv_dev, const uint64_t vf1[3], const uint64_t vf2[3], uint32_t nBitsExt,
                         uint64_t* f_dev);
 
+/* Host-buffer form of all of computeFRIStark's arithmetic (:289-334): terms[i].buf_dev are HOST pointers here (each distinct
+ * buffer is uploaded once), the xDivXSubXi table is built on the device from xi_challenge, f_out (2^nBitsExt x 3) and, if
+ * xdiv_out != NULL, the table (2^nBitsExt x n_open x 3) come back.  Synchronous. */
+int pil2gpu_fri_pol(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_t n_terms, const uint64_t* evals, const int32_t* openings,
+                    uint32_t n_open, const uint64_t xi_challenge[3], const uint64_t vf1[3], const uint64_t vf2[3], uint32_t nBits,
+                    uint32_t nBitsExt, uint64_t* f_out, uint64_t* xdiv_out);
+
 /* ---- hashing: src/helpers/hash/poseidon/poseidon.js, linearhash/ *.js -------------------------------------- */
 /* poseidon(inputs[8], capacity[4], nOuts) poseidon.js:57-108: full 12-word permutation of in12 = inputs || capacity. */
 int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[12]);

@@ -57,4 +57,28 @@ async function computeEvalsStark(ctx) {
 function computeXDivXSubXi(ctx) {
     addon.xDivXSubXi(context(), xiOf(ctx), openingsOf(ctx), ctx.nBits, ctx.nBitsExt, flat(ctx.xDivXSubXi_ext));
 }
-module.exports = { extendAndMerkelize, computeQStark, computeEvalsStark, computeXDivXSubXi };
+// computeFRIStark, stark_gen_helpers.js:275-334: the xDivXSubXi table and friExp over the extended domain in one call
+// (replaces the two BigInt loops and callCalculateExps(stage, friExp code, "ext")); fills ctx.xDivXSubXi_ext, ctx.f_ext, ctx.friPol[0].
+async function computeFRIStark(ctx) {
+    const stage = ctx.pilInfo.nStages + 3;
+    const names = [], bufs = [];
+    const meta = new BigInt64Array(5 * ctx.pilInfo.evMap.length);
+    ctx.pilInfo.evMap.forEach((ev, i) => {
+        let name, size, offset, dim;
+        if (ev.type === "const") { name = "const_ext"; size = ctx.pilInfo.nConstants; offset = ev.id; dim = 1; }
+        else if (ev.type === "cm") { const p = ctx.pilInfo.cmPolsMap[ev.id]; name = "cm" + p.stage + "_ext"; size = ctx.pilInfo.mapSectionsN["cm" + p.stage]; offset = p.stagePos; dim = p.dim; }
+        else throw new Error("Invalid ev type: " + ev.type);
+        let bi = names.indexOf(name);
+        if (bi < 0) { bi = names.length; names.push(name); bufs.push(flat(ctx[name])); }
+        meta.set([BigInt(bi), BigInt(size), BigInt(offset), BigInt(dim), BigInt(Number(ev.prime))], 5 * i);
+    });
+    const evals = new BigUint64Array(3 * ctx.evals.length);
+    ctx.evals.forEach((e, i) => { const v = Array.isArray(e) ? e : [e, 0n, 0n]; evals.set(v.map(BigInt), 3 * i); });
+    const fExt = flat(ctx.f_ext);
+    addon.friPol(context(), bufs, meta, evals, openingsOf(ctx), xiOf(ctx), BigUint64Array.from(ctx.challenges[stage][0]),
+        BigUint64Array.from(ctx.challenges[stage][1]), ctx.nBits, ctx.nBitsExt, fExt, flat(ctx.xDivXSubXi_ext));
+    ctx.friPol = []; ctx.friProof = [{}]; ctx.friTrees = [];
+    ctx.friPol[0] = new Array(ctx.extN);
+    for (let i = 0; i < ctx.extN; i++) ctx.friPol[0][i] = [fExt[3 * i], fExt[3 * i + 1], fExt[3 * i + 2]];   // :327-334
+}
+module.exports = { extendAndMerkelize, computeQStark, computeEvalsStark, computeXDivXSubXi, computeFRIStark };

@@ -166,6 +166,33 @@ static napi_value XDivXSubXi(napi_env env, napi_callback_info info) {
     if (pil2gpu_x_div_x_sub_xi(get_ctx(env, a[0]), xi, op, (uint32_t)nop, u32_of(env, a[3]), u32_of(env, a[4]), out)) return fail(env);
     return nullptr;
 }
+// friPol(ctx, bufs: BigUint64Array[], meta: BigInt64Array(5 per term: buffer index, row size, offset, dim, prime), evals(3 per term),
+//        openings Int32Array, xi(3), vf1(3), vf2(3), nBits, nBitsExt, fOut, xdivOut|null)      (computeFRIStark :289-334)
+static napi_value FriPol(napi_env env, napi_callback_info info) {
+    size_t argc = 13; napi_value a[13]; NAPI_OK(napi_get_cb_info(env, info, &argc, a, nullptr, nullptr));
+    std::vector<uint64_t*> bp; std::vector<uint64_t> bw;
+    uint64_t *ev, *xi, *v1, *v2, *fout, *xdout = nullptr; size_t l, nev; int64_t* meta; size_t nmeta; int32_t* op; size_t nop;
+    napi_typedarray_type ty; napi_value ab; size_t off;
+    if (!get_pages(env, a[1], bp, bw) || napi_get_typedarray_info(env, a[2], &ty, &nmeta, (void**)&meta, &ab, &off) != napi_ok || ty != napi_bigint64_array ||
+        !get_u64_array(env, a[3], &ev, &nev) || napi_get_typedarray_info(env, a[4], &ty, &nop, (void**)&op, &ab, &off) != napi_ok || ty != napi_int32_array ||
+        !get_u64_array(env, a[5], &xi, &l) || l != 3 || !get_u64_array(env, a[6], &v1, &l) || l != 3 || !get_u64_array(env, a[7], &v2, &l) || l != 3 ||
+        !get_u64_array(env, a[10], &fout, &l)) {
+        napi_throw_type_error(env, nullptr, "bad argument types"); return nullptr;
+    }
+    get_u64_array(env, a[11], &xdout, &l);
+    const uint32_t n = (uint32_t)(nmeta / 5);
+    if (nev != (size_t)3 * n) { napi_throw_range_error(env, nullptr, "evals must hold 3 words per term"); return nullptr; }
+    std::vector<pil2gpu_fri_term> terms(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const int64_t bi = meta[5 * i];
+        if (bi < 0 || (size_t)bi >= bp.size()) { napi_throw_range_error(env, nullptr, "buffer index out of range"); return nullptr; }
+        terms[i].buf_dev = bp[bi]; terms[i].size = (uint64_t)meta[5 * i + 1]; terms[i].offset = (uint64_t)meta[5 * i + 2];
+        terms[i].dim = (uint32_t)meta[5 * i + 3]; terms[i].prime = (int32_t)meta[5 * i + 4];
+    }
+    if (pil2gpu_fri_pol(get_ctx(env, a[0]), terms.data(), n, ev, op, (uint32_t)nop, xi, v1, v2, u32_of(env, a[8]), u32_of(env, a[9]), fout, xdout))
+        return fail(env);
+    return nullptr;
+}
 
 static napi_value Init(napi_env env, napi_value exports) {
     const napi_property_descriptor props[] = {
@@ -181,6 +208,7 @@ static napi_value Init(napi_env env, napi_value exports) {
         {"computeQ", nullptr, ComputeQ, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"computeEvals", nullptr, ComputeEvals, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"xDivXSubXi", nullptr, XDivXSubXi, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"friPol", nullptr, FriPol, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
     return exports;

@@ -69,6 +69,7 @@ _SIGS = {
     "pil2gpu_compute_evals": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp, c_u64, vp, c_u32, vp]),
     "pil2gpu_x_div_x_sub_xi": (c_int, [vp, vp, vp, c_u32, c_u32, c_u32, vp]),
     "pil2gpu_fri_pol_dev": (c_int, [vp, vp, c_u32, vp, vp, c_u32, vp, vp, vp, c_u32, vp]),
+    "pil2gpu_fri_pol": (c_int, [vp, vp, c_u32, vp, vp, c_u32, vp, vp, vp, c_u32, c_u32, vp, vp]),
     "pil2gpu_poseidon": (c_int, [vp, vp, vp]),
     "pil2gpu_linear_hash": (c_int, [vp, vp, c_u64, c_int, vp]),
     "pil2gpu_merkle_nnodes": (c_u64, [c_u64]),

@@ -218,6 +218,26 @@ class Context:
         out.free()
         return res
 
+    def fri_pol_host(self, terms, evals, openings, xi_challenge, vf1, vf2, n_bits, n_bits_ext, want_xdiv=False):
+        """All of computeFRIStark's arithmetic with HOST buffers: terms as (numpy buffer, row size, offset, dim, prime)."""
+        n = len(terms)
+        arr = (_lib.FriTerm * n)()
+        keep = []
+        for i, (buf, size, offset, dim, prime) in enumerate(terms):
+            _as_u64(buf, "extended buffer")
+            if buf.size != size << n_bits_ext:
+                raise ValueError("buffer size does not match size * 2^nBitsExt")
+            keep.append(buf)
+            arr[i] = _lib.FriTerm(buf.ctypes.data, int(size), int(offset), int(dim), int(prime))
+        ev = np.ascontiguousarray(np.asarray(evals, dtype=np.uint64).reshape(-1))
+        op = (ctypes.c_int32 * len(openings))(*[int(o) for o in openings])
+        xi, a, b = (np.ascontiguousarray(v, dtype=np.uint64).reshape(-1) for v in (xi_challenge, vf1, vf2))
+        f = np.empty(3 << n_bits_ext, dtype=np.uint64)
+        xd = np.empty(3 * len(openings) << n_bits_ext, dtype=np.uint64) if want_xdiv else None
+        check(self._L.pil2gpu_fri_pol(self.handle, arr, n, _ptr(ev), op, len(openings), _ptr(xi), _ptr(a), _ptr(b), n_bits, n_bits_ext, _ptr(f),
+                                      _ptr(xd) if want_xdiv else None))
+        return (f.reshape(-1, 3), xd) if want_xdiv else f.reshape(-1, 3)
+
     # ---- device-resident commit ----
     def commit(self, src, n_pols, n_bits, n_bits_ext, split=False):
         """interpolate + merkelize with the LDE kept in HBM.  Returns (DeviceTree, root[4])."""

@@ -790,6 +790,42 @@ int pil2gpu_fri_pol_dev(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_
     return check_launch(ctx, launches, "fri_pol");
 }
 
+// Host-buffer form of the whole of computeFRIStark's arithmetic (:289-334): uploads every distinct extended buffer once, builds
+// the xDivXSubXi table on the device and returns f_ext (and the table, if wanted).  terms[i].buf_dev holds HOST pointers here.
+int pil2gpu_fri_pol(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_t n_terms, const uint64_t* evals, const int32_t* openings,
+                    uint32_t n_open, const uint64_t xi_challenge[3], const uint64_t vf1[3], const uint64_t vf2[3], uint32_t nBits,
+                    uint32_t nBitsExt, uint64_t* f_out, uint64_t* xdiv_out) {
+    ENTER(ctx);
+    if (!terms || !f_out || n_terms == 0 || n_open == 0) return fail(PIL2GPU_E_INVALID, "null or empty argument");
+    if (nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    const u64 E = 1ULL << nBitsExt;
+    struct BufRef { const uint64_t* host; uint64_t size; size_t off; };
+    std::vector<BufRef> bufs;
+    size_t words = 0;
+    for (uint32_t i = 0; i < n_terms; i++) {
+        if (!terms[i].buf_dev) return fail(PIL2GPU_E_INVALID, "term %u: null buffer", i);
+        bool seen = false;
+        for (const BufRef& b : bufs) seen |= (b.host == terms[i].buf_dev && b.size == terms[i].size);
+        if (!seen) { bufs.push_back(BufRef{terms[i].buf_dev, terms[i].size, words}); words += ev2(E * terms[i].size); }
+    }
+    const size_t xw = ev2((size_t)3 * n_open * E), fw = 3 * E;
+    int rc = ensure_ws(ctx, words + xw + fw);
+    if (rc) return rc;
+    u64 *xd = ctx->ws + words, *f = ctx->ws + words + xw;
+    for (const BufRef& b : bufs) CU(cudaMemcpyAsync(ctx->ws + b.off, b.host, E * b.size * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<pil2gpu_fri_term> dterms(terms, terms + n_terms);
+    for (uint32_t i = 0; i < n_terms; i++)
+        for (const BufRef& b : bufs) if (b.host == terms[i].buf_dev && b.size == terms[i].size) dterms[i].buf_dev = ctx->ws + b.off;
+    rc = pil2gpu_x_div_x_sub_xi_dev(ctx, xi_challenge, openings, n_open, nBits, nBitsExt, xd);
+    if (rc) return rc;
+    rc = pil2gpu_fri_pol_dev(ctx, dterms.data(), n_terms, evals, openings, n_open, xd, vf1, vf2, nBitsExt, f);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(f_out, f, fw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xdiv_out) CU(cudaMemcpyAsync(xdiv_out, xd, (size_t)3 * n_open * E * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
 // Gather a paged host buffer into device memory / scatter back (async on the ctx stream).
 static int pages_to_dev(pil2gpu_ctx* ctx, u64* dev, const uint64_t* const* pages, const uint64_t* page_words, uint32_t n_pages, size_t expect) {
     size_t off = 0;

@@ -119,20 +119,17 @@ def computeFRIPol(ctx, options=None):
     vf1, vf2 = ctx.challenges[stage][0], ctx.challenges[stage][1]
     xi = ctx.challenges[ctx.pilInfo["nStages"] + 1][0]
     openings = [int(o) for o in ctx.pilInfo["openingPoints"]]
-    dev = dict(getattr(ctx, "dev_buffers", {}))
-    owned = []
-    terms = []
-    for ev in ctx.pilInfo["evMap"]:
-        name, size, offset, dim = _pol_ref_ext(ctx, ev)
-        if name not in dev:
-            dev[name] = g.upload(getattr(ctx, name))
-            owned.append(dev[name])
-        terms.append((dev[name], size, offset, dim, int(ev["prime"])))
-    xdiv = g.x_div_x_sub_xi(xi, openings, ctx.nBits, ctx.nBitsExt, download=False)
-    f = g.fri_pol(terms, ctx.evals, openings, xdiv, vf1, vf2, ctx.nBitsExt)
-    xdiv.free()
-    for b in owned:
-        b.free()
+    dev = getattr(ctx, "dev_buffers", {})          # optional: name -> DeviceBuffer of extended buffers already in HBM
+    refs = [_pol_ref_ext(ctx, ev) + (int(ev["prime"]),) for ev in ctx.pilInfo["evMap"]]
+    if all(name in dev for name, _, _, _, _ in refs):
+        xdiv = g.x_div_x_sub_xi(xi, openings, ctx.nBits, ctx.nBitsExt, download=False)
+        f = g.fri_pol([(dev[name], size, offset, dim, prime) for name, size, offset, dim, prime in refs], ctx.evals, openings, xdiv, vf1, vf2,
+                      ctx.nBitsExt)
+        ctx.xDivXSubXi_ext = xdiv.download()
+        xdiv.free()
+    else:
+        f, ctx.xDivXSubXi_ext = g.fri_pol_host([(getattr(ctx, name), size, offset, dim, prime) for name, size, offset, dim, prime in refs],
+                                               ctx.evals, openings, xi, vf1, vf2, ctx.nBits, ctx.nBitsExt, want_xdiv=True)
     ctx.f_ext = f.reshape(-1)
     if not hasattr(ctx, "friPol") or ctx.friPol is None:
         ctx.friPol = {}
