@@ -8,7 +8,9 @@
 
 The trace, the quotient and the challenges are synthetic (constraint evaluation is AIR-specific and stays in the reference's
 JavaScript); everything downstream of them is the real pipeline, so the run ends with the same checks stark_verify.js makes
-on the FRI part of a proof.     usage: python examples/stage_flow.py [nBits=16] [columns=64]
+on the FRI part of a proof.     usage: python examples/stage_flow.py [nBits=16] [columns=64] [host|device]
+"device" keeps the committed buffers and trees in HBM (ctx.device_resident): only roots, evaluations, f_ext and the opened
+rows cross PCIe; "host" (default) returns every extended buffer to the host like the reference's BigBuffers.
 """
 import sys
 import time
@@ -32,6 +34,7 @@ def field(rng, n):
 def main():
     n_bits = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     cols = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    device = len(sys.argv) > 3 and sys.argv[3] == "device"
     ext_bits = n_bits + 1
     N, extN = 1 << n_bits, 1 << ext_bits
     steps = [ext_bits]
@@ -47,13 +50,17 @@ def main():
                     [{"type": "cm", "id": cols, "prime": 0}, {"type": "cm", "id": cols + 1, "prime": 0}] +
                     [{"type": "const", "id": c, "prime": 0} for c in range(4)])
     ctx = types.SimpleNamespace(pilInfo=pil, nBits=n_bits, nBitsExt=ext_bits, N=N, extN=extN, extendBits=1, trees={}, gpu=gpu,
-                                MH=m.buildMerkleHash(False, gpu), challenges={}, cm2_ext=None)
+                                MH=m.buildMerkleHash(False, gpu), challenges={}, cm2_ext=None, device_resident=device, dev_buffers=None)
     ctx.cm1_n = field(rng, cols * N)
     ctx.cm1_ext = np.empty(cols * extN, dtype=np.uint64)
     const_n = field(rng, 4 * N)
-    ctx.const_ext = np.empty(4 * extN, dtype=np.uint64)
-    m.interpolate(const_n, 4, n_bits, ctx.const_ext, ext_bits, ctx=gpu)
-    ctx.constTree = ctx.MH.merkelize(ctx.const_ext, 4, extN)
+    if device:
+        ctx.constTree, _ = gpu.commit(const_n, 4, n_bits, ext_bits)
+        ctx.dev_buffers = {"const_ext": ctx.constTree.elements_ptr}
+    else:
+        ctx.const_ext = np.empty(4 * extN, dtype=np.uint64)
+        m.interpolate(const_n, 4, n_bits, ctx.const_ext, ext_bits, ctx=gpu)
+        ctx.constTree = ctx.MH.merkelize(ctx.const_ext, 4, extN)
     # a synthetic quotient of degree < qDeg * N: its evaluations on the extended coset
     q_n = field(rng, 3 * extN)
     ctx.q_ext = np.empty(3 * extN, dtype=np.uint64)
@@ -103,7 +110,8 @@ def main():
     max_deg = 1 << (steps[-1] - (ext_bits - n_bits))
     assert not coef.reshape(-1, 3)[max_deg:].any(), "final FRI polynomial exceeds the degree bound"
     print(f"2^{n_bits} rows x {cols} columns, blowup 2, FRI steps {steps}, {len(queries)} queries")
-    print("  (host-buffer entry points on pageable numpy arrays: every stage pays its PCIe transfers; bench.py has the device-resident and pinned numbers)")
+    print("  mode: " + ("device-resident buffers and trees" if device else
+                        "host buffers (pageable numpy arrays: every stage pays its PCIe transfers; bench.py has the pinned numbers)"))
     for name, dt in timings:
         print(f"  {name:44s} {dt * 1e3:9.2f} ms")
     print(f"verified {ok_paths} Merkle paths of the stage/const trees; final polynomial has degree < {max_deg}: OK")

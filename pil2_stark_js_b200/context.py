@@ -129,6 +129,26 @@ class Context:
                                         _ptr(ext) if want_ext else None, _ptr(nodes) if want_nodes else None, _ptr(root)))
         return ext, nodes, root
 
+    def compute_q_tree(self, q_ext, q_dim, q_deg, n_bits, n_bits_ext, split=False):
+        """computeQStark (stark_gen_helpers.js:168-208) with the result kept in HBM: q_ext (host) is uploaded, cmQ_ext and
+        its tree never leave the device.  Returns (DeviceTree, root[4])."""
+        _as_u64(q_ext, "q_ext")
+        if q_ext.size != q_dim << n_bits_ext:
+            raise ValueError("buffer size does not match qDim * 2^nBitsExt")
+        q_dev = self.upload(q_ext)
+        tree = self.tree_alloc(q_dim * q_deg, 1 << n_bits_ext)
+        try:
+            check(self._L.pil2gpu_compute_q_dev(self.handle, q_dev.ptr, q_dim, q_deg, n_bits, n_bits_ext, vp(tree.elements_ptr)))
+            check(self._L.pil2gpu_merkelize_dev(self.handle, vp(tree.elements_ptr), q_dim * q_deg, 1 << n_bits_ext, int(split),
+                                                vp(tree.nodes_ptr)))
+            root = tree.root()
+        except Exception:
+            tree.free()
+            raise
+        finally:
+            q_dev.free()
+        return tree, root
+
     def alloc(self, words):
         return DeviceBuffer(self, words)
 

@@ -11,6 +11,10 @@ against the GPU library:
     computeFRIQueries(ctx, friQueries)      :358-360
     getPermutationsStark(ctx, challenge)    :474-493
 
+With ctx.device_resident = True the committed buffers and trees stay in HBM (ctx.trees[stage] is a DeviceTree, ctx.dev_buffers
+maps "cmK_ext" to its device address): evaluations, the FRI polynomial and the query openings then read them in place and
+only roots, evaluations, f_ext and the opened rows cross PCIe -- the integration INTEGRATION.md section 3 describes.
+
 `ctx` is any attribute bag (types.SimpleNamespace) carrying the reference's field names: pilInfo (dict with qDim, qDeg,
 nStages, mapSectionsN, openingPoints, evMap, cmPolsMap, nConstants, starkStruct), nBits, nBitsExt, N, extN, extendBits,
 cm<stage>_n / cm<stage>_ext / const_ext / q_ext (numpy uint64, row-major), trees, MH, challenges, fri, friPol, friProof,
@@ -31,6 +35,12 @@ def _split(ctx):
     return bool(getattr(ctx.MH, "splitLinearHash", False))
 
 
+def _dev_buffers(ctx):
+    if getattr(ctx, "dev_buffers", None) is None:
+        ctx.dev_buffers = {}
+    return ctx.dev_buffers
+
+
 def _tree(buff, nodes, width, height):
     return {"elements": buff, "nodes": nodes, "width": width, "height": height}
 
@@ -39,6 +49,11 @@ def extendAndMerkelize(stage, ctx, options=None):
     """stark_gen_helpers.js:388-412.  One fused call: the extended buffer stays in HBM between the LDE and the hashing."""
     n_pols = ctx.pilInfo["mapSectionsN"].get("cm%d" % stage, 0)
     buff_from = getattr(ctx, "cm%d_n" % stage)
+    if getattr(ctx, "device_resident", False):
+        tree, root = _gpu(ctx).commit(buff_from, n_pols, ctx.nBits, ctx.nBitsExt, split=_split(ctx))
+        ctx.trees[stage] = tree
+        _dev_buffers(ctx)["cm%d_ext" % stage] = tree.elements_ptr
+        return [[int(x) for x in root]]
     dst, nodes, root = _gpu(ctx).extend_and_merkelize(buff_from, n_pols, ctx.nBits, ctx.nBitsExt, split=_split(ctx))
     getattr(ctx, "cm%d_ext" % stage)[:] = dst
     ctx.trees[stage] = _tree(getattr(ctx, "cm%d_ext" % stage), nodes, n_pols, ctx.extN)
@@ -49,6 +64,13 @@ def computeQStark(ctx, options=None):
     """stark_gen_helpers.js:168-208."""
     q_stage = ctx.pilInfo["nStages"] + 1
     q_dim, q_deg = ctx.pilInfo["qDim"], ctx.pilInfo["qDeg"]
+    if getattr(ctx, "device_resident", False):
+        if ctx.pilInfo["mapSectionsN"].get("cm%d" % q_stage, 0) != q_dim * q_deg:
+            raise ValueError("mapSectionsN.cm%d != qDim*qDeg" % q_stage)
+        tree, root = _gpu(ctx).compute_q_tree(ctx.q_ext, q_dim, q_deg, ctx.nBits, ctx.nBitsExt, split=_split(ctx))
+        ctx.trees[q_stage] = tree
+        _dev_buffers(ctx)["cm%d_ext" % q_stage] = tree.elements_ptr
+        return [[int(x) for x in root]]
     ext, nodes, root = _gpu(ctx).compute_q(ctx.q_ext, q_dim, q_deg, ctx.nBits, ctx.nBitsExt, split=_split(ctx))
     name = "cm%d_ext" % q_stage
     if getattr(ctx, name, None) is None:
@@ -86,7 +108,7 @@ def computeEvalsStark(ctx, options=None):
         name, size, offset, dim = _pol_ref_ext(ctx, ev)
         by_buffer.setdefault((name, size), []).append((i, offset, dim, openings.index(int(ev["prime"]))))
     out = [None] * len(ev_map)
-    dev = getattr(ctx, "dev_buffers", {})          # optional: name -> DeviceBuffer of extended buffers already in HBM
+    dev = getattr(ctx, "dev_buffers", None) or {}  # optional: name -> DeviceBuffer / device address of buffers already in HBM
     levs = g.compute_levs(xi, openings, ctx.nBits) if any(name in dev for name, _ in by_buffer) else None
     for (name, size), items in by_buffer.items():
         descs = [(o, d, l) for _, o, d, l in items]
@@ -119,7 +141,7 @@ def computeFRIPol(ctx, options=None):
     vf1, vf2 = ctx.challenges[stage][0], ctx.challenges[stage][1]
     xi = ctx.challenges[ctx.pilInfo["nStages"] + 1][0]
     openings = [int(o) for o in ctx.pilInfo["openingPoints"]]
-    dev = getattr(ctx, "dev_buffers", {})          # optional: name -> DeviceBuffer of extended buffers already in HBM
+    dev = getattr(ctx, "dev_buffers", None) or {}  # optional: name -> DeviceBuffer / device address of buffers already in HBM
     refs = [_pol_ref_ext(ctx, ev) + (int(ev["prime"]),) for ev in ctx.pilInfo["evMap"]]
     if all(name in dev for name, _, _, _, _ in refs):
         xdiv = g.x_div_x_sub_xi(xi, openings, ctx.nBits, ctx.nBitsExt, download=False)

@@ -261,6 +261,19 @@ def test_stark_gen_helpers_stage_flow(ctx):
     want_f = C.fri_polynomial({"cm1": (want1, 10), "cm2": (want2, 6), "const": (c.const_ext, 4)}, ev_map_o, np.array(evals, dtype=np.uint64), [0, 1],
                               xd, np.array(c.challenges[4][0], dtype=np.uint64), np.array(c.challenges[4][1], dtype=np.uint64), ext_bits)
     assert np.array_equal(f, want_f)
+    # the same stages with everything kept in HBM (ctx.device_resident): identical roots, evaluations, f_ext and openings
+    d = types.SimpleNamespace(pilInfo=pil, nBits=n_bits, nBitsExt=ext_bits, N=N, extN=extN, extendBits=1, trees={}, gpu=ctx, MH=c.MH,
+                              device_resident=True, cm1_n=c.cm1_n, q_ext=c.q_ext, challenges=c.challenges, dev_buffers=None)
+    assert H.extendAndMerkelize(1, d) == root1 and H.computeQStark(d) == root2
+    const_dev = ctx.upload(c.const_ext)
+    d.dev_buffers["const_ext"] = const_dev
+    assert isinstance(d.trees[1], m.DeviceTree) and set(d.dev_buffers) == {"cm1_ext", "cm2_ext", "const_ext"}
+    assert H.computeEvalsStark(d) == evals
+    assert np.array_equal(H.computeFRIPol(d), f)
+    for idx in (0, 5, extN - 1):
+        assert c.MH.getGroupProof(d.trees[1], idx) == c.MH.getGroupProof(c.trees[1], idx)
+        assert c.MH.getGroupProof(d.trees[2], idx) == c.MH.getGroupProof(c.trees[2], idx)
+    const_dev.free(); d.trees[1].free(); d.trees[2].free()
     c.fri = m.FRI(pil["starkStruct"], c.MH)
     c.friPol, c.friProof, c.friTrees = {0: f}, {0: {}}, {}
     H.computeFRIFolding(0, c, [0, 0, 0])
