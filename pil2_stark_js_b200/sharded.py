@@ -131,8 +131,109 @@ class GpuEngine:
         finally:
             self.L.pil2gpu_tree_free(None, t)       # a wrapper: owns nothing on the device
 
+    # ---- evaluations at xi / FRI polynomial on device tensors (the rows next to the commit) ----
+    def compute_levs(self, xi, openings, n_bits):
+        lev = self.empty(len(openings) * (3 << n_bits))
+        xi = np.ascontiguousarray(xi, dtype=np.uint64)
+        for i, o in enumerate(openings):
+            self.check(self.L.pil2gpu_compute_lev_dev(self.h, ctypes.c_void_p(xi.ctypes.data), int(o), n_bits,
+                                                      ctypes.c_void_p(lev.data_ptr() + 8 * i * (3 << n_bits))))
+        return lev
+
+    def compute_evals(self, buf_ptr, size, n_bits, ext_bits, descs, lev, n_lev):
+        from . import _lib
+        n = len(descs)
+        out = np.empty((n, 3), dtype=np.uint64)
+        if n:
+            arr = (_lib.EvalDesc * n)(*[_lib.EvalDesc(int(o), int(d), int(l)) for o, d, l in descs])
+            self.check(self.L.pil2gpu_compute_evals_dev(self.h, ctypes.c_void_p(buf_ptr), size, n_bits, ext_bits, arr, n, self._p(lev), n_lev,
+                                                        ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def x_div_x_sub_xi(self, xi, openings, n_bits, ext_bits):
+        out = self.empty(3 * len(openings) << ext_bits)
+        xi = np.ascontiguousarray(xi, dtype=np.uint64)
+        op = (ctypes.c_int32 * len(openings))(*[int(o) for o in openings])
+        self.check(self.L.pil2gpu_x_div_x_sub_xi_dev(self.h, ctypes.c_void_p(xi.ctypes.data), op, len(openings), n_bits, ext_bits, self._p(out)))
+        return out
+
+    def fri_pol(self, terms, evals, openings, xdiv, vf1, vf2, ext_bits):
+        from . import _lib
+        n = len(terms)
+        arr = (_lib.FriTerm * n)(*[_lib.FriTerm(int(p), int(size), int(off), int(dim), int(prime)) for p, size, off, dim, prime in terms])
+        ev = np.ascontiguousarray(np.asarray(evals, dtype=np.uint64).reshape(-1))
+        op = (ctypes.c_int32 * len(openings))(*[int(o) for o in openings])
+        a, b = (np.ascontiguousarray(v, dtype=np.uint64).reshape(-1) for v in (vf1, vf2))
+        f = self.empty(3 << ext_bits)
+        self.check(self.L.pil2gpu_fri_pol_dev(self.h, arr, n, ctypes.c_void_p(ev.ctypes.data), op, len(openings), self._p(xdiv),
+                                              ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(b.ctypes.data), ext_bits, self._p(f)))
+        return f
+
     def launches(self):
         return int(self.L.pil2gpu_launch_count(self.h))
+
+
+def _tile_terms(tree, offset, dim):
+    """(tile pointer, column inside the tile) of a polynomial of a ShardedTree; its columns must lie in one tile."""
+    t = offset // tree.tile_cols
+    local = offset - t * tree.tile_cols
+    if local + dim > tree.tile_cols:
+        raise ValueError("a polynomial's columns straddle two column tiles")
+    return tree.tiles.data_ptr() + 8 * t * tree.rows_local * tree.tile_cols, local
+
+
+def sharded_evals(engine, dist, rank, world, trees, ev_map, xi, openings, n_bits, ext_bits):
+    """computeEvalsStark (stark_gen_helpers.js:210-273) over row-sharded extended buffers: every rank sums over the base rows it
+    holds (its slice of the LEv vectors), the per-rank partial sums are gathered and added mod p.  trees: name -> ShardedTree;
+    ev_map: list of (tree name, column, dim, opening index).  Returns the (n, 3) uint64 array on every rank."""
+    import torch
+    g_bits = world.bit_length() - 1
+    nb, neb = n_bits - g_bits, ext_bits - g_bits
+    if nb < 0:
+        raise ValueError("more ranks than base rows")
+    n_lev, Nl = len(openings), 1 << nb
+    lev = engine.compute_levs(xi, openings, n_bits).view(n_lev, 1 << n_bits, 3)[:, rank * Nl:(rank + 1) * Nl, :].contiguous().view(-1)
+    out = np.zeros((len(ev_map), 3), dtype=object)
+    by_tile = {}
+    for i, (name, off, dim, oi) in enumerate(ev_map):
+        ptr, local = _tile_terms(trees[name], off, dim)
+        by_tile.setdefault((ptr, trees[name].tile_cols), []).append((i, local, dim, oi))
+    P = 0xFFFFFFFF00000001
+    part = np.zeros((len(ev_map), 3), dtype=np.uint64)
+    for (ptr, size), items in by_tile.items():
+        vals = engine.compute_evals(ptr, size, nb, neb, [(l, d, o) for _, l, d, o in items], lev, n_lev)
+        for (i, _, _, _), v in zip(items, vals):
+            part[i] = v
+    if world == 1:
+        return part
+    mine = torch.from_numpy(part.view(np.int64).reshape(-1)).to(engine.device)
+    allp = engine.empty(world * mine.numel())
+    dist.all_gather_into_tensor(allp, mine)
+    allp = allp.cpu().numpy().view(np.uint64).reshape(world, len(ev_map), 3)
+    for i in range(len(ev_map)):
+        for c in range(3):
+            out[i, c] = sum(int(allp[r, i, c]) for r in range(world)) % P
+    return out.astype(np.uint64)
+
+
+def sharded_fri_pol(engine, dist, rank, world, trees, ev_map, evals, xi, openings, vf1, vf2, n_bits, ext_bits):
+    """computeFRIStark (stark_gen_helpers.js:275-334) over row-sharded extended buffers: f_ext is row-local, so every rank
+    evaluates friExp on the rows it holds (each column tile enters as one buffer of pil2gpu_fri_pol_dev) and one all-gather
+    assembles the 2^ext_bits x 3 polynomial for the FRI chain.  ev_map: list of (tree name, column, dim, prime)."""
+    g_bits = world.bit_length() - 1
+    neb = ext_bits - g_bits
+    R, n_open = 1 << neb, len(openings)
+    xdiv = engine.x_div_x_sub_xi(xi, openings, n_bits, ext_bits).view(1 << ext_bits, n_open * 3)[rank * R:(rank + 1) * R].contiguous().view(-1)
+    terms = []
+    for name, off, dim, prime in ev_map:
+        ptr, local = _tile_terms(trees[name], off, dim)
+        terms.append((ptr, trees[name].tile_cols, local, dim, prime))
+    f_local = engine.fri_pol(terms, evals, openings, xdiv, vf1, vf2, neb)
+    if world == 1:
+        return f_local
+    f = engine.empty(3 << ext_bits)
+    dist.all_gather_into_tensor(f, f_local)
+    return f
 
 
 class ShardedTree:

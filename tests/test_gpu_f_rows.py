@@ -401,3 +401,29 @@ def test_fri_pol_low_degree_large(ctx):
     assert coef.reshape(ne, 3)[n:].any()
     for b in (dext, levs, xdiv):
         b.free()
+
+
+def test_sharded_rows_single_rank_two_tiles(ctx):
+    """sharded_evals / sharded_fri_pol on one rank whose buffer is stored as two column tiles (the layout the row exchange
+    delivers): the tile -> buffer mapping, without any collective."""
+    import torch
+    from pil2_stark_js_b200.sharded import GpuEngine, ShardedTree, sharded_evals, sharded_fri_pol
+    n_bits, ext_bits, cols = 10, 11, 64
+    ne, cg = 1 << ext_bits, 32
+    ext = C.lde(rnd_field(3, cols << n_bits), cols, n_bits, ext_bits).reshape(ne, cols)
+    tiles = np.concatenate([np.ascontiguousarray(ext[:, t * cg:(t + 1) * cg]).reshape(-1) for t in range(2)])
+    eng = GpuEngine(torch, 0)
+    dt = torch.from_numpy(tiles.view(np.int64)).cuda()
+    tree = ShardedTree(eng, None, 0, 1, dt, 2, cg, ne, None, None, None)
+    xi, vf1, vf2 = rnd_field(4, 3), rnd_field(5, 3), rnd_field(6, 3)
+    ev_map = [("t", c, 1, o) for o in (0, 1) for c in range(0, cols, 5)] + [("t", 29, 3, 1), ("t", 33, 3, 0)]
+    ev = sharded_evals(eng, None, 0, 1, {"t": tree}, ev_map, xi, [0, 1], n_bits, ext_bits)
+    want_ev = C.evals({"t": (ext.reshape(-1), cols)}, ev_map, [C.lev(xi, o, n_bits) for o in (0, 1)], n_bits, 1)
+    assert np.array_equal(ev, want_ev)
+    f = sharded_fri_pol(eng, None, 0, 1, {"t": tree}, ev_map, ev, xi, [0, 1], vf1, vf2, n_bits, ext_bits)
+    want_f = C.fri_polynomial({"t": (ext.reshape(-1), cols)}, ev_map, want_ev, [0, 1], C.x_div_x_sub_xi(xi, [0, 1], n_bits, ext_bits), vf1, vf2,
+                              ext_bits)
+    torch.cuda.synchronize()
+    assert np.array_equal(f.cpu().numpy().view(np.uint64).reshape(-1, 3), want_f)
+    with pytest.raises(ValueError):
+        sharded_evals(eng, None, 0, 1, {"t": tree}, [("t", 31, 3, 0)], xi, [0, 1], n_bits, ext_bits)      # straddles the two tiles

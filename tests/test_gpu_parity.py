@@ -358,9 +358,19 @@ def _mgpu_worker(rank, world, port, n_bits, blow, cols, q, mode="peer"):
         eng = sc.e
         lt, lroot = sc.commit_rows(layer, lw, lh, eng.empty(eng.nnodes(lh // world)), eng.empty(4 * world), eng.empty(max(8, eng.nnodes(world))))
         lrows, lsib = lt.open(torch.tensor([0, lh - 1, lh // 2 + 1], dtype=torch.int64, device="cuda"))
+        # the rows next to the commit over the row-sharded buffer: evaluations at xi and the FRI polynomial
+        from pil2_stark_js_b200.sharded import sharded_evals, sharded_fri_pol
+        frng = np.random.default_rng(11)
+        xi, vf1, vf2 = (frng.integers(0, P, size=3, dtype=np.uint64) for _ in range(3))
+        ev_map = [("t", c, 1, o) for o in (0, 1) for c in range(0, cols, 3)] + [("t", 29, 3, 1), ("t", 33, 3, 0)]
+        trees = {"t": buf["tree"]}
+        sev = sharded_evals(eng, dist, rank, world, trees, [(n_, c, d, o) for n_, c, d, o in ev_map], xi, [0, 1], n_bits, n_bits + blow)
+        sf = sharded_fri_pol(eng, dist, rank, world, trees, [(n_, c, d, (0, 1)[o]) for n_, c, d, o in ev_map], sev, xi, [0, 1], vf1, vf2, n_bits,
+                             n_bits + blow)
         torch.cuda.synchronize()
         u = lambda t: t.cpu().numpy().view(np.uint64).copy()
-        q.put((rank, u(root), u(buf["nodes"]), u(buf["top"]), sc.exchange_kind(buf), (qs, u(rows_q), u(sib_q), layer_np, u(lroot), u(lrows), u(lsib))))
+        q.put((rank, u(root), u(buf["nodes"]), u(buf["top"]), sc.exchange_kind(buf),
+               (qs, u(rows_q), u(sib_q), layer_np, u(lroot), u(lrows), u(lsib)), (xi, vf1, vf2, ev_map, sev, u(sf))))
         dist.barrier()
         sc.release(buf)
     finally:
@@ -390,7 +400,14 @@ def test_sharded_commit_two_gpus(mode):
     full = rng.integers(0, P, size=(1 << n_bits, cols), dtype=np.uint64)
     ext = C.lde(full.reshape(-1), cols, n_bits, n_bits + blow)
     nodes = C.merkelize(ext, cols, 1 << (n_bits + blow))
-    for _, root, _, _, kind, extra in res:
+    for _, root, _, _, kind, extra, frows in res:
+        xi, vf1, vf2, ev_map, sev, sf = frows                        # sharded evaluations + FRI polynomial == single-process oracle
+        levs = [C.lev(xi, o, n_bits) for o in (0, 1)]
+        want_ev = C.evals({"t": (ext, cols)}, ev_map, levs, n_bits, blow)
+        assert np.array_equal(sev, want_ev)
+        want_f = C.fri_polynomial({"t": (ext, cols)}, [(n_, c, d, (0, 1)[o]) for n_, c, d, o in ev_map], want_ev, [0, 1],
+                                  C.x_div_x_sub_xi(xi, [0, 1], n_bits, n_bits + blow), vf1, vf2, n_bits + blow)
+        assert np.array_equal(sf.reshape(-1, 3), want_f)
         assert np.array_equal(root, nodes[-4:])
         assert ("peer stores" in kind) == (mode == "peer"), f"exchange used: {kind}"
         qs, rows_q, sib_q, layer, lroot, lrows, lsib = extra          # sharded proofQueries + a sharded layer tree
