@@ -30,8 +30,10 @@ GL_D gl3 fri_load3(const u64* __restrict__ p) { return gl3{{p[0], p[1], p[2]}}; 
 template <int FOLD>
 GL_D gl3 fri_fold_point(const u64* __restrict__ pol, u64 g, int cur_bits, gl3 beta, const u64* __restrict__ tw_inv) {
     constexpr int NX = 1 << FOLD;
-    if (FOLD == 0) return fri_load3(pol + 3 * g);
-    gl3 e[NX / 2 > 0 ? NX / 2 : 1];
+    if constexpr (FOLD == 0) {
+        return fri_load3(pol + 3 * g);
+    } else {
+    gl3 e[NX / 2];
     // first fold straight from memory: pairs (j, j + NX/2)
 #pragma unroll
     for (int j = 0; j < NX / 2; j++) {
@@ -54,6 +56,7 @@ GL_D gl3 fri_fold_point(const u64* __restrict__ pol, u64 g, int cur_bits, gl3 be
         }
     }
     return e[0];
+    }
 }
 
 template <int FOLD>

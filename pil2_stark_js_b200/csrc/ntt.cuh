@@ -364,7 +364,7 @@ __device__ __forceinline__ void ntt_tile_store(const ulonglong2* __restrict__ ti
 //   position(k) = (base_hi << (lo+t)) | (k << lo) | base_lo,   tile id = (base_hi << lo) | base_lo
 // gridDim.x = 2^(n-t) tiles, gridDim.y = ceil(C / NTT_W) column chunks, gridDim.z = cosets.
 template <bool DIF, bool INVERSE, bool SC = false>
-__global__ void __launch_bounds__(NTT_THREADS, NTT_PASS_MIN_CTAS) ntt_pass_kernel(const u64* __restrict__ in, u64* __restrict__ out, NttPass P, NttTables tb,
+__global__ void __launch_bounds__(NTT_THREADS, NTT_PASS_MIN_CTAS) ntt_pass_kernel(const u64* in, u64* out, NttPass P, NttTables tb,   // in == out for the in-place passes: no __restrict__
                                                                const __grid_constant__ NttScatter sc) {
     extern __shared__ __align__(16) u64 ntt_smem[];
     const int t = P.t, lo = P.lo;

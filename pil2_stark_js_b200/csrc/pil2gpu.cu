@@ -930,7 +930,7 @@ static int merkelize_tiles(pil2gpu_ctx* ctx, RowTiles t, uint64_t width, uint64_
 
 int pil2gpu_merkelize_dev(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t width, uint64_t height, int split, uint64_t* nodes) {
     ENTER(ctx);
-    if (!nodes || (!elems && width * height)) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (!nodes || (!elems && width * height != 0)) return fail(PIL2GPU_E_INVALID, "null buffer");
     if (height == 0) return fail(PIL2GPU_E_INVALID, "height must be > 0");
     RowTiles t = {(const u64*)elems, width ? width : 1, 0};
     return merkelize_tiles(ctx, t, width, height, split, nodes);
@@ -1232,7 +1232,7 @@ int pil2gpu_synth_dev(pil2gpu_ctx* ctx, uint64_t* dst_dev, uint64_t n_words, uin
 
 int pil2gpu_synth2d_dev(pil2gpu_ctx* ctx, uint64_t* dst_dev, uint64_t rows, uint64_t cols, uint64_t row_stride, uint64_t col0, uint64_t seed) {
     ENTER(ctx);
-    if (!dst_dev && rows * cols) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (!dst_dev && rows * cols != 0) return fail(PIL2GPU_E_INVALID, "null buffer");
     if (rows * cols == 0) return PIL2GPU_OK;
     synth2d_kernel<<<148 * 16, 256, 0, ctx->stream>>>((u64*)dst_dev, rows, cols, row_stride, col0, seed);
     return check_launch(ctx, 1, "synth2d");
@@ -1278,7 +1278,7 @@ int pil2gpu_tree_from_host(pil2gpu_ctx* ctx, const uint64_t* elems, uint64_t wid
     t->tile_cols = width ? width : 1;
     t->height = height;
     t->own_elems = t->own_nodes = true;
-    cudaError_t e = cudaMalloc(&t->elems, (width * height ? width * height : 1) * 8);
+    cudaError_t e = cudaMalloc(&t->elems, (width * height != 0 ? width * height : 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&t->nodes, merkle_nnodes_words(height) * 8);
     if (e != cudaSuccess) { pil2gpu_tree_free(ctx, t); return fail(PIL2GPU_E_NOMEM, "device allocation failed: %s", cudaGetErrorString(e)); }
     e = cudaMemcpyAsync(t->elems, elems, width * height * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -1301,7 +1301,7 @@ int pil2gpu_tree_alloc(pil2gpu_ctx* ctx, uint64_t width, uint64_t height, pil2gp
     t->tile_cols = width ? width : 1;
     t->height = height;
     t->own_elems = t->own_nodes = true;
-    cudaError_t e = cudaMalloc(&t->elems, (width * height ? width * height : 1) * 8);
+    cudaError_t e = cudaMalloc(&t->elems, (width * height != 0 ? width * height : 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&t->nodes, merkle_nnodes_words(height) * 8);
     if (e != cudaSuccess) { pil2gpu_tree_free(ctx, t); return fail(PIL2GPU_E_NOMEM, "device allocation failed: %s", cudaGetErrorString(e)); }
     *tree_out = t;
