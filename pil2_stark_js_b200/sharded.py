@@ -500,6 +500,31 @@ def bench_main(args, rank, world, local_rank, dist, bench):
     launches = torch.tensor([eng.launches() - l0], device="cuda")
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     torch.cuda.synchronize()
+    # ---- the rows next to the commit over the row-sharded buffer: evaluations at xi and the FRI polynomial for every
+    # column at two openings, timed as whole calls (max over ranks of the wall clock between synchronisations) ----
+    extras = None
+    if not getattr(args, "no_extras", False):
+        import time
+        xi = np.ascontiguousarray(bench.splitmix_field(seed + 10, 0, 3))
+        vf1, vf2 = (np.ascontiguousarray(bench.splitmix_field(seed + 11 + i, 0, 3)) for i in range(2))
+        ev_map = [("t", c, 1, o) for o in (0, 1) for c in range(cols)]
+        trees = {"t": buf["tree"]}
+
+        def wall(fn, reps=2):
+            fn()                                           # warm-up (pool growth, first-launch costs)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = fn()
+            torch.cuda.synchronize()
+            dt = torch.tensor([(time.perf_counter() - t0) / reps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item()), out
+        t_ev, evs = wall(lambda: sharded_evals(eng, dist, rank, world, trees, ev_map, xi, [0, 1], n_bits, ext_bits))
+        t_fp, _ = wall(lambda: sharded_fri_pol(eng, dist, rank, world, trees, ev_map, evs, xi, [0, 1], vf1, vf2, n_bits, ext_bits))
+        extras = {"evals": {"s": t_ev, "shape": f"{len(ev_map)} evaluations, base rows sharded over {world} ranks (LEv vectors + sums + gather)"},
+                  "fri_pol": {"s": t_fp, "shape": f"{len(ev_map)} evMap terms, 2^{ext_bits} rows sharded over {world} ranks (xDivXSubXi + friExp + all-gather)"}}
+
     # ---- e2e: the same sharded commit with HOST buffers: every rank uploads its column slab from pinned memory and
     # downloads its share of the extended rows and of the nodes; rank 0 also moves the FRI polynomial and layers ----
     e2e = None
@@ -606,7 +631,7 @@ def bench_main(args, rank, world, local_rank, dist, bench):
                    "opened on the owning ranks and combined with one all-reduce per tree",
             "gpu_launches": int(launches.item()), "clocks": clocks,
             "root": root,
-            "e2e": e2e, "cpu_baseline": None,
+            "e2e": e2e, "next_rows": extras, "cpu_baseline": None,
             "roofline": {"kernel": "merkle_leaf_kernel (per-rank share)", "bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None,
                          "traffic": None,
                          "note": "per-kernel roofline is reported by the N=1 run (same kernels on 1/N of the rows); N>1 moves "
