@@ -456,6 +456,45 @@ def test_group_proofs_dev_and_rows_only_fold(ctx):
         b.free()
 
 
+def test_paged_bigbuffer_entry_points(ctx):
+    """pilcom BigBuffer = a list of BigUint64Array pages: the _paged twins take ragged page lists (an empty page included) and
+    must give the single-buffer result; page lists that do not add up are rejected."""
+    import ctypes
+    import pil2_stark_js_b200 as m
+    from pil2_stark_js_b200._lib import check
+    L = ctx._L
+    n_bits, ext_bits, cols = 9, 10, 12
+
+    def pages(arr, cuts):
+        parts = np.split(arr, cuts)
+        ptrs = (ctypes.c_void_p * len(parts))(*[p.ctypes.data if p.size else 0 for p in parts])
+        words = np.array([p.size for p in parts], dtype=np.uint64)
+        return parts, ptrs, words
+
+    src = rnd_field(61, cols << n_bits)
+    dst = np.zeros(cols << ext_bits, dtype=np.uint64)
+    sp, sptr, sw = pages(src, [7, 7, 1000, 4097])                                 # ragged, with an empty page
+    dp, dptr, dw = pages(dst, [5000, 5001])
+    check(L.pil2gpu_lde_paged(ctx.handle, sptr, sw.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(sp), dptr,
+                              dw.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(dp), cols, n_bits, ext_bits))
+    want = C.lde(src, cols, n_bits, ext_bits)
+    assert np.array_equal(np.concatenate(dp), want)
+    nodes = np.empty(ctx.merkle_nnodes(1 << ext_bits), dtype=np.uint64)
+    ep, eptr, ew = pages(want, [1, 12 * 3 + 5, 9000])                             # page boundaries inside rows
+    check(L.pil2gpu_merkelize_paged(ctx.handle, eptr, ew.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(ep), cols, 1 << ext_bits, 0,
+                                    nodes.ctypes.data))
+    assert np.array_equal(nodes, C.merkelize(want, cols, 1 << ext_bits))
+    short = np.array([p.size for p in ep[:-1]], dtype=np.uint64)                  # one page missing
+    with pytest.raises(m.Pil2GpuError):
+        check(L.pil2gpu_merkelize_paged(ctx.handle, eptr, short.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(ep) - 1, cols, 1 << ext_bits, 0,
+                                        nodes.ctypes.data))
+    long_w = sw.copy()
+    long_w[0] += 1                                                                # pages hold one word too many
+    with pytest.raises(m.Pil2GpuError):
+        check(L.pil2gpu_lde_paged(ctx.handle, sptr, long_w.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(sp), dptr,
+                                  dw.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(dp), cols, n_bits, ext_bits))
+
+
 # ---------------------------------------------------------------- full-size properties (sizes the oracle cannot sweep)
 def _fadd(a, b):
     """elementwise (a + b) mod p on canonical uint64 arrays"""
