@@ -495,6 +495,37 @@ def test_paged_bigbuffer_entry_points(ctx):
                                   dw.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(dp), cols, n_bits, ext_bits))
 
 
+def test_c_abi_error_behaviour(ctx):
+    """Every failure is a negative return code with a message, never a crash: null pointers, overlapping buffers, sizes beyond
+    the field's 2-adicity, unsupported blow-ups, empty trees -- and the context keeps working afterwards."""
+    import ctypes
+    from pil2_stark_js_b200._lib import vp
+    L = ctx._L
+    a, b = ctx.alloc(64), ctx.alloc(128)
+    msg = lambda: L.pil2gpu_last_error().decode()
+    assert L.pil2gpu_ntt_dev(ctx.handle, None, b.ptr, 2, 3, 0) == -1 and "null" in msg()
+    assert L.pil2gpu_ntt_dev(ctx.handle, a.ptr, a.ptr, 2, 3, 0) == -1 and "overlap" in msg()
+    assert L.pil2gpu_ntt_dev(ctx.handle, a.ptr, b.ptr, 2, 33, 0) == -1 and "2-adicity" in msg()
+    assert L.pil2gpu_ntt_dev(ctx.handle, a.ptr, b.ptr, 0, 3, 0) == -1
+    assert L.pil2gpu_lde_dev(ctx.handle, a.ptr, b.ptr, 2, 4, 3) == -1 and "nBitsExt" in msg()
+    assert L.pil2gpu_lde_dev(ctx.handle, a.ptr, b.ptr, 1, 2, 11) == -5 and "not supported" in msg()
+    assert L.pil2gpu_merkelize_dev(ctx.handle, a.ptr, 4, 0, 0, b.ptr) == -1
+    assert L.pil2gpu_merkelize_dev(ctx.handle, a.ptr, 4, 4, 0, None) == -1
+    assert L.pil2gpu_fri_fold_dev(ctx.handle, a.ptr, 3, 4, -1, 4, vp(np.zeros(3, dtype=np.uint64).ctypes.data), 0, b.ptr, None, None) == -1
+    assert L.pil2gpu_fri_fold_dev(ctx.handle, a.ptr, 10, 3, -1, 10, vp(np.zeros(3, dtype=np.uint64).ctypes.data), 0, b.ptr, None, None) == -5
+    assert L.pil2gpu_compute_q_dev(ctx.handle, a.ptr, 0, 1, 2, 3, b.ptr) == -1
+    t = vp()
+    assert L.pil2gpu_tree_alloc(ctx.handle, 4, 0, ctypes.byref(t)) == -1
+    assert L.pil2gpu_create(99, None, ctypes.byref(t)) == -1 and "out of range" in msg()
+    assert L.pil2gpu_merkle_nnodes(0) == 0 and L.pil2gpu_merkle_depth(0) == 0
+    # still healthy
+    x = rnd_field(1, 16)
+    y = np.empty(16, dtype=np.uint64)
+    ctx.ntt(x, 2, 3, y)
+    assert np.array_equal(y, C.ntt(x, 2, 3))
+    a.free(); b.free()
+
+
 # ---------------------------------------------------------------- full-size properties (sizes the oracle cannot sweep)
 def _fadd(a, b):
     """elementwise (a + b) mod p on canonical uint64 arrays"""
