@@ -563,6 +563,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
+    if args.impl == "ours" and args.warmup < 3:
+        args.warmup = 3                     # timing rule: at least 3 untimed warm-up steps; the JSON line reports what was run
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
