@@ -399,69 +399,84 @@ def run_ours(args, rank, world, local_rank):
     # with CUDA events like the phases above; GB/s are ALGORITHMIC bytes over the measured time ----
     extras = None
     if not args.no_extras:
-        from pil2_stark_js_b200._lib import EvalDesc
-        q_dim, q_deg = 3, 1 << blow
-        q_ext = g.dev(q_dim << ext_bits)
-        cmq = g.dev((q_dim * q_deg) << ext_bits)
-        q_nodes = g.dev(g.nnodes(1 << ext_bits))
-        check(L.pil2gpu_synth_dev(g.h, g.ptr(q_ext), q_dim << ext_bits, seed + 9, 0))
-
-        def phase_q():
-            check(L.pil2gpu_compute_q_dev(g.h, g.ptr(q_ext), q_dim, q_deg, n_bits, ext_bits, g.ptr(cmq)))
-            check(L.pil2gpu_merkelize_dev(g.h, g.ptr(cmq), q_dim * q_deg, 1 << ext_bits, 0, g.ptr(q_nodes)))
-        openings = [0, 1]
-        xi = np.ascontiguousarray(splitmix_field(seed + 10, 0, 3))
-        lev = g.dev(len(openings) * (3 << n_bits))
-
-        def phase_lev():
-            for i, o in enumerate(openings):
-                check(L.pil2gpu_compute_lev_dev(g.h, npp(xi), o, n_bits, g.ptr(lev, i * (3 << n_bits))))
-        n_ev = 2 * cols
-        desc = (EvalDesc * n_ev)(*[EvalDesc(c, 1, o) for o in range(2) for c in range(cols)])
-        ev_out = np.empty(3 * n_ev, dtype=np.uint64)
-
-        def phase_evals():
-            check(L.pil2gpu_compute_evals_dev(g.h, g.ptr(dst), cols, n_bits, ext_bits, desc, n_ev, g.ptr(lev), len(openings), npp(ev_out)))
-        xd = g.dev(3 * len(openings) << ext_bits)
-        op_arr = (ctypes.c_int32 * len(openings))(*openings)
-
-        def phase_xdiv():
-            check(L.pil2gpu_x_div_x_sub_xi_dev(g.h, npp(xi), op_arr, len(openings), n_bits, ext_bits, g.ptr(xd)))
-        from pil2_stark_js_b200._lib import FriTerm
-        fterms = (FriTerm * n_ev)(*[FriTerm(dst.data_ptr(), cols, c, 1, o) for o in openings for c in range(cols)])
-        f_ext = g.dev(3 << ext_bits)
-        vf = [np.ascontiguousarray(splitmix_field(seed + 11 + i, 0, 3)) for i in range(2)]
-
-        def phase_fripol():
-            check(L.pil2gpu_fri_pol_dev(g.h, fterms, n_ev, npp(ev_out), op_arr, len(openings), g.ptr(xd), npp(vf[0]), npp(vf[1]), ext_bits,
-                                        g.ptr(f_ext)))
-        for f in (phase_q, phase_lev, phase_evals, phase_xdiv, phase_fripol):
-            f()
-        t_q, t_lev, t_ev, t_xd, t_fp = (time_phase(f, reps) for f in (phase_q, phase_lev, phase_evals, phase_xdiv, phase_fripol))
-        Ew, Nw = 1 << ext_bits, 1 << n_bits
-        q_bytes = 8 * Ew * q_dim * (1 + q_deg) + 8 * Ew * q_dim * q_deg + 64 * Ew
-        ev_bytes = 8 * Nw * cols + 24 * Nw * len(openings)
-        xd_bytes = 24 * Ew * len(openings)
-        fp_bytes = 8 * Ew * cols + 24 * Ew * len(openings) + 24 * Ew
-        extras = {
-            "fri_pol": {"s": t_fp, "shape": f"{n_ev} evMap terms over the 2^{ext_bits} rows of the {cols}-column extended buffer (friExp -> f_ext)",
-                        "algorithmic_bytes": fp_bytes, "GBps": fp_bytes / t_fp / 1e9, "frac_hbm": fp_bytes / t_fp / 1e9 / hbm_peak},
-            "q_commit": {"s": t_q, "shape": f"qDim {q_dim}, qDeg {q_deg}, 2^{ext_bits} rows (INTT + split + {q_deg} coset NTTs + merkelize)",
-                         "algorithmic_bytes": q_bytes, "GBps": q_bytes / t_q / 1e9, "frac_hbm": q_bytes / t_q / 1e9 / hbm_peak},
-            "lev": {"s": t_lev, "shape": f"{len(openings)} openings x 2^{n_bits} F3 (powers + INTT)"},
-            "evals": {"s": t_ev, "shape": f"{n_ev} evaluations over the 2^{n_bits} base rows of the {cols}-column extended buffer",
-                      "algorithmic_bytes": ev_bytes, "GBps": ev_bytes / t_ev / 1e9, "frac_hbm": ev_bytes / t_ev / 1e9 / hbm_peak,
-                      "mulmod_per_s": 3.0 * n_ev * Nw / t_ev},
-            "x_div_x_sub_xi": {"s": t_xd, "shape": f"{len(openings)} openings x 2^{ext_bits} points", "algorithmic_bytes": xd_bytes,
-                               "GBps": xd_bytes / t_xd / 1e9, "frac_hbm": xd_bytes / t_xd / 1e9 / hbm_peak},
-        }
-        del q_ext, cmq, q_nodes, lev, xd, f_ext
+        try:
+            extras = run_next_rows(g, L, check, vp, npp, torch, time_phase, reps, n_bits, cols, blow, ext_bits, seed, dst, hbm_peak)
+        except RuntimeError as ex:          # reported next to the headline, never instead of it
+            extras = {"error": str(ex)[:300]}
 
     # ---- e2e: the same commit through the host-buffer entry points (pinned host memory) ----
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(g, args, torch, n_bits, cols, blow, steps, src, fri_pol[0], chal, queries, root_dev)
+    return finish_line(args, n_bits, cols, blow, sec_per_commit, t_lde, t_mk, t_leaf, t_fri, roofline, roofline_lde, e2e, extras, launches, clocks,
+                       root_dev, seed)
 
+
+def run_next_rows(g, L, check, vp, npp, torch, time_phase, reps, n_bits, cols, blow, ext_bits, seed, dst, hbm_peak):
+    """Device-resident times of the rows next to the commit at the workload's size; GB/s are ALGORITHMIC bytes
+     over the measured time."""
+    from pil2_stark_js_b200._lib import EvalDesc
+    q_dim, q_deg = 3, 1 << blow
+    q_ext = g.dev(q_dim << ext_bits)
+    cmq = g.dev((q_dim * q_deg) << ext_bits)
+    q_nodes = g.dev(g.nnodes(1 << ext_bits))
+    check(L.pil2gpu_synth_dev(g.h, g.ptr(q_ext), q_dim << ext_bits, seed + 9, 0))
+
+    def phase_q():
+        check(L.pil2gpu_compute_q_dev(g.h, g.ptr(q_ext), q_dim, q_deg, n_bits, ext_bits, g.ptr(cmq)))
+        check(L.pil2gpu_merkelize_dev(g.h, g.ptr(cmq), q_dim * q_deg, 1 << ext_bits, 0, g.ptr(q_nodes)))
+    openings = [0, 1]
+    xi = np.ascontiguousarray(splitmix_field(seed + 10, 0, 3))
+    lev = g.dev(len(openings) * (3 << n_bits))
+
+    def phase_lev():
+        for i, o in enumerate(openings):
+            check(L.pil2gpu_compute_lev_dev(g.h, npp(xi), o, n_bits, g.ptr(lev, i * (3 << n_bits))))
+    n_ev = 2 * cols
+    desc = (EvalDesc * n_ev)(*[EvalDesc(c, 1, o) for o in range(2) for c in range(cols)])
+    ev_out = np.empty(3 * n_ev, dtype=np.uint64)
+
+    def phase_evals():
+        check(L.pil2gpu_compute_evals_dev(g.h, g.ptr(dst), cols, n_bits, ext_bits, desc, n_ev, g.ptr(lev), len(openings), npp(ev_out)))
+    xd = g.dev(3 * len(openings) << ext_bits)
+    op_arr = (ctypes.c_int32 * len(openings))(*openings)
+
+    def phase_xdiv():
+        check(L.pil2gpu_x_div_x_sub_xi_dev(g.h, npp(xi), op_arr, len(openings), n_bits, ext_bits, g.ptr(xd)))
+    from pil2_stark_js_b200._lib import FriTerm
+    fterms = (FriTerm * n_ev)(*[FriTerm(dst.data_ptr(), cols, c, 1, o) for o in openings for c in range(cols)])
+    f_ext = g.dev(3 << ext_bits)
+    vf = [np.ascontiguousarray(splitmix_field(seed + 11 + i, 0, 3)) for i in range(2)]
+
+    def phase_fripol():
+        check(L.pil2gpu_fri_pol_dev(g.h, fterms, n_ev, npp(ev_out), op_arr, len(openings), g.ptr(xd), npp(vf[0]), npp(vf[1]), ext_bits,
+                                    g.ptr(f_ext)))
+    for f in (phase_q, phase_lev, phase_evals, phase_xdiv, phase_fripol):
+        f()
+    t_q, t_lev, t_ev, t_xd, t_fp = (time_phase(f, reps) for f in (phase_q, phase_lev, phase_evals, phase_xdiv, phase_fripol))
+    Ew, Nw = 1 << ext_bits, 1 << n_bits
+    q_bytes = 8 * Ew * q_dim * (1 + q_deg) + 8 * Ew * q_dim * q_deg + 64 * Ew
+    ev_bytes = 8 * Nw * cols + 24 * Nw * len(openings)
+    xd_bytes = 24 * Ew * len(openings)
+    fp_bytes = 8 * Ew * cols + 24 * Ew * len(openings) + 24 * Ew
+    extras = {
+        "fri_pol": {"s": t_fp, "shape": f"{n_ev} evMap terms over the 2^{ext_bits} rows of the {cols}-column extended buffer (friExp -> f_ext)",
+                    "algorithmic_bytes": fp_bytes, "GBps": fp_bytes / t_fp / 1e9, "frac_hbm": fp_bytes / t_fp / 1e9 / hbm_peak},
+        "q_commit": {"s": t_q, "shape": f"qDim {q_dim}, qDeg {q_deg}, 2^{ext_bits} rows (INTT + split + {q_deg} coset NTTs + merkelize)",
+                     "algorithmic_bytes": q_bytes, "GBps": q_bytes / t_q / 1e9, "frac_hbm": q_bytes / t_q / 1e9 / hbm_peak},
+        "lev": {"s": t_lev, "shape": f"{len(openings)} openings x 2^{n_bits} F3 (powers + INTT)"},
+        "evals": {"s": t_ev, "shape": f"{n_ev} evaluations over the 2^{n_bits} base rows of the {cols}-column extended buffer",
+                  "algorithmic_bytes": ev_bytes, "GBps": ev_bytes / t_ev / 1e9, "frac_hbm": ev_bytes / t_ev / 1e9 / hbm_peak,
+                  "mulmod_per_s": 3.0 * n_ev * Nw / t_ev},
+        "x_div_x_sub_xi": {"s": t_xd, "shape": f"{len(openings)} openings x 2^{ext_bits} points", "algorithmic_bytes": xd_bytes,
+                           "GBps": xd_bytes / t_xd / 1e9, "frac_hbm": xd_bytes / t_xd / 1e9 / hbm_peak},
+    }
+    del q_ext, cmq, q_nodes, lev, xd, f_ext
+    return extras
+
+
+def finish_line(args, n_bits, cols, blow, sec_per_commit, t_lde, t_mk, t_leaf, t_fri, roofline, roofline_lde, e2e, extras, launches, clocks, root_dev,
+                seed):
     cpu = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
