@@ -13,9 +13,41 @@ from oracle import gl_oracle as C
 from pil2_stark_js_b200.sharded import ShardedCommit, assemble_nodes
 
 
+def _at(ptr, words):
+    """numpy view of `words` u64 at a host address (the sharded helpers hand tile pointers to the engine)."""
+    import ctypes
+    return np.ctypeslib.as_array((ctypes.c_uint64 * int(words)).from_address(int(ptr)))
+
+
 class OracleEngine:
+    device = "cpu"
+
     def empty(self, words):
         return torch.zeros(int(words), dtype=torch.int64)
+
+    # ---- rows next to the commit: stand-ins with the GpuEngine signatures, arithmetic by the C oracle ----
+    def compute_levs(self, xi, openings, n_bits):
+        lev = np.concatenate([C.lev(np.asarray(xi, dtype=np.uint64), o, n_bits, threads=1).reshape(-1) for o in openings])
+        return torch.from_numpy(lev.view(np.int64).copy())
+
+    def compute_evals(self, buf_ptr, size, n_bits, ext_bits, descs, lev, n_lev):
+        buf = _at(buf_ptr, size << ext_bits).copy()
+        levs = self._u(lev).reshape(n_lev, 1 << n_bits, 3)
+        return C.evals({"b": (buf, size)}, [("b", o, d, l) for o, d, l in descs], [levs[i] for i in range(n_lev)], n_bits, ext_bits - n_bits)
+
+    def x_div_x_sub_xi(self, xi, openings, n_bits, ext_bits):
+        x = C.x_div_x_sub_xi(np.asarray(xi, dtype=np.uint64), openings, n_bits, ext_bits, threads=1).reshape(-1)
+        return torch.from_numpy(x.view(np.int64).copy())
+
+    def fri_pol(self, terms, evals, openings, xdiv, vf1, vf2, ext_bits):
+        bufs, ev_map = {}, []
+        for ptr, size, off, dim, prime in terms:
+            bufs.setdefault((ptr, size), (_at(ptr, size << ext_bits).copy(), size))
+            ev_map.append(((ptr, size), off, dim, prime))
+        # xdiv here is the rank's ROW SLICE of the table: the oracle only indexes it by row, so the slice is a table of its own
+        f = C.fri_polynomial(bufs, ev_map, evals, openings, self._u(xdiv), np.asarray(vf1, dtype=np.uint64), np.asarray(vf2, dtype=np.uint64),
+                             ext_bits, threads=1)
+        return torch.from_numpy(f.reshape(-1).view(np.int64).copy())
 
     def nnodes(self, height):
         return C.merkle_nnodes(height)
@@ -101,6 +133,14 @@ def _worker(rank, world, port, n_bits, blow, cols, split, q, peer=False):
         lrows, lsib = lt.open(torch.tensor([0, lh - 1, lh // 2], dtype=torch.int64))
         extra = (qs, rows_q.numpy().view(np.uint64).copy(), sib_q.numpy().view(np.uint64).copy(), layer.numpy().view(np.uint64).copy(),
                  lroot.numpy().view(np.uint64).copy(), lrows.numpy().view(np.uint64).copy(), lsib.numpy().view(np.uint64).copy())
+        # evaluations at xi and the FRI polynomial over the row-sharded buffer
+        from pil2_stark_js_b200.sharded import sharded_evals, sharded_fri_pol
+        frng = np.random.default_rng(11)
+        xi, vf1, vf2 = (frng.integers(0, 0xFFFFFFFF00000001, size=3, dtype=np.uint64) for _ in range(3))
+        ev_map = [("t", c, 1, o) for o in (0, 1) for c in range(0, cols, 3)] + [("t", 9, 3, 1), ("t", 16, 3, 0)]
+        sev = sharded_evals(eng, dist, rank, world, {"t": buf["tree"]}, ev_map, xi, [0, 1], n_bits, n_bits + blow)
+        sf = sharded_fri_pol(eng, dist, rank, world, {"t": buf["tree"]}, ev_map, sev, xi, [0, 1], vf1, vf2, n_bits, n_bits + blow)
+        extra = extra + ((xi, vf1, vf2, ev_map, sev, sf.numpy().view(np.uint64).copy()),)
         if peer:
             assert eng.scatter_calls == 1 and "peer stores" in sc.exchange_kind(buf)
             root = sc.commit(slab, cols, n_bits, n_bits + blow, buf, split)      # buffers are reusable
@@ -142,7 +182,13 @@ def test_sharded_commit_matches_single_process(world, split, peer):
     E = 1 << (n_bits + blow)
     for _, root, _, _, extra in res:
         assert np.array_equal(root, nodes[-4:])
-        qs, rows_q, sib_q, layer, lroot, lrows, lsib = extra
+        qs, rows_q, sib_q, layer, lroot, lrows, lsib, frows = extra
+        xi, vf1, vf2, ev_map, sev, sf = frows                        # sharded evaluations + FRI polynomial == single-process oracle
+        want_ev = C.evals({"t": (ext, cols)}, ev_map, [C.lev(xi, o, n_bits) for o in (0, 1)], n_bits, blow)
+        assert np.array_equal(sev, want_ev)
+        want_f = C.fri_polynomial({"t": (ext, cols)}, ev_map, want_ev, [0, 1], C.x_div_x_sub_xi(xi, [0, 1], n_bits, n_bits + blow), vf1, vf2,
+                                  n_bits + blow)
+        assert np.array_equal(sf.reshape(-1, 3), want_f)
         for k, qi in enumerate(qs):
             r, sb = C.group_proof(ext, nodes, cols, E, qi)
             assert np.array_equal(rows_q[k], r) and np.array_equal(sib_q[k].reshape(-1), np.asarray(sb, dtype=np.uint64).reshape(-1)), f"query {qi}"
