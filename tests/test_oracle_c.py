@@ -108,3 +108,27 @@ def test_fri_fold_vs_spec():
     r2 = S.fri_fold(steps, 2, r1["pol"], ch2)
     pol3, rows3 = C.fri_fold(pol2, 5, 2, None, 9, ch2)
     assert rows3 is None and pol3.tolist() == r2["pol"]
+
+
+@pytest.mark.parametrize("n_bits,ext_bits,steps", [(6, 7, [7, 4, 2]), (8, 10, [10, 6, 3]), (7, 8, [8, 3])])
+def test_fri_chain_keeps_low_degree(n_bits, ext_bits, steps):
+    """The property FRI.verify relies on (fri.js:158-171), independent of how the fold is coded: folding the evaluations of a
+    polynomial of degree < N on the coset 7<w_ext> through the whole chain leaves a final polynomial of degree < 2^(last -
+    (ext - n)); a polynomial of full degree does not."""
+    rng = np.random.default_rng(n_bits)
+    base = rng.integers(0, S.P, size=(1 << n_bits) * 3, dtype=np.uint64)
+    low = C.lde(base, 3, n_bits, ext_bits).reshape(-1, 3)                 # an F3 polynomial of degree < N, coordinate-wise
+    full = rng.integers(0, S.P, size=(1 << ext_bits, 3), dtype=np.uint64)
+    for pol, expect_low in ((low, True), (full, False)):
+        cur = pol
+        for s in range(1, len(steps)):
+            ch = [int(x) for x in rng.integers(0, S.P, size=3, dtype=np.uint64)]
+            nxt = steps[s + 1] if s + 1 < len(steps) else None
+            cur, rows = C.fri_fold(cur, steps[s - 1], steps[s], nxt, steps[0], ch)
+            if nxt is not None:                                           # rows = getTransposedBuffer of the folded layer (fri.js:187-202)
+                w = 1 << nxt
+                assert np.array_equal(rows.reshape(w, -1, 3), cur.reshape(-1, w, 3).transpose(1, 0, 2))
+        coeffs = S.intt([[int(v) for v in e] for e in cur])
+        max_deg = 1 << (steps[-1] - (ext_bits - n_bits))
+        high_is_zero = all(c == [0, 0, 0] for c in coeffs[max_deg:])
+        assert high_is_zero == expect_low
