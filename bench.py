@@ -55,6 +55,16 @@ def splitmix_field(seed, first, n):
         return np.where(z >= np.uint64(P), z - np.uint64(P), z)
 
 
+def splitmix_field_idx(seed, idx):
+    """splitmix64(seed ^ idx) mod p for an array of u64 indices."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) ^ idx) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return np.where(z >= np.uint64(P), z - np.uint64(P), z)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # clocks sampling (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------------------------
@@ -138,11 +148,18 @@ def cpu_commit_sample(n_bits, cols, blow, sample_bits, threads, seed):
     return {"sample_s": t3 - t0, "lde_s": t_lde, "merkle_s": t_mk, "fri_s": t_fri, "estimate_full_s": est}
 
 
-def pick_sample_bits(n_bits, cols, threads):
-    # ~10-30 s of CPU work: the C oracle does roughly 0.25 M Poseidon permutations per second per thread
-    perms_per_row = 2 * (cols // 8 + 1)
-    budget = 15.0 * 0.25e6 * threads
-    bits = int(np.log2(max(2.0, budget / perms_per_row)))
+def pick_sample_bits(n_bits, cols, threads, blow=1, target_s=8.0):
+    """Rows of the CPU sample: the port's permutation rate is measured on a small tree first, then the sample is sized for
+    about `target_s` seconds per step (hashing is ~85% of the port's time), so that a whole --steps K --warmup W run of the
+    reference arm stays within a few minutes whatever the host."""
+    from oracle import gl_oracle as C
+    probe = splitmix_field(1, 0, 8 << 15)
+    C.merkelize(probe[: 8 << 10], 8, 1 << 10, threads=threads)              # warm (library load, thread start)
+    t0 = time.perf_counter()
+    C.merkelize(probe, 8, 1 << 15, threads=threads)
+    rate = (2 << 15) / max(time.perf_counter() - t0, 1e-6)                   # permutations per second, all threads
+    perms_per_row = (1 << blow) * ((cols + 7) // 8 + 1)
+    bits = int(np.log2(max(2.0, 0.85 * target_s * rate / perms_per_row)))
     return max(10, min(n_bits, bits))
 
 
@@ -151,13 +168,14 @@ def run_reference(args, rank, world):
         return
     n_bits, cols, blow = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    sample_bits = pick_sample_bits(n_bits, cols, threads)
-    times, detail = [], None
+    sample_bits = pick_sample_bits(n_bits, cols, threads, blow)
+    times, walls, detail = [], [], None
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         detail = cpu_commit_sample(n_bits, cols, blow, sample_bits, threads, 0x5EED0003)
         if i >= args.warmup:
             times.append(detail["estimate_full_s"])
+            walls.append(detail["sample_s"])
         if time.perf_counter() - t0 > 60 and i >= args.warmup:
             break
     val = statistics.mean(times)
@@ -173,6 +191,10 @@ def run_reference(args, rank, world):
                          "sample_wall_s": detail["sample_s"]},
         "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # `value` is NOT the wall time of a step: every step ran a 2^sample_bits-row sample and scaled it (see `sample`);
+        # the law is validated against full-row-count runs of the port in profiles/r02_cpu_port_scaling.json
+        "extrapolated": sample_bits < n_bits, "sample_rows": 1 << sample_bits, "full_rows": 1 << n_bits,
+        "sample_wall_s_per_step": statistics.mean(walls), "extrapolation": "lde*rows_ratio*log_ratio + (merkle + fri)*rows_ratio",
     }
     print(json.dumps(line), flush=True)
 
@@ -376,17 +398,8 @@ def run_ours(args, rank, world, local_rank):
     leaf_perms = E * ((cols + 7) // 8)
     leaf_bytes = 8 * cols * E + 32 * E                    # algorithmic: read every extended row once, write one digest per row
     traffic = TRAFFIC.get(args.workload, {})
-    roofline = {
-        "kernel": "merkle_leaf_kernel", "bound": "hbm", "achieved": leaf_bytes / t_leaf / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": leaf_bytes / t_leaf / 1e9 / hbm_peak, "traffic": traffic.get("merkle_leaf_kernel"),
-        "peak_src": peak_src, "algorithmic_bytes": leaf_bytes, "launch_s": t_leaf, "share_of_step": t_leaf / sec_per_commit,
-        "note": "HBM is not what limits this kernel: it is bound by the integer pipes (ncu: fmaheavy pipe 88% busy, alu 66%, dram 1%; "
-                "profiles/). The figures below give the rate against the live-measured integer multiply rate.",
-        "int_pipes": {"perms_per_s": leaf_perms / t_leaf, "mulmod_per_s_measured": mm.value, "imad_wide_per_s_measured": iw.value,
-                      "sbox_only_bound_perms_per_s": mm.value / 472.0, "frac_of_sbox_only_bound": leaf_perms / t_leaf / (mm.value / 472.0),
-                      "def": "472 S-box multiplies per permutation are irreducible; the MDS, constant additions and domain conversions count "
-                             "against the fraction"},
-    }
+    roofline = leaf_roofline(leaf_perms, leaf_bytes, t_leaf, sec_per_commit, mm.value, iw.value, hbm_peak, peak_src,
+                             traffic.get("merkle_leaf_kernel"))
     lde_bytes = 8 * cols * (1 << n_bits) * (1 + (1 << blow))
     npass = (n_bits + 8) // 9
     roofline_lde = {"kernel": "ntt_pass_kernel x%d + ntt_lde_fused_kernel (whole LDE)" % (2 * npass - 2), "bound": "hbm",
@@ -394,6 +407,17 @@ def run_ours(args, rank, world, local_rank):
                     "peak_src": peak_src, "algorithmic_bytes": lde_bytes, "traffic": traffic.get("lde"),
                     "note": "integer-pipe bound as well: %.3g butterflies at the measured register-only butterfly rate is the floor"
                             % (3 * cols * (1 << n_bits) * n_bits / 2)}
+
+    # ---- parity spot check of the buffers the timed steps produced (outside every timed region) ----
+    spot = None
+    if not args.no_verify:
+        step()                              # the buffers of one whole step, as timed above
+        torch.cuda.synchronize()
+        try:
+            spot = parity_spot_check(torch, n_bits, cols, blow, seed, dst, nodes, root_dev, queries, q_rows, q_sib, steps, chal, fri_pol, fri_nodes,
+                                     fq_rows, fq_sib)
+        except Exception as ex:             # reported, never hidden: "parity_spot_check" then says why it did not run
+            spot = {"status": "error: " + str(ex)[:200]}
 
     # ---- rows next to the commit: quotient commit, evaluations at xi, FRI denominators -- device-resident, timed
     # with CUDA events like the phases above; GB/s are ALGORITHMIC bytes over the measured time ----
@@ -409,7 +433,112 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_e2e:
         e2e = run_e2e(g, args, torch, n_bits, cols, blow, steps, src, fri_pol[0], chal, queries, root_dev)
     return finish_line(args, n_bits, cols, blow, sec_per_commit, t_lde, t_mk, t_leaf, t_fri, roofline, roofline_lde, e2e, extras, launches, clocks,
-                       root_dev, seed)
+                       root_dev, seed, spot)
+
+
+def parity_spot_check(torch, n_bits, cols, blow, seed, dst, nodes, root_dev, queries, q_rows, q_sib, steps, chal, fri_pol, fri_nodes,
+                      fq_rows, fq_sib, n_cols_checked=16, n_leaves_checked=256):
+    """Outside the timed region: the buffers the timed steps produced, against the CPU oracle (oracle/ is the checker here,
+    never the thing measured).  (1) `n_cols_checked` random columns of the extended buffer re-derived with the oracle's LDE
+    from the synthetic trace; (2) `n_leaves_checked` random leaf digests re-hashed from the extended rows; (3) every opened
+    row + sibling path of the main tree verified up to the root (merklehash_p.js:170-209); (4) every opened FRI group
+    verified to its layer root and folded with the step challenge into the next layer's opened value / the final polynomial
+    (fri.js:121-127).  Returns a dict for the JSON line; raises nothing (a mismatch is reported, not hidden)."""
+    from oracle import gl_oracle as C
+    from oracle import gl_spec as S
+    t0 = time.perf_counter()
+    ext_bits = n_bits + blow
+    N, E = 1 << n_bits, 1 << ext_bits
+    rng = np.random.default_rng(20261018)
+    res = {"columns": 0, "leaves": 0, "main_paths": 0, "fri_paths": 0, "fri_fold_links": 0, "failures": []}
+    u64 = lambda t: t.cpu().numpy().view(np.uint64)
+    # (1) columns
+    pick = np.sort(rng.choice(cols, size=min(n_cols_checked, cols), replace=False))
+    r = np.arange(N, dtype=np.uint64) * np.uint64(cols)
+    src_cols = np.stack([splitmix_field_idx(seed, r + np.uint64(c)) for c in pick], axis=1).reshape(-1)
+    want = C.lde(src_cols, len(pick), n_bits, ext_bits).reshape(E, len(pick))
+    got = u64(dst.view(E, cols)[:, torch.as_tensor(pick, device=dst.device)].contiguous())
+    bad = np.nonzero((got != want).any(axis=0))[0]
+    res["columns"] = int(len(pick))
+    if bad.size:
+        res["failures"].append("extended columns %s differ from the oracle LDE" % [int(pick[b]) for b in bad])
+    del want, got, src_cols
+    # (2) leaf digests
+    rows = np.unique(np.concatenate([rng.integers(0, E, size=n_leaves_checked), [0, E - 1]]))
+    row_vals = u64(dst.view(E, cols)[torch.as_tensor(rows, device=dst.device)].contiguous())
+    digs = u64(nodes.view(-1)[: 4 * E].view(E, 4)[torch.as_tensor(rows, device=dst.device)].contiguous())
+    for k, rw in enumerate(rows):
+        if not np.array_equal(C.linear_hash(row_vals[k]), digs[k]):
+            res["failures"].append("leaf digest of row %d differs from the oracle linear hash" % int(rw))
+    res["leaves"] = int(rows.size)
+
+    def root_from_path(vals, sib, idx):
+        v = C.linear_hash(vals)
+        for s in sib:
+            st = np.concatenate([v, s, np.zeros(4, dtype=np.uint64)]) if (idx & 1) == 0 else np.concatenate([s, v, np.zeros(4, dtype=np.uint64)])
+            v = C.poseidon_perm(st)[:4]
+            idx >>= 1
+        return [int(x) for x in v]
+    # (3) main-tree openings
+    depth = ext_bits
+    for k, q in enumerate(queries):
+        if root_from_path(q_rows[k * cols:(k + 1) * cols], q_sib[k * depth * 4:(k + 1) * depth * 4].reshape(depth, 4), int(q)) != root_dev:
+            res["failures"].append("opening %d of the main tree does not verify" % int(q))
+    res["main_paths"] = int(len(queries))
+    # (4) FRI layers
+    final = u64(fri_pol[-1]).reshape(-1, 3)
+    qs = [int(q) for q in queries]
+    prev_groups = None
+    for s in range(len(steps) - 1):
+        gsz = 1 << (steps[s] - steps[s + 1])
+        d = steps[s + 1]
+        lroot = [int(x) for x in u64(fri_nodes[s][-4:])]
+        qs = [q % (1 << steps[s + 1]) for q in qs]
+        groups = []
+        for k, q in enumerate(qs):
+            vals = fq_rows[s][k * 3 * gsz:(k + 1) * 3 * gsz]
+            if root_from_path(vals, fq_sib[s][k * d * 4:(k + 1) * d * 4].reshape(d, 4), q) != lroot:
+                res["failures"].append("opening %d of FRI layer tree %d does not verify" % (q, s))
+            groups.append([[int(x) for x in vals[3 * j:3 * j + 3]] for j in range(gsz)])
+            res["fri_paths"] += 1
+        # fold link: the group opened in layer tree s (values of fri_pol[s]) folds with chal[s + 1] into fri_pol[s + 1][q]
+        shift = pow(7, 1 << (steps[0] - steps[s]), P)
+        nxt_last = (s + 2 == len(steps))
+        for k, q in enumerate(qs):
+            ev = S.fri_verify_fold(groups[k], steps[s], shift, [int(x) for x in chal[s + 1]], q)
+            if nxt_last:
+                ref = [int(x) for x in final[q]]
+            else:
+                q2, j = q % (1 << steps[s + 2]), q >> steps[s + 2]
+                gs2 = 1 << (steps[s + 1] - steps[s + 2])
+                ref = [int(x) for x in fq_rows[s + 1][(k * gs2 + j) * 3:(k * gs2 + j) * 3 + 3]]
+            if ev != ref:
+                res["failures"].append("fold link layer %d -> %d at %d differs" % (s, s + 1, q))
+            res["fri_fold_links"] += 1
+    res["status"] = "ok" if not res["failures"] else "MISMATCH"
+    res["failures"] = res["failures"][:8]
+    res["seconds"] = round(time.perf_counter() - t0, 2)
+    return res
+
+
+def leaf_roofline(leaf_perms, leaf_bytes, t_leaf, sec_per_step, mulmod_per_s, imad_wide_per_s, hbm_peak, peak_src, traffic):
+    """Roofline object of the dominant kernel (merkle_leaf_kernel).  The kernel is bound by the integer pipes, not by HBM
+    ("= permutations/s / measured-IMAD-bound permutations/s for hash kernels"), so `bound` is "int": `achieved` =
+    permutations/s, `peak` = the live-measured register-only Goldilocks multiply rate / 472 (the S-box multiplies of one
+    permutation are irreducible; the MDS layers, constant additions and domain conversions count against the fraction).
+    The HBM figures of the same launch ride along under "hbm"."""
+    peak = mulmod_per_s / 472.0
+    return {
+        "kernel": "merkle_leaf_kernel", "bound": "int", "achieved": leaf_perms / t_leaf / 1e9, "peak": peak / 1e9, "unit": "Gperm/s",
+        "frac": leaf_perms / t_leaf / peak, "traffic": traffic,
+        "peak_src": "measured live: pil2gpu_bench_int_pipes mulmod/s / 472 S-box multiplies per permutation",
+        "launch_s": t_leaf, "share_of_step": t_leaf / sec_per_step, "perms_per_launch": leaf_perms,
+        "int_pipes": {"mulmod_per_s_measured": mulmod_per_s, "imad_wide_per_s_measured": imad_wide_per_s,
+                      "frac_of_imad_wide_bound": leaf_perms / t_leaf / (imad_wide_per_s / 1888.0),
+                      "def": "1888 = 472 multiplies x 4 IMAD.WIDE; ncu (profiles/): fmaheavy pipe 86-88% busy, alu 66%, dram 1%"},
+        "hbm": {"achieved": leaf_bytes / t_leaf / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": leaf_bytes / t_leaf / 1e9 / hbm_peak,
+                "algorithmic_bytes": leaf_bytes, "peak_src": peak_src},
+    }
 
 
 def run_next_rows(g, L, check, vp, npp, torch, time_phase, reps, n_bits, cols, blow, ext_bits, seed, dst, hbm_peak):
@@ -476,11 +605,11 @@ def run_next_rows(g, L, check, vp, npp, torch, time_phase, reps, n_bits, cols, b
 
 
 def finish_line(args, n_bits, cols, blow, sec_per_commit, t_lde, t_mk, t_leaf, t_fri, roofline, roofline_lde, e2e, extras, launches, clocks, root_dev,
-                seed):
+                seed, spot=None):
     cpu = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
-        sb = pick_sample_bits(n_bits, cols, threads)
+        sb = pick_sample_bits(n_bits, cols, threads, blow, target_s=15.0)
         d = cpu_commit_sample(n_bits, cols, blow, sb, threads, seed)
         cpu = {"value": d["estimate_full_s"], "unit": "s", "cores": threads, "kind": "port",
                "sample": f"oracle/gl_oracle.c on {threads} host threads: 2^{sb}-row x {cols}-col sample ({d['sample_s']:.1f} s wall), "
@@ -492,6 +621,7 @@ def finish_line(args, n_bits, cols, blow, sec_per_commit, t_lde, t_mk, t_leaf, t
         "rows_per_s": (1 << n_bits) / sec_per_commit, "phases_s": {"lde": t_lde, "merkle": t_mk, "merkle_leaf": t_leaf, "fri": t_fri},
         "roofline": roofline, "roofline_lde": roofline_lde, "cpu_baseline": cpu, "e2e": e2e, "next_rows": extras, "gpu_launches": launches,
         "clocks": clocks, "root": root_dev,
+        "parity_spot_check": (spot or {}).get("status", "skipped"), "parity_spot_check_detail": spot,
     }
     print(json.dumps(line), flush=True)
 
@@ -577,6 +707,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle spot check of the timed buffers")
     args = ap.parse_args()
     if args.impl == "ours" and args.warmup < 3:
         args.warmup = 3                     # timing rule: at least 3 untimed warm-up steps; the JSON line reports what was run

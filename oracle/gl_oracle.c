@@ -170,21 +170,29 @@ int orc_lde(const u64 *src, u64 *dst, u64 npols, unsigned bits, unsigned bits_ex
 /* ---------------- Poseidon-GL plain form (glwasm.js:359-390, MDS :428-440) ---------------- */
 static const u64 MDS_CIRC[12] = { 17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20 };
 static inline u64 pow7(u64 a) { u64 a2 = fmul(a, a); u64 a3 = fmul(a, a2); u64 a4 = fmul(a2, a2); return fmul(a3, a4); }
+/* Round constants reduced once (the table holds them as printed in glwasm.js:537-626, all < 2^64). */
+static u64 RC_CANON[360];
+static pthread_once_t rc_once = PTHREAD_ONCE_INIT;
+static void rc_init(void) { for (int i = 0; i < 360; i++) RC_CANON[i] = ORACLE_POSEIDON_RC[i] % GL_P; }
 void orc_poseidon_perm(const u64 in[12], u64 out[12]) {
+    pthread_once(&rc_once, rc_init);
     u64 x[12];
     for (int i = 0; i < 12; i++) x[i] = in[i] % GL_P;
     for (int r = 0; r < 30; r++) {
-        for (int i = 0; i < 12; i++) x[i] = fadd(x[i], ORACLE_POSEIDON_RC[12 * r + i] % GL_P);
+        const u64 *rc = RC_CANON + 12 * r;
+        for (int i = 0; i < 12; i++) x[i] = fadd(x[i], rc[i]);
         if (r < 4 || r >= 26) { for (int i = 0; i < 12; i++) x[i] = pow7(x[i]); }
         else x[0] = pow7(x[0]);
-        u64 y[12];
+        /* y_i = sum_j M[i][j] x_j with M[i][j] = circ[(j - i) mod 12] (+ 8 on [0][0]); the entries are < 2^6, so the sums of
+         * the low and the high 32-bit halves each fit a u64 (the reference's WASM works on 32-bit limbs the same way,
+         * glwasm.js:428-440) and the 128-bit value lo + hi * 2^32 is reduced once. */
+        u64 xl[24], xh[24], y[12];
+        for (int j = 0; j < 12; j++) { xl[j] = xl[j + 12] = x[j] & 0xFFFFFFFFULL; xh[j] = xh[j + 12] = x[j] >> 32; }
         for (int i = 0; i < 12; i++) {
-            u128 acc = 0;
-            for (int j = 0; j < 12; j++) {
-                u64 m = MDS_CIRC[(j - i + 12) % 12] + ((i == 0 && j == 0) ? 8 : 0);
-                acc += (u128)m * x[j];
-            }
-            y[i] = freduce128(acc);
+            u64 al = 0, ah = 0;
+            for (int k = 0; k < 12; k++) { al += MDS_CIRC[k] * xl[i + k]; ah += MDS_CIRC[k] * xh[i + k]; }   /* j = (i + k) mod 12 */
+            if (i == 0) { al += 8 * xl[0]; ah += 8 * xh[0]; }
+            y[i] = freduce128((u128)al + ((u128)ah << 32));
         }
         memcpy(x, y, sizeof(x));
     }

@@ -106,13 +106,18 @@ _lib = None
 
 
 def load():
-    """Load libpil2gpu.so (built in-tree by pil2_stark_js_b200/build.py).  Raises if it is missing."""
+    """Load libpil2gpu.so (built in-tree by pil2_stark_js_b200/build.py; built on first use when missing and nvcc is present).
+    Raises if it is missing and cannot be built."""
     global _lib
     if _lib is None:
         if not LIB_PATH.exists():
-            raise ImportError(
-                f"{LIB_PATH} is missing: build it with `python -m pil2_stark_js_b200.build` (needs nvcc). "
-                "There is no CPU fallback for the commit path.")
+            try:                           # fresh checkout (the .so is git-ignored): build once if nvcc is here
+                from . import build as _build
+                _build.build()
+            except Exception as ex:        # noqa: BLE001
+                raise ImportError(
+                    f"{LIB_PATH} is missing and could not be built ({ex}): run `python -m pil2_stark_js_b200.build` where nvcc "
+                    "is installed.  There is no CPU fallback for the commit path.") from ex
         L = ctypes.CDLL(str(LIB_PATH))
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)          # AttributeError if the .so does not export a declared symbol

@@ -1,4 +1,6 @@
-"""Build libpil2gpu.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo snapshot)."""
+"""Build libpil2gpu.so in-tree with nvcc for sm_100a.  The .so is git-ignored (history stays source-only) but NOT
+gpurun-ignored, so a build made here travels to the GPU box with the working-tree snapshot; a fresh checkout has no .so and
+`_lib.load()` builds it on first use when nvcc is present (and raises otherwise: there is no CPU fallback)."""
 import os
 import pathlib
 import shutil

@@ -60,8 +60,8 @@ GL_D gl3 fri_fold_point(const u64* __restrict__ pol, u64 g, int cur_bits, gl3 be
 }
 
 template <int FOLD>
-__global__ void __launch_bounds__(FOLD >= 5 ? 256 : 512) fri_fold_kernel(const u64* __restrict__ pol, u64* __restrict__ pol2, u64* __restrict__ rows,
-                                                        u64* __restrict__ nodes, FriParams P, NttTables tb) {
+__global__ void __launch_bounds__(FOLD >= 5 ? 256 : 512) fri_fold_kernel(const u64* pol, u64* pol2, u64* __restrict__ rows,   // pol2 == pol for the in-place identity
+                                                        u64* __restrict__ nodes, FriParams P, NttTables tb) {                // step: no __restrict__ on those two
     extern __shared__ u64 fri_rows[];   // [rows_per_cta][3*gs] when fusing the leaf hash
     const int next_bits = P.next_bits < 0 ? P.cur_bits : P.next_bits;
     const u64 gs = 1ULL << (P.cur_bits - next_bits);   // group size (elements per row)

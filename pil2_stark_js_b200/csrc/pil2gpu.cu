@@ -39,6 +39,18 @@ static int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(e__), __FILE__, __LINE__);                                         \
     } while (0)
 
+// Inside the enqueue loops of the multi-stream pipelines an early `return` would skip the drain of the copy streams (which
+// still target the workspace and the caller's host buffers): record the failure in `rc` and leave the loop instead.
+#define CU_BREAK(call)                                                                                        \
+    {                                                                                                         \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            rc = fail(e__ == cudaErrorMemoryAllocation ? PIL2GPU_E_NOMEM : PIL2GPU_E_CUDA, "%s: %s (%s:%d)", #call, \
+                      cudaGetErrorString(e__), __FILE__, __LINE__);                                           \
+            break;                                                                                            \
+        }                                                                                                     \
+    }
+
 struct pil2gpu_ctx {
     int device;
     cudaStream_t stream;
@@ -239,11 +251,17 @@ int pil2gpu_sync(pil2gpu_ctx* ctx) {
 }
 uint64_t pil2gpu_launch_count(const pil2gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// The pipelined entry points also enqueue on the two copy streams; whatever frees or reuses the workspace waits for all three.
+static cudaError_t sync_all_streams(pil2gpu_ctx* ctx) {
+    cudaError_t e1 = cudaStreamSynchronize(ctx->stream), e2 = ctx->in_stream ? cudaStreamSynchronize(ctx->in_stream) : cudaSuccess,
+                e3 = ctx->copy_stream ? cudaStreamSynchronize(ctx->copy_stream) : cudaSuccess;
+    return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+}
 static inline size_t ev2(size_t w) { return (w + 1) & ~(size_t)1; }   // keep 16-byte alignment of workspace carve-outs
 static int ensure_ws(pil2gpu_ctx* ctx, size_t words) {
     if (ctx->ws_words >= words) return PIL2GPU_OK;
     if (ctx->ws) {
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(sync_all_streams(ctx));
         CU(cudaFree(ctx->ws));
         ctx->ws = nullptr;
         ctx->ws_words = 0;
@@ -254,10 +272,9 @@ static int ensure_ws(pil2gpu_ctx* ctx, size_t words) {
 }
 int pil2gpu_release_workspace(pil2gpu_ctx* ctx) {
     ENTER(ctx);
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(sync_all_streams(ctx));
     if (ctx->pool) CU(cudaMemPoolTrimTo(ctx->pool, 0));
     if (ctx->ws) {
-        CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaFree(ctx->ws));
         ctx->ws = nullptr;
         ctx->ws_words = 0;
@@ -411,19 +428,20 @@ int pil2gpu_lde_scatter(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t src_pitc
     CU(pool.make(&ev_start));
     CU(cudaEventRecord(ev_start, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->in_stream, ev_start, 0));
+    rc = PIL2GPU_OK;
     for (u64 s = 0; s < nslabs; s++) {
         const int b = (int)(s & 1);
-        if (s >= 2) CU(cudaStreamWaitEvent(ctx->in_stream, ev_done[s - 2], 0));      // sbuf[b] is free again
-        CU(cudaMemcpy2DAsync(sbuf[b], cs * 8, src + s * cs, src_pitch_cols * 8, cs * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
-        CU(cudaEventRecord(ev_in[s], ctx->in_stream));
-        CU(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
+        if (s >= 2) CU_BREAK(cudaStreamWaitEvent(ctx->in_stream, ev_done[s - 2], 0));      // sbuf[b] is free again
+        CU_BREAK(cudaMemcpy2DAsync(sbuf[b], cs * 8, src + s * cs, src_pitch_cols * 8, cs * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
+        CU_BREAK(cudaEventRecord(ev_in[s], ctx->in_stream));
+        CU_BREAK(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
         NttScatter sc;
         rc = make_scatter(sc, cs, nBitsExt, peer_recv_dev, n_ranks, rank, nPols, s * cs);
         if (rc) break;
         int l = ntt_launch_lde(sbuf[b], dbuf[b], cs, (int)nBits, (int)nBitsExt, ctx->tb, ctx->stream, &sc);
         rc = check_launch(ctx, l, "lde_scatter");
         if (rc) break;
-        CU(cudaEventRecord(ev_done[s], ctx->stream));
+        CU_BREAK(cudaEventRecord(ev_done[s], ctx->stream));
     }
     // the events may be destroyed while still pending (CUDA keeps them alive until they complete); the in_stream must not
     // be left with work that outlives the workspace on the error path
@@ -487,11 +505,13 @@ int pil2gpu_compute_q(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim, ui
         CU(cudaMemcpyAsync(cmq_ext_out, b, cw * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
     rc = pil2gpu_merkelize_dev(ctx, b, qDim * qDeg, E, split, n);
-    if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
-    if (nodes_out) CU(cudaMemcpyAsync(nodes_out, n, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (root_out) CU(cudaMemcpyAsync(root_out, n + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaStreamSynchronize(ctx->copy_stream));
+    for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++) {
+        if (nodes_out) CU_BREAK(cudaMemcpyAsync(nodes_out, n, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (root_out) CU_BREAK(cudaMemcpyAsync(root_out, n + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    cudaError_t es = sync_all_streams(ctx);       // both streams drain on every path: the download targets the caller's buffer
+    if (rc) return rc;
+    if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "compute_q: %s", cudaGetErrorString(es));
     return PIL2GPU_OK;
 }
 
@@ -1009,7 +1029,7 @@ void pil2gpu_tree_free(pil2gpu_ctx* ctx, pil2gpu_tree* t) {
     if (!t) return;
     if (ctx) {
         DeviceGuard guard(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
+        sync_all_streams(ctx);
         if (t->own_elems && t->elems) cudaFree(t->elems);
         if (t->own_nodes && t->nodes) cudaFree(t->nodes);
     }
@@ -1145,29 +1165,30 @@ static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const uint64_t* src,
         const int b = (int)(s & 1);
         const u64 w = width[s];
         u64* sslab = sall.p + N * col0[s];
-        CU(cudaMemcpy2DAsync(sslab, w * 8, src + col0[s], nPols * 8, w * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
-        CU(cudaEventRecord(ev_in[s], ctx->in_stream));
-        CU(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
-        if (s >= 2 && dst_out) CU(cudaStreamWaitEvent(ctx->stream, ev_out[s - 2], 0));   // dbuf[b] was downloaded
+        CU_BREAK(cudaMemcpy2DAsync(sslab, w * 8, src + col0[s], nPols * 8, w * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
+        CU_BREAK(cudaEventRecord(ev_in[s], ctx->in_stream));
+        CU_BREAK(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
+        if (s >= 2 && dst_out) CU_BREAK(cudaStreamWaitEvent(ctx->stream, ev_out[s - 2], 0));   // dbuf[b] was downloaded
         rc = pil2gpu_lde_dev(ctx, sslab, dbuf[b].p, w, nBits, nBitsExt);
         if (rc) break;
-        CU(cudaEventRecord(ev_lde[s], ctx->stream));
+        CU_BREAK(cudaEventRecord(ev_lde[s], ctx->stream));
         if (dst_out) {
-            CU(cudaStreamWaitEvent(ctx->copy_stream, ev_lde[s], 0));
-            CU(cudaMemcpy2DAsync(dst_out + col0[s], nPols * 8, dbuf[b].p, w * 8, w * 8, E, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            CU(cudaEventRecord(ev_out[s], ctx->copy_stream));
+            CU_BREAK(cudaStreamWaitEvent(ctx->copy_stream, ev_lde[s], 0));
+            CU_BREAK(cudaMemcpy2DAsync(dst_out + col0[s], nPols * 8, dbuf[b].p, w * 8, w * 8, E, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CU_BREAK(cudaEventRecord(ev_out[s], ctx->copy_stream));
         }
         merkle_absorb_kernel<<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(dbuf[b].p, w, E, state.p, s == 0, s + 1 == nslabs, nodes.p);
         rc = check_launch(ctx, 1, "absorb");
-        if (trace) CU(cudaEventRecord(ev_abs[s], ctx->stream));
+        if (rc) break;
+        if (trace) CU_BREAK(cudaEventRecord(ev_abs[s], ctx->stream));
     }
     if (rc == PIL2GPU_OK) {
         int l = merkle_launch_tree(nodes.p, E, ctx->stream);
         rc = check_launch(ctx, l, "tree");
     }
-    if (rc == PIL2GPU_OK) {
-        if (nodes_out) CU(cudaMemcpyAsync(nodes_out, nodes.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (root_out) CU(cudaMemcpyAsync(root_out, nodes.p + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++) {
+        if (nodes_out) CU_BREAK(cudaMemcpyAsync(nodes_out, nodes.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (root_out) CU_BREAK(cudaMemcpyAsync(root_out, nodes.p + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
     }
     // every stream must drain before the workspace is reused, on the error paths too
     cudaError_t e1 = cudaStreamSynchronize(ctx->in_stream), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(ctx->copy_stream);
@@ -1211,11 +1232,13 @@ int pil2gpu_extend_and_merkelize(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t
         CU(cudaMemcpyAsync(dst_out, b.p, dw * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
     rc = pil2gpu_merkelize_dev(ctx, b.p, nPols, height, split, n.p);
-    if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
-    if (nodes_out) CU(cudaMemcpyAsync(nodes_out, n.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (root_out) CU(cudaMemcpyAsync(root_out, n.p + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaStreamSynchronize(ctx->copy_stream));
+    for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++) {
+        if (nodes_out) CU_BREAK(cudaMemcpyAsync(nodes_out, n.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (root_out) CU_BREAK(cudaMemcpyAsync(root_out, n.p + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    cudaError_t es = sync_all_streams(ctx);
+    if (rc) return rc;
+    if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "extend_and_merkelize: %s", cudaGetErrorString(es));
     return PIL2GPU_OK;
 }
 
@@ -1378,6 +1401,12 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
     if (curBits > prevBits || prevBits > step0Bits || step0Bits > 32) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
     if (nextBits >= 0 && ((uint32_t)nextBits > curBits || !rows_out)) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
     if (prevBits - curBits > FRI_MAX_FOLD_BITS) return fail(PIL2GPU_E_UNSUPPORTED, "fold by 2^%u not supported (max 2^%d)", prevBits - curBits, FRI_MAX_FOLD_BITS);
+    {   // aliasing: the identity step (fri.js:48-49) may run in place (pol_out == pol: every thread rewrites the three words it
+        // read); any other overlap of the output with the input is a cross-CTA race and is rejected
+        const u64 *a = (const u64*)pol, *b = (const u64*)pol_out;
+        const bool overlap = a < b + ((size_t)3 << curBits) && b < a + ((size_t)3 << prevBits);
+        if (overlap && !(prevBits == curBits && a == b)) return fail(PIL2GPU_E_INVALID, "pol_out overlaps pol (only the identity step may run in place)");
+    }
     FriParams P;
     P.prev_bits = (int)prevBits;
     P.cur_bits = (int)curBits;
@@ -1410,8 +1439,10 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
 int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
                      const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out) {
     ENTER(ctx);
-    if (!pol || !pol_out) return fail(PIL2GPU_E_INVALID, "null argument");
-    if (prevBits > 32 || curBits > prevBits) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
+    if (!pol || !pol_out || !challenge) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (prevBits > 32 || curBits > prevBits || prevBits > step0Bits || step0Bits > 32) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
+    if (nextBits >= 0 && (uint32_t)nextBits > curBits) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
+    if (prevBits - curBits > FRI_MAX_FOLD_BITS) return fail(PIL2GPU_E_UNSUPPORTED, "fold by 2^%u not supported (max 2^%d)", prevBits - curBits, FRI_MAX_FOLD_BITS);
     const size_t pw = (size_t)3 << prevBits, cw = (size_t)3 << curBits;
     const u64 height = nextBits >= 0 ? (1ULL << nextBits) : 0;
     int rc = ensure_ws(ctx, ev2(pw) + 2 * ev2(cw) + (nextBits >= 0 ? merkle_nnodes_words(height) : 0));

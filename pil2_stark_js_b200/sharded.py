@@ -500,6 +500,36 @@ def bench_main(args, rank, world, local_rank, dist, bench):
     launches = torch.tensor([eng.launches() - l0], device="cuda")
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     torch.cuda.synchronize()
+    # ---- per-phase device times of one more step (CUDA events on the launching stream, max over ranks; outside the headline
+    # region) and the dominant kernel's own launch time on this rank's share of the rows ----
+    def timed(fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        return out, (a, b)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    tiles, ev_lde = timed(lambda: sc.extend_exchange(src, cols, n_bits, ext_bits, buf))
+    rows_local = (1 << ext_bits) // world
+    _, ev_hash = timed(lambda: eng.merkelize_tiled(tiles, world, cg, rows_local, buf["nodes"]))
+    _, ev_tree = timed(lambda: eng.tree_from_digests(buf["nodes"], rows_local))      # the levels again: leaf kernel = hash - tree
+    buf["tree"] = ShardedTree(eng, dist, rank, world, tiles, world, cg, rows_local, buf["nodes"], buf["sub"], buf["top"])
+    _, ev_top = timed(lambda: buf["tree"].reduce_to_root())
+    _, ev_fri = timed(fri_chain)
+    _, ev_q = timed(open_queries)
+    torch.cuda.synchronize()
+    ph = torch.tensor([a.elapsed_time(b) / 1e3 for a, b in (ev_lde, ev_hash, ev_tree, ev_top, ev_fri, ev_q)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    t_lde, t_hash, t_tree, t_top, t_fri, t_q = (float(x) for x in ph.tolist())
+    phases = {"lde+exchange": t_lde, "hash (leaves + local subtree)": t_hash, "local subtree levels": t_tree, "sub-root gather + top tree": t_top,
+              "fri (first layer sharded, lower layers rank 0)": t_fri, "queries": t_q, "sum": t_lde + t_hash + t_top + t_fri + t_q,
+              "how": "one extra step after the timed region, CUDA events per phase, max over ranks per phase"}
+    mm, iw = ctypes.c_double(), ctypes.c_double()
+    check(L.pil2gpu_bench_int_pipes(eng.h, ctypes.byref(mm), ctypes.byref(iw)))
+    pk = torch.tensor([mm.value, iw.value], device="cuda", dtype=torch.float64)
+    dist.all_reduce(pk, op=dist.ReduceOp.MIN)
+    mm_v, iw_v = (float(x) for x in pk.tolist())
+
     # ---- the rows next to the commit over the row-sharded buffer: evaluations at xi and the FRI polynomial for every
     # column at two openings, timed as whole calls (max over ranks of the wall clock between synchronisations) ----
     extras = None
@@ -628,6 +658,20 @@ def bench_main(args, rank, world, local_rank, dist, bench):
         sec = float(ms.item()) / 1e3 / args.steps
         root = [int(x) & 0xFFFFFFFFFFFFFFFF for x in root_host.tolist()]
         a2a = 8 * (cg << ext_bits) * (world - 1) // world
+        peaks = {}
+        try:
+            import os as _os
+            peaks = json.load(open(_os.path.join(bench.ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        t_leaf = max(t_hash - t_tree, 1e-9)
+        roofline = bench.leaf_roofline(rows_local * ((cols + 7) // 8), 8 * cols * rows_local + 32 * rows_local, t_leaf, sec, mm_v, iw_v, hbm_peak,
+                                       "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md, 6.65 TB/s)",
+                                       None)
+        roofline["kernel"] = f"merkle_leaf_kernel (per rank: {rows_local} of the 2^{ext_bits} rows, slowest rank)"
+        roofline["note"] = (f"between the LDE and the hashing every GPU moves {a2a >> 20} MiB over NVLink ({sc.exchange_kind(buf)}); "
+                            "ncu traffic is captured at N=1 only (profiles/)")
         line = {
             "metric": bench.METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -638,10 +682,8 @@ def bench_main(args, rank, world, local_rank, dist, bench):
             "gpu_launches": int(launches.item()), "clocks": clocks,
             "root": root,
             "e2e": e2e, "next_rows": extras, "cpu_baseline": None,
-            "roofline": {"kernel": "merkle_leaf_kernel (per-rank share)", "bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None,
-                         "traffic": None,
-                         "note": "per-kernel roofline is reported by the N=1 run (same kernels on 1/N of the rows); N>1 moves "
-                                 f"{a2a >> 20} MiB per GPU over NVLink between the LDE and the hashing ({sc.exchange_kind(buf)})"},
+            "phases_s": phases,
+            "roofline": roofline,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

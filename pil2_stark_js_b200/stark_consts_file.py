@@ -113,11 +113,16 @@ def readPilStarkConstsFile(constsFilename, ctx=None, tree_to_device=False):
         if tree_to_device:
             from .context import default_context
             g = ctx or default_context()
+            if n_el != width * height:
+                raise ValueError(f"const tree section: {n_el} elements, expected width*height = {width * height}")
             tree = g.tree_alloc(width, height)
             chunk = 1 << 25
             for which, total in ((0, n_el), (1, None)):
                 if which == 1:
                     (total,) = struct.unpack("<I", f.read(4))
+                    if total != g.merkle_nnodes(height):       # a short section would leave uninitialised device words in a tree
+                        tree.free()                            # that later serves proofs
+                        raise ValueError(f"const tree section: {total} node words, expected {g.merkle_nnodes(height)}")
                 off = 0
                 while off < total:
                     m = min(chunk, total - off)

@@ -1,0 +1,115 @@
+"""GPU parity at the HEADLINE sizes (BASELINE.json configs 3, 4, 5): the same pass plans and index widths the bench runs,
+compared bit-exactly with the C oracle.
+
+What each case pins ("What's weak" #1):
+  * LDE 2^23 rows, blowup 2: ntt_plan(23) = 8/8/7, three in-place coset passes over E = 2^24 rows (cfg3's plan; 16 columns =
+    one column chunk of the 256 -- columns are independent, blockIdx.y only selects the chunk);
+  * LDE 2^22 rows, blowup 4: ntt_plan(22) = 8/7/7 with four cosets over E = 2^24 rows (cfg5's plan);
+  * Merkle tree over 2^24 leaves: every level offset of the reference layout at the headline height;
+  * the FRI chain of config 4, 24 -> 20 -> 16 -> 12 -> 8 -> 4 from 2^24 seeded F3 values, every layer and every layer tree.
+Sizes are chosen so that the oracle side stays within tens of seconds on the GPU box's host cores (the full 256-column
+buffer would take the C oracle ~10 minutes); the 256-column buffer itself is spot-checked against the oracle by
+`bench.py --verify` on the real cfg3 buffers (33 permutations per row, offsets beyond 2^32 bytes).
+reference: test/fft_p.test.js:193 (interpolate == extendPol), test/merklehash_p.test.js:79 (merkelize + proofs)."""
+import numpy as np
+import pytest
+
+from oracle import gl_spec as S
+from oracle import gl_oracle as C
+
+pytestmark = pytest.mark.gpu
+P = S.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import pil2_stark_js_b200 as m
+    c = m.default_context(0)
+    yield c
+    c._L.pil2gpu_release_workspace(c.handle)
+
+
+def splitmix_field(seed, first, n):
+    """SURVEY 8(d) synthetic generator: splitmix64(seed ^ index) mod p."""
+    with np.errstate(over="ignore"):
+        i = np.arange(first, first + n, dtype=np.uint64)
+        z = (np.uint64(seed) ^ i) + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return np.where(z >= np.uint64(P), z - np.uint64(P), z)
+
+
+def _check_tree_against_oracle(nodes, elems, width, height, rng, n_samples=2048):
+    """Every level of `nodes` (reference layout) against the oracle's hash on a random sample: leaf digests from the rows,
+    inner nodes from their two children, plus the whole top of the tree (the last 12 levels) in full."""
+    rows = rng.integers(0, height, size=n_samples)
+    rows[:4] = [0, 1, height - 2, height - 1]
+    for r in rows:
+        r = int(r)
+        assert np.array_equal(nodes[4 * r:4 * r + 4], C.linear_hash(elems[r * width:(r + 1) * width])), ("leaf", r)
+    off, n = 0, height
+    while n > 1:
+        nxt = (n + 1) // 2
+        lvl = nodes[off:off + 8 * nxt]                      # padded to an even node count
+        up = nodes[off + 8 * nxt:off + 8 * nxt + 4 * nxt]
+        idx = np.arange(nxt) if nxt <= 4096 else np.unique(np.concatenate([rng.integers(0, nxt, size=n_samples), [0, nxt - 1]]))
+        for i in idx:
+            i = int(i)
+            st = np.concatenate([lvl[8 * i:8 * i + 8], np.zeros(4, dtype=np.uint64)])
+            assert np.array_equal(up[4 * i:4 * i + 4], C.poseidon_perm(st)[:4]), ("level of", n, "node", i)
+        off += 8 * nxt
+        n = nxt
+    assert off + 4 == nodes.size
+
+
+@pytest.mark.parametrize("bits,ext", [(23, 24), (22, 24)])
+def test_lde_and_merkle_headline_plan_vs_oracle(ctx, bits, ext):
+    npols = 16
+    src = splitmix_field(0x5EED0003, 0, npols << bits)
+    dst = np.empty(npols << ext, dtype=np.uint64)
+    ctx.lde(src, npols, bits, dst, ext)
+    want = C.lde(src, npols, bits, ext)
+    assert np.array_equal(dst, want)
+    del want
+    nodes = ctx.merkelize(dst, npols, 1 << ext)
+    assert nodes.size == 8 * (1 << ext) - 4
+    _check_tree_against_oracle(nodes, dst, npols, 1 << ext, np.random.default_rng(bits))
+    # the host-buffer commit (column-slab pipeline is not taken at 16 columns: whole-buffer path) gives the same root
+    _, _, root = ctx.extend_and_merkelize(src, npols, bits, ext, want_dst=False, want_nodes=False)
+    assert np.array_equal(root, nodes[-4:])
+
+
+def test_merkle_2p22_full_tree_vs_oracle(ctx):
+    """A complete oracle tree at the largest height the C oracle hashes in seconds (2^22 x 8: one permutation per leaf)."""
+    h, w = 1 << 22, 8
+    e = splitmix_field(0x5EED0004, 0, w * h)
+    assert np.array_equal(ctx.merkelize(e, w, h), C.merkelize(e, w, h))
+
+
+def test_fri_chain_cfg4_vs_oracle(ctx):
+    """BASELINE config 4: 2^24 F3 evaluations, steps 24 -> 20 -> 16 -> 12 -> 8 -> 4 (fold 2^4 per step), a layer tree per
+    step; challenges splitmix64(seed + 3 s + k) mod p.  Every layer, its transposed rows and its tree against
+    the oracle (fri.js:22-81,187-202)."""
+    steps = [24, 20, 16, 12, 8, 4]
+    seed = 0x5EED0004
+    pol = splitmix_field(seed, 0, 3 << steps[0]).reshape(-1, 3)
+    chal = [[int(x) for x in splitmix_field(seed + 1, 3 * s, 3)] for s in range(len(steps))]
+    # step 0: identity fold + commit of the first layer (2^20 rows of 16 F3 values)
+    p, rows, nodes = ctx.fri_fold(pol, steps[0], steps[0], steps[1], steps[0], chal[0])
+    assert np.array_equal(p, pol)
+    gs = 1 << (steps[0] - steps[1])
+    exp_rows = np.ascontiguousarray(pol.reshape(gs, 1 << steps[1], 3).transpose(1, 0, 2)).reshape(-1)    # fri.js:187-202
+    assert np.array_equal(rows, exp_rows)
+    assert np.array_equal(nodes, C.merkelize(exp_rows, 3 * gs, 1 << steps[1]))
+    cur = pol
+    for s in range(1, len(steps)):
+        nxt = steps[s + 1] if s + 1 < len(steps) else None
+        p, rows, nodes = ctx.fri_fold(cur, steps[s - 1], steps[s], nxt, steps[0], chal[s])
+        ep, erows = C.fri_fold(cur, steps[s - 1], steps[s], nxt, steps[0], chal[s])
+        assert np.array_equal(p, ep), f"layer {s}"
+        if nxt is not None:
+            assert np.array_equal(rows, erows), f"rows of layer {s}"
+            assert np.array_equal(nodes, C.merkelize(erows, 3 << (steps[s] - nxt), 1 << nxt)), f"tree of layer {s}"
+        cur = p
+    assert cur.shape == (16, 3)
