@@ -427,3 +427,50 @@ def test_sharded_rows_single_rank_two_tiles(ctx):
     assert np.array_equal(f.cpu().numpy().view(np.uint64).reshape(-1, 3), want_f)
     with pytest.raises(ValueError):
         sharded_evals(eng, None, 0, 1, {"t": tree}, [("t", 31, 3, 0)], xi, [0, 1], n_bits, ext_bits)      # straddles the two tiles
+
+
+# ---------------------------------------------------------------- pins against the golden proof (verifier.proof.zkin.json)
+def test_golden_evals_on_gpu(ctx, golden):
+    """f3 on the GPU against the reference's own vector: sm_all constant / stage-1 traces -> device-resident commit -> LEv
+    vectors and evaluation sums at the transcript's xi (Transcript hashing on the GPU too) == evals[0..27] of the proof.
+    Evaluation map: verifier.circom:541-672 (tests/test_oracle_f_rows.py:golden_ev_map)."""
+    from oracle import sm_all
+    from pil2_stark_js_b200 import Transcript
+    from test_oracle_f_rows import golden_ev_map, golden_challenges
+    xi, _, _, _, q = golden_challenges(golden, Transcript)
+    assert q == [891, 1628, 1228, 1991, 1856, 415, 833, 296]
+    ev_map = golden_ev_map()
+    levs = ctx.compute_levs(xi, [0, 1], 10)
+    for name, fn in (("const", sm_all.constant_trace), ("stage1", sm_all.committed_trace)):
+        buff, w = fn()
+        tree, root = ctx.commit(np.array(buff, dtype=np.uint64), w, 10, 11)
+        assert [int(x) for x in root] == golden["roots"][name]
+        idx = [i for i, e in enumerate(ev_map) if e[0] == name]
+        got = ctx.compute_evals(tree.elements_ptr, w, 10, 11, [(ev_map[i][1], ev_map[i][2], ev_map[i][3]) for i in idx], levs, 2)
+        assert got.tolist() == [golden["evals"][i] for i in idx], name
+        tree.free()
+    levs.free()
+
+
+def test_golden_fri_polynomial_on_gpu(ctx, golden):
+    """fri_pol + xDivXSubXi on the GPU against the reference's own vector: friExp at the 8 query rows, from the opened rows of
+    all five trees, the proof's evals and the transcript challenges, equals the value the first FRI layer opens there
+    (verifier.circom:501-704)."""
+    from pil2_stark_js_b200 import Transcript
+    from test_oracle_f_rows import golden_ev_map, golden_challenges, _golden_row_buffers
+    xi, vf1, vf2, _, q = golden_challenges(golden, Transcript)
+    ev_map = golden_ev_map()
+    bufs = _golden_row_buffers(golden, q)
+    dev = {k: ctx.upload(v[0]) for k, v in bufs.items()}
+    xdiv = ctx.x_div_x_sub_xi(xi, [0, 1], 10, 11, download=False)
+    terms = [(dev[name], bufs[name][1], off, dim, prime) for name, off, dim, prime in ev_map]
+    f = ctx.fri_pol(terms, golden["evals"], [0, 1], xdiv, vf1, vf2, 11)
+    for k, idx in enumerate(q):
+        j = idx >> 7
+        assert [int(x) for x in f[idx]] == golden["fri1"]["rows"][k][3 * j:3 * j + 3], (k, idx)
+    # and through the host-buffer entry point a JS caller uses (computeFRIStark's arithmetic in one call)
+    hterms = [(bufs[name][0], bufs[name][1], off, dim, prime) for name, off, dim, prime in ev_map]
+    f2 = ctx.fri_pol_host(hterms, golden["evals"], [0, 1], xi, vf1, vf2, 10, 11)
+    assert np.array_equal(f2, f)
+    for b in list(dev.values()) + [xdiv]:
+        b.free()
