@@ -635,8 +635,17 @@ except Exception:
 
 
 def run_e2e(g, args, torch, n_bits, cols, blow, steps, src_dev, fri0_dev, chal, queries, root_dev):
+    """The same commit through the reference-facing host-buffer calls, host<->device copies inside the timed region.  Three
+    variants, all on BigBuffer page lists (pages of 2^28 u64 = 2 GiB, what a JS BigBuffer holds at this size):
+      pinned_fused          e2e.value: extendAndMerkelize as ONE call (pil2gpu_extend_and_merkelize_paged) on pinned pages (the addon's
+                            page allocator), FRI folds through pil2gpu_fri_fold -- what js/stark_gen_helpers.js calls;
+      pageable_fused        the same call on ordinary pageable pages (plain BigUint64Arrays): staged through the pinned ring;
+      pageable_module_swap  only fft_p / merklehash_p swapped: interpolate (pil2gpu_lde_paged) then merkelize
+                            (pil2gpu_merkelize_paged) on pageable pages -- the extended buffer crosses PCIe three times."""
+    from pil2_stark_js_b200.bigbuffer import BigBuffer
     L, check, vp = g.L, g.check, g.vp
     ext_bits = n_bits + blow
+    page = 1 << 28
 
     def pinned(words):
         p = vp()
@@ -645,11 +654,14 @@ def run_e2e(g, args, torch, n_bits, cols, blow, steps, src_dev, fri0_dev, chal, 
 
     sw, dw, nw = cols << n_bits, cols << ext_bits, g.nnodes(1 << ext_bits)
     bufs = []
-    hp_src, h_src = pinned(sw); bufs.append(hp_src)
-    hp_dst, h_dst = pinned(dw); bufs.append(hp_dst)
+    b_src = BigBuffer(sw, page_len=page, pinned=True, zero=False)
+    b_dst = BigBuffer(dw, page_len=page, pinned=True, zero=False)
     hp_nodes, h_nodes = pinned(nw); bufs.append(hp_nodes)
     hp_pol, h_pol = pinned(3 << steps[0]); bufs.append(hp_pol)
-    check(L.pil2gpu_d2h(g.h, hp_src, g.ptr(src_dev), sw * 8))
+    off = 0
+    for pg in b_src.buffers:                       # synthetic trace: device -> the pinned pages (outside the timed region)
+        check(L.pil2gpu_d2h(g.h, vp(pg.ctypes.data), g.ptr(src_dev, off), pg.size * 8))
+        off += pg.size
     check(L.pil2gpu_d2h(g.h, hp_pol, g.ptr(fri0_dev), (3 << steps[0]) * 8))
     check(L.pil2gpu_sync(g.h))
     layer = []
@@ -665,15 +677,15 @@ def run_e2e(g, args, torch, n_bits, cols, blow, steps, src_dev, fri0_dev, chal, 
     npp = lambda a: vp(a.ctypes.data)
     h2d = sw * 8
     d2h = (dw + nw) * 8 + 32
+    fri_h2d = fri_d2h = 0
     for s in range(len(steps)):
         prev = steps[s - 1] if s else steps[0]
-        h2d += (3 << prev) * 8
-        d2h += (3 << steps[s]) * 8
+        fri_h2d += (3 << prev) * 8
+        fri_d2h += (3 << steps[s]) * 8
         if s + 1 < len(steps):
-            d2h += ((3 << steps[s]) + g.nnodes(1 << steps[s + 1])) * 8
+            fri_d2h += ((3 << steps[s]) + g.nnodes(1 << steps[s + 1])) * 8
 
-    def step():
-        check(L.pil2gpu_extend_and_merkelize(g.h, hp_src, cols, n_bits, ext_bits, 0, hp_dst, hp_nodes, npp(root)))
+    def fri_chain():
         cur = hp_pol
         for s in range(len(steps)):
             last = s == len(steps) - 1
@@ -683,18 +695,56 @@ def run_e2e(g, args, torch, n_bits, cols, blow, steps, src_dev, fri0_dev, chal, 
             cur = pp
         # query openings are host-side gathers on the downloaded trees in the drop-in JS path (merklehash_p.js:142-168)
 
+    def fused(bs, bd, nodes_ptr):
+        sp, spw, sn = bs.pages()
+        dp, dpw, dn = bd.pages()
+        check(L.pil2gpu_extend_and_merkelize_paged(g.h, sp, spw, sn, cols, n_bits, ext_bits, 0, dp, dpw, dn, nodes_ptr, npp(root)))
+
+    def module_swap(bs, bd, nodes_ptr):
+        sp, spw, sn = bs.pages()
+        dp, dpw, dn = bd.pages()
+        check(L.pil2gpu_lde_paged(g.h, sp, spw, sn, dp, dpw, dn, cols, n_bits, ext_bits))                       # fft_p.interpolate
+        check(L.pil2gpu_merkelize_paged(g.h, dp, dpw, dn, cols, 1 << ext_bits, 0, nodes_ptr))                   # merklehash_p.merkelize
+        root[:] = np.ctypeslib.as_array(ctypes.cast(nodes_ptr, ctypes.POINTER(ctypes.c_uint64)), shape=(nw,))[-4:]
+
+    def timed(fn, n):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t0) / n
+
     n = max(1, min(args.steps, 3))
-    step()
-    t0 = time.perf_counter()
-    for _ in range(n):
-        step()
-    t = (time.perf_counter() - t0) / n
+    t = timed(lambda: (fused(b_src, b_dst, hp_nodes), fri_chain()), n)
     ok = [int(x) for x in root] == root_dev
+    variants = {"pinned_fused": {"value": t, "h2d_bytes_per_step": int(h2d + fri_h2d), "d2h_bytes_per_step": int(d2h + fri_d2h),
+                                 "root_matches_device_run": ok}}
+    if not getattr(args, "no_e2e_variants", False):
+        try:
+            # ordinary (pageable) pages with the same cut; filled from the pinned ones; the warm-up call of timed() faults them in
+            p_src = BigBuffer(sw, page_len=page, zero=False)
+            for a, b in zip(p_src.buffers, b_src.buffers):
+                a[:] = b
+            p_dst = BigBuffer(dw, page_len=page, zero=False)
+            p_nodes = np.empty(nw, dtype=np.uint64)
+            t_pf = timed(lambda: (fused(p_src, p_dst, npp(p_nodes)), fri_chain()), max(1, n - 1))
+            ok_pf = [int(x) for x in root] == root_dev and all(np.array_equal(a, b) for a, b in zip(p_dst.buffers[:2], b_dst.buffers[:2]))
+            t_ms = timed(lambda: (module_swap(p_src, p_dst, npp(p_nodes)), fri_chain()), 1)
+            ok_ms = [int(x) for x in root] == root_dev
+            variants["pageable_fused"] = {"value": t_pf, "h2d_bytes_per_step": int(h2d + fri_h2d), "d2h_bytes_per_step": int(d2h + fri_d2h),
+                                          "root_matches_device_run": ok_pf}
+            variants["pageable_module_swap"] = {"value": t_ms, "h2d_bytes_per_step": int(h2d + dw * 8 + fri_h2d),
+                                                "d2h_bytes_per_step": int(d2h + fri_d2h), "root_matches_device_run": ok_ms}
+            del p_src, p_dst, p_nodes
+        except (MemoryError, RuntimeError) as ex:
+            variants["pageable_error"] = str(ex)[:200]
     for p in bufs:
         L.pil2gpu_host_free(p)
-    return {"value": t, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n,
-            "root_matches_device_run": ok,
-            "call": "pil2gpu_extend_and_merkelize (host src -> host dst + nodes) + pil2gpu_fri_fold per step, pinned host buffers"}
+    b_src.free(); b_dst.free()
+    return {"value": t, "unit": "s", "h2d_bytes_per_step": int(h2d + fri_h2d), "d2h_bytes_per_step": int(d2h + fri_d2h), "steps": n,
+            "root_matches_device_run": ok, "variants": variants,
+            "call": "pil2gpu_extend_and_merkelize_paged (BigBuffer pages of 2^28 words: host src -> host dst + nodes, one call) + pil2gpu_fri_fold "
+                    "per step; `value` = pinned pages; variants: the same call on pageable pages, and interpolate + merkelize as two calls"}
 
 
 def main():
@@ -708,6 +758,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle spot check of the timed buffers")
+    ap.add_argument("--no-e2e-variants", action="store_true", help="e2e on pinned pages only (skip the pageable-page variants)")
     args = ap.parse_args()
     if args.impl == "ours" and args.warmup < 3:
         args.warmup = 3                     # timing rule: at least 3 untimed warm-up steps; the JSON line reports what was run

@@ -71,7 +71,14 @@ int pil2gpu_ntt_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t* dst_dev
  * ignored, unlike the reference which needs a zeroed dst: fft_p.js:265).  No scratch buffer is used. */
 int pil2gpu_lde(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt);
 int pil2gpu_lde_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t* dst_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt);
-/* BigBuffer twin (pilcom BigBuffer = list of BigUint64Array pages): page p holds page_words[p] u64. */
+/* BigBuffer twins (pilcom BigBuffer = list of BigUint64Array pages; the reference passes BigBuffers of any size to fft / ifft /
+ * interpolate, fft_p.js:178-297): page p holds page_words[p] u64, pages are concatenated in order and need not hold whole
+ * rows.  Every host-pointer entry point of this library accepts pinned memory (pil2gpu_host_alloc: copied by DMA directly)
+ * and ordinary pageable memory (an ordinary BigUint64Array: staged through a ring of pinned slots by a few copy threads,
+ * PIL2GPU_COPY_THREADS) -- detected per page with cudaPointerGetAttributes. */
+int pil2gpu_ntt_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const uint64_t* src_page_words, uint32_t n_src_pages,
+                      uint64_t* const* dst_pages, const uint64_t* dst_page_words, uint32_t n_dst_pages, uint64_t nPols, uint32_t nBits,
+                      int inverse);
 int pil2gpu_lde_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const uint64_t* src_page_words, uint32_t n_src_pages,
                       uint64_t* const* dst_pages, const uint64_t* dst_page_words, uint32_t n_dst_pages, uint64_t nPols,
                       uint32_t nBits, uint32_t nBitsExt);
@@ -105,6 +112,10 @@ int pil2gpu_compute_q_dev(pil2gpu_ctx* ctx, const uint64_t* q_ext_dev, uint64_t 
                           uint64_t* cmq_ext_dev);
 int pil2gpu_compute_q(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim, uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt, int split,
                       uint64_t* cmq_ext_out, uint64_t* nodes_out, uint64_t root_out[4]);
+/* BigBuffer twin: ctx.q_ext and ctx.cm<Q>_ext are BigBuffers (stark_gen_helpers.js:174-176); cmq_pages may be NULL / 0 pages. */
+int pil2gpu_compute_q_paged(pil2gpu_ctx* ctx, const uint64_t* const* q_pages, const uint64_t* q_page_words, uint32_t n_q_pages, uint64_t qDim,
+                            uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt, int split, uint64_t* const* cmq_pages,
+                            const uint64_t* cmq_page_words, uint32_t n_cmq_pages, uint64_t* nodes_out, uint64_t root_out[4]);
 
 /* ---- evaluations at the challenge point: computeEvalsStark, src/stark/stark_gen_helpers.js:210-273 ------------------ */
 /* LEv vector of one opening point (:216-231): lev_dev (2^nBits x 3 words) = F3 ifft of the powers of
@@ -197,6 +208,14 @@ int pil2gpu_commit_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t nPols
 int pil2gpu_extend_and_merkelize(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
                                  uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]);
 
+/* BigBuffer twin of extendAndMerkelize: cm<stage>_n (16 GiB at 2^23 x 256) and cm<stage>_ext are BigBuffers.  Pages that hold
+ * whole rows (always the case for power-of-two nPols) go through the column-slab pipeline -- upload | LDE + hashing | download
+ * overlapped, one strided copy per (slab, page); other page cuts upload everything, extend, and download under the hashing.
+ * dst_pages may be NULL / 0 pages (root and nodes only). */
+int pil2gpu_extend_and_merkelize_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const uint64_t* src_page_words, uint32_t n_src_pages,
+                                       uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split, uint64_t* const* dst_pages,
+                                       const uint64_t* dst_page_words, uint32_t n_dst_pages, uint64_t* nodes_out, uint64_t root_out[4]);
+
 int pil2gpu_tree_wrap_tiled_dev(pil2gpu_ctx* ctx, const uint64_t* tiles_dev, uint32_t n_tiles, uint64_t tile_cols, uint64_t tile_stride,
                                 const uint64_t* nodes_dev, uint64_t height, pil2gpu_tree** tree_out);
 
@@ -243,6 +262,12 @@ int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, u
 int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol_dev, uint32_t prevBits, uint32_t curBits, int32_t nextBits,
                          uint32_t step0Bits, const uint64_t challenge[3], int split, uint64_t* pol_out_dev, uint64_t* rows_out_dev,
                          uint64_t* nodes_out_dev);
+/* Paged twin (a 2^27-point first layer is 3 GiB, more than one BigUint64Array page): pol / pol_out / rows_out as page lists;
+ * rows_pages may be NULL / 0 pages. */
+int pil2gpu_fri_fold_paged(pil2gpu_ctx* ctx, const uint64_t* const* pol_pages, const uint64_t* pol_page_words, uint32_t n_pol_pages,
+                           uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits, const uint64_t challenge[3], int split,
+                           uint64_t* const* out_pages, const uint64_t* out_page_words, uint32_t n_out_pages, uint64_t* const* rows_pages,
+                           const uint64_t* rows_page_words, uint32_t n_rows_pages, uint64_t* nodes_out);
 /* Wrap device buffers produced by the *_dev FRI calls into a tree handle (not owned: tree_free leaves them alone). */
 int pil2gpu_tree_wrap_dev(pil2gpu_ctx* ctx, const uint64_t* elems_dev, const uint64_t* nodes_dev, uint64_t width, uint64_t height,
                           pil2gpu_tree** tree_out);

@@ -12,6 +12,7 @@ CPU fallback, so importing works anywhere but every operation needs a CUDA devic
 """
 from ._lib import Pil2GpuError, OutOfRange, load as load_library   # noqa: F401
 from .context import Context, DeviceTree, default_context          # noqa: F401
+from .bigbuffer import BigBuffer                                    # noqa: F401
 from . import fft_p, merklehash_p, fri, transcript, stark_gen_helpers, stark_consts_file   # noqa: F401
 from .fft_p import fft, ifft, interpolate                           # noqa: F401
 from .merklehash_p import buildMerkleHash, MerkleHash               # noqa: F401

@@ -56,6 +56,13 @@ _SIGS = {
     "pil2gpu_lde": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32]),
     "pil2gpu_lde_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32]),
     "pil2gpu_lde_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u32, c_u32]),
+    "pil2gpu_ntt_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u32, c_int]),
+    "pil2gpu_extend_and_merkelize_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), u64p, c_u32,
+                                                   vp, vp]),
+    "pil2gpu_compute_q_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), u64p, c_u32,
+                                        vp, vp]),
+    "pil2gpu_fri_fold_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u32, c_u32, c_i32, c_u32, vp, c_int, ctypes.POINTER(vp), u64p, c_u32,
+                                       ctypes.POINTER(vp), u64p, c_u32, vp]),
     "pil2gpu_ipc_export": (c_int, [vp, vp, vp]),
     "pil2gpu_ipc_open": (c_int, [vp, vp, ctypes.POINTER(vp)]),
     "pil2gpu_ipc_close": (c_int, [vp, vp]),

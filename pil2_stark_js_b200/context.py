@@ -5,6 +5,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import vp, check
+from .bigbuffer import BigBuffer, as_pages
 
 
 def _as_u64(a, name="buffer"):
@@ -49,18 +50,20 @@ class Context:
     def launch_count(self):
         return int(self._L.pil2gpu_launch_count(self.handle))
 
-    # ---- host-buffer entry points (numpy uint64 in / out) ----
+    # ---- host-buffer entry points (numpy uint64 arrays or BigBuffers in / out) ----
     def ntt(self, src, n_pols, n_bits, dst, inverse=False):
-        _as_u64(src, "buffSrc"); _as_u64(dst, "buffDst")
-        if src.size != n_pols << n_bits or dst.size != n_pols << n_bits:
+        sp, sw, sn, ssz = as_pages(src, "buffSrc")
+        dp, dw, dn, dsz = as_pages(dst, "buffDst")
+        if ssz != n_pols << n_bits or dsz != n_pols << n_bits:
             raise ValueError("buffer size does not match nPols * 2^nBits")
-        check(self._L.pil2gpu_ntt(self.handle, _ptr(src), _ptr(dst), n_pols, n_bits, int(inverse)))
+        check(self._L.pil2gpu_ntt_paged(self.handle, sp, sw, sn, dp, dw, dn, n_pols, n_bits, int(inverse)))
 
     def lde(self, src, n_pols, n_bits, dst, n_bits_ext):
-        _as_u64(src, "buffSrc"); _as_u64(dst, "buffDst")
-        if src.size != n_pols << n_bits or dst.size != n_pols << n_bits_ext:
+        sp, sw, sn, ssz = as_pages(src, "buffSrc")
+        dp, dw, dn, dsz = as_pages(dst, "buffDst")
+        if ssz != n_pols << n_bits or dsz != n_pols << n_bits_ext:
             raise ValueError("buffer size does not match nPols * 2^nBits / 2^nBitsExt")
-        check(self._L.pil2gpu_lde(self.handle, _ptr(src), _ptr(dst), n_pols, n_bits, n_bits_ext))
+        check(self._L.pil2gpu_lde_paged(self.handle, sp, sw, sn, dp, dw, dn, n_pols, n_bits, n_bits_ext))
 
     def poseidon(self, in12):
         a = np.ascontiguousarray(in12, dtype=np.uint64)
@@ -80,11 +83,11 @@ class Context:
         return int(self._L.pil2gpu_merkle_nnodes(height))
 
     def merkelize(self, elems, width, height, split=False):
-        _as_u64(elems, "buff")
-        if elems.size != width * height:
+        ep, ew, en, esz = as_pages(elems, "buff")
+        if esz != width * height:
             raise ValueError("buffer size does not match width * height")
         nodes = np.empty(self.merkle_nnodes(height), dtype=np.uint64)
-        check(self._L.pil2gpu_merkelize(self.handle, _ptr(elems), width, height, int(split), _ptr(nodes)))
+        check(self._L.pil2gpu_merkelize_paged(self.handle, ep, ew, en, width, height, int(split), _ptr(nodes)))
         return nodes
 
     def fri_fold(self, pol, prev_bits, cur_bits, next_bits, step0_bits, challenge, split=False):
@@ -103,30 +106,46 @@ class Context:
                                        _ptr(rows) if rows is not None else None, _ptr(nodes) if nodes is not None else None))
         return pol2.reshape(-1, 3), rows, nodes
 
-    def extend_and_merkelize(self, src, n_pols, n_bits, n_bits_ext, split=False, want_dst=True, want_nodes=True):
-        """extendAndMerkelize (stark_gen_helpers.js:388-412) with host buffers: returns (dst|None, nodes|None, root[4]).
-        Wide standard-hash traces go through the column-slab pipeline (H2D | LDE + hashing | D2H overlapped)."""
-        _as_u64(src, "buffSrc")
-        if src.size != n_pols << n_bits:
+    def extend_and_merkelize(self, src, n_pols, n_bits, n_bits_ext, split=False, want_dst=True, want_nodes=True, dst=None):
+        """extendAndMerkelize (stark_gen_helpers.js:388-412) with host buffers (numpy arrays or BigBuffers): returns
+        (dst|None, nodes|None, root[4]); `dst` may be a caller-allocated array / BigBuffer (cm<stage>_ext) that is filled in
+        place.  Wide standard-hash traces go through the column-slab pipeline (H2D | LDE + hashing | D2H overlapped)."""
+        sp, sw, sn, ssz = as_pages(src, "buffSrc")
+        if ssz != n_pols << n_bits:
             raise ValueError("buffer size does not match nPols * 2^nBits")
-        dst = np.empty(n_pols << n_bits_ext, dtype=np.uint64) if want_dst else None
+        if dst is None and want_dst:
+            dst = np.empty(n_pols << n_bits_ext, dtype=np.uint64)
+        if dst is not None:
+            dp, dw, dn, dsz = as_pages(dst, "buffDst")
+            if dsz != n_pols << n_bits_ext:
+                raise ValueError("buffer size does not match nPols * 2^nBitsExt")
+        else:
+            dp, dw, dn = None, None, 0
         nodes = np.empty(self.merkle_nnodes(1 << n_bits_ext), dtype=np.uint64) if want_nodes else None
         root = np.empty(4, dtype=np.uint64)
-        check(self._L.pil2gpu_extend_and_merkelize(self.handle, _ptr(src), n_pols, n_bits, n_bits_ext, int(split),
-                                                   _ptr(dst) if want_dst else None, _ptr(nodes) if want_nodes else None, _ptr(root)))
+        check(self._L.pil2gpu_extend_and_merkelize_paged(self.handle, sp, sw, sn, n_pols, n_bits, n_bits_ext, int(split), dp, dw, dn,
+                                                         _ptr(nodes) if want_nodes else None, _ptr(root)))
         return dst, nodes, root
 
     # ---- quotient polynomial / evaluations (stark_gen_helpers.js:168-323) ----
-    def compute_q(self, q_ext, q_dim, q_deg, n_bits, n_bits_ext, split=False, want_ext=True, want_nodes=True):
-        """computeQStark (stark_gen_helpers.js:168-208) with host buffers: returns (cmQ_ext|None, nodes|None, root[4])."""
-        _as_u64(q_ext, "q_ext")
-        if q_ext.size != q_dim << n_bits_ext:
+    def compute_q(self, q_ext, q_dim, q_deg, n_bits, n_bits_ext, split=False, want_ext=True, want_nodes=True, ext=None):
+        """computeQStark (stark_gen_helpers.js:168-208) with host buffers (numpy arrays or BigBuffers): returns
+        (cmQ_ext|None, nodes|None, root[4]); `ext` may be the caller's cm<Q>_ext buffer."""
+        qp, qw, qn, qsz = as_pages(q_ext, "q_ext")
+        if qsz != q_dim << n_bits_ext:
             raise ValueError("buffer size does not match qDim * 2^nBitsExt")
-        ext = np.empty((q_dim * q_deg) << n_bits_ext, dtype=np.uint64) if want_ext else None
+        if ext is None and want_ext:
+            ext = np.empty((q_dim * q_deg) << n_bits_ext, dtype=np.uint64)
+        if ext is not None:
+            cp, cw, cn, csz = as_pages(ext, "cmQ_ext")
+            if csz != (q_dim * q_deg) << n_bits_ext:
+                raise ValueError("buffer size does not match qDim * qDeg * 2^nBitsExt")
+        else:
+            cp, cw, cn = None, None, 0
         nodes = np.empty(self.merkle_nnodes(1 << n_bits_ext), dtype=np.uint64) if want_nodes else None
         root = np.empty(4, dtype=np.uint64)
-        check(self._L.pil2gpu_compute_q(self.handle, _ptr(q_ext), q_dim, q_deg, n_bits, n_bits_ext, int(split),
-                                        _ptr(ext) if want_ext else None, _ptr(nodes) if want_nodes else None, _ptr(root)))
+        check(self._L.pil2gpu_compute_q_paged(self.handle, qp, qw, qn, q_dim, q_deg, n_bits, n_bits_ext, int(split), cp, cw, cn,
+                                              _ptr(nodes) if want_nodes else None, _ptr(root)))
         return ext, nodes, root
 
     def compute_q_tree(self, q_ext, q_dim, q_deg, n_bits, n_bits_ext, split=False):

@@ -8,7 +8,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pil2gpu.h"
@@ -51,6 +55,87 @@ static int fail(int code, const char* fmt, ...) {
         }                                                                                                     \
     }
 
+// ---- host staging for PAGEABLE caller memory ------------------------------------------------------------------------
+// A JS BigBuffer page is an ordinary (pageable) BigUint64Array unless it came from the addon's pinned allocator.  The driver
+// stages pageable cudaMemcpyAsync copies through one internal bounce buffer on one thread (measured ~6-12 GB/s).  Here a
+// small pool of host threads copies between the caller's page and a ring of pinned slots while the DMA engine moves the
+// previous slot, so pageable pages travel at several times that rate and pinned pages (detected with
+// cudaPointerGetAttributes) skip the ring entirely.
+struct CopyPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(int)> job;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+    explicit CopyPool(int n) {
+        for (int i = 0; i < n; i++) th.emplace_back([this, i] { run(i); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> l(m); stop = true; }
+        cv_work.notify_all();
+        for (std::thread& t : th) t.join();
+    }
+    void run(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void(int)> f;
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv_work.wait(l, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+                f = job;
+            }
+            f(id);
+            { std::lock_guard<std::mutex> l(m); if (--pending == 0) cv_done.notify_all(); }
+        }
+    }
+    // runs fn(worker) on every worker and waits
+    void all(const std::function<void(int)>& fn) {
+        std::unique_lock<std::mutex> l(m);
+        job = fn;
+        pending = (int)th.size();
+        gen++;
+        cv_work.notify_all();
+        cv_done.wait(l, [&] { return pending == 0; });
+    }
+    // rows x row_bytes block copy with independent pitches (pitch == row_bytes: one flat memcpy), split over the workers
+    void copy2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t row_bytes, size_t rows) {
+        const int n = (int)th.size();
+        if (rows * row_bytes < (1u << 20) || n <= 1) {
+            if (dpitch == row_bytes && spitch == row_bytes) memcpy(dst, src, rows * row_bytes);
+            else for (size_t r = 0; r < rows; r++) memcpy(dst + r * dpitch, src + r * spitch, row_bytes);
+            return;
+        }
+        if (dpitch == row_bytes && spitch == row_bytes) {   // flat: split by bytes
+            const size_t total = rows * row_bytes, per = ((total + n - 1) / n + 63) & ~(size_t)63;
+            all([&](int w) {
+                const size_t a = (size_t)w * per, b = a + per < total ? a + per : total;
+                if (a < b) memcpy(dst + a, src + a, b - a);
+            });
+        } else {
+            const size_t per = (rows + n - 1) / n;
+            all([&](int w) {
+                const size_t a = (size_t)w * per, b = a + per < rows ? a + per : rows;
+                for (size_t r = a; r < b; r++) memcpy(dst + r * dpitch, src + r * spitch, row_bytes);
+            });
+        }
+    }
+};
+#define STAGE_SLOTS 4
+#define STAGE_SLOT_BYTES ((size_t)32 << 20)
+struct StageRing {
+    char* slot[STAGE_SLOTS] = {};
+    cudaEvent_t ev[STAGE_SLOTS] = {};
+    CopyPool* pool = nullptr;
+    ~StageRing() {
+        delete pool;
+        for (int i = 0; i < STAGE_SLOTS; i++) { if (slot[i]) cudaFreeHost(slot[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+    }
+};
+
 struct pil2gpu_ctx {
     int device;
     cudaStream_t stream;
@@ -67,6 +152,7 @@ struct pil2gpu_ctx {
                                 // next call pays for mapping hundreds of MiB again (measured: 2x on the quotient commit)
     u64* ws;                    // grow-only device workspace of the host-pointer entry points (cudaMalloc/cudaFree of tens of GiB
     size_t ws_words;            // per call cost ~0.3 s at cfg3); released by pil2gpu_destroy / pil2gpu_release_workspace
+    StageRing* stage;           // pinned slots + copy threads for pageable caller pages (created on first use)
 };
 
 struct pil2gpu_tree {
@@ -178,6 +264,7 @@ int pil2gpu_create(int device, void* stream, pil2gpu_ctx** out) {
     ctx->ev = nullptr;
     ctx->ws = nullptr;
     ctx->ws_words = 0;
+    ctx->stage = nullptr;
     ctx->pool = nullptr;
     ctx->tables = nullptr;
     ctx->stream = nullptr;
@@ -240,6 +327,7 @@ void pil2gpu_destroy(pil2gpu_ctx* ctx) {
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->tables) cudaFree(ctx->tables);
     if (ctx->ws) cudaFree(ctx->ws);
+    delete ctx->stage;
     if (ctx->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(ctx->pool); }
     delete ctx;
 }
@@ -484,35 +572,6 @@ int pil2gpu_compute_q_dev(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim
     cudaFreeAsync(S, ctx->stream);
     cudaFreeAsync(T, ctx->stream);
     return check_launch(ctx, l < 0 ? -1 : launches, "compute_q");
-}
-
-int pil2gpu_compute_q(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim, uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt, int split,
-                      uint64_t* cmq_ext_out, uint64_t* nodes_out, uint64_t root_out[4]) {
-    ENTER(ctx);
-    if (!q_ext) return fail(PIL2GPU_E_INVALID, "null buffer");
-    if (qDim == 0 || qDeg == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad sizes");
-    const u64 E = 1ULL << nBitsExt;
-    const size_t qw = E * qDim, cw = E * qDim * qDeg, nw = merkle_nnodes_words(E);
-    int rc = ensure_ws(ctx, ev2(qw) + ev2(cw) + nw);
-    if (rc) return rc;
-    u64 *a = ctx->ws, *b = ctx->ws + ev2(qw), *n = ctx->ws + ev2(qw) + ev2(cw);
-    CU(cudaMemcpyAsync(a, q_ext, qw * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = pil2gpu_compute_q_dev(ctx, a, qDim, qDeg, nBits, nBitsExt, b);
-    if (rc) return rc;
-    if (cmq_ext_out) {   // download the extended buffer on the copy stream while the main stream hashes it
-        CU(cudaEventRecord(ctx->ev, ctx->stream));
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev, 0));
-        CU(cudaMemcpyAsync(cmq_ext_out, b, cw * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    }
-    rc = pil2gpu_merkelize_dev(ctx, b, qDim * qDeg, E, split, n);
-    for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++) {
-        if (nodes_out) CU_BREAK(cudaMemcpyAsync(nodes_out, n, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (root_out) CU_BREAK(cudaMemcpyAsync(root_out, n + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    cudaError_t es = sync_all_streams(ctx);       // both streams drain on every path: the download targets the caller's buffer
-    if (rc) return rc;
-    if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "compute_q: %s", cudaGetErrorString(es));
-    return PIL2GPU_OK;
 }
 
 // ---- evaluations at xi and FRI denominators: computeEvalsStark / computeFRIStark (stark_gen_helpers.js:210-323) ----
@@ -846,25 +905,172 @@ int pil2gpu_fri_pol(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_t n_
     return PIL2GPU_OK;
 }
 
-// Gather a paged host buffer into device memory / scatter back (async on the ctx stream).
-static int pages_to_dev(pil2gpu_ctx* ctx, u64* dev, const uint64_t* const* pages, const uint64_t* page_words, uint32_t n_pages, size_t expect) {
-    size_t off = 0;
-    for (uint32_t p = 0; p < n_pages; p++) {
-        if (off + page_words[p] > expect) return fail(PIL2GPU_E_INVALID, "pages hold more than %zu words", expect);
-        if (page_words[p]) CU(cudaMemcpyAsync(dev + off, pages[p], page_words[p] * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-        off += page_words[p];
+// ---- host <-> device copies that accept pinned OR pageable host memory ------------------------------------------------
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+static int ensure_stage(pil2gpu_ctx* ctx) {
+    if (ctx->stage) return PIL2GPU_OK;
+    StageRing* r = new (std::nothrow) StageRing();
+    if (!r) return fail(PIL2GPU_E_NOMEM, "out of host memory");
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        if (cudaHostAlloc((void**)&r->slot[i], STAGE_SLOT_BYTES, cudaHostAllocPortable) != cudaSuccess ||
+            cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete r;
+            return fail(PIL2GPU_E_NOMEM, "pinned staging ring allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
     }
-    if (off != expect) return fail(PIL2GPU_E_INVALID, "pages hold %zu words, expected %zu", off, expect);
+    int n = (int)std::thread::hardware_concurrency();
+    n = n >= 16 ? 8 : (n >= 4 ? n / 2 : 1);
+    if (const char* e = getenv("PIL2GPU_COPY_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n = v; }
+    r->pool = new (std::nothrow) CopyPool(n);
+    if (!r->pool) { delete r; return fail(PIL2GPU_E_NOMEM, "out of host memory"); }
+    ctx->stage = r;
     return PIL2GPU_OK;
 }
-static int dev_to_pages(pil2gpu_ctx* ctx, const u64* dev, uint64_t* const* pages, const uint64_t* page_words, uint32_t n_pages, size_t expect) {
-    size_t off = 0;
-    for (uint32_t p = 0; p < n_pages; p++) {
-        if (off + page_words[p] > expect) return fail(PIL2GPU_E_INVALID, "pages hold more than %zu words", expect);
-        if (page_words[p]) CU(cudaMemcpyAsync(pages[p], dev + off, page_words[p] * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-        off += page_words[p];
+// A copy is cut into chunks that fit one staging slot: a flat copy (both pitches == row_bytes) into byte ranges, a strided one
+// into row ranges.
+struct StageChunks {
+    bool flat;
+    size_t row_bytes, rows, per, n;
+    StageChunks(size_t row_bytes_, size_t rows_, size_t hpitch, size_t dpitch) : row_bytes(row_bytes_), rows(rows_) {
+        flat = (hpitch == row_bytes && dpitch == row_bytes);
+        if (flat) { const size_t total = rows * row_bytes; per = STAGE_SLOT_BYTES; n = (total + per - 1) / per; }
+        else { per = STAGE_SLOT_BYTES / row_bytes; n = per ? (rows + per - 1) / per : 0; }
     }
-    if (off != expect) return fail(PIL2GPU_E_INVALID, "pages hold %zu words, expected %zu", off, expect);
+    // chunk c: offsets in rows (strided) or bytes (flat), and its extent as (row_bytes, rows)
+    void get(size_t c, size_t& first, size_t& rb, size_t& nr) const {
+        if (flat) { const size_t total = rows * row_bytes; first = c * per; rb = total - first < per ? total - first : per; nr = 1; }
+        else { first = c * per; rb = row_bytes; nr = rows - first < per ? rows - first : per; }
+    }
+};
+// rows x row_bytes, host (pitch hpitch) -> device (pitch dpitch), on stream st.  Pinned host memory: one asynchronous 2-D copy.
+// Pageable: through the pinned ring -- the host threads fill slot k+1 while the DMA engine drains slot k.
+static int h2d_2d(pil2gpu_ctx* ctx, char* dev, size_t dpitch, const char* host, size_t hpitch, size_t row_bytes, size_t rows, cudaStream_t st) {
+    if (rows == 0 || row_bytes == 0) return PIL2GPU_OK;
+    if (host_is_pinned(host)) {
+        if (dpitch == row_bytes && hpitch == row_bytes) CU(cudaMemcpyAsync(dev, host, rows * row_bytes, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpy2DAsync(dev, dpitch, host, hpitch, row_bytes, rows, cudaMemcpyHostToDevice, st));
+        return PIL2GPU_OK;
+    }
+    int rc = ensure_stage(ctx);
+    if (rc) return rc;
+    StageRing* r = ctx->stage;
+    if (row_bytes > STAGE_SLOT_BYTES && !(dpitch == row_bytes && hpitch == row_bytes))
+        return fail(PIL2GPU_E_UNSUPPORTED, "row segment of %zu bytes exceeds the staging slot", row_bytes);
+    const StageChunks ch(row_bytes, rows, hpitch, dpitch);
+    for (size_t c = 0; c < ch.n; c++) {
+        const int k = (int)(c % STAGE_SLOTS);
+        size_t first, rb, nr;
+        ch.get(c, first, rb, nr);
+        const size_t ho = ch.flat ? first : first * hpitch, dofs = ch.flat ? first : first * dpitch;
+        CU(cudaEventSynchronize(r->ev[k]));                       // the last DMA that used this slot is done
+        r->pool->copy2d(r->slot[k], rb, host + ho, ch.flat ? rb : hpitch, rb, nr);
+        CU(cudaMemcpy2DAsync(dev + dofs, ch.flat ? rb : dpitch, r->slot[k], rb, rb, nr, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(r->ev[k], st));
+    }
+    return PIL2GPU_OK;
+}
+// device -> host twin.  Pinned: asynchronous.  Pageable: returns when the data is in the caller's memory.
+static int d2h_2d(pil2gpu_ctx* ctx, char* host, size_t hpitch, const char* dev, size_t dpitch, size_t row_bytes, size_t rows, cudaStream_t st) {
+    if (rows == 0 || row_bytes == 0) return PIL2GPU_OK;
+    if (host_is_pinned(host)) {
+        if (dpitch == row_bytes && hpitch == row_bytes) CU(cudaMemcpyAsync(host, dev, rows * row_bytes, cudaMemcpyDeviceToHost, st));
+        else CU(cudaMemcpy2DAsync(host, hpitch, dev, dpitch, row_bytes, rows, cudaMemcpyDeviceToHost, st));
+        return PIL2GPU_OK;
+    }
+    int rc = ensure_stage(ctx);
+    if (rc) return rc;
+    StageRing* r = ctx->stage;
+    if (row_bytes > STAGE_SLOT_BYTES && !(dpitch == row_bytes && hpitch == row_bytes))
+        return fail(PIL2GPU_E_UNSUPPORTED, "row segment of %zu bytes exceeds the staging slot", row_bytes);
+    const StageChunks ch(row_bytes, rows, hpitch, dpitch);
+    for (size_t c = 0; c < ch.n + STAGE_SLOTS; c++) {
+        size_t first, rb, nr;
+        if (c >= STAGE_SLOTS && c - STAGE_SLOTS < ch.n) {          // drain chunk c - SLOTS into the caller's memory
+            const size_t j = c - STAGE_SLOTS;
+            const int k = (int)(j % STAGE_SLOTS);
+            ch.get(j, first, rb, nr);
+            CU(cudaEventSynchronize(r->ev[k]));
+            r->pool->copy2d(host + (ch.flat ? first : first * hpitch), ch.flat ? rb : hpitch, r->slot[k], rb, rb, nr);
+        }
+        if (c < ch.n) {
+            const int k = (int)(c % STAGE_SLOTS);
+            ch.get(c, first, rb, nr);
+            if (c < STAGE_SLOTS) CU(cudaEventSynchronize(r->ev[k]));   // a slot last used by an earlier call (later ones were drained above)
+            CU(cudaMemcpy2DAsync(r->slot[k], rb, dev + (ch.flat ? first : first * dpitch), ch.flat ? rb : dpitch, rb, nr, cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(r->ev[k], st));
+        }
+    }
+    return PIL2GPU_OK;
+}
+
+// A paged host buffer (pilcom BigBuffer = list of BigUint64Array pages): page p holds words[p] u64.
+struct PageList {
+    const uint64_t* const* pages;
+    const uint64_t* words;
+    uint32_t n;
+};
+static int check_pages(const PageList& pl, size_t expect, const char* what) {
+    if ((!pl.pages || !pl.words) && pl.n) return fail(PIL2GPU_E_INVALID, "%s: null page list", what);
+    size_t off = 0;
+    for (uint32_t p = 0; p < pl.n; p++) {
+        if (pl.words[p] && !pl.pages[p]) return fail(PIL2GPU_E_INVALID, "%s: page %u is null", what, p);
+        if (pl.words[p] > expect - off) return fail(PIL2GPU_E_INVALID, "%s: pages hold more than %zu words", what, expect);
+        off += pl.words[p];
+    }
+    if (off != expect) return fail(PIL2GPU_E_INVALID, "%s: pages hold %zu words, expected %zu", what, off, expect);
+    return PIL2GPU_OK;
+}
+// Gather a paged host buffer into device memory / scatter back, on stream st (see h2d_2d / d2h_2d for pinned vs pageable pages).
+static int pages_to_dev(pil2gpu_ctx* ctx, u64* dev, const PageList& pl, size_t expect, cudaStream_t st) {
+    int rc = check_pages(pl, expect, "source");
+    size_t off = 0;
+    for (uint32_t p = 0; p < pl.n && !rc; p++) {
+        rc = h2d_2d(ctx, (char*)(dev + off), pl.words[p] * 8, (const char*)pl.pages[p], pl.words[p] * 8, pl.words[p] * 8, pl.words[p] ? 1 : 0, st);
+        off += pl.words[p];
+    }
+    return rc;
+}
+static int dev_to_pages(pil2gpu_ctx* ctx, const u64* dev, const PageList& pl, size_t expect, cudaStream_t st) {
+    int rc = check_pages(pl, expect, "destination");
+    size_t off = 0;
+    for (uint32_t p = 0; p < pl.n && !rc; p++) {
+        rc = d2h_2d(ctx, (char*)pl.pages[p], pl.words[p] * 8, (const char*)(dev + off), pl.words[p] * 8, pl.words[p] * 8, pl.words[p] ? 1 : 0, st);
+        off += pl.words[p];
+    }
+    return rc;
+}
+// Columns [c0, c0 + w) of every row of a row-major paged buffer (row = nPols words) <-> a dense device slab [rows][w].
+// Needs pages that hold whole rows.  All rows of a page go in one strided copy.
+static bool pages_row_aligned(const PageList& pl, size_t nPols) {
+    for (uint32_t p = 0; p < pl.n; p++) if (pl.words[p] % nPols) return false;
+    return true;
+}
+static bool pages_all_pinned(const PageList& pl) {
+    for (uint32_t p = 0; p < pl.n; p++) if (pl.words[p] && !host_is_pinned(pl.pages[p])) return false;
+    return true;
+}
+static int slab_from_pages(pil2gpu_ctx* ctx, u64* slab, const PageList& pl, size_t nPols, size_t c0, size_t w, cudaStream_t st) {
+    size_t row = 0;
+    for (uint32_t p = 0; p < pl.n; p++) {
+        const size_t nr = pl.words[p] / nPols;
+        int rc = h2d_2d(ctx, (char*)(slab + row * w), w * 8, (const char*)(pl.pages[p] + c0), nPols * 8, w * 8, nr, st);
+        if (rc) return rc;
+        row += nr;
+    }
+    return PIL2GPU_OK;
+}
+static int slab_to_pages(pil2gpu_ctx* ctx, const u64* slab, const PageList& pl, size_t nPols, size_t c0, size_t w, cudaStream_t st) {
+    size_t row = 0;
+    for (uint32_t p = 0; p < pl.n; p++) {
+        const size_t nr = pl.words[p] / nPols;
+        int rc = d2h_2d(ctx, (char*)(const_cast<uint64_t*>(pl.pages[p]) + c0), nPols * 8, (const char*)(slab + row * w), w * 8, w * 8, nr, st);
+        if (rc) return rc;
+        row += nr;
+    }
     return PIL2GPU_OK;
 }
 
@@ -874,28 +1080,52 @@ struct DevBuf {   // RAII device allocation for the host-pointer entry points
     ~DevBuf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t words) { return cudaMalloc(&p, (words ? words : 1) * sizeof(u64)); }
 };
+struct PoolBuf {  // stream-ordered scratch from the ctx pool: no device-wide synchronisation on allocation or release (cudaMalloc /
+    u64* p = nullptr;   // cudaFree cost ~0.1 ms each and serialise against every stream -- measured on the query-opening path)
+    pil2gpu_ctx* ctx;
+    explicit PoolBuf(pil2gpu_ctx* c) : ctx(c) {}
+    ~PoolBuf() { if (p) cudaFreeAsync(p, ctx->stream); }
+    cudaError_t alloc(size_t words) { return cudaMallocFromPoolAsync(&p, (words ? words : 1) * sizeof(u64), ctx->pool, ctx->stream); }
+};
 
-int pil2gpu_ntt(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, int inverse) {
+int pil2gpu_ntt_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const uint64_t* src_page_words, uint32_t n_src_pages,
+                      uint64_t* const* dst_pages, const uint64_t* dst_page_words, uint32_t n_dst_pages, uint64_t nPols, uint32_t nBits,
+                      int inverse) {
     ENTER(ctx);
-    int rc = check_ntt_args(src, dst, nPols, nBits);
-    if (rc) return rc;
+    if (!src_pages || !dst_pages || !src_page_words || !dst_page_words) return fail(PIL2GPU_E_INVALID, "null page list");
+    if (nPols == 0) return fail(PIL2GPU_E_INVALID, "nPols must be > 0");
+    if (nBits > 32) return fail(PIL2GPU_E_INVALID, "nBits %u exceeds the 2-adicity of the field (32)", nBits);
     const size_t words = (size_t)nPols << nBits;
-    rc = ensure_ws(ctx, 2 * ev2(words));
+    const PageList sp = {src_pages, src_page_words, n_src_pages}, dp = {(const uint64_t* const*)dst_pages, dst_page_words, n_dst_pages};
+    int rc = check_pages(sp, words, "source");
+    if (!rc) rc = check_pages(dp, words, "destination");
+    if (!rc) rc = ensure_ws(ctx, 2 * ev2(words));
     if (rc) return rc;
-    struct { u64* p; } a = {ctx->ws}, b = {ctx->ws + ev2(words)};
-    CU(cudaMemcpyAsync(a.p, src, words * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = pil2gpu_ntt_dev(ctx, a.p, b.p, nPols, nBits, inverse);
+    u64 *a = ctx->ws, *b = ctx->ws + ev2(words);
+    rc = pages_to_dev(ctx, a, sp, words, ctx->stream);
+    if (!rc) rc = pil2gpu_ntt_dev(ctx, a, b, nPols, nBits, inverse);
+    if (!rc) rc = dev_to_pages(ctx, b, dp, words, ctx->stream);
+    cudaError_t es = sync_all_streams(ctx);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(dst, b.p, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "ntt: %s", cudaGetErrorString(es));
     return PIL2GPU_OK;
 }
 
+int pil2gpu_ntt(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, int inverse) {
+    if (!src || !dst) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (nBits > 32) return fail(PIL2GPU_E_INVALID, "nBits %u exceeds the 2-adicity of the field (32)", nBits);
+    const uint64_t words = nPols << nBits;
+    const uint64_t* sp[1] = {src};
+    uint64_t* dp[1] = {dst};
+    return pil2gpu_ntt_paged(ctx, sp, &words, 1, dp, &words, 1, nPols, nBits, inverse);
+}
+
 int pil2gpu_lde(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t* dst, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt) {
+    if (!src || !dst) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad LDE shape");
     const uint64_t sw = nPols << nBits, dw = nPols << nBitsExt;
     const uint64_t* sp[1] = {src};
     uint64_t* dp[1] = {dst};
-    if (!src || !dst) return fail(PIL2GPU_E_INVALID, "null buffer");
     return pil2gpu_lde_paged(ctx, sp, &sw, 1, dp, &dw, 1, nPols, nBits, nBitsExt);
 }
 
@@ -906,17 +1136,68 @@ int pil2gpu_lde_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const 
     if (!src_pages || !dst_pages || !src_page_words || !dst_page_words) return fail(PIL2GPU_E_INVALID, "null page list");
     if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad LDE shape");
     const size_t sw = (size_t)nPols << nBits, dw = (size_t)nPols << nBitsExt;
-    int rc = ensure_ws(ctx, ev2(sw) + dw);
+    const PageList sp = {src_pages, src_page_words, n_src_pages}, dp = {(const uint64_t* const*)dst_pages, dst_page_words, n_dst_pages};
+    int rc = check_pages(sp, sw, "source");
+    if (!rc) rc = check_pages(dp, dw, "destination");
+    if (!rc) rc = ensure_ws(ctx, ev2(sw) + dw);
     if (rc) return rc;
-    struct { u64* p; } a = {ctx->ws}, b = {ctx->ws + ev2(sw)};
-    rc = pages_to_dev(ctx, a.p, src_pages, src_page_words, n_src_pages, sw);
+    u64 *a = ctx->ws, *b = ctx->ws + ev2(sw);
+    rc = pages_to_dev(ctx, a, sp, sw, ctx->stream);
+    if (!rc) rc = pil2gpu_lde_dev(ctx, a, b, nPols, nBits, nBitsExt);
+    if (!rc) rc = dev_to_pages(ctx, b, dp, dw, ctx->stream);
+    cudaError_t es = sync_all_streams(ctx);
     if (rc) return rc;
-    rc = pil2gpu_lde_dev(ctx, a.p, b.p, nPols, nBits, nBitsExt);
-    if (rc) return rc;
-    rc = dev_to_pages(ctx, b.p, dst_pages, dst_page_words, n_dst_pages, dw);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "lde: %s", cudaGetErrorString(es));
     return PIL2GPU_OK;
+}
+
+// computeQStark with host buffers (stark_gen_helpers.js:168-208): q_ext up, cmQ_ext and tree.nodes down; the download of cmQ_ext
+// runs under the hashing.
+int pil2gpu_compute_q_paged(pil2gpu_ctx* ctx, const uint64_t* const* q_pages, const uint64_t* q_page_words, uint32_t n_q_pages, uint64_t qDim,
+                            uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt, int split, uint64_t* const* cmq_pages, const uint64_t* cmq_page_words,
+                            uint32_t n_cmq_pages, uint64_t* nodes_out, uint64_t root_out[4]) {
+    ENTER(ctx);
+    if (!q_pages || !q_page_words) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (qDim == 0 || qDeg == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    const u64 E = 1ULL << nBitsExt;
+    const size_t qw = E * qDim, cw = E * qDim * qDeg, nw = merkle_nnodes_words(E);
+    const PageList qp = {q_pages, q_page_words, n_q_pages}, cp = {(const uint64_t* const*)cmq_pages, cmq_page_words, n_cmq_pages};
+    const bool want_ext = cmq_pages != nullptr && n_cmq_pages > 0;
+    int rc = check_pages(qp, qw, "q_ext");
+    if (!rc && want_ext) rc = check_pages(cp, cw, "cmQ_ext");
+    if (!rc) rc = ensure_ws(ctx, ev2(qw) + ev2(cw) + nw);
+    if (rc) return rc;
+    u64 *a = ctx->ws, *b = ctx->ws + ev2(qw), *n = ctx->ws + ev2(qw) + ev2(cw);
+    rc = pages_to_dev(ctx, a, qp, qw, ctx->stream);
+    if (!rc) rc = pil2gpu_compute_q_dev(ctx, a, qDim, qDeg, nBits, nBitsExt, b);
+    for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++) {
+        CU_BREAK(cudaEventRecord(ctx->ev, ctx->stream));
+        rc = pil2gpu_merkelize_dev(ctx, b, qDim * qDeg, E, split, n);
+        if (rc) break;
+        if (want_ext) {
+            CU_BREAK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev, 0));
+            rc = dev_to_pages(ctx, b, cp, cw, ctx->copy_stream);
+            if (rc) break;
+        }
+        if (nodes_out) rc = d2h_2d(ctx, (char*)nodes_out, nw * 8, (const char*)n, nw * 8, nw * 8, 1, ctx->stream);
+        if (rc) break;
+        if (root_out) CU_BREAK(cudaMemcpyAsync(root_out, n + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    cudaError_t es = sync_all_streams(ctx);       // both streams drain on every path: the download targets the caller's buffer
+    if (rc) return rc;
+    if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "compute_q: %s", cudaGetErrorString(es));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_compute_q(pil2gpu_ctx* ctx, const uint64_t* q_ext, uint64_t qDim, uint64_t qDeg, uint32_t nBits, uint32_t nBitsExt, int split,
+                      uint64_t* cmq_ext_out, uint64_t* nodes_out, uint64_t root_out[4]) {
+    if (!q_ext) return fail(PIL2GPU_E_INVALID, "null buffer");
+    if (qDim == 0 || qDeg == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad sizes");
+    const uint64_t qw = qDim << nBitsExt, cw = (qDim * qDeg) << nBitsExt;
+    const uint64_t* qp[1] = {q_ext};
+    uint64_t* cp[1] = {cmq_ext_out};
+    return pil2gpu_compute_q_paged(ctx, qp, &qw, 1, qDim, qDeg, nBits, nBitsExt, split, cmq_ext_out ? cp : nullptr, &cw, cmq_ext_out ? 1 : 0, nodes_out,
+                                   root_out);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -928,7 +1209,7 @@ uint32_t pil2gpu_merkle_depth(uint64_t height) { return height == 0 ? 0 : (uint3
 int pil2gpu_poseidon(pil2gpu_ctx* ctx, const uint64_t in12[12], uint64_t out12[12]) {
     ENTER(ctx);
     if (!in12 || !out12) return fail(PIL2GPU_E_INVALID, "null buffer");
-    DevBuf d;
+    PoolBuf d(ctx);
     CU(d.alloc(24));
     CU(cudaMemcpyAsync(d.p, in12, 96, cudaMemcpyHostToDevice, ctx->stream));
     poseidon_single_kernel<<<1, 32, 0, ctx->stream>>>(d.p, d.p + 12);
@@ -980,7 +1261,7 @@ int pil2gpu_merkle_tree_from_digests_dev(pil2gpu_ctx* ctx, uint64_t* nodes, uint
 int pil2gpu_linear_hash(pil2gpu_ctx* ctx, const uint64_t* vals, uint64_t width, int split, uint64_t out4[4]) {
     ENTER(ctx);
     if (!out4 || (!vals && width)) return fail(PIL2GPU_E_INVALID, "null buffer");
-    DevBuf e, n;
+    PoolBuf e(ctx), n(ctx);
     CU(e.alloc(width));
     CU(n.alloc(8));
     if (width) CU(cudaMemcpyAsync(e.p, vals, width * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -997,15 +1278,17 @@ int pil2gpu_merkelize_paged(pil2gpu_ctx* ctx, const uint64_t* const* elem_pages,
     if (!nodes || !elem_pages || !page_words) return fail(PIL2GPU_E_INVALID, "null buffer");
     if (height == 0) return fail(PIL2GPU_E_INVALID, "height must be > 0");
     const size_t ew = (size_t)width * height, nw = merkle_nnodes_words(height);
-    int rc = ensure_ws(ctx, ev2(ew) + nw);
+    const PageList ep = {elem_pages, page_words, n_pages};
+    int rc = check_pages(ep, ew, "elements");
+    if (!rc) rc = ensure_ws(ctx, ev2(ew) + nw);
     if (rc) return rc;
-    struct { u64* p; } e = {ctx->ws}, n = {ctx->ws + ev2(ew)};
-    rc = pages_to_dev(ctx, e.p, elem_pages, page_words, n_pages, ew);
+    u64 *e = ctx->ws, *n = ctx->ws + ev2(ew);
+    rc = pages_to_dev(ctx, e, ep, ew, ctx->stream);
+    if (!rc) rc = pil2gpu_merkelize_dev(ctx, e, width, height, split, n);
+    if (!rc) rc = d2h_2d(ctx, (char*)nodes, nw * 8, (const char*)n, nw * 8, nw * 8, 1, ctx->stream);
+    cudaError_t es = sync_all_streams(ctx);
     if (rc) return rc;
-    rc = pil2gpu_merkelize_dev(ctx, e.p, width, height, split, n.p);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(nodes, n.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "merkelize: %s", cudaGetErrorString(es));
     return PIL2GPU_OK;
 }
 
@@ -1128,8 +1411,8 @@ int pil2gpu_commit(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32
 // so the call costs max(PCIe down, PCIe up, compute) instead of their sum.  Strided 2D copies of >= 256-byte row
 // segments run at the full PCIe rate (measured 55.6 / 57.2 GB/s up / down, 98.7 GB/s both ways: tools/probe/pcie_probe.cu).
 
-static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, uint64_t cs,
-                                          uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]) {
+static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const PageList& src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, uint64_t cs,
+                                          const PageList* dst_out, uint64_t* nodes_out, uint64_t root_out[4]) {
     const u64 N = 1ULL << nBits, E = 1ULL << nBitsExt;
     const size_t nw = merkle_nnodes_words(E);
     // Slab widths.  The download is the longest leg, and a strided device->host copy only reaches the full PCIe rate with
@@ -1160,36 +1443,43 @@ static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const uint64_t* src,
     CU(cudaStreamWaitEvent(ctx->in_stream, ev_start, 0));
     CU(cudaStreamWaitEvent(ctx->copy_stream, ev_start, 0));
     const unsigned blocks = (unsigned)((E + MERKLE_THREADS - 1) / MERKLE_THREADS);
-    int rc = PIL2GPU_OK;
+    // Enqueue order per slab: LDE(s), absorb(s), upload(s+1), download(s).  With pinned pages every call is asynchronous and the
+    // three streams overlap freely; with pageable pages the staged copies block this thread, and this order keeps the GPU busy
+    // with slab s while slab s+1 is staged up and lets the download of slab s run under the LDE of slab s+1.
+    int rc = slab_from_pages(ctx, sall.p, src, nPols, col0[0], width[0], ctx->in_stream);
+    for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++) CU_BREAK(cudaEventRecord(ev_in[0], ctx->in_stream));
     for (u64 s = 0; s < nslabs && rc == PIL2GPU_OK; s++) {
         const int b = (int)(s & 1);
         const u64 w = width[s];
         u64* sslab = sall.p + N * col0[s];
-        CU_BREAK(cudaMemcpy2DAsync(sslab, w * 8, src + col0[s], nPols * 8, w * 8, N, cudaMemcpyHostToDevice, ctx->in_stream));
-        CU_BREAK(cudaEventRecord(ev_in[s], ctx->in_stream));
         CU_BREAK(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
         if (s >= 2 && dst_out) CU_BREAK(cudaStreamWaitEvent(ctx->stream, ev_out[s - 2], 0));   // dbuf[b] was downloaded
         rc = pil2gpu_lde_dev(ctx, sslab, dbuf[b].p, w, nBits, nBitsExt);
         if (rc) break;
         CU_BREAK(cudaEventRecord(ev_lde[s], ctx->stream));
-        if (dst_out) {
-            CU_BREAK(cudaStreamWaitEvent(ctx->copy_stream, ev_lde[s], 0));
-            CU_BREAK(cudaMemcpy2DAsync(dst_out + col0[s], nPols * 8, dbuf[b].p, w * 8, w * 8, E, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            CU_BREAK(cudaEventRecord(ev_out[s], ctx->copy_stream));
-        }
         merkle_absorb_kernel<<<blocks, MERKLE_THREADS, 0, ctx->stream>>>(dbuf[b].p, w, E, state.p, s == 0, s + 1 == nslabs, nodes.p);
         rc = check_launch(ctx, 1, "absorb");
         if (rc) break;
         if (trace) CU_BREAK(cudaEventRecord(ev_abs[s], ctx->stream));
+        if (s + 1 < nslabs) {
+            rc = slab_from_pages(ctx, sall.p + N * col0[s + 1], src, nPols, col0[s + 1], width[s + 1], ctx->in_stream);
+            if (rc) break;
+            CU_BREAK(cudaEventRecord(ev_in[s + 1], ctx->in_stream));
+        }
+        if (dst_out) {
+            CU_BREAK(cudaStreamWaitEvent(ctx->copy_stream, ev_lde[s], 0));
+            rc = slab_to_pages(ctx, dbuf[b].p, *dst_out, nPols, col0[s], w, ctx->copy_stream);
+            if (rc) break;
+            CU_BREAK(cudaEventRecord(ev_out[s], ctx->copy_stream));
+        }
     }
     if (rc == PIL2GPU_OK) {
         int l = merkle_launch_tree(nodes.p, E, ctx->stream);
         rc = check_launch(ctx, l, "tree");
     }
-    for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++) {
-        if (nodes_out) CU_BREAK(cudaMemcpyAsync(nodes_out, nodes.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rc == PIL2GPU_OK && nodes_out) rc = d2h_2d(ctx, (char*)nodes_out, nw * 8, (const char*)nodes.p, nw * 8, nw * 8, 1, ctx->stream);
+    for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++)
         if (root_out) CU_BREAK(cudaMemcpyAsync(root_out, nodes.p + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    }
     // every stream must drain before the workspace is reused, on the error paths too
     cudaError_t e1 = cudaStreamSynchronize(ctx->in_stream), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(ctx->copy_stream);
     if (rc) return rc;
@@ -1207,39 +1497,64 @@ static int extend_and_merkelize_pipelined(pil2gpu_ctx* ctx, const uint64_t* src,
     return PIL2GPU_OK;
 }
 
-int pil2gpu_extend_and_merkelize(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
-                                 uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]) {
+// extendAndMerkelize over BigBuffer pages (stark_gen_helpers.js:388-412 with cm<stage>_n / cm<stage>_ext as pilcom BigBuffers).
+//  - pages that hold whole rows (any power-of-two nPols): the column-slab pipeline above, one strided copy per (slab, page);
+//  - anything else: pages -> device, LDE, then the page downloads run under the hashing.
+int pil2gpu_extend_and_merkelize_paged(pil2gpu_ctx* ctx, const uint64_t* const* src_pages, const uint64_t* src_page_words, uint32_t n_src_pages,
+                                       uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split, uint64_t* const* dst_pages,
+                                       const uint64_t* dst_page_words, uint32_t n_dst_pages, uint64_t* nodes_out, uint64_t root_out[4]) {
     ENTER(ctx);
-    if (!src) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (!src_pages || !src_page_words) return fail(PIL2GPU_E_INVALID, "null argument");
     if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad commit shape");
     if (nBitsExt - nBits > 8) return fail(PIL2GPU_E_UNSUPPORTED, "blowup 2^%u not supported (max 2^8)", nBitsExt - nBits);
-    // slab pipeline: standard hash only (split batches do not align with slabs), wide traces only
-    const uint64_t cs = (nPols % 32 == 0) ? 32 : 16;
-    if (!split && nPols % 16 == 0 && nPols / cs >= 4 && nBits >= 12)
-        return extend_and_merkelize_pipelined(ctx, src, nPols, nBits, nBitsExt, cs, dst_out, nodes_out, root_out);
     const size_t sw = (size_t)nPols << nBits, dw = (size_t)nPols << nBitsExt;
+    const PageList sp = {src_pages, src_page_words, n_src_pages};
+    const PageList dp = {(const uint64_t* const*)dst_pages, dst_page_words, n_dst_pages};
+    const bool want_dst = dst_pages != nullptr && n_dst_pages > 0;
+    int rc = check_pages(sp, sw, "source");
+    if (!rc && want_dst) rc = check_pages(dp, dw, "destination");
+    if (rc) return rc;
+    // slab pipeline: standard hash only (split batches do not align with slabs), wide traces only, whole rows per page
+    const uint64_t cs = (nPols % 32 == 0) ? 32 : 16;
+    if (!split && nPols % 16 == 0 && nPols / cs >= 4 && nBits >= 12 && pages_row_aligned(sp, nPols) && (!want_dst || pages_row_aligned(dp, nPols)))
+        return extend_and_merkelize_pipelined(ctx, sp, nPols, nBits, nBitsExt, cs, want_dst ? &dp : nullptr, nodes_out, root_out);
     const u64 height = 1ULL << nBitsExt;
     const size_t nw = merkle_nnodes_words(height);
-    int rc = ensure_ws(ctx, ev2(sw) + ev2(dw) + nw);
+    rc = ensure_ws(ctx, ev2(sw) + ev2(dw) + nw);
     if (rc) return rc;
-    struct { u64* p; } a = {ctx->ws}, b = {ctx->ws + ev2(sw)}, n = {ctx->ws + ev2(sw) + ev2(dw)};
-    CU(cudaMemcpyAsync(a.p, src, sw * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = pil2gpu_lde_dev(ctx, a.p, b.p, nPols, nBits, nBitsExt);
-    if (rc) return rc;
-    if (dst_out) {   // download the extended buffer on the copy stream while the main stream hashes it
-        CU(cudaEventRecord(ctx->ev, ctx->stream));
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev, 0));
-        CU(cudaMemcpyAsync(dst_out, b.p, dw * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    }
-    rc = pil2gpu_merkelize_dev(ctx, b.p, nPols, height, split, n.p);
+    u64 *a = ctx->ws, *b = ctx->ws + ev2(sw), *n = ctx->ws + ev2(sw) + ev2(dw);
+    rc = pages_to_dev(ctx, a, sp, sw, ctx->stream);
+    if (!rc) rc = pil2gpu_lde_dev(ctx, a, b, nPols, nBits, nBitsExt);
     for (int once = 0; once < 1 && rc == PIL2GPU_OK; once++) {
-        if (nodes_out) CU_BREAK(cudaMemcpyAsync(nodes_out, n.p, nw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (root_out) CU_BREAK(cudaMemcpyAsync(root_out, n.p + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        // hash first (asynchronous), then download the extended buffer on the copy stream: with pageable pages the staged
+        // download blocks this thread while the main stream hashes
+        CU_BREAK(cudaEventRecord(ctx->ev, ctx->stream));
+        rc = pil2gpu_merkelize_dev(ctx, b, nPols, height, split, n);
+        if (rc) break;
+        if (want_dst) {
+            CU_BREAK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev, 0));
+            rc = dev_to_pages(ctx, b, dp, dw, ctx->copy_stream);
+            if (rc) break;
+        }
+        if (nodes_out) rc = d2h_2d(ctx, (char*)nodes_out, nw * 8, (const char*)n, nw * 8, nw * 8, 1, ctx->stream);
+        if (rc) break;
+        if (root_out) CU_BREAK(cudaMemcpyAsync(root_out, n + nw - 4, 32, cudaMemcpyDeviceToHost, ctx->stream));
     }
     cudaError_t es = sync_all_streams(ctx);
     if (rc) return rc;
     if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "extend_and_merkelize: %s", cudaGetErrorString(es));
     return PIL2GPU_OK;
+}
+
+int pil2gpu_extend_and_merkelize(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt, int split,
+                                 uint64_t* dst_out, uint64_t* nodes_out, uint64_t root_out[4]) {
+    if (!src) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nPols == 0 || nBitsExt > 32 || nBitsExt < nBits) return fail(PIL2GPU_E_INVALID, "bad commit shape");
+    const uint64_t sw = nPols << nBits, dw = nPols << nBitsExt;
+    const uint64_t* sp[1] = {src};
+    uint64_t* dp[1] = {dst_out};
+    return pil2gpu_extend_and_merkelize_paged(ctx, sp, &sw, 1, nPols, nBits, nBitsExt, split, dst_out ? dp : nullptr, &dw, dst_out ? 1 : 0, nodes_out,
+                                              root_out);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1354,7 +1669,7 @@ int pil2gpu_tree_group_proofs(pil2gpu_ctx* ctx, const pil2gpu_tree* t, const uin
         if (idxs[i] >= t->height) return fail(PIL2GPU_E_RANGE, "Out of range");
     if (n_idx == 0) return PIL2GPU_OK;
     const int depth = merkle_depth(t->height);
-    DevBuf di, dr, ds;
+    PoolBuf di(ctx), dr(ctx), ds(ctx);
     CU(di.alloc(n_idx));
     CU(dr.alloc((size_t)n_idx * t->width));
     CU(ds.alloc((size_t)n_idx * depth * 4));
@@ -1436,28 +1751,46 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
     return rc;
 }
 
-int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
-                     const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out) {
+int pil2gpu_fri_fold_paged(pil2gpu_ctx* ctx, const uint64_t* const* pol_pages, const uint64_t* pol_page_words, uint32_t n_pol_pages,
+                           uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits, const uint64_t challenge[3], int split,
+                           uint64_t* const* out_pages, const uint64_t* out_page_words, uint32_t n_out_pages, uint64_t* const* rows_pages,
+                           const uint64_t* rows_page_words, uint32_t n_rows_pages, uint64_t* nodes_out) {
     ENTER(ctx);
-    if (!pol || !pol_out || !challenge) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (!pol_pages || !pol_page_words || !out_pages || !out_page_words || !challenge) return fail(PIL2GPU_E_INVALID, "null argument");
     if (prevBits > 32 || curBits > prevBits || prevBits > step0Bits || step0Bits > 32) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
     if (nextBits >= 0 && (uint32_t)nextBits > curBits) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
-    if (prevBits - curBits > FRI_MAX_FOLD_BITS) return fail(PIL2GPU_E_UNSUPPORTED, "fold by 2^%u not supported (max 2^%d)", prevBits - curBits, FRI_MAX_FOLD_BITS);
     const size_t pw = (size_t)3 << prevBits, cw = (size_t)3 << curBits;
     const u64 height = nextBits >= 0 ? (1ULL << nextBits) : 0;
-    int rc = ensure_ws(ctx, ev2(pw) + 2 * ev2(cw) + (nextBits >= 0 ? merkle_nnodes_words(height) : 0));
+    const size_t nw = nextBits >= 0 ? merkle_nnodes_words(height) : 0;
+    const PageList pp = {pol_pages, pol_page_words, n_pol_pages}, op = {(const uint64_t* const*)out_pages, out_page_words, n_out_pages},
+                   rp = {(const uint64_t* const*)rows_pages, rows_page_words, n_rows_pages};
+    const bool want_rows = nextBits >= 0 && rows_pages != nullptr && n_rows_pages > 0;
+    int rc = check_pages(pp, pw, "pol");
+    if (!rc) rc = check_pages(op, cw, "pol_out");
+    if (!rc && want_rows) rc = check_pages(rp, cw, "rows_out");
+    if (!rc) rc = ensure_ws(ctx, ev2(pw) + 2 * ev2(cw) + nw);
     if (rc) return rc;
-    struct { u64* p; } a = {ctx->ws}, b = {ctx->ws + ev2(pw)}, r = {ctx->ws + ev2(pw) + ev2(cw)}, n = {ctx->ws + ev2(pw) + 2 * ev2(cw)};
-    CU(cudaMemcpyAsync(a.p, pol, pw * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = pil2gpu_fri_fold_dev(ctx, a.p, prevBits, curBits, nextBits, step0Bits, challenge, split, b.p, r.p, n.p);
+    u64 *a = ctx->ws, *b = ctx->ws + ev2(pw), *r = ctx->ws + ev2(pw) + ev2(cw), *n = ctx->ws + ev2(pw) + 2 * ev2(cw);
+    rc = pages_to_dev(ctx, a, pp, pw, ctx->stream);
+    if (!rc) rc = pil2gpu_fri_fold_dev(ctx, a, prevBits, curBits, nextBits, step0Bits, challenge, split, b, r, n);
+    if (!rc) rc = dev_to_pages(ctx, b, op, cw, ctx->stream);
+    if (!rc && want_rows) rc = dev_to_pages(ctx, r, rp, cw, ctx->stream);
+    if (!rc && nextBits >= 0 && nodes_out) rc = d2h_2d(ctx, (char*)nodes_out, nw * 8, (const char*)n, nw * 8, nw * 8, 1, ctx->stream);
+    cudaError_t es = sync_all_streams(ctx);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(pol_out, b.p, cw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (nextBits >= 0) {
-        if (rows_out) CU(cudaMemcpyAsync(rows_out, r.p, cw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (nodes_out) CU(cudaMemcpyAsync(nodes_out, n.p, merkle_nnodes_words(height) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    CU(cudaStreamSynchronize(ctx->stream));
+    if (es != cudaSuccess) return fail(PIL2GPU_E_CUDA, "fri_fold: %s", cudaGetErrorString(es));
     return PIL2GPU_OK;
+}
+
+int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
+                     const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out) {
+    if (!pol || !pol_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (prevBits > 32 || curBits > prevBits) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
+    const uint64_t pw = (uint64_t)3 << prevBits, cw = (uint64_t)3 << curBits;
+    const uint64_t* pp[1] = {pol};
+    uint64_t *op[1] = {pol_out}, *rp[1] = {rows_out};
+    return pil2gpu_fri_fold_paged(ctx, pp, &pw, 1, prevBits, curBits, nextBits, step0Bits, challenge, split, op, &cw, 1, rows_out ? rp : nullptr, &cw,
+                                  rows_out ? 1 : 0, nodes_out);
 }
 
 }   // extern "C"

@@ -54,9 +54,9 @@ def extendAndMerkelize(stage, ctx, options=None):
         ctx.trees[stage] = tree
         _dev_buffers(ctx)["cm%d_ext" % stage] = tree.elements_ptr
         return [[int(x) for x in root]]
-    dst, nodes, root = _gpu(ctx).extend_and_merkelize(buff_from, n_pols, ctx.nBits, ctx.nBitsExt, split=_split(ctx))
-    getattr(ctx, "cm%d_ext" % stage)[:] = dst
-    ctx.trees[stage] = _tree(getattr(ctx, "cm%d_ext" % stage), nodes, n_pols, ctx.extN)
+    buff_to = getattr(ctx, "cm%d_ext" % stage)                 # caller-allocated (numpy array or BigBuffer), filled in place
+    _, nodes, root = _gpu(ctx).extend_and_merkelize(buff_from, n_pols, ctx.nBits, ctx.nBitsExt, split=_split(ctx), dst=buff_to)
+    ctx.trees[stage] = _tree(buff_to, nodes, n_pols, ctx.extN)
     return [[int(x) for x in root]]
 
 
@@ -71,12 +71,10 @@ def computeQStark(ctx, options=None):
         ctx.trees[q_stage] = tree
         _dev_buffers(ctx)["cm%d_ext" % q_stage] = tree.elements_ptr
         return [[int(x) for x in root]]
-    ext, nodes, root = _gpu(ctx).compute_q(ctx.q_ext, q_dim, q_deg, ctx.nBits, ctx.nBitsExt, split=_split(ctx))
     name = "cm%d_ext" % q_stage
+    ext, nodes, root = _gpu(ctx).compute_q(ctx.q_ext, q_dim, q_deg, ctx.nBits, ctx.nBitsExt, split=_split(ctx), ext=getattr(ctx, name, None))
     if getattr(ctx, name, None) is None:
         setattr(ctx, name, ext)
-    else:
-        getattr(ctx, name)[:] = ext
     n_pols_q = ctx.pilInfo["mapSectionsN"].get("cm%d" % q_stage, 0)
     if n_pols_q != q_dim * q_deg:
         raise ValueError("mapSectionsN.cm%d (%d) != qDim*qDeg (%d)" % (q_stage, n_pols_q, q_dim * q_deg))
