@@ -1,18 +1,25 @@
 // Drop-in for src/helpers/fft/fft_p.js (exports at :299-302): same names, same arguments, same buffer contract
-// (caller allocates buffDst, buffSrc untouched, buffDst fully overwritten).  The work runs in libpil2gpu.so.
+// (caller allocates buffDst, buffSrc untouched, buffDst fully overwritten), BigBuffers of any size (multi-page included).
+// The work runs in libpil2gpu.so on a worker thread; the returned Promise resolves when buffDst is complete.
 "use strict";
-const { addon, context, pagesOf } = require("./pil2gpu.js");
+const { addon, context, inPages, outPages } = require("./pil2gpu.js");
 
-// fft_p.js:178-180 / :182-184
+// fft_p.js:178-180 / :182-184 -> pil2gpu_ntt_paged
 async function fft(buffSrc, nPols, nBits, buffDst) {
-    addon.nttPaged(context(), pagesOf(buffSrc), pagesOf(buffDst), nPols, nBits, 0);
+    const dst = outPages(buffDst);
+    await addon.nttPaged(context(), inPages(buffSrc), dst.pages, nPols, nBits, 0);
+    dst.commit();
 }
 async function ifft(buffSrc, nPols, nBits, buffDst) {
-    addon.nttPaged(context(), pagesOf(buffSrc), pagesOf(buffDst), nPols, nBits, 1);
+    const dst = outPages(buffDst);
+    await addon.nttPaged(context(), inPages(buffSrc), dst.pages, nPols, nBits, 1);
+    dst.commit();
 }
 // fft_p.js:187-297 -> pil2gpu_lde_paged
 async function interpolate(buffSrc, nPols, nBits, buffDst, nBitsExt) {
-    addon.ldePaged(context(), pagesOf(buffSrc), pagesOf(buffDst), nPols, nBits, nBitsExt);
+    const dst = outPages(buffDst);
+    await addon.ldePaged(context(), inPages(buffSrc), dst.pages, nPols, nBits, nBitsExt);
+    dst.commit();
 }
 // fft_p.js:20-32: a pure row permutation on caller buffers; kept in JS (it is not on the accelerated path).
 function traspose(buffDst, buffSrc, nPols, nBits, trasposeBits) {

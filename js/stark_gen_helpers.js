@@ -1,24 +1,27 @@
 // GPU replacements for the arithmetic of four functions of src/stark/stark_gen_helpers.js.  Usage: require this file from
 // the reference's stark_gen_helpers.js and delegate, e.g. `module.exports.computeQStark = require(".../js/stark_gen_helpers.js").computeQStark`.
-// ctx is the reference's prover context (same field names); buffers must be single BigUint64Arrays (BigBuffers of one page).
+// ctx is the reference's prover context (same field names).  extendAndMerkelize and computeQStark take BigBuffers of any size
+// (pil2gpu_extend_and_merkelize_paged / pil2gpu_compute_q_paged); the evaluation / FRI-polynomial helpers read single-page buffers
+// (at sizes where the extended buffers are multi-page, keep them on the device: MerkleHash.commitDevice).
 "use strict";
-const { addon, context, pagesOf } = require("./pil2gpu.js");
+const { addon, context, inPages, outPages, zeroCopyPages } = require("./pil2gpu.js");
 
 function flat(buff) {
-    const p = pagesOf(buff);
-    if (p.length !== 1) throw new Error("pil2gpu: this entry point needs a single-page buffer");
+    const p = zeroCopyPages(buff);
+    if (!p || p.length !== 1) throw new Error("pil2gpu: this entry point needs a single-page buffer");
     return p[0];
 }
 const split = (ctx) => (ctx.MH.splitLinearHash ? 1 : 0);
 const xiOf = (ctx) => BigUint64Array.from(ctx.challenges[ctx.pilInfo.nStages + 1][0]);
 const openingsOf = (ctx) => Int32Array.from(ctx.pilInfo.openingPoints.map(Number));
 
-// stark_gen_helpers.js:388-412
+// stark_gen_helpers.js:388-412: interpolate (:397) + merkelize (:400) as ONE call -- the extended buffer crosses PCIe once
 async function extendAndMerkelize(stage, ctx) {
     const nPols = ctx.pilInfo.mapSectionsN["cm" + stage] || 0;
-    const buffTo = flat(ctx["cm" + stage + "_ext"]);
-    const nodes = new BigUint64Array(Number(addon.merkleNNodes(BigInt(ctx.extN))));
-    const root = addon.extendAndMerkelize(context(), flat(ctx["cm" + stage + "_n"]), nPols, ctx.nBits, ctx.nBitsExt, split(ctx), buffTo, nodes);
+    const dst = outPages(ctx["cm" + stage + "_ext"]);
+    const nodes = new BigUint64Array(Number(addon.merkleNNodes(ctx.extN)));
+    const root = await addon.extendAndMerkelizePaged(context(), inPages(ctx["cm" + stage + "_n"]), nPols, ctx.nBits, ctx.nBitsExt, split(ctx), dst.pages, nodes);
+    dst.commit();
     ctx.trees[stage] = { elements: ctx["cm" + stage + "_ext"], nodes, width: nPols, height: ctx.extN };
     return [Array.from(root)];
 }
@@ -26,9 +29,10 @@ async function extendAndMerkelize(stage, ctx) {
 async function computeQStark(ctx) {
     const qStage = ctx.pilInfo.nStages + 1;
     const nPolsQ = ctx.pilInfo.mapSectionsN["cm" + qStage] || 0;
-    const nodes = new BigUint64Array(Number(addon.merkleNNodes(BigInt(ctx.extN))));
-    const root = addon.computeQ(context(), flat(ctx.q_ext), ctx.pilInfo.qDim, ctx.pilInfo.qDeg, ctx.nBits, ctx.nBitsExt, split(ctx),
-        flat(ctx["cm" + qStage + "_ext"]), nodes);
+    const dst = outPages(ctx["cm" + qStage + "_ext"]);
+    const nodes = new BigUint64Array(Number(addon.merkleNNodes(ctx.extN)));
+    const root = await addon.computeQPaged(context(), inPages(ctx.q_ext), ctx.pilInfo.qDim, ctx.pilInfo.qDeg, ctx.nBits, ctx.nBitsExt, split(ctx), dst.pages, nodes);
+    dst.commit();
     ctx.trees[qStage] = { elements: ctx["cm" + qStage + "_ext"], nodes, width: nPolsQ, height: ctx.extN };
     return [Array.from(root)];
 }

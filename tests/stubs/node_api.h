@@ -9,8 +9,16 @@ extern "C" {
 typedef struct napi_env__* napi_env;
 typedef struct napi_value__* napi_value;
 typedef struct napi_callback_info__* napi_callback_info;
+typedef struct napi_ref__* napi_ref;
+typedef struct napi_deferred__* napi_deferred;
+typedef struct napi_async_work__* napi_async_work;
 typedef enum { napi_ok, napi_invalid_arg, napi_generic_failure } napi_status;
 typedef enum { napi_default = 0 } napi_property_attributes;
+typedef enum { napi_undefined, napi_null, napi_boolean, napi_number, napi_string, napi_symbol, napi_object, napi_function, napi_external,
+               napi_bigint } napi_valuetype;
+#define NAPI_AUTO_LENGTH SIZE_MAX
+typedef void (*napi_async_execute_callback)(napi_env env, void* data);
+typedef void (*napi_async_complete_callback)(napi_env env, napi_status status, void* data);
 typedef enum {
     napi_int8_array, napi_uint8_array, napi_uint8_clamped_array, napi_int16_array, napi_uint16_array, napi_int32_array, napi_uint32_array,
     napi_float32_array, napi_float64_array, napi_bigint64_array, napi_biguint64_array
@@ -40,6 +48,25 @@ napi_status napi_create_external(napi_env env, void* data, napi_finalize finaliz
 napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void** data, napi_value* result);
 napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset,
                                    napi_value* result);
+napi_status napi_typeof(napi_env env, napi_value value, napi_valuetype* result);
+napi_status napi_is_array(napi_env env, napi_value value, bool* result);
+napi_status napi_get_undefined(napi_env env, napi_value* result);
+napi_status napi_create_object(napi_env env, napi_value* result);
+napi_status napi_create_double(napi_env env, double value, napi_value* result);
+napi_status napi_set_named_property(napi_env env, napi_value object, const char* utf8name, napi_value value);
+napi_status napi_create_string_utf8(napi_env env, const char* str, size_t length, napi_value* result);
+napi_status napi_create_error(napi_env env, napi_value code, napi_value msg, napi_value* result);
+napi_status napi_create_external_arraybuffer(napi_env env, void* external_data, size_t byte_length, napi_finalize finalize_cb, void* finalize_hint,
+                                             napi_value* result);
+napi_status napi_create_reference(napi_env env, napi_value value, uint32_t initial_refcount, napi_ref* result);
+napi_status napi_delete_reference(napi_env env, napi_ref ref);
+napi_status napi_create_promise(napi_env env, napi_deferred* deferred, napi_value* promise);
+napi_status napi_resolve_deferred(napi_env env, napi_deferred deferred, napi_value resolution);
+napi_status napi_reject_deferred(napi_env env, napi_deferred deferred, napi_value rejection);
+napi_status napi_create_async_work(napi_env env, napi_value async_resource, napi_value async_resource_name, napi_async_execute_callback execute,
+                                   napi_async_complete_callback complete, void* data, napi_async_work* result);
+napi_status napi_queue_async_work(napi_env env, napi_async_work work);
+napi_status napi_delete_async_work(napi_env env, napi_async_work work);
 napi_status napi_define_properties(napi_env env, napi_value object, size_t property_count, const napi_property_descriptor* properties);
 }
 #define NODE_GYP_MODULE_NAME pil2gpu_addon
