@@ -262,6 +262,15 @@ int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, u
 int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol_dev, uint32_t prevBits, uint32_t curBits, int32_t nextBits,
                          uint32_t step0Bits, const uint64_t challenge[3], int split, uint64_t* pol_out_dev, uint64_t* rows_out_dev,
                          uint64_t* nodes_out_dev);
+/* One rank's share of a fold in a sharded FRI chain (no reference counterpart: the reference is single-process): computes rows
+ * [row0, row0 + n_rows) of the next layer's transposed buffer (n_rows == 0: all) at their absolute positions in rows_out_dev, and
+ * pol_out_dev[g] for the same outputs when pol_out_dev != NULL.  in_layout 0: in_dev is the polynomial in fri.js order;
+ * in_layout 1: in_dev is the previous layer's transposed buffer, whose row g holds the 2^(prevBits-curBits) inputs of output g
+ * contiguously, so a chain that all-gathers each layer's rows never needs the polynomial order again.  No hashing: the caller
+ * hashes its rows.  n_rows must be a multiple of 32 (or the whole layer). */
+int pil2gpu_fri_fold_range_dev(pil2gpu_ctx* ctx, const uint64_t* in_dev, int in_layout, uint32_t prevBits, uint32_t curBits, int32_t nextBits,
+                               uint32_t step0Bits, const uint64_t challenge[3], uint64_t row0, uint64_t n_rows, uint64_t* pol_out_dev,
+                               uint64_t* rows_out_dev);
 /* Paged twin (a 2^27-point first layer is 3 GiB, more than one BigUint64Array page): pol / pol_out / rows_out as page lists;
  * rows_pages may be NULL / 0 pages. */
 int pil2gpu_fri_fold_paged(pil2gpu_ctx* ctx, const uint64_t* const* pol_pages, const uint64_t* pol_page_words, uint32_t n_pol_pages,

@@ -61,6 +61,7 @@ _SIGS = {
                                                    vp, vp]),
     "pil2gpu_compute_q_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), u64p, c_u32,
                                         vp, vp]),
+    "pil2gpu_fri_fold_range_dev": (c_int, [vp, vp, c_int, c_u32, c_u32, c_i32, c_u32, vp, c_u64, c_u64, vp, vp]),
     "pil2gpu_fri_fold_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u32, c_u32, c_i32, c_u32, vp, c_int, ctypes.POINTER(vp), u64p, c_u32,
                                        ctypes.POINTER(vp), u64p, c_u32, vp]),
     "pil2gpu_ipc_export": (c_int, [vp, vp, vp]),

@@ -19,6 +19,10 @@ struct FriParams {
     int prev_bits, cur_bits, next_bits;   // next_bits < 0: last step (no rows / tree)
     int write_rows;                        // rows + leaf digests wanted
     int fuse_leaf_hash;                    // standard linear hash computed in-kernel
+    int in_rows;                           // input layout: 0 = polynomial order pol[3*(j*2^cur + g)], 1 = the transposed rows of the
+                                           // previous layer rows[3*(g*nX + j)] (its next_bits == this cur_bits): 16 contiguous inputs per output
+    int write_pol;                         // store pol2[g] (0: rows only -- the sharded chain continues from the rows)
+    u64 row0, n_rows;                      // rows [row0, row0 + n_rows) of the next layer (n_rows == 0: all) -- sharded chains
     u64 shift_inv;                         // (7^(2^(b0-prev)))^-1
     u64 nx_inv;                            // (2^(prev-cur))^-1
     u64 challenge[3];
@@ -28,17 +32,20 @@ GL_D gl3 fri_load3(const u64* __restrict__ p) { return gl3{{p[0], p[1], p[2]}}; 
 
 // Evaluate the interpolant of e_0..e_{nX-1} (on <w_nX>) at beta; FOLD = log2(nX).
 template <int FOLD>
-GL_D gl3 fri_fold_point(const u64* __restrict__ pol, u64 g, int cur_bits, gl3 beta, const u64* __restrict__ tw_inv) {
+GL_D gl3 fri_fold_point(const u64* __restrict__ pol, u64 g, int cur_bits, gl3 beta, const u64* __restrict__ tw_inv, int in_rows) {
     constexpr int NX = 1 << FOLD;
+    // input j of output g: polynomial order base + j * 3 * 2^cur, rows order base + 3 j
+    const u64* __restrict__ base = in_rows ? pol + 3 * g * NX : pol + 3 * g;
+    const u64 sj = in_rows ? 3 : ((u64)3 << cur_bits);
     if constexpr (FOLD == 0) {
-        return fri_load3(pol + 3 * g);
+        return fri_load3(base);
     } else {
     gl3 e[NX / 2];
     // first fold straight from memory: pairs (j, j + NX/2)
 #pragma unroll
     for (int j = 0; j < NX / 2; j++) {
-        const gl3 a = fri_load3(pol + 3 * (((u64)j << cur_bits) + g));
-        const gl3 b = fri_load3(pol + 3 * (((u64)(j + NX / 2) << cur_bits) + g));
+        const gl3 a = fri_load3(base + (u64)j * sj);
+        const gl3 b = fri_load3(base + (u64)(j + NX / 2) * sj);
         const u64 wj = tw_inv[(NX / 2) + j];                         // w_NX^-j (Montgomery form)
         e[j] = gl3_add(gl3_add(a, b), gl3_mul(beta, gl3_mscale(gl3_sub(a, b), wj)));
     }
@@ -70,16 +77,16 @@ __global__ void __launch_bounds__(FOLD >= 5 ? 256 : 512) fri_fold_kernel(const u
     const int ii = threadIdx.x % rb;
     const int jj = threadIdx.x / rb;
     const int jstep = blockDim.x / rb;
-    const u64 i = (u64)blockIdx.x * rb + ii;
+    const u64 i = P.row0 + (u64)blockIdx.x * rb + ii;
     const gl3 alpha = gl3{{P.challenge[0], P.challenge[1], P.challenge[2]}};
     for (u64 j = jj; j < gs; j += jstep) {
         const u64 g = i + (j << next_bits);
         // sinv_g = shift_inv * w_prev^-g
         const u32 E = P.prev_bits == 0 ? 0u : (0u - ((u32)g << (32 - P.prev_bits)));
         const u64 sinv = gl_mmul(P.shift_inv, ntt_root_pow(tb.bytepow, E));   // root in Montgomery form: plain product
-        gl3 v = fri_fold_point<FOLD>(pol, g, P.cur_bits, gl3_scale(alpha, sinv), tb.tw_inv);
+        gl3 v = fri_fold_point<FOLD>(pol, g, P.cur_bits, gl3_scale(alpha, sinv), tb.tw_inv, P.in_rows);
         v = gl3_canon(gl3_scale(v, P.nx_inv));
-        pol2[3 * g] = v.c[0]; pol2[3 * g + 1] = v.c[1]; pol2[3 * g + 2] = v.c[2];
+        if (P.write_pol) { pol2[3 * g] = v.c[0]; pol2[3 * g + 1] = v.c[1]; pol2[3 * g + 2] = v.c[2]; }
         if (P.write_rows) {
             u64* r = rows + (i * gs + j) * 3;
             r[0] = v.c[0]; r[1] = v.c[1]; r[2] = v.c[2];
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(FOLD >= 5 ? 256 : 512) fri_fold_kernel(const u
         if (threadIdx.x < rb) {
             u64 d[4];
             merkle_sponge(fri_rows + (size_t)threadIdx.x * gs * 3, 3 * gs, d);
-            const u64 row = (u64)blockIdx.x * rb + threadIdx.x;
+            const u64 row = P.row0 + (u64)blockIdx.x * rb + threadIdx.x;
 #pragma unroll
             for (int k = 0; k < 4; k++) nodes[4 * row + k] = d[k];
         }
@@ -107,8 +114,10 @@ static int fri_launch_fold(const u64* pol, u64* pol2, u64* rows, u64* nodes, con
     if (fold < 0 || fold > FRI_MAX_FOLD_BITS) return -1;
     const int next_bits = P.next_bits < 0 ? P.cur_bits : P.next_bits;
     const u64 gs = 1ULL << (P.cur_bits - next_bits);
-    const u64 n_rows = 1ULL << next_bits;
-    const int rb = (int)(n_rows < FRI_ROWS_PER_CTA ? n_rows : FRI_ROWS_PER_CTA);
+    const u64 all_rows = 1ULL << next_bits;
+    const u64 n_rows = P.n_rows ? P.n_rows : all_rows;
+    const int rb = (int)(all_rows < FRI_ROWS_PER_CTA ? all_rows : FRI_ROWS_PER_CTA);   // the kernel derives rb from next_bits the same way
+    if (n_rows % rb) return -1;
     u64 jb = gs;
     // registers: the fold keeps NX/2 F3 values live; keep CTAs at <= 256 threads for the wide folds
     const u64 max_threads = fold >= 5 ? 256 : 512;

@@ -24,6 +24,7 @@
 //    canonical, followed by the 3/5-instruction gl_addc / gl_subc (gl.cuh).  DIT data stays lazy (any u64) between layers
 //    and passes; DIF data stays canonical (the sum uses the complement trick in ntt_cadd).
 #pragma once
+#include <cstdlib>
 #include "gl.cuh"
 
 #define NTT_W 16        // columns per tile (128 contiguous bytes per row segment)
@@ -362,41 +363,79 @@ __device__ __forceinline__ void ntt_tile_store(const ulonglong2* __restrict__ ti
 // ---- generic pass ------------------------------------------------------------------------------------------
 // One pass over bits [lo, lo+t) of a 2^n-point transform of every column.
 //   position(k) = (base_hi << (lo+t)) | (k << lo) | base_lo,   tile id = (base_hi << lo) | base_lo
-// gridDim.x = 2^(n-t) tiles, gridDim.y = ceil(C / NTT_W) column chunks, gridDim.z = cosets.
-template <bool DIF, bool INVERSE, bool SC = false>
-__global__ void __launch_bounds__(NTT_THREADS, NTT_PASS_MIN_CTAS) ntt_pass_kernel(const u64* in, u64* out, NttPass P, NttTables tb,   // in == out for the in-place passes: no __restrict__
-                                                               const __grid_constant__ NttScatter sc) {
+// Work items are (tile id, column chunk) pairs, tile-major: item = tile_id * ychunks + y.  A CTA owns `ipc` consecutive items
+// (gridDim.x = ceil(items / ipc), gridDim.z = cosets; default ipc = 1).  With two tile buffers (PIPE) the cp.async loads of item
+// i+1 are in flight while item i is transformed and the twiddle table is built once per tile id -- an A/B variant that measured
+// slower than one item per CTA at 5 CTAs / SM (see ntt_launch_pass).  Per item: barrier (loads landed, previous store finished)
+// -> [prefetch next] -> warp-private butterflies -> barrier -> cooperative store.
+struct NttItems {
+    u32 ychunks;   // column chunks per tile id
+    u32 ipc;       // items per CTA
+    u32 total;     // tiles * ychunks
+};
+template <bool DIF, bool INVERSE, bool SC = false, bool PIPE = true>
+__global__ void __launch_bounds__(NTT_THREADS, PIPE ? 3 : NTT_PASS_MIN_CTAS) ntt_pass_kernel(const u64* in, u64* out, NttPass P, NttTables tb,   // in == out for the in-place passes: no __restrict__
+                                                               const __grid_constant__ NttScatter sc, NttItems it) {
     extern __shared__ __align__(16) u64 ntt_smem[];
     const int t = P.t, lo = P.lo;
     const int RS = ntt_region_elems(t);
-    ulonglong2* tile = reinterpret_cast<ulonglong2*>(ntt_smem);
-    u64* TW = ntt_smem + (size_t)NTT_CP * RS * 2;
+    ulonglong2* tiles[2];
+    tiles[0] = reinterpret_cast<ulonglong2*>(ntt_smem);
+    tiles[1] = PIPE ? tiles[0] + (size_t)NTT_CP * RS : tiles[0];
+    u64* TW = ntt_smem + (size_t)NTT_CP * RS * 2 * (PIPE ? 2 : 1);
     u64* G = TW + ((size_t)1 << t);
-    const u32 tile_id = blockIdx.x;
-    const u32 base_lo = tile_id & ((1u << lo) - 1);
-    const u32 base_hi = tile_id >> lo;
-    const u64 c0 = (u64)blockIdx.y * NTT_W;
-    const int cw = (int)((P.C - c0 < NTT_W) ? (P.C - c0) : NTT_W);
     const u64 z = blockIdx.z;
-    const u64 pos0 = ((u64)base_hi << (lo + t)) | base_lo;
-    // loads first: they are in flight while the twiddle table is built.  position(k) = pos0 + (k << lo); buffer row =
-    // position * mul + z (bit-reversed gather: the helper reverses the position itself, mul is 1 and z is 0 there)
-    const bool async = P.bitrev_in ? ntt_tile_load(tile, in, P.C, c0, cw, t, pos0, (u64)1 << lo, P.n)
-                                   : ntt_tile_load(tile, in, P.C, c0, cw, t, pos0 * P.in_mul + (P.in_z ? z : 0), P.in_mul << lo, -1);
-    ntt_build_tw<INVERSE>(TW, G, t, lo, base_lo, P.coset ? (int)z : -1, P.n, P.ext_bits, tb, P.unit_shift != 0);   // ends with a barrier
-    if (async) { ntt_cp_async_wait(); __syncthreads(); }
-    ulonglong2* reg = tile + (threadIdx.x >> 5) * RS;      // this warp's column pair
-    if (DIF && P.canon_in) {   // the caller's buffer may hold non-canonical words; DIF butterflies need canonical inputs
-        for (int k = threadIdx.x & 31; k < (1 << t); k += 32) {
-            ulonglong2 v = reg[ntt_pad(k)];
-            v.x = gl_canon(v.x); v.y = gl_canon(v.y);
-            reg[ntt_pad(k)] = v;
+    const u32 item0 = blockIdx.x * it.ipc;
+    const u32 item_end = (item0 + it.ipc < it.total) ? item0 + it.ipc : it.total;
+
+    auto issue_load = [&](u32 item, ulonglong2* tile) -> bool {
+        const u32 tile_id = item / it.ychunks, y = item - tile_id * it.ychunks;
+        const u32 base_lo = tile_id & ((1u << lo) - 1), base_hi = tile_id >> lo;
+        const u64 c0 = (u64)y * NTT_W;
+        const int cw = (int)((P.C - c0 < NTT_W) ? (P.C - c0) : NTT_W);
+        const u64 pos0 = ((u64)base_hi << (lo + t)) | base_lo;
+        // position(k) = pos0 + (k << lo); buffer row = position * mul + z (bit-reversed gather: the helper reverses the
+        // position itself, mul is 1 and z is 0 there)
+        const bool async = P.bitrev_in ? ntt_tile_load(tile, in, P.C, c0, cw, t, pos0, (u64)1 << lo, P.n)
+                                       : ntt_tile_load(tile, in, P.C, c0, cw, t, pos0 * P.in_mul + (P.in_z ? z : 0), P.in_mul << lo, -1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        return async;
+    };
+
+    u32 cur_tile = 0xFFFFFFFFu;
+    if (item0 < item_end) issue_load(item0, tiles[0]);
+    for (u32 item = item0; item < item_end; item++) {
+        const int bsel = PIPE ? (int)((item - item0) & 1) : 0;
+        ulonglong2* tile = tiles[bsel];
+        const u32 tile_id = item / it.ychunks, y = item - tile_id * it.ychunks;
+        const u32 base_lo = tile_id & ((1u << lo) - 1), base_hi = tile_id >> lo;
+        if (tile_id != cur_tile) {   // every warp is past the butterflies of the previous item (barrier B below): the table is free
+            ntt_build_tw<INVERSE>(TW, G, t, lo, base_lo, P.coset ? (int)z : -1, P.n, P.ext_bits, tb, P.unit_shift != 0);   // ends with a barrier
+            cur_tile = tile_id;
         }
-        __syncwarp();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // A: this item's rows are in shared memory; the previous store is finished
+        if (PIPE && item + 1 < item_end) issue_load(item + 1, tiles[bsel ^ 1]);
+        ulonglong2* reg = tile + (threadIdx.x >> 5) * RS;      // this warp's column pair
+        if (DIF && P.canon_in) {   // the caller's buffer may hold non-canonical words; DIF butterflies need canonical inputs
+            for (int k = threadIdx.x & 31; k < (1 << t); k += 32) {
+                ulonglong2 v = reg[ntt_pad(k)];
+                v.x = gl_canon(v.x); v.y = gl_canon(v.y);
+                reg[ntt_pad(k)] = v;
+            }
+            __syncwarp();
+        }
+        ntt_warp_transform<DIF>(reg, TW, t);
+        __syncthreads();                                   // B
+        const u64 c0 = (u64)y * NTT_W;
+        const int cw = (int)((P.C - c0 < NTT_W) ? (P.C - c0) : NTT_W);
+        const u64 pos0 = ((u64)base_hi << (lo + t)) | base_lo;
+        ntt_tile_store<SC>(tile, out, P.C, c0, cw, t, P.scale ? 2 : ((!DIF && P.canon_out) ? 1 : 0), P.scale, pos0 * P.out_mul + z, P.out_mul << lo, sc);
+        if (!PIPE && item + 1 < item_end) {
+            __syncthreads();                               // single buffer: the store must finish before the next load overwrites it
+            issue_load(item + 1, tile);
+        }
     }
-    ntt_warp_transform<DIF>(reg, TW, t);
-    __syncthreads();
-    ntt_tile_store<SC>(tile, out, P.C, c0, cw, t, P.scale ? 2 : ((!DIF && P.canon_out) ? 1 : 0), P.scale, pos0 * P.out_mul + z, P.out_mul << lo, sc);
 }
 
 // ---- fused LDE middle kernel ---------------------------------------------------------------------------------
@@ -476,6 +515,45 @@ static inline cudaError_t ntt_set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// Pass launch.  Default: one item per CTA, single tile buffer, 5 CTAs / SM -- co-resident CTAs hide the load latency.
+// Measured on B200 at cfg3 (r02, profiles/r02_lde_pipeline_ab.md): the software-pipelined variant (PIL2GPU_NTT_PIPE=1: two tile
+// buffers, cp.async prefetch of item i+1 under the butterflies of item i, 3 CTAs / SM at 80 registers, PIL2GPU_NTT_IPC items
+// per CTA) runs the LDE in 137-139 ms against 125 ms, and even the unpipelined item loop (IPC=16) costs 132 ms: many small
+// independent CTAs mix the alu- and fmaheavy-heavy phases of the butterfly better than fewer, longer-lived ones.  Both variants stay
+// selectable for A/B runs.
+#ifndef NTT_ITEMS_PER_CTA
+#define NTT_ITEMS_PER_CTA 1
+#endif
+template <bool DIF, bool INVERSE, bool SC>
+static inline int ntt_launch_pass(const u64* in, u64* out, const NttPass& P, unsigned cosets, const NttTables& tb, const NttScatter& sc, cudaStream_t st) {
+    const u32 tiles = 1u << (P.n - P.t);
+    const u32 ychunks = (u32)((P.C + NTT_W - 1) / NTT_W);
+    const u64 total64 = (u64)tiles * ychunks;
+    if (total64 > 0xFFFFFFF0ull) return -1;
+    NttItems it;
+    it.ychunks = ychunks;
+    it.total = (u32)total64;
+    // whole tile ids per CTA (the twiddle table is per tile id), about NTT_ITEMS_PER_CTA items, but keep >= ~8 waves of CTAs
+    static const int env_ipc = getenv("PIL2GPU_NTT_IPC") ? atoi(getenv("PIL2GPU_NTT_IPC")) : 0;       // tuning / A-B knobs
+    static const int env_pipe = getenv("PIL2GPU_NTT_PIPE") ? atoi(getenv("PIL2GPU_NTT_PIPE")) : 0;
+    const u32 want = env_ipc > 0 ? (u32)env_ipc : NTT_ITEMS_PER_CTA;
+    u32 tpc = ychunks >= want ? 1 : want / ychunks;
+    while (tpc > 1 && (u64)(tiles / tpc) * cosets < 148u * 3u * 8u) tpc >>= 1;
+    it.ipc = tpc * ychunks;
+    if (env_ipc > 0 && (u32)env_ipc < it.ipc) it.ipc = (u32)env_ipc;      // below one tile id per CTA: the table is rebuilt per CTA
+    const bool pipe = env_pipe && P.t <= 8 && it.ipc >= 2;
+    dim3 grid((it.total + it.ipc - 1) / it.ipc, 1, cosets);
+    const size_t smem = ntt_smem_bytes(P.t, pipe);
+    if (pipe) {
+        if (ntt_set_smem(ntt_pass_kernel<DIF, INVERSE, SC, true>, smem) != cudaSuccess) return -1;
+        ntt_pass_kernel<DIF, INVERSE, SC, true><<<grid, NTT_THREADS, smem, st>>>(in, out, P, tb, sc, it);
+    } else {
+        if (ntt_set_smem(ntt_pass_kernel<DIF, INVERSE, SC, false>, smem) != cudaSuccess) return -1;
+        ntt_pass_kernel<DIF, INVERSE, SC, false><<<grid, NTT_THREADS, smem, st>>>(in, out, P, tb, sc, it);
+    }
+    return 1;
+}
+
 static inline NttPass ntt_pass_defaults(u64 C, int n, int ext_bits) {
     NttPass P;
     P.C = C; P.n = n; P.lo = 0; P.t = 0; P.in_mul = 1; P.out_mul = 1;
@@ -499,7 +577,6 @@ static int ntt_launch_transform(const u64* src, u64* dst, u64 C, int n, bool inv
     const u64 n_inv = glh_to_mont(glh_inv((1ULL << n) % GL_P));
     const NttScatter nosc = ntt_no_scatter();
     int lo = 0;
-    const unsigned ychunks = (unsigned)((C + NTT_W - 1) / NTT_W);
     int launches = 0;
     for (int i = p.npass - 1; i >= 0; i--) {
         const int t = p.bits[i];
@@ -509,15 +586,8 @@ static int ntt_launch_transform(const u64* src, u64* dst, u64 C, int n, bool inv
         P.bitrev_in = first ? 1 : 0; P.canon_out = last ? 1 : 0;
         P.scale = (last && inverse) ? n_inv : 0;
         const u64* in = first ? src : dst;
-        dim3 grid(1u << (n - t), ychunks, 1);
-        const size_t smem = ntt_smem_bytes(t, false);
-        if (inverse) {
-            if (ntt_set_smem(ntt_pass_kernel<false, true>, smem) != cudaSuccess) return -1;
-            ntt_pass_kernel<false, true><<<grid, NTT_THREADS, smem, st>>>(in, dst, P, tb, nosc);
-        } else {
-            if (ntt_set_smem(ntt_pass_kernel<false, false>, smem) != cudaSuccess) return -1;
-            ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, st>>>(in, dst, P, tb, nosc);
-        }
+        if ((inverse ? ntt_launch_pass<false, true, false>(in, dst, P, 1, tb, nosc, st) : ntt_launch_pass<false, false, false>(in, dst, P, 1, tb, nosc, st)) < 0)
+            return -1;
         launches++;
         lo += t;
     }
@@ -543,10 +613,7 @@ static int ntt_launch_lde(const u64* src, u64* dst, u64 C, int n, int ext_bits, 
         NttPass P = ntt_pass_defaults(C, n, ext_bits);
         P.lo = lo; P.t = t; P.in_mul = (i == 0) ? 1 : (u64)B; P.out_mul = (u64)B;
         P.canon_in = (i == 0) ? 1 : 0;
-        dim3 grid(1u << (n - t), ychunks, 1);
-        const size_t smem = ntt_smem_bytes(t, false);
-        if (ntt_set_smem(ntt_pass_kernel<true, true>, smem) != cudaSuccess) return -1;
-        ntt_pass_kernel<true, true><<<grid, NTT_THREADS, smem, st>>>(i == 0 ? src : dst, dst, P, tb, nosc);
+        if (ntt_launch_pass<true, true, false>(i == 0 ? src : dst, dst, P, 1, tb, nosc, st) < 0) return -1;
         launches++;
         hi = lo;
     }
@@ -573,15 +640,8 @@ static int ntt_launch_lde(const u64* src, u64* dst, u64 C, int n, int ext_bits, 
         NttPass P = ntt_pass_defaults(C, n, ext_bits);
         P.lo = lo; P.t = t; P.in_mul = (u64)B; P.out_mul = (u64)B;
         P.canon_out = (i == 0) ? 1 : 0; P.coset = 1;
-        dim3 grid(1u << (n - t), ychunks, (unsigned)B);
-        const size_t smem = ntt_smem_bytes(t, false);
-        if (i == 0 && sc) {
-            if (ntt_set_smem(ntt_pass_kernel<false, false, true>, smem) != cudaSuccess) return -1;
-            ntt_pass_kernel<false, false, true><<<grid, NTT_THREADS, smem, st>>>(dst, dst, P, tb, *sc);
-        } else {
-            if (ntt_set_smem(ntt_pass_kernel<false, false>, smem) != cudaSuccess) return -1;
-            ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, st>>>(dst, dst, P, tb, nosc);
-        }
+        if (((i == 0 && sc) ? ntt_launch_pass<false, false, true>(dst, dst, P, (unsigned)B, tb, *sc, st)
+                            : ntt_launch_pass<false, false, false>(dst, dst, P, (unsigned)B, tb, nosc, st)) < 0) return -1;
         launches++;
         lo += t;
     }
@@ -593,17 +653,13 @@ static int ntt_launch_lde(const u64* src, u64* dst, u64 C, int n, int ext_bits, 
 static int ntt_launch_intt_bitrev(const u64* src, u64* dst, u64 C, int n, const NttTables& tb, cudaStream_t st) {
     NttPlan p = ntt_plan(n, NTT_TMAX);
     const NttScatter nosc = ntt_no_scatter();
-    const unsigned ychunks = (unsigned)((C + NTT_W - 1) / NTT_W);
     int launches = 0, hi = n;
     for (int i = 0; i < p.npass; i++) {
         const int t = p.bits[i];
         const int lo = hi - t;
         NttPass P = ntt_pass_defaults(C, n, n);
         P.lo = lo; P.t = t; P.canon_in = (i == 0) ? 1 : 0;
-        dim3 grid(1u << (n - t), ychunks, 1);
-        const size_t smem = ntt_smem_bytes(t, false);
-        if (ntt_set_smem(ntt_pass_kernel<true, true>, smem) != cudaSuccess) return -1;
-        ntt_pass_kernel<true, true><<<grid, NTT_THREADS, smem, st>>>(i == 0 ? src : dst, dst, P, tb, nosc);
+        if (ntt_launch_pass<true, true, false>(i == 0 ? src : dst, dst, P, 1, tb, nosc, st) < 0) return -1;
         launches++;
         hi = lo;
     }
@@ -617,7 +673,6 @@ static int ntt_launch_coset_eval(const u64* coef, u64* dst, u64 C, int n, int ex
     NttPlan p = ntt_plan(n, NTT_TMAX);
     const int B = 1 << (ext_bits - n);
     const NttScatter nosc = ntt_no_scatter();
-    const unsigned ychunks = (unsigned)((C + NTT_W - 1) / NTT_W);
     int launches = 0, lo = 0;
     for (int i = p.npass - 1; i >= 0; i--) {
         const int t = p.bits[i];
@@ -625,10 +680,7 @@ static int ntt_launch_coset_eval(const u64* coef, u64* dst, u64 C, int n, int ex
         NttPass P = ntt_pass_defaults(C, n, ext_bits);
         P.lo = lo; P.t = t; P.in_mul = first ? 1 : (u64)B; P.out_mul = (u64)B; P.in_z = first ? 0 : 1;
         P.canon_out = (i == 0) ? 1 : 0; P.coset = 1; P.unit_shift = unit_shift ? 1 : 0;
-        dim3 grid(1u << (n - t), ychunks, (unsigned)B);
-        const size_t smem = ntt_smem_bytes(t, false);
-        if (ntt_set_smem(ntt_pass_kernel<false, false>, smem) != cudaSuccess) return -1;
-        ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, st>>>(first ? coef : dst, dst, P, tb, nosc);
+        if (ntt_launch_pass<false, false, false>(first ? coef : dst, dst, P, (unsigned)B, tb, nosc, st) < 0) return -1;
         launches++;
         lo += t;
     }

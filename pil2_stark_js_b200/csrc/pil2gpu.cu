@@ -1049,10 +1049,6 @@ static bool pages_row_aligned(const PageList& pl, size_t nPols) {
     for (uint32_t p = 0; p < pl.n; p++) if (pl.words[p] % nPols) return false;
     return true;
 }
-static bool pages_all_pinned(const PageList& pl) {
-    for (uint32_t p = 0; p < pl.n; p++) if (pl.words[p] && !host_is_pinned(pl.pages[p])) return false;
-    return true;
-}
 static int slab_from_pages(pil2gpu_ctx* ctx, u64* slab, const PageList& pl, size_t nPols, size_t c0, size_t w, cudaStream_t st) {
     size_t row = 0;
     for (uint32_t p = 0; p < pl.n; p++) {
@@ -1727,6 +1723,10 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
     P.cur_bits = (int)curBits;
     P.next_bits = nextBits;
     P.write_rows = nextBits >= 0;
+    P.in_rows = 0;
+    P.write_pol = 1;
+    P.row0 = 0;
+    P.n_rows = 0;
     u64 si = glh_inv(GL_SHIFT);                                    // fri.js:31-36
     for (uint32_t j = 0; j < step0Bits - prevBits; j++) si = glh_mul(si, si);
     P.shift_inv = si;
@@ -1749,6 +1749,46 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
         }
     }
     return rc;
+}
+
+// Sharded FRI chains: one rank's share of a fold.  Computes rows [row0, row0 + n_rows) of the next layer's
+// transposed buffer (= the outputs g = i + 2^nextBits * j of those rows i) at their absolute positions in rows_out_dev, and
+// pol_out_dev[g] for the same outputs when pol_out_dev != NULL.  in_layout 0: in_dev is the polynomial (fri.js order);
+// in_layout 1: in_dev is the previous layer's transposed buffer (its nextBits == this prevBits - ... == curBits), whose row g holds
+// the 2^(prevBits-curBits) inputs of output g contiguously -- so a chain that all-gathers the rows of every layer never
+// needs the polynomial order again.  No hashing here: the caller hashes its rows (pil2gpu_merkelize_dev on the slice).
+int pil2gpu_fri_fold_range_dev(pil2gpu_ctx* ctx, const uint64_t* in_dev, int in_layout, uint32_t prevBits, uint32_t curBits, int32_t nextBits,
+                               uint32_t step0Bits, const uint64_t challenge[3], uint64_t row0, uint64_t n_rows, uint64_t* pol_out_dev,
+                               uint64_t* rows_out_dev) {
+    ENTER(ctx);
+    if (!in_dev || !challenge || (!pol_out_dev && !rows_out_dev)) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (curBits > prevBits || prevBits > step0Bits || step0Bits > 32) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
+    if (nextBits >= 0 && (uint32_t)nextBits > curBits) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
+    if (prevBits - curBits > FRI_MAX_FOLD_BITS) return fail(PIL2GPU_E_UNSUPPORTED, "fold by 2^%u not supported (max 2^%d)", prevBits - curBits, FRI_MAX_FOLD_BITS);
+    if (in_layout != 0 && in_layout != 1) return fail(PIL2GPU_E_INVALID, "in_layout must be 0 (polynomial) or 1 (rows)");
+    const uint32_t nb = nextBits >= 0 ? (uint32_t)nextBits : curBits;
+    const u64 all_rows = 1ULL << nb;
+    if (n_rows == 0) { row0 = 0; n_rows = all_rows; }
+    if (row0 > all_rows || n_rows > all_rows - row0) return fail(PIL2GPU_E_RANGE, "row range outside the layer");
+    if (nextBits >= 0 && !rows_out_dev) return fail(PIL2GPU_E_INVALID, "rows_out_dev is required when nextBits >= 0");
+    FriParams P;
+    P.prev_bits = (int)prevBits;
+    P.cur_bits = (int)curBits;
+    P.next_bits = nextBits;
+    P.write_rows = nextBits >= 0;
+    P.fuse_leaf_hash = 0;
+    P.in_rows = in_layout;
+    P.write_pol = pol_out_dev != nullptr;
+    P.row0 = row0;
+    P.n_rows = n_rows;
+    u64 si = glh_inv(GL_SHIFT);                                    // fri.js:31-36
+    for (uint32_t j = 0; j < step0Bits - prevBits; j++) si = glh_mul(si, si);
+    P.shift_inv = si;
+    P.nx_inv = glh_inv(1ULL << (prevBits - curBits));
+    for (int k = 0; k < 3; k++) P.challenge[k] = challenge[k];
+    int l = fri_launch_fold((const u64*)in_dev, (u64*)pol_out_dev, (u64*)rows_out_dev, nullptr, P, ctx->tb, ctx->stream);
+    if (l < 0) return fail(PIL2GPU_E_UNSUPPORTED, "row range must be a multiple of %d rows", FRI_ROWS_PER_CTA);
+    return check_launch(ctx, l, "fri_fold_range");
 }
 
 int pil2gpu_fri_fold_paged(pil2gpu_ctx* ctx, const uint64_t* const* pol_pages, const uint64_t* pol_page_words, uint32_t n_pol_pages,
