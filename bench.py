@@ -432,8 +432,10 @@ def run_ours(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(g, args, torch, n_bits, cols, blow, steps, src, fri_pol[0], chal, queries, root_dev)
+    u64l = lambda t: [int(x) & 0xFFFFFFFFFFFFFFFF for x in t.cpu().tolist()]
+    fri_out = {"fri_roots": [u64l(n[-4:]) for n in fri_nodes], "fri_final0": u64l(fri_pol[-1][:3])}
     return finish_line(args, n_bits, cols, blow, sec_per_commit, t_lde, t_mk, t_leaf, t_fri, roofline, roofline_lde, e2e, extras, launches, clocks,
-                       root_dev, seed, spot)
+                       root_dev, seed, spot, fri_out)
 
 
 def parity_spot_check(torch, n_bits, cols, blow, seed, dst, nodes, root_dev, queries, q_rows, q_sib, steps, chal, fri_pol, fri_nodes,
@@ -605,7 +607,7 @@ def run_next_rows(g, L, check, vp, npp, torch, time_phase, reps, n_bits, cols, b
 
 
 def finish_line(args, n_bits, cols, blow, sec_per_commit, t_lde, t_mk, t_leaf, t_fri, roofline, roofline_lde, e2e, extras, launches, clocks, root_dev,
-                seed, spot=None):
+                seed, spot=None, fri_out=None):
     cpu = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -623,6 +625,7 @@ def finish_line(args, n_bits, cols, blow, sec_per_commit, t_lde, t_mk, t_leaf, t
         "clocks": clocks, "root": root_dev,
         "parity_spot_check": (spot or {}).get("status", "skipped"), "parity_spot_check_detail": spot,
     }
+    line.update(fri_out or {})
     print(json.dumps(line), flush=True)
 
 

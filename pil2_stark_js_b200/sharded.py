@@ -169,6 +169,15 @@ class GpuEngine:
                                               ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(b.ctypes.data), ext_bits, self._p(f)))
         return f
 
+    def fri_fold_range(self, src, in_layout, prev_bits, cur_bits, next_bits, step0_bits, challenge, row0, n_rows, pol_out, rows_out):
+        """One rank's share of a FRI fold (pil2gpu_fri_fold_range_dev): rows [row0, row0 + n_rows) of the next layer's
+        transposed buffer at their absolute positions; src is the polynomial (in_layout 0) or the previous layer's rows (1)."""
+        ch = np.ascontiguousarray(challenge, dtype=np.uint64)
+        self.check(self.L.pil2gpu_fri_fold_range_dev(self.h, self._p(src), int(in_layout), prev_bits, cur_bits, -1 if next_bits is None else next_bits,
+                                                     step0_bits, ctypes.c_void_p(ch.ctypes.data), int(row0), int(n_rows),
+                                                     self._p(pol_out) if pol_out is not None else None,
+                                                     self._p(rows_out) if rows_out is not None else None))
+
     def launches(self):
         return int(self.L.pil2gpu_launch_count(self.h))
 
@@ -246,6 +255,7 @@ class ShardedTree:
         self.tiles, self.n_tiles, self.tile_cols, self.rows_local = tiles, n_tiles, tile_cols, rows_local
         self.nodes, self.sub, self.top = nodes, sub, top
         self.width = n_tiles * tile_cols
+        self.replica = None            # (global rank, global world, dist) when this is a whole tree replicated on every rank
 
     def reduce_to_root(self):
         """Sub-root all-gather + the top log2(G) levels (hashed redundantly on every rank).  Returns the 4-word root tensor."""
@@ -259,29 +269,76 @@ class ShardedTree:
         nt = e.nnodes(G)
         return self.top[nt - 4:nt]
 
-    def open(self, queries):
-        """getGroupProof for global leaf indices `queries` (int64 tensor on the engine's device, identical on every rank):
-        every rank gathers the rows it owns, one sum all-reduce combines them (the other ranks contribute zeros), and the
-        top-level siblings come from the replicated top tree.  Returns (rows [Q, width], siblings [Q, depth, 4]) on every rank."""
-        e, G, R = self.e, self.world, self.rows_local
+    def open_words(self, n_queries):
+        """Words of the flat buffer open_local fills: Q rows of `width` words, then Q x local depth x 4 sibling words."""
+        dl = max(self.rows_local.bit_length() - 1, 0)
+        return n_queries * self.width + n_queries * dl * 4
+
+    def open_local(self, queries, flat):
+        """This rank's contribution to getGroupProof for global leaf indices `queries`: the rows and lower siblings of the
+        leaves it owns, zeros for the others, written into `flat` (open_words(Q) words) -- ready for a sum all-reduce."""
+        e, R = self.e, self.rows_local
         Q = int(queries.numel())
         dl = max(R.bit_length() - 1, 0)
         local = queries - self.rank * R
         idx = local.clone()
         idx[(local < 0) | (local >= R)] = -1                              # 0xFFFF...: "not mine"
-        rows_out, sib_local = e.empty(Q * self.width), e.empty(max(1, Q * dl * 4))
-        e.group_proofs(self.tiles, self.n_tiles, self.tile_cols, R, self.nodes, idx, Q, rows_out, sib_local)
-        sib_local = sib_local[:Q * dl * 4].view(Q, dl, 4)
+        rows_out = flat[:Q * self.width]
+        if dl:
+            e.group_proofs(self.tiles, self.n_tiles, self.tile_cols, R, self.nodes, idx, Q, rows_out, flat[Q * self.width:Q * self.width + Q * dl * 4])
+        else:
+            e.group_proofs(self.tiles, self.n_tiles, self.tile_cols, R, self.nodes, idx, Q, rows_out, e.empty(4))
+
+    def open_finish(self, queries, flat):
+        """After the all-reduce of `flat`: (rows [Q, width], siblings [Q, depth, 4]); the top log2(G) siblings come from the
+        replicated top tree."""
+        e, G, R = self.e, self.world, self.rows_local
+        Q = int(queries.numel())
+        dl = max(R.bit_length() - 1, 0)
+        rows = flat[:Q * self.width].view(Q, self.width)
+        sib_local = flat[Q * self.width:Q * self.width + Q * dl * 4].view(Q, dl, 4)
         if G == 1:
-            return rows_out.view(Q, self.width), sib_local
-        self.dist.all_reduce(rows_out)
-        self.dist.all_reduce(sib_local)
+            return rows, sib_local
         dt = G.bit_length() - 1
         owners = (queries // R).contiguous()
         sub_rows, sib_top = e.empty(Q * 4), e.empty(Q * dt * 4)
         e.group_proofs(self.sub, 1, 4, G, self.top, owners, Q, sub_rows, sib_top)
         import torch
-        return rows_out.view(Q, self.width), torch.cat([sib_local, sib_top.view(Q, dt, 4)], dim=1)
+        return rows, torch.cat([sib_local, sib_top.view(Q, dt, 4)], dim=1)
+
+    def open(self, queries):
+        """getGroupProof for global leaf indices `queries` (int64 tensor on the engine's device, identical on every rank):
+        every rank gathers the rows it owns, one sum all-reduce combines them (the other ranks contribute zeros), and the
+        top-level siblings come from the replicated top tree.  Returns (rows [Q, width], siblings [Q, depth, 4]) on every rank."""
+        return open_trees([(self, queries)])[0]
+
+
+def open_trees(pairs):
+    """proofQueries (fri.js:83-105) over several sharded trees with ONE collective: every (tree, queries) pair gathers into its
+    slice of a single flat buffer, one sum all-reduce combines all of them.  Returns [(rows, siblings)] in order."""
+    if not pairs:
+        return []
+    t0 = pairs[0][0]
+    sizes = [t.open_words(int(q.numel())) for t, q in pairs]
+    flat = t0.e.empty(max(1, sum(sizes)))
+    off = 0
+    views = []
+    group = None
+    for (t, q), n in zip(pairs, sizes):
+        v = flat[off:off + n]
+        t.open_local(q, v)
+        if t.replica is not None:
+            if t.replica[0] != 0:
+                v.zero_()              # a replicated tree: rank 0 alone contributes to the sum
+            if t.replica[1] > 1:
+                group = t.replica[2]
+        elif t.world > 1:
+            group = t.dist
+        views.append(v)
+        off += n
+    if group is not None:
+        group.all_reduce(flat)
+    return [t.open_finish(q, v) for (t, q), v in zip(pairs, views)]
 
 
 class ShardedCommit:
@@ -367,6 +424,81 @@ class ShardedCommit:
         return t, t.reduce_to_root()
 
 
+class ShardedFri:
+    """FRI chain (fri.js:22-81 per step) over G ranks that all hold the FRI polynomial.  Layer tree s (over the transposed rows of
+    P_s, fri.js:187-202) is SHARDED while it is big enough to be worth a collective (>= min_rows_per_rank leaves per rank): rank h
+    computes rows [h*R, (h+1)*R) of the layer straight from the previous layer (pil2gpu_fri_fold_range_dev: the outputs a row needs
+    are exactly that row), hashes them, and the rows of the layer are all-gathered so that every rank can fold the next one -- the
+    transposed rows of layer s hold the 2^k inputs of every output of fold s+1 contiguously, so the chain never returns to the
+    polynomial order.  Smaller layers are computed redundantly on every rank (no collective).  Roots, trees and the final
+    polynomial equal the single-process chain."""
+
+    def __init__(self, engine, dist, rank, world, steps, min_rows_per_rank=1024):
+        self.e, self.dist, self.rank, self.world, self.steps = engine, dist, rank, world, list(steps)
+        self.nl = len(steps) - 1
+        e = engine
+        self.sharded = [world > 1 and ((1 << steps[s + 1]) // world) >= min_rows_per_rank and ((1 << steps[s + 1]) // world) % 32 == 0
+                        for s in range(self.nl)]
+        self.rows = [e.empty(3 << steps[s]) for s in range(self.nl)]
+        self.width = [3 << (steps[s] - steps[s + 1]) for s in range(self.nl)]
+        self.height = [1 << steps[s + 1] for s in range(self.nl)]
+        self.nodes, self.sub, self.top, self.trees = [], [], [], [None] * self.nl
+        for s in range(self.nl):
+            if self.sharded[s]:
+                self.nodes.append(e.empty(e.nnodes(self.height[s] // world)))
+                self.sub.append(e.empty(4 * world))
+                self.top.append(e.empty(max(8, e.nnodes(world))))
+            else:
+                self.nodes.append(e.empty(e.nnodes(self.height[s])))
+                self.sub.append(None)
+                self.top.append(None)
+        self.final = e.empty(3 << steps[-1])
+        self.roots = [None] * self.nl
+
+    def run(self, pol0, challenges):
+        """pol0: 3 * 2^steps[0] words (on every rank); challenges[s]: the F3 challenge of fold s (challenges[0] is unused: step
+        0 is the identity fold, fri.js:48-49).  Fills rows / trees / roots / final."""
+        e, G, st = self.e, self.world, self.steps
+        for s in range(self.nl):
+            # layer s holds P_s = fold_s(P_{s-1}) (P_0 = pol0, fold 0 is the identity).  Input of fold s: pol0 for s <= 1, the
+            # (complete) rows of layer s-1 afterwards -- row g of layer s-1 is the input group of output g
+            if s <= 1:
+                src, layout, prev_bits = pol0, 0, st[0]
+            else:
+                src, layout, prev_bits = self.rows[s - 1], 1, st[s - 1]
+            h, w = self.height[s], self.width[s]
+            if self.sharded[s]:
+                R = h // G
+                e.fri_fold_range(src, layout, prev_bits, st[s], st[s + 1], st[0], challenges[s], self.rank * R, R, None, self.rows[s])
+                mine = self.rows[s][self.rank * R * w:(self.rank + 1) * R * w]
+                e.merkelize(mine, w, R, self.nodes[s])
+                t = ShardedTree(e, self.dist, self.rank, G, mine, 1, w, R, self.nodes[s], self.sub[s], self.top[s])
+                self.roots[s] = t.reduce_to_root()
+                self.trees[s] = t
+                if s >= 1:                                  # the next fold reads every row of this layer (layer 0's successor reads pol0)
+                    self.dist.all_gather_into_tensor(self.rows[s], mine if str(getattr(e, "device", "")) != "cpu" else mine.clone())
+            else:
+                e.fri_fold_range(src, layout, prev_bits, st[s], st[s + 1], st[0], challenges[s], 0, 0, None, self.rows[s])
+                e.merkelize(self.rows[s], w, h, self.nodes[s])
+                nn = e.nnodes(h)
+                self.roots[s] = self.nodes[s][nn - 4:nn]
+                self.trees[s] = ShardedTree(e, self.dist, 0, 1, self.rows[s], 1, w, h, self.nodes[s], None, None)
+                self.trees[s].replica = (self.rank, G, self.dist)
+        # last fold: P_{L-1} -> P_L (the final polynomial), no tree (fri.js:72-79)
+        L = len(st) - 1
+        if L == 0:
+            self.final.copy_(pol0)
+        elif L == 1:
+            e.fri_fold_range(pol0, 0, st[0], st[1], None, st[0], challenges[1], 0, 0, self.final, None)
+        else:
+            e.fri_fold_range(self.rows[L - 1], 1, st[L - 1], st[L], None, st[0], challenges[L], 0, 0, self.final, None)
+        return self.roots, self.final
+
+    def query_pairs(self, queries):
+        """(tree, indices) of every layer tree for proofQueries (fri.js:96-104: layer s is opened at q mod 2^steps[s+1])."""
+        return [(self.trees[s], queries % self.height[s]) for s in range(self.nl)]
+
+
 def assemble_nodes(local_nodes_per_rank, top_nodes, rows_local, world, nnodes_fn):
     """Host-side helper (tests / downloads): stitch per-rank subtree node arrays and the top tree into the reference
     `nodes` layout of the full tree (power-of-two sizes)."""
@@ -410,66 +542,29 @@ def bench_main(args, rank, world, local_rank, dist, bench):
     src = eng.empty(cg << n_bits)
     check(L.pil2gpu_synth2d_dev(eng.h, vp(src.data_ptr()), 1 << n_bits, cg, cols, rank * cg, seed))
     buf = sc.buffers(cols, n_bits, ext_bits)
-    # FRI chain: every rank holds the FRI polynomial; the first layer tree (2^steps[1] leaves, ~3/4 of the
-    # chain's hashing) is hashed sharded like the trace tree, the layers below it (16x smaller each) run on rank 0.
+    # FRI chain: every rank holds the FRI polynomial; big layers are sharded by rows (fold + leaf hashing of the
+    # rank's own rows, rows all-gathered for the next fold), small ones are computed redundantly on every rank (ShardedFri)
     steps = bench.fri_steps(ext_bits)
     nl = len(steps) - 1                                   # layer trees
-    w0, h0 = 3 << (steps[0] - steps[1]), 1 << steps[1]
-    shard_l0 = nl >= 1 and h0 // world >= 2
-    fri = {"pol0": eng.empty(3 << steps[0]), "rows0": eng.empty(3 << steps[0]),
-           "chal": [np.ascontiguousarray(bench.splitmix_field(seed + 2 + s, 0, 3)) for s in range(len(steps))]}
-    check(L.pil2gpu_synth_dev(eng.h, vp(fri["pol0"].data_ptr()), 3 << steps[0], seed + 1, 0))
-    if shard_l0:
-        fri["nodes0"], fri["sub0"], fri["top0"] = eng.empty(eng.nnodes(h0 // world)), eng.empty(4 * world), eng.empty(max(8, eng.nnodes(world)))
-    elif rank == 0:
-        fri["nodes0"] = eng.empty(eng.nnodes(h0))
-    if rank == 0:
-        fri["pol"] = [fri["pol0"]] + [eng.empty(3 << b) for b in steps[1:]]
-        fri["rows"] = [fri["rows0"]] + [eng.empty(3 << steps[s]) for s in range(1, nl)]
-        fri["nodes"] = [fri.get("nodes0")] + [eng.empty(eng.nnodes(1 << steps[s + 1])) for s in range(1, nl)]
+    h0 = 1 << steps[1] if nl else 1
+    chal = [np.ascontiguousarray(bench.splitmix_field(seed + 2 + s, 0, 3)) for s in range(len(steps))]
+    fri_pol0 = eng.empty(3 << steps[0])
+    check(L.pil2gpu_synth_dev(eng.h, vp(fri_pol0.data_ptr()), 3 << steps[0], seed + 1, 0))
+    sfri = ShardedFri(eng, dist, rank, world, steps)
+    shard_l0 = bool(nl and sfri.sharded[0])
     npp = lambda a: vp(a.ctypes.data)
-    P = lambda t: vp(t.data_ptr())
     rng = np.random.default_rng(7)
     queries_np = rng.integers(0, 1 << ext_bits, size=bench.N_QUERIES, dtype=np.int64)
     queries = torch.from_numpy(queries_np).to(eng.device)
-    lower = []                                            # rank 0: (tree handle, host outputs) of the unsharded layer trees
-    if rank == 0:
-        for s in range(0 if not shard_l0 else 1, nl):
-            t = vp()
-            gsz = 3 << (steps[s] - steps[s + 1])
-            check(L.pil2gpu_tree_wrap_dev(eng.h, P(fri["rows"][s]), P(fri["nodes"][s]), gsz, 1 << steps[s + 1], ctypes.byref(t)))
-            lower.append((t, steps[s + 1], np.empty(bench.N_QUERIES * gsz, dtype=np.uint64),
-                          np.empty(bench.N_QUERIES * max(1, steps[s + 1]) * 4, dtype=np.uint64)))
     opened = {}
 
     def fri_chain():
-        f = fri
-        # step 0: identity fold (fri.js:48-49) = transposed rows of the first layer, then its tree
-        if shard_l0:
-            check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol0"]), steps[0], steps[0], steps[1], steps[0], npp(f["chal"][0]), 0, P(f["pol0"]),
-                                         P(f["rows0"]), None))
-            f["tree0"], f["root0"] = sc.commit_rows(f["rows0"], w0, h0, f["nodes0"], f["sub0"], f["top0"])
-        elif rank == 0:
-            check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol0"]), steps[0], steps[0], steps[1], steps[0], npp(f["chal"][0]), 0, P(f["pol0"]),
-                                         P(f["rows0"]), P(f["nodes0"])))
-        if rank == 0:
-            for s in range(1, len(steps)):
-                last = s == len(steps) - 1
-                check(L.pil2gpu_fri_fold_dev(eng.h, P(f["pol"][s - 1]), steps[s - 1], steps[s], -1 if last else steps[s + 1], steps[0],
-                                             npp(f["chal"][s]), 0, P(f["pol"][s]), None if last else P(f["rows"][s]),
-                                             None if last else P(f["nodes"][s])))
+        sfri.run(fri_pol0, chal)
 
     def open_queries():
-        # proofQueries (fri.js:83-105): the trace tree and the first FRI layer are opened where their rows live (one
-        # sum all-reduce each); the small lower layers are opened on rank 0
-        opened["main"] = buf["tree"].open(queries)
-        if shard_l0:
-            opened["fri0"] = fri["tree0"].open(queries % h0)
-        if rank == 0:
-            q = queries_np.astype(np.uint64)
-            for t, bits, r_out, s_out in lower:
-                qq = np.ascontiguousarray(q % np.uint64(1 << bits))
-                check(L.pil2gpu_tree_group_proofs(eng.h, t, npp(qq), bench.N_QUERIES, npp(r_out), npp(s_out)))
+        # proofQueries (fri.js:83-105): every tree is opened where its rows live, ONE sum all-reduce combines all of them
+        res = open_trees([(buf["tree"], queries)] + sfri.query_pairs(queries))
+        opened["main"], opened["fri"] = res[0], res[1:]
 
     root_host = torch.empty(4, dtype=torch.int64, pin_memory=True)
 
@@ -522,7 +617,7 @@ def bench_main(args, rank, world, local_rank, dist, bench):
     dist.all_reduce(ph, op=dist.ReduceOp.MAX)
     t_lde, t_hash, t_tree, t_top, t_fri, t_q = (float(x) for x in ph.tolist())
     phases = {"lde+exchange": t_lde, "hash (leaves + local subtree)": t_hash, "local subtree levels": t_tree, "sub-root gather + top tree": t_top,
-              "fri (first layer sharded, lower layers rank 0)": t_fri, "queries": t_q, "sum": t_lde + t_hash + t_top + t_fri + t_q,
+              "fri (big layers sharded, small ones replicated)": t_fri, "queries": t_q, "sum": t_lde + t_hash + t_top + t_fri + t_q,
               "how": "one extra step after the timed region, CUDA events per phase, max over ranks per phase"}
     mm, iw = ctypes.c_double(), ctypes.c_double()
     check(L.pil2gpu_bench_int_pipes(eng.h, ctypes.byref(mm), ctypes.byref(iw)))
@@ -571,15 +666,19 @@ def bench_main(args, rank, world, local_rank, dist, bench):
         src_host.copy_(src)
         ext_dev = buf["recv"] if world > 1 else buf["dst"]
         out_host, nodes_host = pin(ext_dev), pin(buf["nodes"])
-        # FRI: the polynomial goes up on every rank (each hashes its share of the first layer); rank 0 brings the layers down,
-        # every rank its share of the first layer's nodes
-        fri_host = {"pol0": pin(fri["pol0"])}
-        fri_host["pol0"].copy_(fri["pol0"])
+        # FRI: the polynomial goes up on every rank (every rank folds its share of the big layers); sharded layers come down from
+        # the ranks that own them (rows + subtree nodes), replicated ones and the final polynomial from rank 0
+        fri_host = {"pol0": pin(fri_pol0)}
+        fri_host["pol0"].copy_(fri_pol0)
         fri_down = []
-        if shard_l0:
-            fri_down.append(fri["nodes0"])
+        for s_ in range(nl):
+            if sfri.sharded[s_]:
+                R_ = sfri.height[s_] // world
+                fri_down += [sfri.rows[s_][rank * R_ * sfri.width[s_]:(rank + 1) * R_ * sfri.width[s_]], sfri.nodes[s_]]
+            elif rank == 0:
+                fri_down += [sfri.rows[s_], sfri.nodes[s_]]
         if rank == 0:
-            fri_down += fri["pol"] + fri["rows"] + [t for t in fri["nodes"] if t is not None and not (shard_l0 and t is fri.get("nodes0"))]
+            fri_down.append(sfri.final)
         fri_host["down"] = [pin(t) for t in fri_down]
         torch.cuda.synchronize()
 
@@ -618,8 +717,7 @@ def bench_main(args, rank, world, local_rank, dist, bench):
                 mark("rows down")
             # the FRI chain first: its kernels overlap the row download, whereas a device->host copy issued here would queue
             # behind those 32/G GiB on the copy engine and hold the chain back
-            if shard_l0 or rank == 0:
-                fri["pol0"].copy_(fri_host["pol0"], non_blocking=True)
+            fri_pol0.copy_(fri_host["pol0"], non_blocking=True)
             fri_chain()
             mark("fri")
             nodes_host.copy_(buf["nodes"], non_blocking=True)
@@ -643,16 +741,15 @@ def bench_main(args, rank, world, local_rank, dist, bench):
         dist.barrier()
         dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = 8 * (cols << n_bits) + 8 * (3 << steps[0]) * (world if shard_l0 else 1)
-        d2h = 8 * (cols << ext_bits) + 8 * world * buf["nodes"].numel() + 32
-        d2h += 8 * sum(3 << b for b in steps) + 8 * sum(3 << steps[s] for s in range(len(steps) - 1))
-        d2h += 8 * sum(eng.nnodes(1 << steps[s + 1]) for s in range(1, len(steps) - 1))
-        d2h += 8 * (world * eng.nnodes(h0 // world) if shard_l0 else eng.nnodes(h0))
+        h2d = 8 * (cols << n_bits) + 8 * (3 << steps[0]) * world
+        d2h = 8 * (cols << ext_bits) + 8 * world * buf["nodes"].numel() + 32 + 8 * (3 << steps[-1])
+        for s_ in range(nl):              # rows + nodes of every layer, from wherever they live
+            d2h += 8 * (3 << steps[s_]) + 8 * (world * eng.nnodes(sfri.height[s_] // world) if sfri.sharded[s_] else eng.nnodes(sfri.height[s_]))
         e2e = {"value": float(dt.item()), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
                "call": ("per rank: pinned host slab -> pil2gpu_lde_scatter (sub-slab uploads overlapped with the LDE + peer stores) -> hashing "
                         "overlapped with the download of the extended rows; nodes -> pinned host" if peer else
                         "per rank: pinned host slab -> device, ShardedCommit.commit, extended rows + nodes -> pinned host") +
-                       "; FRI polynomial up on every rank, first layer tree sharded, layers down from rank 0"}
+                       "; FRI polynomial up on every rank, sharded layers down from their owners, replicated layers from rank 0"}
     if rank == 0:
         clocks = sampler.stop()
         sec = float(ms.item()) / 1e3 / args.steps
@@ -677,13 +774,15 @@ def bench_main(args, rank, world, local_rank, dist, bench):
             "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": bench.config_dict(args.workload, world),
             "rows_per_s": (1 << n_bits) / sec, "all_to_all_bytes_per_gpu": a2a, "exchange": sc.exchange_kind(buf),
-            "fri": ("first layer tree hashed on all ranks, lower layers on rank 0" if shard_l0 else "rank 0") + f"; {bench.N_QUERIES} queries "
-                   "opened on the owning ranks and combined with one all-reduce per tree",
+            "fri": f"layers sharded by rows: {[bool(x) for x in sfri.sharded]} (the others replicated on every rank); {bench.N_QUERIES} queries "
+                   "opened on the owning ranks, all trees combined with ONE all-reduce",
             "gpu_launches": int(launches.item()), "clocks": clocks,
             "root": root,
             "e2e": e2e, "next_rows": extras, "cpu_baseline": None,
             "phases_s": phases,
             "roofline": roofline,
+            "fri_roots": [[int(x) & 0xFFFFFFFFFFFFFFFF for x in r.tolist()] for r in sfri.roots],
+            "fri_final0": [int(x) & 0xFFFFFFFFFFFFFFFF for x in sfri.final[:3].tolist()],
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

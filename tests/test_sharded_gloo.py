@@ -84,6 +84,28 @@ class OracleEngine:
                 ro[q * width:(q + 1) * width] = r
                 so[q * depth * 4:(q + 1) * depth * 4] = np.asarray(sb, dtype=np.uint64).reshape(-1)
 
+    def fri_fold_range(self, src, in_layout, prev_bits, cur_bits, next_bits, step0_bits, challenge, row0, n_rows, pol_out, rows_out):
+        """stand-in for pil2gpu_fri_fold_range_dev: the whole fold by the oracle, then only the requested rows are written"""
+        nx = 1 << (prev_bits - cur_bits)
+        a = self._u(src)[:3 << prev_bits].reshape(-1, 3)
+        if in_layout == 1:                                           # rows of the previous layer -> polynomial order
+            a = np.ascontiguousarray(a.reshape(1 << cur_bits, nx, 3).transpose(1, 0, 2)).reshape(-1, 3)
+        nb = cur_bits if next_bits is None else next_bits
+        if prev_bits == cur_bits:
+            pol2 = a.copy()
+        else:
+            pol2, _ = C.fri_fold(a, prev_bits, cur_bits, None, step0_bits, [int(x) for x in challenge], threads=1)
+        gs = 1 << (cur_bits - nb)
+        rows = np.ascontiguousarray(pol2.reshape(gs, 1 << nb, 3).transpose(1, 0, 2)).reshape(-1)
+        if n_rows == 0:
+            row0, n_rows = 0, 1 << nb
+        if rows_out is not None:
+            self._u(rows_out)[row0 * 3 * gs:(row0 + n_rows) * 3 * gs] = rows[row0 * 3 * gs:(row0 + n_rows) * 3 * gs]
+        if pol_out is not None:
+            po = self._u(pol_out)[:3 << cur_bits].reshape(-1, 3)
+            for j in range(gs):
+                po[row0 + (j << nb):row0 + n_rows + (j << nb)] = pol2[row0 + (j << nb):row0 + n_rows + (j << nb)]
+
     def tree_from_digests(self, nodes, height):
         d = self._u(nodes)[:4 * height].copy()
         self._u(nodes)[:C.merkle_nnodes(height)] = C.merkelize(d, 4, height, threads=1)   # width 4 = passthrough leaves
@@ -212,3 +234,68 @@ def test_shard_validation():
     with pytest.raises(ValueError):
         sc.shard_cols(16)      # 4 columns per GPU: sponge chunks would straddle tiles
     assert sc.shard_cols(64) == 16
+
+
+# ---------------------------------------------------------------- sharded FRI chain
+def _fri_worker(rank, world, port, steps, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pil2_stark_js_b200.sharded import ShardedFri, open_trees
+        eng = OracleEngine()
+        rng = np.random.default_rng(17)
+        pol0 = rng.integers(0, 0xFFFFFFFF00000001, size=3 << steps[0], dtype=np.uint64)
+        chal = [rng.integers(0, 0xFFFFFFFF00000001, size=3, dtype=np.uint64) for _ in steps]
+        fri = ShardedFri(eng, dist, rank, world, steps, min_rows_per_rank=32)
+        roots, final = fri.run(torch.from_numpy(pol0.view(np.int64).copy()), chal)
+        queries = torch.tensor([0, 1, (1 << steps[0]) - 1, 12345 % (1 << steps[0]), 777], dtype=torch.int64)
+        opened = open_trees(fri.query_pairs(queries))
+        q.put((rank, fri.sharded, [r.numpy().view(np.uint64).copy() for r in roots], final.numpy().view(np.uint64).copy(),
+               [(r.numpy().view(np.uint64).copy(), sb.numpy().view(np.uint64).copy()) for r, sb in opened]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,steps", [(2, [11, 8, 5, 2]), (4, [12, 9, 7, 3]), (2, [9, 4])])
+def test_sharded_fri_chain_matches_single_process(world, steps):
+    """Every layer root, the final polynomial and the opened rows / sibling paths of every layer tree of the sharded chain equal
+    the single-process oracle chain (fri.js:22-105); big layers are sharded, small ones redundant."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fri_worker, args=(r, world, port, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(17)
+    pol0 = rng.integers(0, 0xFFFFFFFF00000001, size=3 << steps[0], dtype=np.uint64)
+    chal = [rng.integers(0, 0xFFFFFFFF00000001, size=3, dtype=np.uint64) for _ in steps]
+    # single-process chain
+    cur = pol0.reshape(-1, 3)
+    L = len(steps) - 1
+    layer_rows, layer_nodes = [], []
+    for s in range(L):
+        if s >= 1:
+            cur, _ = C.fri_fold(cur, steps[s - 1], steps[s], None, steps[0], [int(x) for x in chal[s]])
+        gs = 1 << (steps[s] - steps[s + 1])
+        rows = np.ascontiguousarray(cur.reshape(gs, 1 << steps[s + 1], 3).transpose(1, 0, 2)).reshape(-1)
+        layer_rows.append(rows)
+        layer_nodes.append(C.merkelize(rows, 3 * gs, 1 << steps[s + 1]))
+    final, _ = C.fri_fold(cur, steps[L - 1], steps[L], None, steps[0], [int(x) for x in chal[L]])
+    queries = [0, 1, (1 << steps[0]) - 1, 12345 % (1 << steps[0]), 777]
+    assert any(res[0][1]) or len(steps) == 2                               # at least one layer really is sharded (the 2-step case is all replicas)
+    for _, sharded, roots, fin, opened in res:
+        assert np.array_equal(fin.reshape(-1, 3), final)
+        for s in range(L):
+            assert np.array_equal(roots[s], layer_nodes[s][-4:]), f"root of layer {s}"
+            w, h = 3 << (steps[s] - steps[s + 1]), 1 << steps[s + 1]
+            rows_q, sib_q = opened[s]
+            for k, qi in enumerate(queries):
+                r, sb = C.group_proof(layer_rows[s], layer_nodes[s], w, h, qi % h)
+                assert np.array_equal(rows_q[k], r), (s, qi)
+                assert np.array_equal(sib_q[k].reshape(-1), np.asarray(sb, dtype=np.uint64).reshape(-1)), (s, qi)
