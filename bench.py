@@ -582,6 +582,44 @@ def run_next_rows(g, L, check, vp, npp, torch, time_phase, reps, n_bits, cols, b
     def phase_fripol():
         check(L.pil2gpu_fri_pol_dev(g.h, fterms, n_ev, npp(ev_out), op_arr, len(openings), g.ptr(xd), npp(vf[0]), npp(vf[1]), ext_bits,
                                     g.ptr(f_ext)))
+    # f4: the quotient-constraint program the reference generated for its sm_all AIR (169 records, tests/golden/sm_all_q_code.json)
+    # run over 2^ext_bits rows of synthetic stage buffers by the expression interpreter
+    expr = None
+    try:
+        import types
+        from pil2_stark_js_b200 import prover_helpers as PH
+        from pil2_stark_js_b200._lib import ExprBuffer
+        qc = json.load(open(os.path.join(ROOT, "tests", "golden", "sm_all_q_code.json")))
+        info = qc["starkInfo"]
+        evm = info["evMap"]
+        code = []
+        for c in qc["qVerifier"]["code"]:
+            srcs = [({"type": evm[s_["id"]]["type"], "id": evm[s_["id"]]["id"], "prime": evm[s_["id"]]["prime"]} if s_["type"] == "eval" else dict(s_))
+                    for s_ in c["src"]]
+            code.append({"op": c["op"], "dest": dict(c["dest"]), "src": srcs})
+        code[-1]["dest"] = {"type": "q", "id": 0, "dim": 3}
+        pctx = types.SimpleNamespace(pilInfo=info, nBits=n_bits, nBitsExt=ext_bits, publics=[1, 2, 3],
+                                     challenges=[[], *[[[int(x) for x in splitmix_field(seed + 20 + k, 0, 3)] for _ in range(m)] for k, m in enumerate((2, 3, 1, 1))]])
+        cc = PH.compile_code(pctx, code, "ext")
+        ebufs, keep, words = (ExprBuffer * len(cc.buffers))(), [], 0
+        for bi, (name, rw) in enumerate(cc.buffers):
+            t = g.dev(rw << ext_bits)
+            check(L.pil2gpu_synth_dev(g.h, g.ptr(t), rw << ext_bits, seed + 30 + bi, 0))
+            keep.append(t)
+            ebufs[bi] = ExprBuffer(t.data_ptr(), rw)
+            words += rw << ext_bits
+
+        def phase_expr():
+            check(L.pil2gpu_calculate_exps_dev(g.h, vp(cc.ops.ctypes.data), len(code), vp(cc.consts.ctypes.data), cc.consts.size // 3, ebufs, len(cc.buffers),
+                                               ext_bits, 1))
+        phase_expr()
+        t_ex = time_phase(phase_expr, reps)
+        expr = {"s": t_ex, "shape": f"{len(code)}-record quotient program of the sm_all AIR (51 columns in 4 buffers, {cc.n_slots} live temporaries) over 2^{ext_bits} rows",
+                "algorithmic_bytes": 8 * words, "GBps": 8 * words / t_ex / 1e9, "frac_hbm": 8 * words / t_ex / 1e9 / hbm_peak,
+                "records_per_s": len(code) * float(1 << ext_bits) / t_ex}
+        del keep
+    except Exception as ex:       # reported next to the other rows, never instead of them
+        expr = {"error": str(ex)[:200]}
     for f in (phase_q, phase_lev, phase_evals, phase_xdiv, phase_fripol):
         f()
     t_q, t_lev, t_ev, t_xd, t_fp = (time_phase(f, reps) for f in (phase_q, phase_lev, phase_evals, phase_xdiv, phase_fripol))
@@ -599,6 +637,7 @@ def run_next_rows(g, L, check, vp, npp, torch, time_phase, reps, n_bits, cols, b
         "evals": {"s": t_ev, "shape": f"{n_ev} evaluations over the 2^{n_bits} base rows of the {cols}-column extended buffer",
                   "algorithmic_bytes": ev_bytes, "GBps": ev_bytes / t_ev / 1e9, "frac_hbm": ev_bytes / t_ev / 1e9 / hbm_peak,
                   "mulmod_per_s": 3.0 * n_ev * Nw / t_ev},
+        "expressions": expr,
         "x_div_x_sub_xi": {"s": t_xd, "shape": f"{len(openings)} openings x 2^{ext_bits} points", "algorithmic_bytes": xd_bytes,
                            "GBps": xd_bytes / t_xd / 1e9, "frac_hbm": xd_bytes / t_xd / 1e9 / hbm_peak},
     }

@@ -145,6 +145,27 @@ int pil2gpu_x_div_x_sub_xi_dev(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3],
 int pil2gpu_x_div_x_sub_xi(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], const int32_t* openings, uint32_t n_open, uint32_t nBits,
                            uint32_t nBitsExt, uint64_t* out);
 
+/* ---- constraint expressions over a domain: calculateExps / callCalculateExps, src/prover/prover_helpers.js:23-110 ------------ */
+/* The reference evaluates a straight-line program of {op, dest, src} records (add / sub / mul / copy on base-field or F3 operands,
+ * f3g.js:47-104) at every row i of the domain; operands are rows (i + next) mod N of the stage buffers, uniform values (numbers,
+ * publics, challenges, evals, subproof values), x_i and temporaries (getRef / setRef, prover_helpers.js:112-265).  Here the host
+ * compiles the program into fixed records of 16 u32 words:
+ *     [ opcode, n_src, 0, 0,  dest[3],  src0[3],  src1[3],  src2[3] ]        opcode: 0 add, 1 sub, 2 mul, 3 copy (1 source), 4 muladd (3)
+ * an operand is  [ kind | dim << 8 | buffer << 16,  a,  row_offset ]  with dim 1 (base field) or 3 (F3) and
+ *     kind 0 tmp      a = slot < 64 (slots are assigned by liveness on the host; a temporary is 3 words per thread)
+ *     kind 1 const    a = index into consts (n_consts entries of 3 words; a base-field value is (v, 0, 0))          [source only]
+ *     kind 2 buffer   a = first column inside a row of bufs[buffer]; the row is (i + row_offset) mod 2^domain_bits
+ *     kind 3 x        x_i = w^i of the domain, times the coset shift 7 when x_shift != 0 (ctx.x_n / ctx.x_ext)      [source only]
+ * (Zi_ext, xDivXSubXi_ext, q_ext, f_ext and the stage buffers are all "buffer" operands).  A program must not read, at a non-zero
+ * row offset, a column it also writes (the reference runs the rows in order; here they run concurrently).  Asynchronous on the
+ * ctx stream.  The Python mirror (pil2_stark_js_b200/prover_helpers.py) compiles the reference's code objects into this form. */
+typedef struct pil2gpu_expr_buffer {
+    uint64_t* ptr_dev;
+    uint64_t row_words;
+} pil2gpu_expr_buffer;
+int pil2gpu_calculate_exps_dev(pil2gpu_ctx* ctx, const uint32_t* ops, uint32_t n_ops, const uint64_t* consts, uint32_t n_consts,
+                               const pil2gpu_expr_buffer* bufs, uint32_t n_bufs, uint32_t domain_bits, int x_shift);
+
 /* ---- FRI polynomial: computeFRIStark after the xDivXSubXi table, src/stark/stark_gen_helpers.js:325-334 ------------- */
 /* One entry of pilInfo.evMap, in evMap order (the Horner order of friPolinomial.js:26-40 depends on it): the polynomial's
  * extended buffer on the device (2^nBitsExt rows of `size` words), its first column, dim 1 or 3, and the opening (prime). */

@@ -30,6 +30,11 @@ class EvalDesc(ctypes.Structure):
     _fields_ = [("offset", ctypes.c_uint64), ("dim", ctypes.c_uint32), ("lev", ctypes.c_uint32)]
 
 
+class ExprBuffer(ctypes.Structure):
+    """pil2gpu_expr_buffer (include/pil2gpu.h)"""
+    _fields_ = [("ptr_dev", ctypes.c_void_p), ("row_words", ctypes.c_uint64)]
+
+
 class FriTerm(ctypes.Structure):
     """pil2gpu_fri_term (include/pil2gpu.h)"""
     _fields_ = [("buf_dev", ctypes.c_void_p), ("size", ctypes.c_uint64), ("offset", ctypes.c_uint64), ("dim", ctypes.c_uint32),
@@ -61,6 +66,7 @@ _SIGS = {
                                                    vp, vp]),
     "pil2gpu_compute_q_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), u64p, c_u32,
                                         vp, vp]),
+    "pil2gpu_calculate_exps_dev": (c_int, [vp, vp, c_u32, vp, c_u32, vp, c_u32, c_u32, c_int]),
     "pil2gpu_fri_fold_range_dev": (c_int, [vp, vp, c_int, c_u32, c_u32, c_i32, c_u32, vp, c_u64, c_u64, vp, vp]),
     "pil2gpu_fri_fold_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u32, c_u32, c_i32, c_u32, vp, c_int, ctypes.POINTER(vp), u64p, c_u32,
                                        ctypes.POINTER(vp), u64p, c_u32, vp]),

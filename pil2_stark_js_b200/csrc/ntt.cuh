@@ -372,7 +372,13 @@ struct NttItems {
     u32 ychunks;   // column chunks per tile id
     u32 ipc;       // items per CTA
     u32 total;     // tiles * ychunks
+    u32 tiles;     // tile ids; ipc == 1 numbers the items chunk-major (item = y * tiles + tile_id: neighbouring CTAs work on
+                   // neighbouring rows of the same column chunk, the order r01 measured fastest), ipc > 1 tile-major
 };
+__device__ __forceinline__ void ntt_item_decode(const NttItems& it, u32 item, u32& tile_id, u32& y) {
+    if (it.ipc == 1) { y = item / it.tiles; tile_id = item - y * it.tiles; }
+    else { tile_id = item / it.ychunks; y = item - tile_id * it.ychunks; }
+}
 template <bool DIF, bool INVERSE, bool SC = false, bool PIPE = true>
 __global__ void __launch_bounds__(NTT_THREADS, PIPE ? 3 : NTT_PASS_MIN_CTAS) ntt_pass_kernel(const u64* in, u64* out, NttPass P, NttTables tb,   // in == out for the in-place passes: no __restrict__
                                                                const __grid_constant__ NttScatter sc, NttItems it) {
@@ -389,7 +395,8 @@ __global__ void __launch_bounds__(NTT_THREADS, PIPE ? 3 : NTT_PASS_MIN_CTAS) ntt
     const u32 item_end = (item0 + it.ipc < it.total) ? item0 + it.ipc : it.total;
 
     auto issue_load = [&](u32 item, ulonglong2* tile) -> bool {
-        const u32 tile_id = item / it.ychunks, y = item - tile_id * it.ychunks;
+        u32 tile_id, y;
+        ntt_item_decode(it, item, tile_id, y);
         const u32 base_lo = tile_id & ((1u << lo) - 1), base_hi = tile_id >> lo;
         const u64 c0 = (u64)y * NTT_W;
         const int cw = (int)((P.C - c0 < NTT_W) ? (P.C - c0) : NTT_W);
@@ -407,7 +414,8 @@ __global__ void __launch_bounds__(NTT_THREADS, PIPE ? 3 : NTT_PASS_MIN_CTAS) ntt
     for (u32 item = item0; item < item_end; item++) {
         const int bsel = PIPE ? (int)((item - item0) & 1) : 0;
         ulonglong2* tile = tiles[bsel];
-        const u32 tile_id = item / it.ychunks, y = item - tile_id * it.ychunks;
+        u32 tile_id, y;
+        ntt_item_decode(it, item, tile_id, y);
         const u32 base_lo = tile_id & ((1u << lo) - 1), base_hi = tile_id >> lo;
         if (tile_id != cur_tile) {   // every warp is past the butterflies of the previous item (barrier B below): the table is free
             ntt_build_tw<INVERSE>(TW, G, t, lo, base_lo, P.coset ? (int)z : -1, P.n, P.ext_bits, tb, P.unit_shift != 0);   // ends with a barrier
@@ -532,6 +540,7 @@ static inline int ntt_launch_pass(const u64* in, u64* out, const NttPass& P, uns
     if (total64 > 0xFFFFFFF0ull) return -1;
     NttItems it;
     it.ychunks = ychunks;
+    it.tiles = tiles;
     it.total = (u32)total64;
     // whole tile ids per CTA (the twiddle table is per tile id), about NTT_ITEMS_PER_CTA items, but keep >= ~8 waves of CTAs
     static const int env_ipc = getenv("PIL2GPU_NTT_IPC") ? atoi(getenv("PIL2GPU_NTT_IPC")) : 0;       // tuning / A-B knobs

@@ -23,6 +23,7 @@
 #include "qpath.cuh"
 #include "evals.cuh"
 #include "fripol.cuh"
+#include "expr.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -735,6 +736,69 @@ int pil2gpu_x_div_x_sub_xi(pil2gpu_ctx* ctx, const uint64_t xi_challenge[3], con
     CU(cudaMemcpyAsync(out, ctx->ws, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return PIL2GPU_OK;
+}
+
+// ---- constraint expressions over a domain: calculateExps (prover_helpers.js:33-110) ----
+int pil2gpu_calculate_exps_dev(pil2gpu_ctx* ctx, const uint32_t* ops, uint32_t n_ops, const uint64_t* consts, uint32_t n_consts,
+                               const pil2gpu_expr_buffer* bufs, uint32_t n_bufs, uint32_t domain_bits, int x_shift) {
+    ENTER(ctx);
+    if (n_ops == 0) return PIL2GPU_OK;
+    if (!ops || (!consts && n_consts) || (!bufs && n_bufs)) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (domain_bits > 32) return fail(PIL2GPU_E_INVALID, "domain of 2^%u rows exceeds the 2-adicity of the field", domain_bits);
+    if (n_bufs > EXPR_MAX_BUFS) return fail(PIL2GPU_E_UNSUPPORTED, "more than %d buffers", EXPR_MAX_BUFS);
+    ExprBufs eb;
+    memset(&eb, 0, sizeof(eb));
+    for (uint32_t b = 0; b < n_bufs; b++) {
+        if (!bufs[b].ptr_dev || bufs[b].row_words == 0) return fail(PIL2GPU_E_INVALID, "buffer %u: null pointer or empty rows", b);
+        eb.ptr[b] = (u64*)bufs[b].ptr_dev;
+        eb.row_words[b] = bufs[b].row_words;
+    }
+    const u64 N = 1ULL << domain_bits;
+    auto check_operand = [&](const uint32_t* o, bool is_dest, uint32_t k, const char* what) -> int {
+        const uint32_t kind = o[0] & 255, dim = (o[0] >> 8) & 255, b = o[0] >> 16;
+        if (dim != 1 && dim != 3) return fail(PIL2GPU_E_INVALID, "record %u: %s has dimension %u (1 or 3)", k, what, dim);
+        switch (kind) {
+            case EXPR_K_TMP:
+                if (o[1] >= EXPR_MAX_SLOTS) return fail(PIL2GPU_E_UNSUPPORTED, "record %u: more than %d live temporaries", k, EXPR_MAX_SLOTS);
+                return PIL2GPU_OK;
+            case EXPR_K_CONST:
+                if (is_dest) break;
+                if (o[1] >= n_consts) return fail(PIL2GPU_E_RANGE, "record %u: constant %u out of range", k, o[1]);
+                return PIL2GPU_OK;
+            case EXPR_K_BUF:
+                if (b >= n_bufs) return fail(PIL2GPU_E_RANGE, "record %u: buffer %u out of range", k, b);
+                if ((u64)o[1] + dim > eb.row_words[b]) return fail(PIL2GPU_E_RANGE, "record %u: columns [%u, %u) outside a row of %llu words", k, o[1], o[1] + dim,
+                                                                   (unsigned long long)eb.row_words[b]);
+                if ((u64)o[2] >= N && N > 0 && o[2] != 0) return fail(PIL2GPU_E_RANGE, "record %u: row offset %u outside the domain", k, o[2]);
+                return PIL2GPU_OK;
+            case EXPR_K_X:
+                if (is_dest) break;
+                if (dim != 1) return fail(PIL2GPU_E_INVALID, "record %u: x is a base-field value", k);
+                return PIL2GPU_OK;
+            default: break;
+        }
+        return fail(PIL2GPU_E_INVALID, "record %u: invalid %s kind %u", k, what, kind);
+    };
+    for (uint32_t k = 0; k < n_ops; k++) {
+        const uint32_t* o = ops + (size_t)k * EXPR_OP_WORDS;
+        if (o[0] > EXPR_MULADD) return fail(PIL2GPU_E_INVALID, "record %u: invalid opcode %u", k, o[0]);
+        const uint32_t nsrc = o[0] == EXPR_COPY ? 1 : (o[0] == EXPR_MULADD ? 3 : 2);
+        if (o[1] != nsrc) return fail(PIL2GPU_E_INVALID, "record %u: opcode %u takes %u sources", k, o[0], nsrc);
+        int rc = check_operand(o + 4, true, k, "destination");
+        for (uint32_t j = 0; j < nsrc && !rc; j++) rc = check_operand(o + 7 + 3 * j, false, k, "source");
+        if (rc) return rc;
+    }
+    const size_t op_bytes = (size_t)n_ops * EXPR_OP_WORDS * sizeof(uint32_t), c_bytes = (size_t)(n_consts ? n_consts : 1) * 3 * sizeof(u64);
+    char* scratch = nullptr;
+    CU(cudaMallocFromPoolAsync(&scratch, ((op_bytes + 15) & ~(size_t)15) + c_bytes, ctx->pool, ctx->stream));
+    u32* d_ops = reinterpret_cast<u32*>(scratch);
+    u64* d_consts = reinterpret_cast<u64*>(scratch + ((op_bytes + 15) & ~(size_t)15));
+    cudaError_t e = cudaMemcpyAsync(d_ops, ops, op_bytes, cudaMemcpyHostToDevice, ctx->stream);          // pageable sources: staged before return
+    if (e == cudaSuccess && n_consts) e = cudaMemcpyAsync(d_consts, consts, (size_t)n_consts * 3 * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) expr_kernel<<<(unsigned)((N + EXPR_THREADS - 1) / EXPR_THREADS), EXPR_THREADS, 0, ctx->stream>>>(d_ops, n_ops, d_consts, eb, (int)domain_bits, x_shift != 0, ctx->tb);
+    cudaFreeAsync(scratch, ctx->stream);
+    if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "calculate_exps: %s", cudaGetErrorString(e));
+    return check_launch(ctx, 1, "calculate_exps");
 }
 
 // ---- FRI polynomial: computeFRIStark after the xDivXSubXi table (stark_gen_helpers.js:325-334; friPolinomial.js:26-56) ----
