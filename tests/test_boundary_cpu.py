@@ -78,3 +78,27 @@ def test_js_shims_bind_only_exported_addon_functions():
     for f in (ROOT / "js").glob("*.js"):
         used |= set(re.findall(r"\baddon\.([A-Za-z0-9]+)\(", f.read_text()))
     assert used and used <= registered, f"js uses unregistered addon functions: {sorted(used - registered)}"
+
+
+def _build_addon_driver(tmp_path):
+    import subprocess
+    exe = tmp_path / "napi_mock"
+    lib_dir = ROOT / "pil2_stark_js_b200"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", str(ROOT / "tests" / "stubs"), "-o", str(exe),
+                        str(ROOT / "tests" / "stubs" / "napi_mock.cc"), str(ROOT / "napi" / "pil2gpu_addon.cc"), "-L", str(lib_dir), "-l:libpil2gpu.so",
+                        f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+def test_addon_argument_checks_execute_under_a_mock_napi(tmp_path):
+    """The N-API addon never runs under Node here, so its checks are EXECUTED against a small in-process model of the N-API calls it
+    makes (tests/stubs/napi_mock.cc): wrong-sized buffers and page lists are RangeErrors, wrong types and null contexts TypeErrors,
+    all raised before anything reaches libpil2gpu (the context handed in is a fake pointer that must never be dereferenced)."""
+    import subprocess
+    from pil2_stark_js_b200 import _lib
+    _lib.load()
+    exe = _build_addon_driver(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL CHECKS PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+    assert r.stdout.count("ok  :") >= 25

@@ -165,3 +165,15 @@ def test_staged_copy_large_pageable(ctx):
     want = C.lde(tr, cols, 16, 17)
     assert np.array_equal(out, want)
     assert np.array_equal(root, C.merkelize(want, cols, 1 << 17)[-4:])
+
+
+def test_addon_end_to_end_under_the_mock_napi(ctx, tmp_path):
+    """With a GPU the same driver also runs REAL calls through the addon's marshalling (page lists, async work, device-tree
+    handles): fft/ifft round trip over ragged pages, extendAndMerkelizePaged vs commit vs merkelizePaged roots, group proofs from
+    the device tree, "Out of range", pinned page allocation."""
+    import subprocess
+    from test_boundary_cpu import _build_addon_driver
+    exe = _build_addon_driver(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL CHECKS PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+    assert "functional checks through the addon" in r.stdout and "FAIL" not in r.stdout
