@@ -1769,19 +1769,13 @@ int pil2gpu_tree_download(pil2gpu_ctx* ctx, const pil2gpu_tree* t, uint64_t* ele
 // ------------------------------------------------------------------------------------------------------------
 // FRI
 // ------------------------------------------------------------------------------------------------------------
-int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
-                         const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out) {
-    ENTER(ctx);
-    if (!pol || !pol_out || !challenge) return fail(PIL2GPU_E_INVALID, "null argument");
-    if (curBits > prevBits || prevBits > step0Bits || step0Bits > 32) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
-    if (nextBits >= 0 && ((uint32_t)nextBits > curBits || !rows_out)) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
-    if (prevBits - curBits > FRI_MAX_FOLD_BITS) return fail(PIL2GPU_E_UNSUPPORTED, "fold by 2^%u not supported (max 2^%d)", prevBits - curBits, FRI_MAX_FOLD_BITS);
-    {   // aliasing: the identity step (fri.js:48-49) may run in place (pol_out == pol: every thread rewrites the three words it
-        // read); any other overlap of the output with the input is a cross-CTA race and is rejected
-        const u64 *a = (const u64*)pol, *b = (const u64*)pol_out;
-        const bool overlap = a < b + ((size_t)3 << curBits) && b < a + ((size_t)3 << prevBits);
-        if (overlap && !(prevBits == curBits && a == b)) return fail(PIL2GPU_E_INVALID, "pol_out overlaps pol (only the identity step may run in place)");
-    }
+// One kernel folds by at most 2^FRI_MAX_FOLD_BITS (the interpolant of a group lives in registers).  Wider folds -- fri.js:38-41 puts
+// no bound on steps[s-1].nBits - steps[s].nBits -- are split: the fold evaluates the group's interpolant by radix-2 halvings with
+// beta, beta^2, beta^4, ... (fri.cuh), and the first a halvings of the group of output g are exactly the standard fold by 2^a of
+// the whole polynomial (same pairs (j, j + 2^(prev-1)), same twiddles shift_inv * w_prev^-(g + j 2^cur)), so
+//     fold_{2^(a+b)}(P, alpha) = fold_{2^b}( fold_{2^a}(P, alpha), alpha^(2^a) )        with the standard parameters of each size.
+static int fri_fold_one(pil2gpu_ctx* ctx, const u64* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits, const u64 challenge[3],
+                        int split, u64* pol_out, u64* rows_out, u64* nodes_out) {
     FriParams P;
     P.prev_bits = (int)prevBits;
     P.cur_bits = (int)curBits;
@@ -1800,18 +1794,58 @@ int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBit
     // The in-kernel leaf hash runs on FRI_ROWS_PER_CTA threads of each CTA: worth it only for small layers, where it saves
     // a launch; big layers (the first FRI tree has 2^20 leaves at cfg3) go through the full-width leaf kernel instead.
     P.fuse_leaf_hash = (nextBits >= 0) && nodes_out && (!split || 3 * gs <= 4) && (gs * 3 * 8 * FRI_ROWS_PER_CTA <= 160 * 1024) && nextBits <= 12;
-    int l = fri_launch_fold((const u64*)pol, (u64*)pol_out, (u64*)rows_out, (u64*)nodes_out, P, ctx->tb, ctx->stream);
+    int l = fri_launch_fold(pol, pol_out, rows_out, nodes_out, P, ctx->tb, ctx->stream);
     int rc = check_launch(ctx, l, "fri_fold");
     if (rc) return rc;
     if (nextBits >= 0 && nodes_out) {
         const u64 height = 1ULL << nextBits;
         if (P.fuse_leaf_hash) {
-            l = merkle_launch_tree((u64*)nodes_out, height, ctx->stream);
+            l = merkle_launch_tree(nodes_out, height, ctx->stream);
             rc = check_launch(ctx, l, "fri_tree");
         } else {
             rc = pil2gpu_merkelize_dev(ctx, rows_out, 3 * gs, height, split, nodes_out);
         }
     }
+    return rc;
+}
+
+int pil2gpu_fri_fold_dev(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, uint32_t curBits, int32_t nextBits, uint32_t step0Bits,
+                         const uint64_t challenge[3], int split, uint64_t* pol_out, uint64_t* rows_out, uint64_t* nodes_out) {
+    ENTER(ctx);
+    if (!pol || !pol_out || !challenge) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (curBits > prevBits || prevBits > step0Bits || step0Bits > 32) return fail(PIL2GPU_E_INVALID, "bad FRI step sizes");
+    if (nextBits >= 0 && ((uint32_t)nextBits > curBits || !rows_out)) return fail(PIL2GPU_E_INVALID, "bad next-layer description");
+    {   // aliasing: the identity step (fri.js:48-49) may run in place (pol_out == pol: every thread rewrites the three words it
+        // read); any other overlap of the output with the input is a cross-CTA race and is rejected
+        const u64 *a = (const u64*)pol, *b = (const u64*)pol_out;
+        const bool overlap = a < b + ((size_t)3 << curBits) && b < a + ((size_t)3 << prevBits);
+        if (overlap && !(prevBits == curBits && a == b)) return fail(PIL2GPU_E_INVALID, "pol_out overlaps pol (only the identity step may run in place)");
+    }
+    u64 ch[3] = {challenge[0] % GL_P, challenge[1] % GL_P, challenge[2] % GL_P};
+    if (prevBits - curBits <= FRI_MAX_FOLD_BITS)
+        return fri_fold_one(ctx, (const u64*)pol, prevBits, curBits, nextBits, step0Bits, ch, split, (u64*)pol_out, (u64*)rows_out, (u64*)nodes_out);
+    // wide fold: chunks of FRI_MAX_FOLD_BITS through two ping-pong scratch polynomials, the challenge squared once per halving
+    u64 *sa = nullptr, *sb = nullptr;
+    const size_t sw = (size_t)3 << (prevBits - FRI_MAX_FOLD_BITS);
+    CU(cudaMallocFromPoolAsync(&sa, sw * sizeof(u64), ctx->pool, ctx->stream));
+    cudaError_t e = cudaMallocFromPoolAsync(&sb, (sw >> FRI_MAX_FOLD_BITS ? sw >> FRI_MAX_FOLD_BITS : 3) * sizeof(u64), ctx->pool, ctx->stream);
+    if (e != cudaSuccess) { cudaFreeAsync(sa, ctx->stream); return fail(PIL2GPU_E_NOMEM, "scratch allocation failed: %s", cudaGetErrorString(e)); }
+    const u64* in = (const u64*)pol;
+    uint32_t at = prevBits;
+    int rc = PIL2GPU_OK, turn = 0;
+    while (rc == PIL2GPU_OK && at - curBits > FRI_MAX_FOLD_BITS) {
+        u64* out = turn ? sb : sa;
+        rc = fri_fold_one(ctx, in, at, at - FRI_MAX_FOLD_BITS, -1, step0Bits, ch, split, out, nullptr, nullptr);
+        h3 c = {{ch[0], ch[1], ch[2]}};
+        for (int k = 0; k < FRI_MAX_FOLD_BITS; k++) c = h3_mul(c, c);
+        ch[0] = c.c[0]; ch[1] = c.c[1]; ch[2] = c.c[2];
+        in = out;
+        at -= FRI_MAX_FOLD_BITS;
+        turn ^= 1;
+    }
+    if (rc == PIL2GPU_OK) rc = fri_fold_one(ctx, in, at, curBits, nextBits, step0Bits, ch, split, (u64*)pol_out, (u64*)rows_out, (u64*)nodes_out);
+    cudaFreeAsync(sa, ctx->stream);
+    cudaFreeAsync(sb, ctx->stream);
     return rc;
 }
 

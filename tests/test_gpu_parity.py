@@ -266,6 +266,25 @@ def test_fri_chain_vs_oracle(ctx, steps, split):
         cur = p
 
 
+@pytest.mark.parametrize("steps", [[14, 6, 2], [13, 0], [15, 8, 1], [12, 5]])
+def test_fri_wide_folds_vs_oracle(ctx, steps):
+    """fri.js:38-41 puts no bound on the fold width; folds wider than one kernel handles (2^6) are split into chunks with the
+    challenge squared once per halving -- same field elements as the reference's ifft + Horner (the oracle)."""
+    pol = rnd_field(sum(steps) + 3, 3 << steps[0]).reshape(-1, 3)
+    rng = random.Random(11)
+    cur = pol
+    for s in range(1, len(steps)):
+        ch = [rng.randrange(P) for _ in range(3)]
+        nxt = steps[s + 1] if s + 1 < len(steps) else None
+        p, rows, nodes = ctx.fri_fold(cur, steps[s - 1], steps[s], nxt, steps[0], ch)
+        ep, erows = C.fri_fold(cur, steps[s - 1], steps[s], nxt, steps[0], ch)
+        assert np.array_equal(p, ep), (steps, s)
+        if nxt is not None:
+            assert np.array_equal(rows, erows)
+            assert np.array_equal(nodes, C.merkelize(erows, 3 << (steps[s] - nxt), 1 << nxt))
+        cur = p
+
+
 def test_fri_class_prove_then_verify(ctx):
     # the reference's integration style (test/stark/helpers.js): prove, then the verifier must accept
     from pil2_stark_js_b200 import FRI, buildMerkleHash, Transcript
@@ -512,7 +531,7 @@ def test_c_abi_error_behaviour(ctx):
     assert L.pil2gpu_merkelize_dev(ctx.handle, a.ptr, 4, 0, 0, b.ptr) == -1
     assert L.pil2gpu_merkelize_dev(ctx.handle, a.ptr, 4, 4, 0, None) == -1
     assert L.pil2gpu_fri_fold_dev(ctx.handle, a.ptr, 3, 4, -1, 4, vp(np.zeros(3, dtype=np.uint64).ctypes.data), 0, b.ptr, None, None) == -1
-    assert L.pil2gpu_fri_fold_dev(ctx.handle, a.ptr, 10, 3, -1, 10, vp(np.zeros(3, dtype=np.uint64).ctypes.data), 0, b.ptr, None, None) == -5
+    assert L.pil2gpu_fri_fold_range_dev(ctx.handle, a.ptr, 0, 10, 3, -1, 10, vp(np.zeros(3, dtype=np.uint64).ctypes.data), 0, 0, b.ptr, None) == -5
     assert L.pil2gpu_compute_q_dev(ctx.handle, a.ptr, 0, 1, 2, 3, b.ptr) == -1
     t = vp()
     assert L.pil2gpu_tree_alloc(ctx.handle, 4, 0, ctypes.byref(t)) == -1
