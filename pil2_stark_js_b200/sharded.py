@@ -169,6 +169,9 @@ class GpuEngine:
                                               ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(b.ctypes.data), ext_bits, self._p(f)))
         return f
 
+    def compute_q(self, q_ext, q_dim, q_deg, n_bits, ext_bits, cmq):
+        self.check(self.L.pil2gpu_compute_q_dev(self.h, self._p(q_ext), q_dim, q_deg, n_bits, ext_bits, self._p(cmq)))
+
     def fri_fold_range(self, src, in_layout, prev_bits, cur_bits, next_bits, step0_bits, challenge, row0, n_rows, pol_out, rows_out):
         """One rank's share of a FRI fold (pil2gpu_fri_fold_range_dev): rows [row0, row0 + n_rows) of the next layer's
         transposed buffer at their absolute positions; src is the polynomial (in_layout 0) or the previous layer's rows (1)."""
@@ -243,6 +246,16 @@ def sharded_fri_pol(engine, dist, rank, world, trees, ev_map, evals, xi, opening
     f = engine.empty(3 << ext_bits)
     dist.all_gather_into_tensor(f, f_local)
     return f
+
+
+def sharded_compute_q(sc, q_ext, q_dim, q_deg, n_bits, ext_bits, cmq, nodes, sub, top):
+    """computeQStark (stark_gen_helpers.js:168-208) over G ranks that all hold q_ext (the quotient is evaluated row-locally, so after
+    an all-gather -- or when every rank evaluates the whole domain -- each rank has it): the 3-6 column transforms are too narrow
+    to shard and run on every rank, the tree -- two thirds of the cost at production sizes -- is hashed sharded by rows
+    (ShardedCommit.commit_rows).  cmq: qDim*qDeg << ext_bits words; nodes: nnodes(2^ext_bits / G); sub: 4 G; top: nnodes(G).
+    Returns (ShardedTree, root tensor)."""
+    sc.e.compute_q(q_ext, q_dim, q_deg, n_bits, ext_bits, cmq)
+    return sc.commit_rows(cmq, q_dim * q_deg, 1 << ext_bits, nodes, sub, top)
 
 
 class ShardedTree:
@@ -650,7 +663,15 @@ def bench_main(args, rank, world, local_rank, dist, bench):
         try:
             t_ev, evs = wall(lambda: sharded_evals(eng, dist, rank, world, trees, ev_map, xi, [0, 1], n_bits, ext_bits))
             t_fp, _ = wall(lambda: sharded_fri_pol(eng, dist, rank, world, trees, ev_map, evs, xi, [0, 1], vf1, vf2, n_bits, ext_bits))
-            extras = {"evals": {"s": t_ev, "shape": f"{len(ev_map)} evaluations, base rows sharded over {world} ranks (LEv vectors + sums + gather)"},
+            qd, qg = 3, 1 << blow
+            q_ext = eng.empty(qd << ext_bits)
+            check(L.pil2gpu_synth_dev(eng.h, vp(q_ext.data_ptr()), qd << ext_bits, seed + 9, 0))
+            cmq, qn = eng.empty((qd * qg) << ext_bits), eng.empty(eng.nnodes((1 << ext_bits) // world))
+            qs, qt = eng.empty(4 * world), eng.empty(max(8, eng.nnodes(world)))
+            t_q, _ = wall(lambda: sharded_compute_q(sc, q_ext, qd, qg, n_bits, ext_bits, cmq, qn, qs, qt))
+            del q_ext, cmq, qn
+            extras = {"q_commit": {"s": t_q, "shape": f"qDim {qd}, qDeg {qg}, 2^{ext_bits} rows: transforms on every rank, tree hashed sharded over {world} ranks"},
+                      "evals": {"s": t_ev, "shape": f"{len(ev_map)} evaluations, base rows sharded over {world} ranks (LEv vectors + sums + gather)"},
                       "fri_pol": {"s": t_fp, "shape": f"{len(ev_map)} evMap terms, 2^{ext_bits} rows sharded over {world} ranks (xDivXSubXi + friExp + "
                                                       "all-gather)"}}
         except (ValueError, RuntimeError) as ex:

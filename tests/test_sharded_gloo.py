@@ -84,6 +84,9 @@ class OracleEngine:
                 ro[q * width:(q + 1) * width] = r
                 so[q * depth * 4:(q + 1) * depth * 4] = np.asarray(sb, dtype=np.uint64).reshape(-1)
 
+    def compute_q(self, q_ext, q_dim, q_deg, n_bits, ext_bits, cmq):
+        self._u(cmq)[:] = C.compute_q(self._u(q_ext).copy(), q_dim, q_deg, n_bits, ext_bits, threads=1)
+
     def fri_fold_range(self, src, in_layout, prev_bits, cur_bits, next_bits, step0_bits, challenge, row0, n_rows, pol_out, rows_out):
         """stand-in for pil2gpu_fri_fold_range_dev: the whole fold by the oracle, then only the requested rows are written"""
         nx = 1 << (prev_bits - cur_bits)
@@ -251,8 +254,17 @@ def _fri_worker(rank, world, port, steps, q):
         roots, final = fri.run(torch.from_numpy(pol0.view(np.int64).copy()), chal)
         queries = torch.tensor([0, 1, (1 << steps[0]) - 1, 12345 % (1 << steps[0]), 777], dtype=torch.int64)
         opened = open_trees(fri.query_pairs(queries))
+        # quotient commit: transforms replicated, tree sharded
+        from pil2_stark_js_b200.sharded import sharded_compute_q, ShardedCommit
+        qe = rng.integers(0, 0xFFFFFFFF00000001, size=3 << 7, dtype=np.uint64)
+        sc = ShardedCommit(eng, dist, rank, world)
+        cmq = eng.empty(6 << 7)
+        qt, qroot = sharded_compute_q(sc, torch.from_numpy(qe.view(np.int64).copy()), 3, 2, 6, 7, cmq, eng.empty(eng.nnodes(128 // world)), eng.empty(4 * world),
+                                      eng.empty(max(8, eng.nnodes(world))))
+        qrows, qsib = qt.open(torch.tensor([0, 127, 64], dtype=torch.int64))
         q.put((rank, fri.sharded, [r.numpy().view(np.uint64).copy() for r in roots], final.numpy().view(np.uint64).copy(),
-               [(r.numpy().view(np.uint64).copy(), sb.numpy().view(np.uint64).copy()) for r, sb in opened]))
+               [(r.numpy().view(np.uint64).copy(), sb.numpy().view(np.uint64).copy()) for r, sb in opened],
+               (qe, qroot.numpy().view(np.uint64).copy(), qrows.numpy().view(np.uint64).copy(), qsib.numpy().view(np.uint64).copy())))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -289,7 +301,14 @@ def test_sharded_fri_chain_matches_single_process(world, steps):
     final, _ = C.fri_fold(cur, steps[L - 1], steps[L], None, steps[0], [int(x) for x in chal[L]])
     queries = [0, 1, (1 << steps[0]) - 1, 12345 % (1 << steps[0]), 777]
     assert any(res[0][1]) or len(steps) == 2                               # at least one layer really is sharded (the 2-step case is all replicas)
-    for _, sharded, roots, fin, opened in res:
+    for _, sharded, roots, fin, opened, qres in res:
+        qe, qroot, qrows, qsib = qres                                      # sharded quotient commit == single-process oracle
+        want_q = C.compute_q(qe, 3, 2, 6, 7)
+        qnodes = C.merkelize(want_q, 6, 128)
+        assert np.array_equal(qroot, qnodes[-4:])
+        for k, qi in enumerate([0, 127, 64]):
+            r, sb = C.group_proof(want_q, qnodes, 6, 128, qi)
+            assert np.array_equal(qrows[k], r) and np.array_equal(qsib[k].reshape(-1), np.asarray(sb, dtype=np.uint64).reshape(-1))
         assert np.array_equal(fin.reshape(-1, 3), final)
         for s in range(L):
             assert np.array_equal(roots[s], layer_nodes[s][-4:]), f"root of layer {s}"
