@@ -4,7 +4,10 @@ import ctypes
 import pathlib
 
 _PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libpil2gpu.so"
+import os
+
+# PIL2GPU_LIB: an alternative build of the same library (A/B measurements of kernel variants); default: the in-tree build
+LIB_PATH = pathlib.Path(os.environ["PIL2GPU_LIB"]).resolve() if os.environ.get("PIL2GPU_LIB") else _PKG / "libpil2gpu.so"
 
 OK, E_INVALID, E_RANGE, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 

@@ -11,7 +11,7 @@ PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libpil2gpu.so"
 SOURCES = ["pil2gpu.cu"]
-HEADERS = ["gl.cuh", "poseidon.cuh", "poseidon_rc.inc", "poseidon_rc_limbs.inc", "poseidon_rc_limbs_partial.inc", "ntt.cuh", "merkle.cuh", "fri.cuh", "qpath.cuh", "evals.cuh", "fripol.cuh", "expr.cuh"]
+HEADERS = ["gl.cuh", "poseidon.cuh", "poseidon_rc.inc", "poseidon_rc_limbs.inc", "poseidon_rc_limbs_partial.inc", "poseidon_rc_f64p.inc", "ntt.cuh", "merkle.cuh", "fri.cuh", "qpath.cuh", "evals.cuh", "fripol.cuh", "expr.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-cudart", "static",
@@ -33,18 +33,22 @@ def needs_build():
     return any(d.stat().st_mtime > t for d in deps if d.exists())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: an A/B build of the same sources under another name (e.g. defines=["POSEIDON_F64P"], out=PKG / "libpil2gpu_f64p.so")."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+    out = pathlib.Path(out) if out else LIB
+    cmd = [find_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(out)] + [str(CSRC / s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libpil2gpu.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

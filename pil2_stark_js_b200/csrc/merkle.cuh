@@ -13,6 +13,9 @@
 #include "poseidon.cuh"
 
 #define MERKLE_THREADS 128
+#ifndef MERKLE_MIN_CTAS
+#define MERKLE_MIN_CTAS 5      // occupancy hint of the hashing kernels: 96 registers with the FP64 partial rounds (measured best of 4/5/6)
+#endif
 #define MERKLE_TAIL 512    // pairs handled by the single-CTA tail kernel (512 threads keeps 128 regs/thread)
 
 // _getNNodes(height*4) of merklehash_p.js:28-42, in words.
@@ -102,7 +105,7 @@ GL_D void merkle_sponge_tiled(const RowTiles& t, u64 row, u64 c0, u64 w, u64 out
 }
 
 // Standard linear hash of every row: nodes[4*row ..] = L(row).
-__global__ void __launch_bounds__(MERKLE_THREADS) merkle_leaf_kernel(RowTiles t, u64 width, u64 height, u64* __restrict__ nodes) {
+__global__ void __launch_bounds__(MERKLE_THREADS, MERKLE_MIN_CTAS) merkle_leaf_kernel(RowTiles t, u64 width, u64 height, u64* __restrict__ nodes) {
     const u64 row = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
     if (row >= height) return;
     u64 d[4];
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(MERKLE_THREADS) merkle_leaf_kernel(RowTiles t,
 // `cols` more columns of every row (a row-major slab [height][cols], cols % 8 == 0 except for the last slab) into the
 // running sponge state.  state[row*4 ..] holds the capacity words in Montgomery form between slabs; the last slab
 // writes the canonical digest to nodes[row*4 ..].  Equivalent to merkle_sponge over the concatenated slabs (total > 4).
-__global__ void __launch_bounds__(MERKLE_THREADS) merkle_absorb_kernel(const u64* __restrict__ slab, u64 cols, u64 height,
+__global__ void __launch_bounds__(MERKLE_THREADS, MERKLE_MIN_CTAS) merkle_absorb_kernel(const u64* __restrict__ slab, u64 cols, u64 height,
                                                                        u64* __restrict__ state, int first, int last, u64* __restrict__ nodes) {
     const u64 row = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
     if (row >= height) return;
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(MERKLE_THREADS) merkle_absorb_kernel(const u64
 }
 
 // Split linear hash, stage 1: one thread per (row, batch): digests[(row*nb + b)*4 ..] = L(row[b*batch .. ]).
-__global__ void __launch_bounds__(MERKLE_THREADS) merkle_batch_kernel(RowTiles t, u64 width, u64 height, u64 batch, u64 nb,
+__global__ void __launch_bounds__(MERKLE_THREADS, MERKLE_MIN_CTAS) merkle_batch_kernel(RowTiles t, u64 width, u64 height, u64 batch, u64 nb,
                                                                       u64* __restrict__ digests) {
     const u64 id = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
     if (id >= height * nb) return;
@@ -184,7 +187,7 @@ GL_D void merkle_pair(const u64* __restrict__ in, u64* __restrict__ out, u64 i) 
     o[0] = make_ulonglong2(gl_from_mont(x[0]), gl_from_mont(x[1]));
     o[1] = make_ulonglong2(gl_from_mont(x[2]), gl_from_mont(x[3]));
 }
-__global__ void __launch_bounds__(MERKLE_THREADS) merkle_level_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 pairs) {
+__global__ void __launch_bounds__(MERKLE_THREADS, MERKLE_MIN_CTAS) merkle_level_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 pairs) {
     const u64 i = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
     if (i < pairs) merkle_pair(in, out, i);
 }

@@ -197,3 +197,29 @@ def test_fri_fold_prover_matches_verifier():
         assert grp2[q1 // 4] == ev
         ev2 = S.fri_verify_fold(grp2, 5, pow(S.SHIFT, 8, P), ch[2], q2)
         assert ev2 == r2["pol"][q2]
+
+
+def test_fp64_partial_round_constants_model_vs_oracle():
+    """csrc/poseidon.cuh runs the partial rounds with deferred round constants (tools/gen_poseidon_f64_consts.py): the generator's
+    pure-Python model of that form, for every block length it emits tables for, is the oracle permutation; the emitted table is the
+    one the generator would write now (i.e. the committed .inc is not stale)."""
+    import importlib.util
+    import pathlib
+    import random
+    root = pathlib.Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("gen_f64", root / "tools" / "gen_poseidon_f64_consts.py")
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    rnd = random.Random(11)
+    for nr in g.NRS:
+        st = [rnd.randrange(S.P) for _ in range(12)]
+        assert g.model_perm(st, nr) == S.poseidon_perm(st)
+    assert g.plain_perm(list(range(12))) == S.poseidon_perm(list(range(12)))
+    # the conversion constants: magic + halves of (c - K), all exact doubles below 2^53
+    lane0, final = g.deferred_tables(g.R, 22)
+    for c in lane0 + final:
+        lo, hi = g.halves(c)
+        assert lo < 2.0 ** 53 and hi < 2.0 ** 53
+        assert ((int(lo) - g.MAGIC) + ((int(hi) - g.MAGIC) << 32) + g.K) % S.P == c
+    inc = (root / "pil2_stark_js_b200/csrc/poseidon_rc_f64p.inc").read_text()
+    assert "%.1f" % g.halves(lane0[0])[0] in inc and "POSEIDON_RC_F64P_22[66]" in inc

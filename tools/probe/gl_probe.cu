@@ -19,11 +19,19 @@ __device__ __forceinline__ u64 splitmix(u64 z) {
 // VAR: 0 shipped, 1 64-bit lanes, 2 FP64-pipe MDS, 3 u64-state loop with two-input adds forced to IADD3, 4 previous shipped loop (u64 state)
 template <int VAR>
 __device__ __forceinline__ void permute_mont_var(u64 x[12]) {
-    if (VAR == 0) poseidon_permute_mont(x);
+    if (VAR == 0) poseidon_permute_mont_limb(x);
     if (VAR == 1) poseidon_permute_lanes64(x);
     if (VAR == 2) poseidon_permute_fp64(x);
     if (VAR == 3) poseidon_permute_mont_z(x);
     if (VAR == 4) poseidon_permute_mont_u64state(x);
+    if (VAR == 5) poseidon_permute_mont_f64p<22>(x);
+    if (VAR == 6) poseidon_permute_mont_f64p<6>(x);
+    if (VAR == 7) poseidon_permute_mont_f64p<8>(x);
+    if (VAR == 8) poseidon_permute_mont_f64p<10>(x);
+    if (VAR == 9) poseidon_permute_mont_f64p<12>(x);
+    if (VAR == 10) poseidon_permute_mont_f64p<14>(x);
+    if (VAR == 11) poseidon_permute_mont_f64p<16>(x);
+    if (VAR == 12) poseidon_permute_mont_f64p<18>(x);
 }
 
 template <int VAR>
@@ -87,6 +95,26 @@ __global__ void __launch_bounds__(256) k_arith(u64* out, int iters, u64 w) {
     out[(u64)blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3;
 }
 
+
+// Pipe concurrency: MODE bits 1 = DFMA chains (FP64 pipe), 2 = IMAD chains (fmaheavy), 4 = IADD3/LOP3 chains (alu); 4 independent
+// chains of each selected kind per thread, interleaved instruction by instruction.  If the pipes run side by side the time of a
+// mixed mode is the maximum of its parts, if they share an issue port it is their sum.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_mix(u64* out, int iters, u32 m, double dm) {
+    double d0 = threadIdx.x + 1.0, d1 = blockIdx.x + 3.0, d2 = d0 * 0.5, d3 = d1 * 0.25;
+    u32 a0 = threadIdx.x + 1, a1 = blockIdx.x + 3, a2 = a0 ^ 0x1234567u, a3 = a0 + a1 + 77;
+    u32 b0 = a0 * 3, b1 = a1 * 5, b2 = a2 * 7, b3 = a3 * 9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (MODE & 1) { d0 = fma(d0, dm, d1); d1 = fma(d1, dm, d2); d2 = fma(d2, dm, d3); d3 = fma(d3, dm, d0); }
+            if (MODE & 2) { a0 = a0 * m + a1; a1 = a1 * m + a2; a2 = a2 * m + a3; a3 = a3 * m + a0; }
+            if (MODE & 4) { b0 = (b0 + b1 + m) ^ b2; b1 = (b1 + b2 + m) ^ b3; b2 = (b2 + b3 + m) ^ b0; b3 = (b3 + b0 + m) ^ b1; }
+        }
+    }
+    out[(u64)blockIdx.x * blockDim.x + threadIdx.x] = (u64)__double_as_longlong(d0 + d1 + d2 + d3) ^ a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
+}
+
 __global__ void k_arith_check(const u64* a, const u64* b, u64* o, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -141,11 +169,19 @@ int main() {
         for (int lazy = 0; lazy < 2; lazy++) {
             k_check<0><<<blocks, threads>>>(o0, 777 + lazy, lazy); CK(cudaDeviceSynchronize());
             CK(cudaMemcpy(h0, o0, n * 96, cudaMemcpyDeviceToHost));
-            for (int var = 1; var <= 4; var++) {
+            for (int var = 1; var <= 12; var++) {
                 if (var == 1) k_check<1><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 if (var == 2) k_check<2><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 if (var == 3) k_check<3><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 if (var == 4) k_check<4><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 5) k_check<5><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 6) k_check<6><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 7) k_check<7><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 8) k_check<8><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 9) k_check<9><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 10) k_check<10><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 11) k_check<11><<<blocks, threads>>>(o1, 777 + lazy, lazy);
+                if (var == 12) k_check<12><<<blocks, threads>>>(o1, 777 + lazy, lazy);
                 CK(cudaDeviceSynchronize());
                 CK(cudaMemcpy(h1, o1, n * 96, cudaMemcpyDeviceToHost));
                 long bad = 0;
@@ -154,9 +190,10 @@ int main() {
             }
         }
     }
-    const char* pn[5] = {"shipped (limb-resident partial rounds)", "64-bit lanes", "FP64-pipe MDS", "u64 state, adds forced to IADD3",
-                         "u64 state at every round (previous)"};
-    for (int var = 0; var < 5; var++) {
+    const char* pn[13] = {"limb-resident partial rounds", "64-bit lanes", "FP64-pipe MDS", "u64 state, adds forced to IADD3",
+                          "u64 state at every round (previous)", "FP64 partial rounds x22", "FP64 partial rounds x6", "FP64 partial rounds x8",
+                          "FP64 partial rounds x10", "FP64 partial rounds x12", "FP64 partial rounds x14", "FP64 partial rounds x16", "FP64 partial rounds x18"};
+    for (int var = 0; var < 13; var++) {
         float best = 1e30f; int iters = 64;
         for (int rep = 0; rep < 3; rep++) {
             CK(cudaEventRecord(e0));
@@ -165,6 +202,14 @@ int main() {
             if (var == 2) k_chain<2><<<blocks, threads>>>(o0, iters);
             if (var == 3) k_chain<3><<<blocks, threads>>>(o0, iters);
             if (var == 4) k_chain<4><<<blocks, threads>>>(o0, iters);
+            if (var == 5) k_chain<5><<<blocks, threads>>>(o0, iters);
+            if (var == 6) k_chain<6><<<blocks, threads>>>(o0, iters);
+            if (var == 7) k_chain<7><<<blocks, threads>>>(o0, iters);
+            if (var == 8) k_chain<8><<<blocks, threads>>>(o0, iters);
+            if (var == 9) k_chain<9><<<blocks, threads>>>(o0, iters);
+            if (var == 10) k_chain<10><<<blocks, threads>>>(o0, iters);
+            if (var == 11) k_chain<11><<<blocks, threads>>>(o0, iters);
+            if (var == 12) k_chain<12><<<blocks, threads>>>(o0, iters);
             CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
         }
@@ -186,6 +231,25 @@ int main() {
         }
         double ops = (double)n * iters * 8 * 4;
         printf("%-28s %.3f ms  %.1f Gop/s\n", an[mode], best, ops / best / 1e6);
+    }
+    for (int mode = 1; mode < 8; mode++) {
+        float best = 1e30f; int iters = 1024;
+        for (int rep = 0; rep < 3; rep++) {
+            CK(cudaEventRecord(e0));
+            switch (mode) {
+                case 1: k_mix<1><<<blocks, threads>>>(o0, iters, 0x9E3779B1u, 0.99999991); break;
+                case 2: k_mix<2><<<blocks, threads>>>(o0, iters, 0x9E3779B1u, 0.99999991); break;
+                case 3: k_mix<3><<<blocks, threads>>>(o0, iters, 0x9E3779B1u, 0.99999991); break;
+                case 4: k_mix<4><<<blocks, threads>>>(o0, iters, 0x9E3779B1u, 0.99999991); break;
+                case 5: k_mix<5><<<blocks, threads>>>(o0, iters, 0x9E3779B1u, 0.99999991); break;
+                case 6: k_mix<6><<<blocks, threads>>>(o0, iters, 0x9E3779B1u, 0.99999991); break;
+                case 7: k_mix<7><<<blocks, threads>>>(o0, iters, 0x9E3779B1u, 0.99999991); break;
+            }
+            CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+        }
+        printf("pipe mix %s%s%s  %.3f ms  (%.1f G chain-steps/s per kind)\n", (mode & 1) ? "DFMA " : "     ", (mode & 2) ? "IMAD " : "     ",
+               (mode & 4) ? "IADD3+LOP3 " : "           ", best, (double)n * iters * 16 * 4 / best / 1e6);
     }
     return 0;
 }
