@@ -104,6 +104,46 @@ int pil2gpu_lde_scatter_dev(pil2gpu_ctx* ctx, const uint64_t* src_dev, uint64_t*
 int pil2gpu_lde_scatter(pil2gpu_ctx* ctx, const uint64_t* src, uint64_t src_pitch_cols, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
                         uint64_t* const* peer_recv_dev, uint32_t n_ranks, uint32_t rank);
 
+/* ---- multi-GPU commit group: peer-mapped buffers, flag barriers, no collective library (no reference counterpart) --------------
+ * The choreography of SURVEY 8(e) behind the C ABI, so that ANY host can drive it -- Node workers (one process per GPU, the handles
+ * travel over the fork channel), one Node / Python thread driving several GPUs (pil2gpu_shard_connect_local), or the torch.distributed
+ * launcher bench.py uses.  rank g owns columns [g*nPols/world, (g+1)*nPols/world) of the trace and, after the exchange, rows
+ * [g*E/world, (g+1)*E/world) of the extended trace (E = 2^nBitsExt) as `world` column tiles in its receive buffer.  Every call below
+ * only ENQUEUES work on the context's stream (no host synchronisation), and every rank must issue the same sequence of calls: the
+ * ranks order themselves with flag barriers -- a one-CTA kernel stores this rank's epoch into every peer's mailbox (release.sys) and
+ * spins on its own (acquire.sys) -- so compute and signal share the stream.  A peer that never arrives trips a timeout
+ * (PIL2GPU_SHARD_TIMEOUT_MS, default 20000) reported by pil2gpu_shard_status instead of hanging the GPU. */
+typedef struct pil2gpu_shard pil2gpu_shard;
+/* recv_words >= (nPols/world) << nBitsExt of the largest commit; stage_words >= n_idx * (nPols + 4*nBitsExt) of the largest
+ * pil2gpu_shard_open_dev (0: no queries).  world: power of two <= 16. */
+int pil2gpu_shard_create(pil2gpu_ctx* ctx, uint32_t rank, uint32_t world, uint64_t recv_words, uint64_t stage_words, pil2gpu_shard** out);
+int pil2gpu_shard_destroy(pil2gpu_shard* sh);
+/* One process per GPU: export this rank's 2 x 64-byte CUDA IPC handles (receive buffer, mailbox); gather the pairs of all ranks in rank
+ * order by any means; connect. */
+int pil2gpu_shard_handles(pil2gpu_shard* sh, uint8_t handles_out[128]);
+int pil2gpu_shard_connect(pil2gpu_shard* sh, const uint8_t* handles /* world x 128 bytes */, uint32_t n_ranks);
+/* One process, several GPUs (or several contexts of one GPU): wire group[r] (rank r of n_ranks) to each other directly, enabling peer
+ * access between the devices where needed. */
+int pil2gpu_shard_connect_local(pil2gpu_shard* const* group, uint32_t n_ranks);
+uint64_t* pil2gpu_shard_recv_dev(pil2gpu_shard* sh);               /* this rank's rows: tile t at t * (E/world) * (nPols/world) words */
+uint64_t* const* pil2gpu_shard_peer_recv(pil2gpu_shard* sh);       /* host array of `world` device pointers for pil2gpu_lde_scatter[_dev] */
+int pil2gpu_shard_barrier(pil2gpu_shard* sh);                      /* enqueue one flag barrier (all ranks) */
+int pil2gpu_shard_status(pil2gpu_shard* sh);                       /* synchronises the stream; PIL2GPU_E_CUDA if a barrier timed out */
+/* extendAndMerkelize (stark_gen_helpers.js:388-412) over the group: barrier -> LDE of this rank's 2^nBits x nPols/world column slab
+ * whose last pass stores every row into its owner's receive buffer (work_dev: (nPols/world) << nBitsExt words of scratch) -> barrier
+ * -> hashing + subtree of the local rows in place (nodes_dev: pil2gpu_merkle_nnodes(E/world) words, reference layout of a
+ * height-E/world tree) -> sub-roots stored into every mailbox -> barrier -> top log2(world) levels.  root_out_dev (device, 4 words,
+ * may be NULL) receives the root of the whole tree on every rank; it equals the single-GPU root. */
+int pil2gpu_shard_commit_dev(pil2gpu_shard* sh, const uint64_t* src_slab_dev, uint64_t* work_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
+                             int split, uint64_t* nodes_dev, uint64_t* root_out_dev);
+/* The hashing half alone, for rows delivered by other means (pil2gpu_lde_scatter from host slabs + pil2gpu_shard_barrier). */
+int pil2gpu_shard_hash_dev(pil2gpu_shard* sh, uint64_t nPols, uint32_t nBitsExt, int split, uint64_t* nodes_dev, uint64_t* root_out_dev);
+/* getGroupProof (merklehash_p.js:142-168) for n_idx global leaf indices (device array, identical on every rank): the owner of each leaf
+ * stores its row, the siblings inside its subtree and those of the top tree into every rank's mailbox; after the barrier every rank
+ * holds rows_out_dev[q*nPols ..] and siblings_out_dev[(q*nBitsExt + level)*4 ..] of the single-GPU tree. */
+int pil2gpu_shard_open_dev(pil2gpu_shard* sh, const uint64_t* nodes_dev, uint64_t nPols, uint32_t nBitsExt, const uint64_t* idxs_dev, uint32_t n_idx,
+                           uint64_t* rows_out_dev, uint64_t* siblings_out_dev);
+
 /* ---- quotient polynomial: computeQStark, src/stark/stark_gen_helpers.js:168-208 ----------------------------------- */
 /* q_ext: 2^nBitsExt x qDim evaluations of Q on 7<w_ext>.  cmq_ext (2^nBitsExt x qDim*qDeg): column p*qDim + k holds the
  * evaluations on 7<w_ext> of the p-th degree-<2^nBits chunk of Q (ifft :177, shift-split :179-190, fft :192).  qDeg must

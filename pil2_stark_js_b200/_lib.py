@@ -59,6 +59,18 @@ _SIGS = {
     "pil2gpu_host_free": (c_int, [vp]),
     "pil2gpu_h2d": (c_int, [vp, vp, vp, c_size]),
     "pil2gpu_d2h": (c_int, [vp, vp, vp, c_size]),
+    "pil2gpu_shard_create": (c_int, [vp, c_u32, c_u32, c_u64, c_u64, ctypes.POINTER(vp)]),
+    "pil2gpu_shard_destroy": (c_int, [vp]),
+    "pil2gpu_shard_handles": (c_int, [vp, vp]),
+    "pil2gpu_shard_connect": (c_int, [vp, vp, c_u32]),
+    "pil2gpu_shard_connect_local": (c_int, [ctypes.POINTER(vp), c_u32]),
+    "pil2gpu_shard_recv_dev": (vp, [vp]),
+    "pil2gpu_shard_peer_recv": (vp, [vp]),
+    "pil2gpu_shard_barrier": (c_int, [vp]),
+    "pil2gpu_shard_status": (c_int, [vp]),
+    "pil2gpu_shard_commit_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32, c_int, vp, vp]),
+    "pil2gpu_shard_hash_dev": (c_int, [vp, c_u64, c_u32, c_int, vp, vp]),
+    "pil2gpu_shard_open_dev": (c_int, [vp, vp, c_u64, c_u32, vp, c_u32, vp, vp]),
     "pil2gpu_ntt": (c_int, [vp, vp, vp, c_u64, c_u32, c_int]),
     "pil2gpu_ntt_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_int]),
     "pil2gpu_lde": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32]),

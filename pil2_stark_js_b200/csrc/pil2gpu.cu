@@ -22,6 +22,7 @@
 #include "ntt.cuh"
 #include "qpath.cuh"
 #include "evals.cuh"
+#include "shard.cuh"
 #include "fripol.cuh"
 #include "expr.cuh"
 
@@ -1929,6 +1930,243 @@ int pil2gpu_fri_fold(pil2gpu_ctx* ctx, const uint64_t* pol, uint32_t prevBits, u
     uint64_t *op[1] = {pol_out}, *rp[1] = {rows_out};
     return pil2gpu_fri_fold_paged(ctx, pp, &pw, 1, prevBits, curBits, nextBits, step0Bits, challenge, split, op, &cw, 1, rows_out ? rp : nullptr, &cw,
                                   rows_out ? 1 : 0, nodes_out);
+}
+
+// ---- multi-GPU commit group (shard.cuh): peer-mapped receive buffers + mailboxes, flag barriers, no collective library ----
+struct pil2gpu_shard {
+    pil2gpu_ctx* ctx;
+    uint32_t rank, world;
+    uint64_t recv_words, stage_words;
+    u64 *recv, *mail;                                    // own allocations
+    u64 *peer_recv[SHARD_MAX_RANKS], *peer_mail[SHARD_MAX_RANKS];   // every rank's buffers as seen from this device (own included)
+    bool ipc_recv[SHARD_MAX_RANKS], ipc_mail[SHARD_MAX_RANKS];      // opened with cudaIpcOpenMemHandle (to be closed)
+    bool connected;
+    uint64_t epoch, timeout_ns;
+    ShardPeers peers() const {
+        ShardPeers P;
+        for (int i = 0; i < SHARD_MAX_RANKS; i++) P.mail[i] = peer_mail[i];
+        return P;
+    }
+};
+
+static int shard_check(const pil2gpu_shard* sh, bool need_connected) {
+    if (!sh || !sh->ctx) return fail(PIL2GPU_E_INVALID, "null shard");
+    if (need_connected && !sh->connected) return fail(PIL2GPU_E_INVALID, "shard is not connected to its peers (pil2gpu_shard_connect[_local])");
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_shard_create(pil2gpu_ctx* ctx, uint32_t rank, uint32_t world, uint64_t recv_words, uint64_t stage_words, pil2gpu_shard** out) {
+    ENTER(ctx);
+    if (!out) return fail(PIL2GPU_E_INVALID, "null out");
+    if (world == 0 || world > SHARD_MAX_RANKS || (world & (world - 1)) || rank >= world)
+        return fail(PIL2GPU_E_INVALID, "bad rank description (world must be a power of two <= %d)", SHARD_MAX_RANKS);
+    pil2gpu_shard* sh = new (std::nothrow) pil2gpu_shard();
+    if (!sh) return fail(PIL2GPU_E_NOMEM, "out of host memory");
+    sh->ctx = ctx; sh->rank = rank; sh->world = world; sh->recv_words = recv_words; sh->stage_words = stage_words;
+    sh->recv = sh->mail = nullptr; sh->connected = false; sh->epoch = 0;
+    const char* tm = getenv("PIL2GPU_SHARD_TIMEOUT_MS");
+    sh->timeout_ns = (uint64_t)(tm ? atoll(tm) : 20000) * 1000000ull;
+    for (int i = 0; i < SHARD_MAX_RANKS; i++) { sh->peer_recv[i] = sh->peer_mail[i] = nullptr; sh->ipc_recv[i] = sh->ipc_mail[i] = false; }
+    const size_t mail_bytes = (SHARD_STAGE + stage_words) * sizeof(u64);
+    cudaError_t e = cudaMalloc(&sh->recv, (recv_words ? recv_words : 2) * sizeof(u64));
+    if (e == cudaSuccess) e = cudaMalloc(&sh->mail, mail_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sh->mail, 0, mail_bytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (sh->recv) cudaFree(sh->recv);
+        if (sh->mail) cudaFree(sh->mail);
+        delete sh;
+        return fail(e == cudaErrorMemoryAllocation ? PIL2GPU_E_NOMEM : PIL2GPU_E_CUDA, "shard_create: %s", cudaGetErrorString(e));
+    }
+    sh->peer_recv[rank] = sh->recv;
+    sh->peer_mail[rank] = sh->mail;
+    if (world == 1) sh->connected = true;
+    *out = sh;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_shard_destroy(pil2gpu_shard* sh) {
+    if (!sh) return PIL2GPU_OK;
+    ENTER(sh->ctx);
+    sync_all_streams(sh->ctx);
+    for (uint32_t r = 0; r < sh->world; r++) {
+        if (sh->ipc_recv[r]) cudaIpcCloseMemHandle(sh->peer_recv[r]);
+        if (sh->ipc_mail[r]) cudaIpcCloseMemHandle(sh->peer_mail[r]);
+    }
+    cudaFree(sh->recv);
+    cudaFree(sh->mail);
+    delete sh;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_shard_handles(pil2gpu_shard* sh, uint8_t handles_out[128]) {
+    int rc = shard_check(sh, false);
+    if (rc) return rc;
+    ENTER(sh->ctx);
+    if (!handles_out) return fail(PIL2GPU_E_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, sh->recv));
+    memcpy(handles_out, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, sh->mail));
+    memcpy(handles_out + 64, &h, 64);
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_shard_connect(pil2gpu_shard* sh, const uint8_t* handles, uint32_t n_ranks) {
+    int rc = shard_check(sh, false);
+    if (rc) return rc;
+    ENTER(sh->ctx);
+    if (!handles || n_ranks != sh->world) return fail(PIL2GPU_E_INVALID, "need the 128-byte handle pair of each of the %u ranks", sh->world);
+    if (sh->connected && sh->world > 1) return fail(PIL2GPU_E_INVALID, "shard is already connected");
+    for (uint32_t r = 0; r < sh->world; r++) {
+        if (r == sh->rank) continue;
+        cudaIpcMemHandle_t h;
+        void* p = nullptr;
+        memcpy(&h, handles + 128 * r, 64);
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        sh->peer_recv[r] = (u64*)p; sh->ipc_recv[r] = true;
+        memcpy(&h, handles + 128 * r + 64, 64);
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        sh->peer_mail[r] = (u64*)p; sh->ipc_mail[r] = true;
+    }
+    sh->connected = true;
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_shard_connect_local(pil2gpu_shard* const* group, uint32_t n_ranks) {
+    if (!group || n_ranks == 0 || n_ranks > SHARD_MAX_RANKS) return fail(PIL2GPU_E_INVALID, "bad group");
+    for (uint32_t r = 0; r < n_ranks; r++)
+        if (!group[r] || group[r]->rank != r || group[r]->world != n_ranks) return fail(PIL2GPU_E_INVALID, "group[%u] is not rank %u of %u", r, r, n_ranks);
+    for (uint32_t a = 0; a < n_ranks; a++) {
+        pil2gpu_shard* sa = group[a];
+        DeviceGuard g(sa->ctx->device);
+        if (!g.ok) return fail(PIL2GPU_E_CUDA, "cudaSetDevice(%d) failed", sa->ctx->device);
+        for (uint32_t b = 0; b < n_ranks; b++) {
+            pil2gpu_shard* sb = group[b];
+            if (sb->ctx->device != sa->ctx->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, sa->ctx->device, sb->ctx->device));
+                if (!can) return fail(PIL2GPU_E_UNSUPPORTED, "device %d cannot map device %d", sa->ctx->device, sb->ctx->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(sb->ctx->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            }
+            sa->peer_recv[b] = sb->recv;
+            sa->peer_mail[b] = sb->mail;
+        }
+        sa->connected = true;
+    }
+    return PIL2GPU_OK;
+}
+
+uint64_t* pil2gpu_shard_recv_dev(pil2gpu_shard* sh) { return sh ? (uint64_t*)sh->recv : nullptr; }
+uint64_t* const* pil2gpu_shard_peer_recv(pil2gpu_shard* sh) { return sh ? (uint64_t* const*)sh->peer_recv : nullptr; }
+
+static int shard_barrier_enqueue(pil2gpu_shard* sh) {
+    sh->epoch++;
+    if (sh->world > 1) {
+        shard_barrier_kernel<<<1, SHARD_MAX_RANKS, 0, sh->ctx->stream>>>(sh->peers(), sh->rank, sh->world, sh->epoch, sh->timeout_ns);
+        return check_launch(sh->ctx, 1, "shard_barrier");
+    }
+    return PIL2GPU_OK;
+}
+int pil2gpu_shard_barrier(pil2gpu_shard* sh) {
+    int rc = shard_check(sh, true);
+    if (rc) return rc;
+    ENTER(sh->ctx);
+    return shard_barrier_enqueue(sh);
+}
+
+int pil2gpu_shard_status(pil2gpu_shard* sh) {
+    int rc = shard_check(sh, false);
+    if (rc) return rc;
+    ENTER(sh->ctx);
+    u64 err = 0;
+    CU(cudaMemcpyAsync(&err, sh->mail + SHARD_ERR, sizeof(u64), cudaMemcpyDeviceToHost, sh->ctx->stream));
+    CU(cudaStreamSynchronize(sh->ctx->stream));
+    if (err) return fail(PIL2GPU_E_CUDA, "shard barrier %llu timed out on rank %u: a peer never arrived", (unsigned long long)err, sh->rank);
+    return PIL2GPU_OK;
+}
+
+// after the barrier that follows shard_publish: tree over the sub-roots in this rank's mailbox -> root
+static int shard_top_tree(pil2gpu_shard* sh, uint64_t* root_out_dev) {
+    pil2gpu_ctx* ctx = sh->ctx;
+    u64* top = sh->mail + SHARD_TOP;
+    const u64 nt = merkle_nnodes_words(sh->world);
+    if (sh->world > 1) {
+        CU(cudaMemcpyAsync(top, sh->mail + SHARD_SUB, 4 * sh->world * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+        int l = merkle_launch_tree(top, sh->world, ctx->stream);
+        int rc = check_launch(ctx, l, "shard top tree");
+        if (rc) return rc;
+    }
+    if (root_out_dev)
+        CU(cudaMemcpyAsync(root_out_dev, sh->world > 1 ? top + nt - 4 : sh->mail + SHARD_SUB, 4 * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    return PIL2GPU_OK;
+}
+
+int pil2gpu_shard_hash_dev(pil2gpu_shard* sh, uint64_t nPols, uint32_t nBitsExt, int split, uint64_t* nodes_dev, uint64_t* root_out_dev) {
+    int rc = shard_check(sh, true);
+    if (rc) return rc;
+    pil2gpu_ctx* ctx = sh->ctx;
+    ENTER(ctx);
+    if (!nodes_dev) return fail(PIL2GPU_E_INVALID, "null nodes");
+    if (nPols == 0 || nPols % sh->world) return fail(PIL2GPU_E_INVALID, "nPols (%llu) must be a positive multiple of the number of ranks", (unsigned long long)nPols);
+    if (nBitsExt > 40 || ((u64)1 << nBitsExt) < sh->world) return fail(PIL2GPU_E_INVALID, "fewer extended rows than ranks");
+    const u64 cg = nPols / sh->world, rows_local = ((u64)1 << nBitsExt) / sh->world;
+    if (cg * rows_local * sh->world > sh->recv_words) return fail(PIL2GPU_E_INVALID, "receive buffer too small: %llu words needed", (unsigned long long)(cg * rows_local * sh->world));
+    rc = pil2gpu_merkelize_tiled_dev(ctx, sh->recv, sh->world, cg, rows_local * cg, rows_local, split, nodes_dev);
+    if (rc) return rc;
+    const u64 nn = merkle_nnodes_words(rows_local);
+    shard_publish_kernel<<<1, 4 * SHARD_MAX_RANKS, 0, ctx->stream>>>(sh->peers(), sh->rank, sh->world, (const u64*)nodes_dev + nn - 4);
+    rc = check_launch(ctx, 1, "shard_publish");
+    if (!rc) rc = shard_barrier_enqueue(sh);
+    if (!rc) rc = shard_top_tree(sh, root_out_dev);
+    return rc;
+}
+
+int pil2gpu_shard_commit_dev(pil2gpu_shard* sh, const uint64_t* src_slab_dev, uint64_t* work_dev, uint64_t nPols, uint32_t nBits, uint32_t nBitsExt,
+                             int split, uint64_t* nodes_dev, uint64_t* root_out_dev) {
+    int rc = shard_check(sh, true);
+    if (rc) return rc;
+    pil2gpu_ctx* ctx = sh->ctx;
+    ENTER(ctx);
+    if (nPols == 0 || nPols % sh->world) return fail(PIL2GPU_E_INVALID, "nPols (%llu) must be a positive multiple of the number of ranks", (unsigned long long)nPols);
+    const u64 cg = nPols / sh->world;
+    if (sh->world > 1 && cg % 8) return fail(PIL2GPU_E_UNSUPPORTED, "columns per rank must be a multiple of 8 (sponge chunks must not straddle tiles)");
+    if (nBitsExt > 40 || (cg << nBitsExt) > sh->recv_words) return fail(PIL2GPU_E_INVALID, "receive buffer too small");
+    rc = shard_barrier_enqueue(sh);                 // every peer is done with its receive buffer (previous commit, queries, downloads)
+    if (!rc) rc = pil2gpu_lde_scatter_dev(ctx, src_slab_dev, work_dev, cg, nBits, nBitsExt, (uint64_t* const*)sh->peer_recv, sh->world, sh->rank, 0, 0);
+    if (!rc) rc = shard_barrier_enqueue(sh);        // every rank's rows have landed
+    if (!rc) rc = pil2gpu_shard_hash_dev(sh, nPols, nBitsExt, split, nodes_dev, root_out_dev);
+    return rc;
+}
+
+int pil2gpu_shard_open_dev(pil2gpu_shard* sh, const uint64_t* nodes_dev, uint64_t nPols, uint32_t nBitsExt, const uint64_t* idxs_dev, uint32_t n_idx,
+                           uint64_t* rows_out_dev, uint64_t* siblings_out_dev) {
+    int rc = shard_check(sh, true);
+    if (rc) return rc;
+    pil2gpu_ctx* ctx = sh->ctx;
+    ENTER(ctx);
+    if (!nodes_dev || !idxs_dev || !rows_out_dev || !siblings_out_dev) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (nPols == 0 || nPols % sh->world || nBitsExt > 40 || ((u64)1 << nBitsExt) < sh->world) return fail(PIL2GPU_E_INVALID, "bad shape");
+    if (n_idx == 0) return PIL2GPU_OK;
+    const u64 cg = nPols / sh->world, rows_local = ((u64)1 << nBitsExt) / sh->world;
+    int dl = 0, dt = 0;
+    while (((u64)1 << dl) < rows_local) dl++;
+    while ((1u << dt) < sh->world) dt++;
+    const u64 slot = nPols + 4 * (u64)(dl + dt);
+    if (slot * n_idx > sh->stage_words) return fail(PIL2GPU_E_INVALID, "mailbox staging too small: %llu words needed, %llu available",
+                                                    (unsigned long long)(slot * n_idx), (unsigned long long)sh->stage_words);
+    rc = shard_barrier_enqueue(sh);                 // the peers have consumed the staging area of the previous call
+    if (rc) return rc;
+    RowTiles t = {sh->recv, cg, rows_local * cg};
+    shard_group_proof_kernel<<<n_idx, 128, 0, ctx->stream>>>(t, (const u64*)nodes_dev, nPols, rows_local, (const u64*)idxs_dev, dl, dt, sh->peers(), sh->rank,
+                                                             sh->world);
+    rc = check_launch(ctx, 1, "shard_group_proof");
+    if (!rc) rc = shard_barrier_enqueue(sh);        // every owner has delivered
+    if (rc) return rc;
+    shard_unpack_kernel<<<n_idx, 128, 0, ctx->stream>>>(sh->mail + SHARD_STAGE, nPols, dl + dt, (u64*)rows_out_dev, (u64*)siblings_out_dev);
+    return check_launch(ctx, 1, "shard_unpack");
 }
 
 }   // extern "C"
