@@ -127,6 +127,10 @@ int pil2gpu_shard_connect(pil2gpu_shard* sh, const uint8_t* handles /* world x 1
 int pil2gpu_shard_connect_local(pil2gpu_shard* const* group, uint32_t n_ranks);
 uint64_t* pil2gpu_shard_recv_dev(pil2gpu_shard* sh);               /* this rank's rows: tile t at t * (E/world) * (nPols/world) words */
 uint64_t* const* pil2gpu_shard_peer_recv(pil2gpu_shard* sh);       /* host array of `world` device pointers for pil2gpu_lde_scatter[_dev] */
+/* After a commit / hash: the `world` sub-roots (4 words each, rank order) and the tree over them (pil2gpu_merkle_nnodes(world) words,
+ * reference layout of a height-`world` tree; for world == 1 the root is sub-root 0), both in this rank's mailbox. */
+const uint64_t* pil2gpu_shard_sub_roots_dev(pil2gpu_shard* sh);
+const uint64_t* pil2gpu_shard_top_nodes_dev(pil2gpu_shard* sh);
 int pil2gpu_shard_barrier(pil2gpu_shard* sh);                      /* enqueue one flag barrier (all ranks) */
 int pil2gpu_shard_status(pil2gpu_shard* sh);                       /* synchronises the stream; PIL2GPU_E_CUDA if a barrier timed out */
 /* extendAndMerkelize (stark_gen_helpers.js:388-412) over the group: barrier -> LDE of this rank's 2^nBits x nPols/world column slab

@@ -66,6 +66,8 @@ _SIGS = {
     "pil2gpu_shard_connect_local": (c_int, [ctypes.POINTER(vp), c_u32]),
     "pil2gpu_shard_recv_dev": (vp, [vp]),
     "pil2gpu_shard_peer_recv": (vp, [vp]),
+    "pil2gpu_shard_sub_roots_dev": (vp, [vp]),
+    "pil2gpu_shard_top_nodes_dev": (vp, [vp]),
     "pil2gpu_shard_barrier": (c_int, [vp]),
     "pil2gpu_shard_status": (c_int, [vp]),
     "pil2gpu_shard_commit_dev": (c_int, [vp, vp, vp, c_u64, c_u32, c_u32, c_int, vp, vp]),

@@ -1949,6 +1949,36 @@ struct pil2gpu_shard {
     }
 };
 
+// CUDA loads kernels lazily, and loading one synchronises with the kernels that are running.  When one host thread drives several ranks,
+// a rank spinning in a flag barrier would therefore block the load of a kernel its peer still has to launch -- until the barrier times
+// out.  Every kernel of the commit / open path is loaded when a group member is created, before any barrier can be in flight.
+extern "C++" {
+template <typename K>
+static void shard_preload_one(K kernel) {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess) cudaGetLastError();
+}
+}
+static void shard_preload_kernels() {
+    shard_preload_one(ntt_pass_kernel<true, true, false, false>);
+    shard_preload_one(ntt_pass_kernel<true, true, false, true>);
+    shard_preload_one(ntt_pass_kernel<false, false, false, false>);
+    shard_preload_one(ntt_pass_kernel<false, false, false, true>);
+    shard_preload_one(ntt_pass_kernel<false, false, true, false>);
+    shard_preload_one(ntt_pass_kernel<false, false, true, true>);
+    shard_preload_one(ntt_lde_fused_kernel<false>);
+    shard_preload_one(ntt_lde_fused_kernel<true>);
+    shard_preload_one(merkle_leaf_kernel);
+    shard_preload_one(merkle_batch_kernel);
+    shard_preload_one(merkle_level_kernel);
+    shard_preload_one(merkle_tail_kernel);
+    shard_preload_one(merkle_pad_kernel);
+    shard_preload_one(shard_barrier_kernel);
+    shard_preload_one(shard_publish_kernel);
+    shard_preload_one(shard_group_proof_kernel);
+    shard_preload_one(shard_unpack_kernel);
+}
+
 static int shard_check(const pil2gpu_shard* sh, bool need_connected) {
     if (!sh || !sh->ctx) return fail(PIL2GPU_E_INVALID, "null shard");
     if (need_connected && !sh->connected) return fail(PIL2GPU_E_INVALID, "shard is not connected to its peers (pil2gpu_shard_connect[_local])");
@@ -1962,6 +1992,7 @@ int pil2gpu_shard_create(pil2gpu_ctx* ctx, uint32_t rank, uint32_t world, uint64
         return fail(PIL2GPU_E_INVALID, "bad rank description (world must be a power of two <= %d)", SHARD_MAX_RANKS);
     pil2gpu_shard* sh = new (std::nothrow) pil2gpu_shard();
     if (!sh) return fail(PIL2GPU_E_NOMEM, "out of host memory");
+    shard_preload_kernels();
     sh->ctx = ctx; sh->rank = rank; sh->world = world; sh->recv_words = recv_words; sh->stage_words = stage_words;
     sh->recv = sh->mail = nullptr; sh->connected = false; sh->epoch = 0;
     const char* tm = getenv("PIL2GPU_SHARD_TIMEOUT_MS");
@@ -2061,6 +2092,8 @@ int pil2gpu_shard_connect_local(pil2gpu_shard* const* group, uint32_t n_ranks) {
 
 uint64_t* pil2gpu_shard_recv_dev(pil2gpu_shard* sh) { return sh ? (uint64_t*)sh->recv : nullptr; }
 uint64_t* const* pil2gpu_shard_peer_recv(pil2gpu_shard* sh) { return sh ? (uint64_t* const*)sh->peer_recv : nullptr; }
+const uint64_t* pil2gpu_shard_sub_roots_dev(pil2gpu_shard* sh) { return sh ? (const uint64_t*)(sh->mail + SHARD_SUB) : nullptr; }
+const uint64_t* pil2gpu_shard_top_nodes_dev(pil2gpu_shard* sh) { return sh ? (const uint64_t*)(sh->mail + SHARD_TOP) : nullptr; }
 
 static int shard_barrier_enqueue(pil2gpu_shard* sh) {
     sh->epoch++;

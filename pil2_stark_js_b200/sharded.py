@@ -9,7 +9,8 @@
        pass tile by tile and only a one-word all-reduce (the "all stores have landed" barrier) remains.  Fallback
        (PIL2GPU_EXCHANGE=nccl, or IPC mapping unavailable): local LDE followed by one NCCL all_to_all_single.
     3. leaf hashing + subtree of the E/G local rows straight from the tiles (pil2gpu_merkelize_tiled_dev, no repack)
-    4. all-gather of the G sub-roots (G x 32 bytes); the top log2(G) levels are hashed redundantly on every rank
+    4. the G sub-roots (G x 32 bytes) reach every rank -- stored into the peers' mailboxes + a flag barrier (pil2gpu_shard_hash_dev), or
+       an all-gather on the NCCL path; the top log2(G) levels are hashed redundantly on every rank
 The root (and every node) equals the single-GPU tree: contiguous leaf ranges make each local root the level-log2(E/G)
 node of the reference layout.  The reference has no counterpart (it is single-process, workerpool threads).
 
@@ -47,59 +48,66 @@ class GpuEngine:
     def lde(self, src, cols, n_bits, ext_bits, dst):
         self.check(self.L.pil2gpu_lde_dev(self.h, self._p(src), self._p(dst), cols, n_bits, ext_bits))
 
-    # ---- peer-memory exchange (CUDA IPC through the C ABI; torch.distributed only carries the 64-byte handles) ----
-    def open_exchange(self, dist, rank, world, recv_words):
-        """Allocate this rank's receive buffer, map every peer's, and return {"recv": tensor view, "peers": [ptr], ...} or
-        None when peer mapping is unavailable on any rank (the caller then uses the NCCL all-to-all)."""
+    # ---- peer-memory exchange: the commit group of the C ABI (pil2gpu_shard_*: receive buffers + mailboxes mapped with CUDA IPC,
+    # flag barriers on the stream); torch.distributed only carries the 2 x 64-byte handles of every rank, once ----
+    def _tensor_view(self, ptr, words):
+        class _Raw:       # torch view of a raw device allocation
+            pass
+        view = _Raw()
+        view.__cuda_array_interface__ = {"shape": (int(words),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+        return self.torch.as_tensor(view, device=self.device)
+
+    def open_exchange(self, dist, rank, world, recv_words, stage_words=0):
+        """Create this rank's end of the commit group and connect it to its peers.  Returns {"recv": tensor view of the receive
+        buffer, "peers": host array of device pointers, "shard": handle, ...} or None when peer mapping is unavailable on any rank
+        (the caller then uses the NCCL all-to-all)."""
         import os
         torch = self.torch
         if os.environ.get("PIL2GPU_EXCHANGE", "peer") == "nccl":
             return None
-        ok, raw, peers, err = 1, ctypes.c_void_p(), [None] * world, ""
+        ok, sh, err = 1, ctypes.c_void_p(), ""
         try:
-            self.check(self.L.pil2gpu_dev_alloc(self.h, int(recv_words) * 8, ctypes.byref(raw)))
-            handle = (ctypes.c_uint8 * 64)()
-            self.check(self.L.pil2gpu_ipc_export(self.h, raw, handle))
-            handles = [None] * world
-            dist.all_gather_object(handles, bytes(handle))
-            for r in range(world):
-                if r == rank:
-                    peers[r] = raw.value
-                else:
-                    p = ctypes.c_void_p()
-                    hb = (ctypes.c_uint8 * 64).from_buffer_copy(handles[r])
-                    self.check(self.L.pil2gpu_ipc_open(self.h, hb, ctypes.byref(p)))
-                    peers[r] = p.value
+            self.check(self.L.pil2gpu_shard_create(self.h, rank, world, int(recv_words), int(stage_words), ctypes.byref(sh)))
+            handle = (ctypes.c_uint8 * 128)()
+            self.check(self.L.pil2gpu_shard_handles(sh, handle))
         except Exception as ex:       # noqa: BLE001 -- any failure means "no peer mapping here"; all ranks must agree below
             ok, err = 0, str(ex)
+            handle = (ctypes.c_uint8 * 128)()
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle))
+        if ok:
+            try:
+                allh = (ctypes.c_uint8 * (128 * world)).from_buffer_copy(b"".join(handles))
+                self.check(self.L.pil2gpu_shard_connect(sh, allh, world))
+            except Exception as ex:   # noqa: BLE001
+                ok, err = 0, str(ex)
         flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             if err:
                 print(f"[pil2gpu] rank {rank}: peer exchange unavailable ({err}); using NCCL all_to_all", flush=True)
-            self._close_peers(rank, peers, raw)
+            if sh:
+                self.L.pil2gpu_shard_destroy(sh)
             return None
-
-        class _Raw:       # torch view of the raw allocation (for D2H copies and the fallback-compatible interface)
-            pass
-        view = _Raw()
-        view.__cuda_array_interface__ = {"shape": (int(recv_words),), "typestr": "<i8", "data": (raw.value, False), "version": 2}
-        recv = torch.as_tensor(view, device=self.device)
-        arr = (ctypes.c_void_p * world)(*peers)
-        return {"recv": recv, "peers": arr, "peer_list": peers, "raw": raw, "rank": rank, "world": world,
-                "flag": torch.zeros(1, device=self.device, dtype=torch.int32)}
-
-    def _close_peers(self, rank, peers, raw):
-        for r, p in enumerate(peers):
-            if p and r != rank:
-                self.L.pil2gpu_ipc_close(self.h, ctypes.c_void_p(p))
-        if raw and raw.value:
-            self.L.pil2gpu_dev_free(self.h, raw)
+        recv = self._tensor_view(self.L.pil2gpu_shard_recv_dev(sh), recv_words)
+        peers = ctypes.cast(self.L.pil2gpu_shard_peer_recv(sh), ctypes.POINTER(ctypes.c_void_p))
+        sub = self._tensor_view(self.L.pil2gpu_shard_sub_roots_dev(sh), 4 * world)
+        top = self._tensor_view(self.L.pil2gpu_shard_top_nodes_dev(sh), max(8, self.nnodes(world)))
+        return {"recv": recv, "peers": peers, "shard": sh, "rank": rank, "world": world, "sub": sub, "top": top}
 
     def close_exchange(self, ex):
         if ex:
             self.torch.cuda.synchronize()
-            self._close_peers(ex["rank"], ex["peer_list"], ex["raw"])
+            self.check(self.L.pil2gpu_shard_status(ex["shard"]))
+            self.L.pil2gpu_shard_destroy(ex["shard"])
+
+    def exchange_barrier(self, ex):
+        """Flag barrier over the mailboxes, enqueued on the stream (no NCCL call, no host round trip)."""
+        self.check(self.L.pil2gpu_shard_barrier(ex["shard"]))
+
+    def shard_hash(self, ex, cols, ext_bits, split, nodes, root_out):
+        """Leaf hashing + local subtree + sub-root exchange (peer stores + flag barrier) + top tree: the root on every rank."""
+        self.check(self.L.pil2gpu_shard_hash_dev(ex["shard"], cols, ext_bits, int(split), self._p(nodes), self._p(root_out)))
 
     def lde_scatter(self, src, cols, n_bits, ext_bits, dst, ex):
         self.check(self.L.pil2gpu_lde_scatter_dev(self.h, self._p(src), self._p(dst), cols, n_bits, ext_bits, ex["peers"], ex["world"],
@@ -377,6 +385,7 @@ class ShardedCommit:
         if self.world > 1 and hasattr(e, "open_exchange"):
             buf["exchange"] = e.open_exchange(self.dist, self.rank, self.world, cg << ext_bits)
         buf["recv"] = buf["exchange"]["recv"] if buf["exchange"] else e.empty(cg << ext_bits)
+        buf["root"] = e.empty(4)
         return buf
 
     def release(self, buf):
@@ -385,7 +394,11 @@ class ShardedCommit:
             buf["exchange"] = None
 
     def exchange_kind(self, buf):
-        return "peer stores fused into the last LDE pass (CUDA IPC over NVLink)" if buf.get("exchange") else "NCCL all_to_all_single"
+        if not buf.get("exchange"):
+            return "NCCL all_to_all_single"
+        if buf["exchange"].get("shard") is not None:
+            return "peer stores fused into the last LDE pass (CUDA IPC over NVLink), flag barriers + sub-roots over peer mailboxes (no NCCL in the commit)"
+        return "peer stores fused into the last LDE pass (CUDA IPC over NVLink)"
 
     def commit(self, src_slab, cols, n_bits, ext_bits, buf, split=False):
         """src_slab: this rank's N x C/G column slab (row-major, on the device).  Returns the 4-word root tensor (on every rank)."""
@@ -404,13 +417,13 @@ class ShardedCommit:
             raise ValueError("host-source extension needs the peer exchange")
         if G > 1 and ex:
             # Barrier BEFORE the stores: whatever the peers still do with their receive buffers (hashing of the previous
-            # commit, a download) is stream-ordered before their contribution to this one-word all-reduce.
-            self.dist.all_reduce(ex["flag"])
+            # commit, a download) is stream-ordered before their signal.
+            self._barrier(ex)
             if host_src:
                 e.lde_scatter_host(src_slab, cg, n_bits, ext_bits, ex)
             else:
                 e.lde_scatter(src_slab, cg, n_bits, ext_bits, buf["dst"], ex)
-            self.dist.all_reduce(ex["flag"])                                # every rank's stores have landed (stream-ordered)
+            self._barrier(ex)                                               # every rank's stores have landed (stream-ordered)
             return buf["recv"]
         e.lde(src_slab, cg, n_bits, ext_bits, buf["dst"])
         if G > 1:
@@ -418,10 +431,23 @@ class ShardedCommit:
             return buf["recv"]
         return buf["dst"]
 
+    def _barrier(self, ex):
+        if hasattr(self.e, "exchange_barrier"):
+            self.e.exchange_barrier(ex)                                     # flag barrier on the stream (C ABI)
+        else:
+            self.dist.all_reduce(ex["flag"])                                # stand-in engines: a one-word all-reduce
+
     def hash_and_root(self, tiles, cols, ext_bits, buf, split=False):
         G, e = self.world, self.e
         cg = self.shard_cols(cols)
         rows_local = (1 << ext_bits) // G
+        ex = buf.get("exchange")
+        if G > 1 and ex and ex.get("shard") is not None and tiles is buf["recv"]:
+            # the whole second half in the library: hashing, sub-roots stored into every mailbox, flag barrier, top tree
+            e.shard_hash(ex, cols, ext_bits, split, buf["nodes"], buf["root"])
+            buf["sub"], buf["top"] = ex["sub"], ex["top"]                   # the gathered sub-roots / top tree live in the mailbox
+            buf["tree"] = ShardedTree(e, self.dist, self.rank, G, tiles, G, cg, rows_local, buf["nodes"], ex["sub"], ex["top"])
+            return buf["root"]
         e.merkelize_tiled(tiles, G, cg, rows_local, buf["nodes"], split)
         buf["tree"] = ShardedTree(e, self.dist, self.rank, G, tiles, G, cg, rows_local, buf["nodes"], buf["sub"], buf["top"])
         return buf["tree"].reduce_to_root()
