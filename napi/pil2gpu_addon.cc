@@ -704,6 +704,198 @@ napi_value FriPol(napi_env env, napi_callback_info info) {
     return rc ? fail_now(env, rc) : nullptr;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// multi-GPU commit group (pil2gpu_shard_*): one handle per GPU, wired across worker processes (shardHandles / shardConnect: the
+// 128-byte handle pairs travel over the fork channel as BigUint64Array(16)) or inside one process (shardConnectLocal).
+// shardCommit / shardOpen only ENQUEUE on the rank's stream and return at once -- the ranks meet in flag barriers on the GPUs, so a
+// single thread can drive every GPU and no libuv worker ever waits for another; shardRoot / shardProofs are the asynchronous reads.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ShardBox {
+    pil2gpu_ctx* ctx;
+    pil2gpu_shard* sh;
+    uint32_t rank, world;
+    uint64_t recv_words, stage_words;
+    void *src = nullptr, *work = nullptr, *nodes = nullptr, *root = nullptr, *idx = nullptr, *rows = nullptr, *sib = nullptr;
+    uint64_t src_words = 0, work_words = 0, nodes_words = 0, idx_words = 0, rows_words = 0, sib_words = 0;
+    uint64_t nPols = 0; uint32_t nBitsExt = 0, n_idx = 0;
+    int grow(void** p, uint64_t* have, uint64_t want) {
+        if (*have >= want) return PIL2GPU_OK;
+        if (*p) pil2gpu_dev_free(ctx, *p);
+        *p = nullptr; *have = 0;
+        int rc = pil2gpu_dev_alloc(ctx, (size_t)want * 8, p);
+        if (!rc) *have = want;
+        return rc;
+    }
+    void release() {
+        if (sh) pil2gpu_shard_destroy(sh);
+        sh = nullptr;
+        void** all[] = {&src, &work, &nodes, &root, &idx, &rows, &sib};
+        for (void** q : all) { if (*q) pil2gpu_dev_free(ctx, *q); *q = nullptr; }
+    }
+};
+void shard_finalize(napi_env, void* data, void*) {
+    ShardBox* b = (ShardBox*)data;
+    b->release();
+    delete b;
+}
+ShardBox* shard_arg(Args& a, size_t i) {
+    ShardBox* b = (ShardBox*)a.external(i, "expected a shard handle (addon.shardCreate())");
+    if (b && !b->sh) { a.type_error("the shard handle has been freed"); return nullptr; }
+    return b;
+}
+// shardCreate(ctx, rank, world, recvWords, stageWords) -> handle
+napi_value ShardCreate(napi_env env, napi_callback_info info) {
+    Args a(env, info, 5);
+    pil2gpu_ctx* ctx = a.ctx(0);
+    const uint32_t rank = a.u32(1), world = a.u32(2);
+    const uint64_t recv = a.u64(3), stage = a.u64(4);
+    a.need(world >= 1 && world <= 16 && (world & (world - 1)) == 0 && rank < world, "world must be a power of two <= 16 and rank < world");
+    a.need(recv <= ((uint64_t)1 << 40) && stage <= ((uint64_t)1 << 36), "buffer sizes out of range");
+    if (!a.ok) return nullptr;
+    ShardBox* b = new ShardBox{ctx, nullptr, rank, world, recv, stage};
+    int rc = pil2gpu_shard_create(ctx, rank, world, recv, stage, &b->sh);
+    if (!rc) rc = pil2gpu_dev_alloc(ctx, 32, &b->root);
+    if (rc) { b->release(); delete b; return fail_now(env, rc); }
+    napi_value ext;
+    if (napi_create_external(env, b, shard_finalize, nullptr, &ext) != napi_ok) { shard_finalize(env, b, nullptr); napi_throw_error(env, nullptr, "napi_create_external failed"); return nullptr; }
+    return ext;
+}
+// shardHandles(shard) -> BigUint64Array(16): the CUDA IPC handles of this rank's receive buffer and mailbox
+napi_value ShardHandles(napi_env env, napi_callback_info info) {
+    Args a(env, info, 1);
+    ShardBox* b = shard_arg(a, 0);
+    if (!a.ok) return nullptr;
+    uint64_t h[16];
+    int rc = pil2gpu_shard_handles(b->sh, (uint8_t*)h);
+    if (rc) return fail_now(env, rc);
+    return make_u64_array(env, h, 16);
+}
+// shardConnect(shard, handles): handles = BigUint64Array(16 * world), the pairs of all ranks in rank order
+napi_value ShardConnect(napi_env env, napi_callback_info info) {
+    Args a(env, info, 2);
+    ShardBox* b = shard_arg(a, 0);
+    uint64_t* h = nullptr; size_t n = 0;
+    a.u64_array(1, &h, &n);
+    if (a.ok) a.need(n == 16 * (size_t)b->world, "handles must hold 16 words per rank");
+    if (!a.ok) return nullptr;
+    int rc = pil2gpu_shard_connect(b->sh, (const uint8_t*)h, b->world);
+    return rc ? fail_now(env, rc) : nullptr;
+}
+// shardConnectLocal([shard0, shard1, ...]): every rank lives in this process
+napi_value ShardConnectLocal(napi_env env, napi_callback_info info) {
+    Args a(env, info, 1);
+    uint32_t n = 0; bool is_arr = false;
+    if (a.ok && (napi_is_array(env, a.v[0], &is_arr) != napi_ok || !is_arr || napi_get_array_length(env, a.v[0], &n) != napi_ok)) a.type_error("expected an Array of shard handles");
+    a.need(n >= 1 && n <= 16, "between 1 and 16 shards");
+    std::vector<pil2gpu_shard*> g;
+    for (uint32_t k = 0; a.ok && k < n; k++) {
+        napi_value e; void* q = nullptr;
+        if (napi_get_element(env, a.v[0], k, &e) != napi_ok || napi_get_value_external(env, e, &q) != napi_ok || !q || !((ShardBox*)q)->sh) { a.type_error("expected an Array of shard handles"); break; }
+        g.push_back(((ShardBox*)q)->sh);
+    }
+    if (!a.ok) return nullptr;
+    int rc = pil2gpu_shard_connect_local(g.data(), n);
+    return rc ? fail_now(env, rc) : nullptr;
+}
+// shardCommit(shard, slabPages, nPols, nBits, nBitsExt, split): extendAndMerkelize over the group (stark_gen_helpers.js:388-412).  slabPages
+// hold THIS rank's column slab, 2^nBits rows x nPols/world columns; nPols is the width of the whole trace.  Enqueues and returns.
+napi_value ShardCommit(napi_env env, napi_callback_info info) {
+    Args a(env, info, 6);
+    ShardBox* b = shard_arg(a, 0);
+    Pages s;
+    a.pages(1, s.p, s.w, &s.total);
+    const uint64_t nPols = a.u64(2); const uint32_t nBits = a.u32(3), nBitsExt = a.u32(4); const int32_t split = a.i32(5);
+    uint64_t sw = 0, dw = 0;
+    if (a.ok) {
+        a.need(nBitsExt <= 32 && nBits <= nBitsExt && nPols > 0 && nPols % b->world == 0, "bad commit shape (nPols must be a multiple of the number of ranks)");
+        a.need(shl_fits(nPols / b->world, nBits, &sw) && shl_fits(nPols / b->world, nBitsExt, &dw), "bad commit shape");
+        a.need(s.total == sw, "slab does not hold (nPols / world) * 2^nBits elements");
+        a.need(dw <= b->recv_words, "the shard's receive buffer is too small for this commit");
+        a.need(((uint64_t)1 << nBitsExt) >= b->world, "fewer extended rows than ranks");
+    }
+    if (!a.ok) return nullptr;
+    const uint64_t nn = pil2gpu_merkle_nnodes(((uint64_t)1 << nBitsExt) / b->world);
+    int rc = b->grow(&b->src, &b->src_words, sw);
+    if (!rc) rc = b->grow(&b->work, &b->work_words, dw);
+    if (!rc) rc = b->grow(&b->nodes, &b->nodes_words, nn);
+    size_t off = 0;
+    for (uint32_t k = 0; k < s.n() && !rc; k++) { rc = pil2gpu_h2d(b->ctx, (uint64_t*)b->src + off, s.p[k], s.w[k] * 8); off += s.w[k]; }
+    if (!rc) rc = pil2gpu_shard_commit_dev(b->sh, (const uint64_t*)b->src, (uint64_t*)b->work, nPols, nBits, nBitsExt, split, (uint64_t*)b->nodes, (uint64_t*)b->root);
+    if (rc) return fail_now(env, rc);
+    b->nPols = nPols; b->nBitsExt = nBitsExt;
+    return nullptr;
+}
+// shardRoot(shard) -> Promise<BigUint64Array(4)>: waits for this rank's stream; rejects if a peer never reached a barrier
+napi_value ShardRoot(napi_env env, napi_callback_info info) {
+    Args a(env, info, 1);
+    ShardBox* b = shard_arg(a, 0);
+    if (a.ok) a.need(b->nPols != 0, "no commit has been enqueued on this shard");
+    if (!a.ok) return nullptr;
+    auto root = std::make_shared<std::vector<uint64_t>>(4);
+    Job* j = new Job;
+    j->run = [=] {
+        int rc = pil2gpu_d2h(b->ctx, root->data(), b->root, 32);
+        if (!rc) rc = pil2gpu_shard_status(b->sh);
+        return rc;
+    };
+    j->result = [=](napi_env e) -> napi_value { return make_u64_array(e, root->data(), 4); };
+    return launch(env, j, a.v, 1, "pil2gpu.shardRoot");
+}
+// shardOpen(shard, idxs): getGroupProof (merklehash_p.js:142-168) of the last commit for global leaf indices (the same on every rank).  Enqueues.
+napi_value ShardOpen(napi_env env, napi_callback_info info) {
+    Args a(env, info, 2);
+    ShardBox* b = shard_arg(a, 0);
+    uint64_t* idx = nullptr; size_t n = 0;
+    a.u64_array(1, &idx, &n);
+    if (a.ok) {
+        a.need(b->nPols != 0, "no commit has been enqueued on this shard");
+        a.need(n >= 1 && n <= (1u << 20), "between 1 and 2^20 indices");
+        a.need(n * (b->nPols + 4 * (uint64_t)b->nBitsExt) <= b->stage_words, "the shard's staging area is too small for this many proofs");
+        for (size_t k = 0; a.ok && k < n; k++) if (idx[k] >> b->nBitsExt) { napi_throw_error(env, nullptr, "Out of range"); return nullptr; }
+    }
+    if (!a.ok) return nullptr;
+    int rc = b->grow(&b->idx, &b->idx_words, n);
+    if (!rc) rc = b->grow(&b->rows, &b->rows_words, n * b->nPols);
+    if (!rc) rc = b->grow(&b->sib, &b->sib_words, n * 4 * (uint64_t)b->nBitsExt);
+    if (!rc) rc = pil2gpu_h2d(b->ctx, b->idx, idx, n * 8);
+    if (!rc) rc = pil2gpu_sync(b->ctx);                       // idx is the caller's array: do not let it go while the copy is pending
+    if (!rc) rc = pil2gpu_shard_open_dev(b->sh, (const uint64_t*)b->nodes, b->nPols, b->nBitsExt, (const uint64_t*)b->idx, (uint32_t)n, (uint64_t*)b->rows, (uint64_t*)b->sib);
+    if (rc) return fail_now(env, rc);
+    b->n_idx = (uint32_t)n;
+    return nullptr;
+}
+// shardProofs(shard) -> Promise<{ rows: BigUint64Array(n * nPols), siblings: BigUint64Array(n * nBitsExt * 4) }>
+napi_value ShardProofs(napi_env env, napi_callback_info info) {
+    Args a(env, info, 1);
+    ShardBox* b = shard_arg(a, 0);
+    if (a.ok) a.need(b->n_idx != 0, "no shardOpen has been enqueued on this shard");
+    if (!a.ok) return nullptr;
+    const size_t nr = (size_t)b->n_idx * b->nPols, ns = (size_t)b->n_idx * 4 * b->nBitsExt;
+    auto rows = std::make_shared<std::vector<uint64_t>>(nr), sib = std::make_shared<std::vector<uint64_t>>(ns);
+    Job* j = new Job;
+    j->run = [=] {
+        int rc = pil2gpu_d2h(b->ctx, rows->data(), b->rows, nr * 8);
+        if (!rc) rc = pil2gpu_d2h(b->ctx, sib->data(), b->sib, ns * 8);
+        if (!rc) rc = pil2gpu_shard_status(b->sh);
+        return rc;
+    };
+    j->result = [=](napi_env e) -> napi_value {
+        napi_value obj, r = make_u64_array(e, rows->data(), nr), sv = make_u64_array(e, sib->data(), ns);
+        if (!r || !sv || napi_create_object(e, &obj) != napi_ok || napi_set_named_property(e, obj, "rows", r) != napi_ok ||
+            napi_set_named_property(e, obj, "siblings", sv) != napi_ok) return nullptr;
+        return obj;
+    };
+    return launch(env, j, a.v, 1, "pil2gpu.shardProofs");
+}
+// shardFree(shard)
+napi_value ShardFree(napi_env env, napi_callback_info info) {
+    Args a(env, info, 1);
+    ShardBox* b = (ShardBox*)a.external(0, "expected a shard handle (addon.shardCreate())");
+    if (!a.ok) return nullptr;
+    b->release();
+    return nullptr;
+}
+
 napi_value Init(napi_env env, napi_value exports) {
     const napi_property_descriptor props[] = {
         {"create", nullptr, Create, nullptr, nullptr, nullptr, napi_default, nullptr},
@@ -728,6 +920,15 @@ napi_value Init(napi_env env, napi_value exports) {
         {"computeEvals", nullptr, ComputeEvals, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"xDivXSubXi", nullptr, XDivXSubXi, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"friPol", nullptr, FriPol, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardCreate", nullptr, ShardCreate, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardHandles", nullptr, ShardHandles, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardConnect", nullptr, ShardConnect, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardConnectLocal", nullptr, ShardConnectLocal, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardCommit", nullptr, ShardCommit, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardRoot", nullptr, ShardRoot, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardOpen", nullptr, ShardOpen, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardProofs", nullptr, ShardProofs, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"shardFree", nullptr, ShardFree, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     if (napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props) != napi_ok) napi_throw_error(env, nullptr, "pil2gpu addon: registration failed");
     return exports;

@@ -139,7 +139,8 @@ int main() {
     printf("registered %zu functions\n", env->exports.size());
     const char* must[] = {"create", "allocPinnedPage", "nttPaged", "ldePaged", "merkelizePaged", "extendAndMerkelizePaged", "computeQPaged", "friFoldPaged", "commit",
                           "treeRoot", "treeGroupProofs", "treeDownload", "treeFree", "treeFromPages", "poseidon", "linearHash", "merkleNNodes", "computeEvals",
-                          "xDivXSubXi", "friPol"};
+                          "xDivXSubXi", "friPol", "shardCreate", "shardHandles", "shardConnect", "shardConnectLocal", "shardCommit", "shardRoot", "shardOpen",
+                          "shardProofs", "shardFree"};
     for (const char* m : must) if (!env->exports.count(m)) { printf("FAIL: %s missing\n", m); failures++; }
     napi_value fake_ctx = ext((void*)0x1);      // never dereferenced: every call below must be rejected before it reaches the library
 
@@ -177,6 +178,10 @@ int main() {
     expect_throw(env, "nttPaged: nBits is a string-like object", "nttPaged", {fake_ctx, arr({u64arr(16)}), arr({u64arr(16)}), num(2), arr({}), num(0)}, "TypeError", "32-bit");
     expect_throw(env, "too few arguments", "ldePaged", {fake_ctx}, "TypeError", "too few");
     expect_throw(env, "treeRoot: not a tree handle", "treeRoot", {num(3)}, "TypeError", "tree");
+    expect_throw(env, "shardCreate: world 3", "shardCreate", {fake_ctx, num(0), num(3), num(64), num(0)}, "RangeError", "power of two");
+    expect_throw(env, "shardCreate: rank == world", "shardCreate", {fake_ctx, num(2), num(2), num(64), num(0)}, "RangeError", "rank < world");
+    expect_throw(env, "shardCommit: not a shard", "shardCommit", {num(1), arr({u64arr(16)}), num(2), num(3), num(4), num(0)}, "TypeError", "shard");
+    expect_throw(env, "shardConnectLocal: not an array", "shardConnectLocal", {num(1)}, "TypeError", "Array");
     // create(): without a CUDA device the library refuses (no CPU fallback) and the addon turns that into an Error
     { Result r = call(env, "create", {num(0)});
       if (!r.exc_type.empty()) { const bool ok = r.exc_type == "Error" && r.exc_msg.find("CUDA") != std::string::npos;
@@ -233,6 +238,53 @@ int main() {
               Result af = call(env, "treeRoot", {tree});
               ok = af.exc_type == "TypeError";
               printf("%s: a freed tree handle is rejected\n", ok ? "ok  " : "FAIL"); if (!ok) failures++;
+          }
+          // multi-GPU commit group, two ranks in this process (two contexts on device 0): shardCommit / shardOpen only enqueue, the ranks meet
+          // in flag barriers on the GPU; root and proofs must equal the single-context device tree of the same trace
+          {
+              const uint32_t gB = 9, gE = 10, gC = 16, W = 2, cg = gC / W; const size_t gw = (size_t)gC << gB;
+              napi_value full = u64arr(gw); fill(full);
+              Result c1 = call(env, "create", {num(0)}), c2 = call(env, "create", {num(0)});
+              const uint64_t recv = (uint64_t)cg << gE, stage = 4 * (gC + 4 * gE);
+              Result s1 = call(env, "shardCreate", {c1.value, num(0), num(W), big(recv), big(stage)}), s2 = call(env, "shardCreate", {c2.value, num(1), num(W), big(recv), big(stage)});
+              bool ok = s1.exc_type.empty() && s2.exc_type.empty() && s1.value && s2.value;
+              if (ok) { Result cl = call(env, "shardConnectLocal", {arr({s1.value, s2.value})}); ok = cl.exc_type.empty(); }
+              napi_value slab[2] = {u64arr((size_t)cg << gB), u64arr((size_t)cg << gB)};
+              for (uint32_t g = 0; g < W; g++) for (size_t r = 0; r < ((size_t)1 << gB); r++)
+                  memcpy((uint64_t*)slab[g]->data + r * cg, (uint64_t*)full->data + r * gC + g * cg, cg * 8);
+              napi_value sh[2] = {s1.value, s2.value};
+              for (uint32_t g = 0; ok && g < W; g++) { Result q = call(env, "shardCommit", {sh[g], arr({slab[g]}), num(gC), num(gB), num(gE), num(0)}); ok = q.exc_type.empty(); }
+              Result whole = call(env, "commit", {ctx, arr({full}), num(gC), num(gB), num(gE), num(0)});
+              ok = ok && settled_ok(whole, "commit (whole trace)");
+              napi_value idx = u64arr(4); uint64_t qs[4] = {0, (1u << gE) - 1, 1u << (gE - 1), (1u << (gE - 1)) - 1}; memcpy(idx->data, qs, 32);
+              for (uint32_t g = 0; ok && g < W; g++) {
+                  Result rr = call(env, "shardRoot", {sh[g]});
+                  ok = settled_ok(rr, "shardRoot") && !memcmp(rr.value->settled->data, whole.value->settled->props["root"]->data, 32);
+              }
+              printf("%s: shard group of 2 ranks: root on every rank == root of the whole-trace commit\n", ok ? "ok  " : "FAIL"); if (!ok) failures++;
+              for (uint32_t g = 0; ok && g < W; g++) { Result q = call(env, "shardOpen", {sh[g], idx}); ok = q.exc_type.empty(); }
+              if (ok) {
+                  Result gp = call(env, "treeGroupProofs", {whole.value->settled->props["tree"], idx});
+                  for (uint32_t g = 0; ok && g < W; g++) {
+                      Result pr = call(env, "shardProofs", {sh[g]});
+                      ok = settled_ok(pr, "shardProofs") && gp.exc_type.empty() &&
+                           pr.value->settled->props["rows"]->length == 4 * gC && pr.value->settled->props["siblings"]->length == 4 * gE * 4 &&
+                           !memcmp(pr.value->settled->props["rows"]->data, gp.value->props["rows"]->data, 4 * gC * 8) &&
+                           !memcmp(pr.value->settled->props["siblings"]->data, gp.value->props["siblings"]->data, 4 * gE * 4 * 8);
+                  }
+              }
+              printf("%s: shard group: rows + sibling paths on every rank == treeGroupProofs of the whole tree\n", ok ? "ok  " : "FAIL"); if (!ok) failures++;
+              ((uint64_t*)idx->data)[1] = 1u << gE;
+              Result oor = call(env, "shardOpen", {sh[0], idx});
+              ok = oor.exc_type == "Error" && oor.exc_msg == "Out of range";
+              printf("%s: shardOpen: out-of-range index -> Error(\"Out of range\")\n", ok ? "ok  " : "FAIL"); if (!ok) failures++;
+              Result big_commit = call(env, "shardCommit", {sh[0], arr({u64arr((size_t)cg << (gB + 1))}), num(gC), num(gB + 1), num(gE + 1), num(0)});
+              ok = big_commit.exc_type == "RangeError" && big_commit.exc_msg.find("receive buffer") != std::string::npos;
+              printf("%s: shardCommit larger than the receive buffer -> RangeError\n", ok ? "ok  " : "FAIL"); if (!ok) failures++;
+              call(env, "shardFree", {sh[0]}); call(env, "shardFree", {sh[1]});
+              Result af = call(env, "shardRoot", {sh[0]});
+              ok = af.exc_type == "TypeError";
+              printf("%s: a freed shard handle is rejected\n", ok ? "ok  " : "FAIL"); if (!ok) failures++;
           }
           napi_value pg = call(env, "allocPinnedPage", {num(4096)}).value;
           const bool pok = pg && pg->kind == napi_value__::TYPEDARRAY && pg->length == 4096 && ((uint64_t*)pg->data)[4095] == 0;
