@@ -537,7 +537,9 @@ def leaf_roofline(leaf_perms, leaf_bytes, t_leaf, sec_per_step, mulmod_per_s, im
         "launch_s": t_leaf, "share_of_step": t_leaf / sec_per_step, "perms_per_launch": leaf_perms,
         "int_pipes": {"mulmod_per_s_measured": mulmod_per_s, "imad_wide_per_s_measured": imad_wide_per_s,
                       "frac_of_imad_wide_bound": leaf_perms / t_leaf / (imad_wide_per_s / 1888.0),
-                      "def": "1888 = 472 multiplies x 4 IMAD.WIDE; ncu (profiles/): fmaheavy pipe 86-88% busy, alu 66%, dram 1%"},
+                      "def": "1888 = 472 multiplies x 4 IMAD.WIDE",
+                      "ncu": "profiles/r02_ncu_cfg3.md: 16.7 k instructions per permutation of which 5.0 k FP64 (two issue slots each) -> 86 % of the "
+                             "issue slots used; fmaheavy 67 %, alu 45 %, fp64 34 % busy, dram 1 % (r01, all-integer: fmaheavy 86 %)"},
         "hbm": {"achieved": leaf_bytes / t_leaf / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": leaf_bytes / t_leaf / 1e9 / hbm_peak,
                 "algorithmic_bytes": leaf_bytes, "peak_src": peak_src},
     }
