@@ -407,6 +407,11 @@ def run_ours(args, rank, world, local_rank):
                     "peak_src": peak_src, "algorithmic_bytes": lde_bytes, "traffic": traffic.get("lde"),
                     "note": "integer-pipe bound as well: %.3g butterflies at the measured register-only butterfly rate is the floor"
                             % (3 * cols * (1 << n_bits) * n_bits / 2)}
+    n_bfly = (1 + (1 << blow)) * cols * (1 << n_bits) * n_bits / 2          # INTT + one size-N NTT per coset, n/2 * log n butterflies per column each
+    roofline_lde["int"] = {"achieved": n_bfly / t_lde / 1e12, "peak": mm.value / 1e12, "unit": "T butterflies/s", "frac": n_bfly / t_lde / mm.value,
+                           "def": "one modular multiply per butterfly: peak = the live-measured register-only multiply rate (pil2gpu_bench_int_pipes); the "
+                                  "register-only butterfly loop (multiply + add + sub) reaches 0.90 T/s in tools/probe, i.e. 0.64 of this peak",
+                           "butterflies": n_bfly}
 
     # ---- parity spot check of the buffers the timed steps produced (outside every timed region) ----
     spot = None
