@@ -11,7 +11,7 @@ PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libpil2gpu.so"
 SOURCES = ["pil2gpu.cu"]
-HEADERS = ["gl.cuh", "poseidon.cuh", "poseidon_rc.inc", "poseidon_rc_limbs.inc", "poseidon_rc_limbs_partial.inc", "poseidon_rc_f64p.inc", "ntt.cuh", "merkle.cuh", "fri.cuh", "qpath.cuh", "evals.cuh", "fripol.cuh", "expr.cuh", "shard.cuh"]
+HEADERS = ["gl.cuh", "poseidon.cuh", "poseidon_rc.inc", "poseidon_rc_limbs.inc", "poseidon_rc_limbs_partial.inc", "poseidon_rc_f64p.inc", "poseidon_tc.cuh", "poseidon_tc_consts.inc", "ntt.cuh", "merkle.cuh", "fri.cuh", "qpath.cuh", "evals.cuh", "fripol.cuh", "expr.cuh", "shard.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-cudart", "static",

@@ -11,6 +11,7 @@
 // words; a tree of height 1 is L(row) followed by four zero words (reference quirk, root = 0).
 #pragma once
 #include "poseidon.cuh"
+#include "poseidon_tc.cuh"
 
 #define MERKLE_THREADS 128
 #ifndef MERKLE_MIN_CTAS
@@ -113,6 +114,78 @@ __global__ void __launch_bounds__(MERKLE_THREADS, MERKLE_MIN_CTAS) merkle_leaf_k
     ulonglong2* o = reinterpret_cast<ulonglong2*>(nodes + 4 * row);
     o[0] = make_ulonglong2(d[0], d[1]);
     o[1] = make_ulonglong2(d[2], d[3]);
+}
+
+// The same leaf hash with the partial rounds of every permutation in tensor-core form (poseidon_tc.cuh): persistent CTAs of
+// MERKLE_TC_THREADS threads (one per SM: the fragment tables, 66 KB, and a 288-byte row per thread live in shared memory), each warp
+// hashes 32 rows in lock step; rows past the end are clamped and not stored.  width > 4 only.
+#define MERKLE_TC_THREADS 512
+#ifndef MERKLE_TC_DEFAULT
+#define MERKLE_TC_DEFAULT 0         // PIL2GPU_LEAF_TC=1 / =0 in the environment overrides
+#endif
+#ifndef MERKLE_TC_MIN_ROWS
+#define MERKLE_TC_MIN_ROWS 4096     // below this the table copy per CTA is not worth it
+#endif
+__global__ void __launch_bounds__(MERKLE_TC_THREADS, 1) merkle_leaf_tc_kernel(RowTiles t, u64 width, u64 height, u64* __restrict__ nodes) {
+    extern __shared__ __align__(16) unsigned char ptc_smem[];
+    poseidon_tc_setup(ptc_smem, MERKLE_TC_THREADS, threadIdx.x);
+    const u64* tab = reinterpret_cast<const u64*>(ptc_smem);
+    const int lane = threadIdx.x & 31;
+    unsigned char* wrows = ptc_smem + PTC_TABLE_BYTES + (threadIdx.x >> 5) * PTC_WARP_BYTES;
+    const u64 ntiles = (height + MERKLE_TC_THREADS - 1) / MERKLE_TC_THREADS;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u64 row = tile * MERKLE_TC_THREADS + threadIdx.x;
+        const u64 r = row < height ? row : height - 1;
+        u64 x[12];
+#pragma unroll
+        for (int i = 8; i < 12; i++) x[i] = 0;
+        for (u64 off = 0; off < width; off += 8) {
+            const u64* v = tiles_ptr(t, r, off);
+            if (off + 8 <= width) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = gl_to_mont(v[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = (off + i < width) ? gl_to_mont(v[i]) : 0;
+            }
+            poseidon_permute_mont_tc(x, wrows, tab, lane);
+#pragma unroll
+            for (int i = 0; i < 4; i++) x[8 + i] = x[i];
+        }
+        if (row < height) {
+            ulonglong2* o = reinterpret_cast<ulonglong2*>(nodes + 4 * row);
+            o[0] = make_ulonglong2(gl_from_mont(x[8]), gl_from_mont(x[9]));
+            o[1] = make_ulonglong2(gl_from_mont(x[10]), gl_from_mont(x[11]));
+        }
+    }
+}
+// Launch helper: returns false when the tensor-core kernel does not apply (the caller uses merkle_leaf_kernel).
+static int merkle_tc_sms = 0;
+static bool merkle_launch_leaf_tc(RowTiles t, u64 width, u64 height, u64* nodes, cudaStream_t st) {
+    if (width <= 4 || height < MERKLE_TC_MIN_ROWS) return false;
+    if (merkle_tc_sms == 0) {
+        // Measured on B200 (profiles/r02_poseidon_tc.md): 107 ms against 97 ms for the FP64-resident kernel at 2^22 x 256 -- the
+        // tensor-core form has 27 % fewer issue slots but only 4 warps per scheduler fit next to its tables, so it stays opt-in.
+        const char* env = getenv("PIL2GPU_LEAF_TC");
+        const bool on = env ? (env[0] == '1') : (MERKLE_TC_DEFAULT != 0);
+        int dev = 0, sms = 0;
+        if (!on) {
+            merkle_tc_sms = -1;
+        } else if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+            merkle_tc_sms = -1;
+        } else if (cudaFuncSetAttribute(merkle_leaf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POSEIDON_TC_SMEM(MERKLE_TC_THREADS)) !=
+                   cudaSuccess) {
+            (void)cudaGetLastError();
+            merkle_tc_sms = -1;
+        } else {
+            merkle_tc_sms = sms;
+        }
+    }
+    if (merkle_tc_sms < 0) return false;
+    const u64 ntiles = (height + MERKLE_TC_THREADS - 1) / MERKLE_TC_THREADS;
+    const unsigned grid = (unsigned)(ntiles < (u64)merkle_tc_sms ? ntiles : (u64)merkle_tc_sms);
+    merkle_leaf_tc_kernel<<<grid, MERKLE_TC_THREADS, POSEIDON_TC_SMEM(MERKLE_TC_THREADS), st>>>(t, width, height, nodes);
+    return true;
 }
 
 // Incremental standard linear hash for the column-slab pipeline (pil2gpu.cu: pipelined extend-and-merkelize): absorbs
@@ -261,7 +334,7 @@ static int merkle_launch(RowTiles t, u64 width, u64 height, int split, u64* node
     if (height == 0) return 0;
     const unsigned blocks = (unsigned)((height + MERKLE_THREADS - 1) / MERKLE_THREADS);
     if (!split || width <= 4) {
-        merkle_leaf_kernel<<<blocks, MERKLE_THREADS, 0, st>>>(t, width, height, nodes);
+        if (!merkle_launch_leaf_tc(t, width, height, nodes, st)) merkle_leaf_kernel<<<blocks, MERKLE_THREADS, 0, st>>>(t, width, height, nodes);
         launches++;
     } else {
         const u64 batch = merkle_split_batch(width);

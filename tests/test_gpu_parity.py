@@ -128,6 +128,29 @@ def test_merkelize_vs_oracle(ctx, n, npols, split):
     assert np.array_equal(nodes, C.merkelize(buff, npols, n, split))
 
 
+def test_leaf_hash_tensor_core_form_vs_oracle(tmp_path):
+    """The opt-in leaf kernel with the partial rounds on the tensor cores (PIL2GPU_LEAF_TC=1, csrc/poseidon_tc.cuh): same nodes as the
+    oracle for ragged heights (clamped tail rows), widths with a partial last chunk, and all-(p-1) / zero rows.  Runs in a child
+    process because the switch is read once per process."""
+    import os, subprocess, sys, pathlib
+    root = pathlib.Path(__file__).resolve().parents[1]
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import pil2_stark_js_b200 as m\n"
+        "ctx = m.default_context(0)\n"
+        "rng = np.random.default_rng(5)\n"
+        "for k, (n, w) in enumerate([(4099, 40), (8192, 9), (5000, 256), (4096, 5)]):\n"
+        "    buff = rng.integers(0, 0xFFFFFFFF00000001, size=n * w, dtype=np.uint64)\n"
+        "    buff[:w] = 0xFFFFFFFF00000000; buff[w:2 * w] = 0\n"
+        "    np.save(%r + '/in%%d.npy' %% k, buff); np.save(%r + '/out%%d.npy' %% k, ctx.merkelize(buff, w, n, False))\n"
+    ) % (str(root), str(tmp_path), str(tmp_path))
+    env = dict(os.environ, PIL2GPU_LEAF_TC="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    for k, (n, w) in enumerate([(4099, 40), (8192, 9), (5000, 256), (4096, 5)]):
+        buff = np.load(tmp_path / ("in%d.npy" % k))
+        assert np.array_equal(np.load(tmp_path / ("out%d.npy" % k)), C.merkelize(buff, w, n, False))
+
+
 @pytest.mark.parametrize("split", [False, True])
 def test_merklehash_p_interface(ctx, split, tmp_path):
     # test/merklehash_p.test.js: merkelize -> getGroupProof -> verifyGroupProof, (2^18, 10); file save/restore :101-132

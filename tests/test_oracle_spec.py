@@ -223,3 +223,37 @@ def test_fp64_partial_round_constants_model_vs_oracle():
         assert ((int(lo) - g.MAGIC) + ((int(hi) - g.MAGIC) << 32) + g.K) % S.P == c
     inc = (root / "pil2_stark_js_b200/csrc/poseidon_rc_f64p.inc").read_text()
     assert "%.1f" % g.halves(lane0[0])[0] in inc and "POSEIDON_RC_F64P_22[66]" in inc
+
+
+def test_tensor_core_partial_rounds_model_vs_oracle():
+    """csrc/poseidon_tc.cuh (opt-in leaf kernel) runs the 22 partial rounds as constant-matrix GEMMs over byte limbs plus 71 lazy
+    multiply-adds (tools/gen_poseidon_tc_consts.py).  The generator's lane-exact model of that data flow (emulated m16n8k32 MMA, the
+    kernel's fragment and row layout) equals the oracle's rounds 4..25 for a warp of states incl. all-ones / zero words, and the
+    committed table is the one the generator writes now."""
+    import importlib.util
+    import pathlib
+    import random
+    root = pathlib.Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("gen_tc", root / "tools" / "gen_poseidon_tc_consts.py")
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    R = (1 << 64) % S.P
+    rinv = pow(R, S.P - 2, S.P)
+    rnd = random.Random(13)
+    ys = [[rnd.randrange(1 << 64) for _ in range(12)] for _ in range(32)]
+    ys[0] = [(1 << 64) - 1] * 12
+    ys[1] = [0] * 12
+    ys[2] = [S.P - 1] * 12
+    got = g.model_partial_warp(ys)
+    for y, out in zip(ys, got):
+        s = [v * rinv % S.P for v in y]                       # Montgomery form -> plain S-box inputs of round 4
+        for r in range(4, 26):
+            s = [pow(s[0], 7, S.P)] + s[1:]
+            s = [sum(S.MDS[i][j] * s[j] for j in range(12)) % S.P for i in range(12)]
+            s = [(a + S.RC[12 * (r + 1) + i]) % S.P for i, a in enumerate(s)]
+        assert out == [v * R % S.P for v in s]
+    # mu_d of the in-block multiply-adds: small integers below 2^52 (the kernel's lazy accumulator relies on it)
+    assert g.MU[1] == 25 and all(g.MU[d] < (1 << 52) for d in range(1, 8)) and all(g.MU[d] < (1 << 32) for d in range(1, 5))
+    blocks, final = g.tables()
+    inc = (root / "pil2_stark_js_b200/csrc/poseidon_tc_consts.inc").read_text()
+    assert "0x%016xULL" % blocks[1][100] in inc and "0x%016xULL" % final[-1] in inc and "POSEIDON_TC_WORDS 8448" in inc
