@@ -5,8 +5,8 @@
 //                      width<=4 passthrough src/helpers/hash/merklehash/merklehash_worker.js:42-49
 //   merkelize          src/helpers/hash/merklehash/merklehash_p.js:44-133 (node layout _getNNodes :28-42)
 //   getGroupProof      src/helpers/hash/merklehash/merklehash_p.js:142-168
-// One row (or one batch of a row in split mode) per thread; the tree is reduced level by level with the last
-// <= MERKLE_TAIL pairs finished inside a single CTA.  `nodes` uses the reference layout exactly: level l starts
+// One row (or one batch of a row in split mode) per thread; the tree is reduced three levels per launch (private depth-3 subtrees per thread) with the
+// last <= MERKLE_TAIL pairs finished inside a single CTA.  `nodes` uses the reference layout exactly: level l starts
 // right after level l-1, every level is padded with a zero node to an even node count, the root is the last 4
 // words; a tree of height 1 is L(row) followed by four zero words (reference quirk, root = 0).
 #pragma once
@@ -17,6 +17,7 @@
 #ifndef MERKLE_MIN_CTAS
 #define MERKLE_MIN_CTAS 5      // occupancy hint of the hashing kernels: 96 registers with the FP64 partial rounds (measured best of 4/5/6)
 #endif
+#define MERKLE_FULL_WAVE (1u << 17)   // threads that fill 148 SMs x 640 resident threads
 #define MERKLE_TAIL 512    // pairs handled by the single-CTA tail kernel (512 threads keeps 128 regs/thread)
 
 // _getNNodes(height*4) of merklehash_p.js:28-42, in words.
@@ -260,10 +261,6 @@ GL_D void merkle_pair(const u64* __restrict__ in, u64* __restrict__ out, u64 i) 
     o[0] = make_ulonglong2(gl_from_mont(x[0]), gl_from_mont(x[1]));
     o[1] = make_ulonglong2(gl_from_mont(x[2]), gl_from_mont(x[3]));
 }
-__global__ void __launch_bounds__(MERKLE_THREADS, MERKLE_MIN_CTAS) merkle_level_kernel(const u64* __restrict__ in, u64* __restrict__ out, u64 pairs) {
-    const u64 i = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
-    if (i < pairs) merkle_pair(in, out, i);
-}
 // All remaining levels inside one CTA (pairs <= MERKLE_TAIL at entry).  nodes + p_in is the current level.
 __global__ void __launch_bounds__(MERKLE_TAIL) merkle_tail_kernel(u64* __restrict__ nodes, u64 p_in, u64 n64) {
     u64 next = ((n64 - 1) / 8 + 1) * 4;
@@ -296,28 +293,125 @@ __global__ void merkle_pad_kernel(u64* __restrict__ nodes, u64 height) {
     }
 }
 
-// Reduce leaf digests already stored at nodes[0 .. 4*height) to the root.  Returns launches or -1.
+// Up to three tree levels per launch (merkelize, merklehash_p.js:87-132): thread i owns the 2^LV input nodes [2^LV i, 2^LV (i+1)) and
+// walks its private subtree depth-first -- 4 + 2 + 1 permutations for LV = 3 -- so every lane stays busy, nothing crosses threads, and
+// each level is still written to its place in the reference layout.  A node that does not exist counts as the zero padding node (the
+// stored pads of odd levels are zeroed up front by merkle_pad_kernel; power-of-two heights have none).
+GL_D void merkle_hash2(const u64 a[4], const u64 b[4], u64 out[4]) {
+    u64 x[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = gl_to_mont(a[k]);
+        x[4 + k] = gl_to_mont(b[k]);
+        x[8 + k] = 0;
+    }
+    poseidon_permute_mont(x);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = gl_from_mont(x[k]);
+}
+GL_D void merkle_load4(const u64* __restrict__ p, u64 v[4]) {
+    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+    const ulonglong2 a = q[0], b = q[1];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+GL_D void merkle_store4(u64* __restrict__ p, const u64 v[4]) {
+    ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
+    q[0] = make_ulonglong2(v[0], v[1]);
+    q[1] = make_ulonglong2(v[2], v[3]);
+}
+// Thread i walks the depth-LV subtree over the input nodes [2^LV i, 2^LV (i+1)) in post-order -- leaf pair, leaf pair, their parent, ...
+// -- as ONE rolled loop of 2^LV - 1 steps with a single copy of the permutation (seven inlined copies would be 250 KB of code):
+// a step either hashes the next pair of input nodes (level 1) or the pending left sibling with the node just produced.
+template <int LV>
+__global__ void __launch_bounds__(MERKLE_THREADS, MERKLE_MIN_CTAS) merkle_levels_kernel(u64* __restrict__ nodes, u64 p_in, u64 n_in) {
+    const u64 i = (u64)blockIdx.x * MERKLE_THREADS + threadIdx.x;
+    const u64 first = i << LV;
+    if (first >= n_in) return;
+    u64 off[LV + 1];                       // word offset of level l above the input (reference layout: even-padded levels)
+    off[0] = p_in;
+    {
+        u64 n = n_in;
+#pragma unroll
+        for (int l = 1; l <= LV; l++) { off[l] = off[l - 1] + 4 * (n + (n & 1)); n = (n + 1) / 2; }
+    }
+    u64 left[LV][4];                       // left[l]: finished level-l node waiting for its right sibling (l = 1..LV-1)
+    u64 cur[4] = {0, 0, 0, 0};
+    int k = 0, pending = 0;                // k: input pairs consumed; pending: level of the waiting left sibling whose parent is next, 0 = none
+#pragma unroll 1
+    for (int step = 0; step < (1 << LV) - 1; step++) {
+        u64 a[4], b[4];
+        int lvl;
+        u64 idx;                           // the node produced by this step: level lvl, index idx (global)
+        if (pending == 0) {
+            lvl = 1;
+            idx = (first >> 1) + k;
+            const u64 n0 = 2 * idx;        // first + 2k
+            if (n0 < n_in) {
+                merkle_load4(nodes + p_in + 4 * n0, a);
+                merkle_load4(nodes + p_in + 4 * (n0 + 1), b);      // n0 + 1 == n_in (odd level): the stored zero pad
+            }
+            k++;
+        } else {
+            lvl = pending + 1;
+            idx = (first >> lvl) + ((k - 1) >> pending);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                u64 v = left[1 % LV][c];
+#pragma unroll
+                for (int l = 2; l < LV; l++) v = (pending == l) ? left[l][c] : v;
+                a[c] = v;
+                b[c] = cur[c];
+            }
+        }
+        if ((idx << lvl) < n_in) {         // the node exists iff its first input node does; a missing node counts as the zero pad
+            merkle_hash2(a, b, cur);
+            merkle_store4(nodes + off[(lvl < LV) ? lvl : LV] + 4 * idx, cur);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) cur[c] = 0;
+        }
+        // odd index within the subtree: the left sibling is waiting, its parent comes next; even: park it and go back to the input level
+        const int j = (int)((k - 1) >> (lvl - 1));
+        if ((j & 1) && lvl < LV) {
+            pending = lvl;
+        } else {
+#pragma unroll
+            for (int l = 1; l < LV; l++)
+                if (lvl == l) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) left[l][c] = cur[c];
+                }
+            pending = 0;
+        }
+    }
+}
+
+// Reduce leaf digests already stored at nodes[0 .. 4*height) to the root: three levels per launch while the level above still has more
+// than MERKLE_TAIL pairs, then the single-CTA tail.  Returns launches or -1.
 static int merkle_launch_tree(u64* nodes, u64 height, cudaStream_t st) {
     int launches = 0;
-    merkle_pad_kernel<<<1, 32, 0, st>>>(nodes, height);
-    launches++;
-    u64 p_in = 0, n64 = height * 4;
-    u64 next = ((n64 - 1) / 8 + 1) * 4;
-    u64 p_out = p_in + next * 2;
-    while (n64 > 4) {
-        const u64 pairs = next / 4;
-        if (pairs <= MERKLE_TAIL) {
-            merkle_tail_kernel<<<1, MERKLE_TAIL, 0, st>>>(nodes, p_in, n64);
+    if ((height & (height - 1)) != 0 || height == 1) {        // power-of-two heights > 1 have no padding nodes
+        merkle_pad_kernel<<<1, 32, 0, st>>>(nodes, height);
+        launches++;
+    }
+    u64 p_in = 0, n = height;                                // n = nodes of the current level
+    while (n > 1) {
+        if ((n + 1) / 2 <= MERKLE_TAIL) {
+            merkle_tail_kernel<<<1, MERKLE_TAIL, 0, st>>>(nodes, p_in, n * 4);
             launches++;
             break;
         }
-        merkle_level_kernel<<<(unsigned)((pairs + MERKLE_THREADS - 1) / MERKLE_THREADS), MERKLE_THREADS, 0, st>>>(nodes + p_in, nodes + p_out,
-                                                                                                                  pairs);
+        // levels this launch: as many as leave a full wave of threads (a thread walks its subtree sequentially, so on a level that
+        // no longer fills the GPU one launch per level is faster: measured +0.4 ms on the 2^24-leaf tree with 3 levels everywhere)
+        int lv = 1;
+        for (u64 m = (n + 1) / 2; lv < 3 && (m + 1) / 2 > MERKLE_TAIL && (n >> (lv + 1)) >= MERKLE_FULL_WAVE; lv++) m = (m + 1) / 2;
+        const u64 threads = (n + (1ull << lv) - 1) >> lv;
+        const unsigned blocks = (unsigned)((threads + MERKLE_THREADS - 1) / MERKLE_THREADS);
+        if (lv == 3) merkle_levels_kernel<3><<<blocks, MERKLE_THREADS, 0, st>>>(nodes, p_in, n);
+        else if (lv == 2) merkle_levels_kernel<2><<<blocks, MERKLE_THREADS, 0, st>>>(nodes, p_in, n);
+        else merkle_levels_kernel<1><<<blocks, MERKLE_THREADS, 0, st>>>(nodes, p_in, n);
         launches++;
-        n64 = next;
-        next = ((n64 - 1) / 8 + 1) * 4;
-        p_in = p_out;
-        p_out = p_in + next * 2;
+        for (int l = 0; l < lv; l++) { p_in += 4 * (n + (n & 1)); n = (n + 1) / 2; }
     }
     return launches;
 }

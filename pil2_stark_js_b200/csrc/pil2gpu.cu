@@ -1970,7 +1970,9 @@ static void shard_preload_kernels() {
     shard_preload_one(ntt_lde_fused_kernel<true>);
     shard_preload_one(merkle_leaf_kernel);
     shard_preload_one(merkle_batch_kernel);
-    shard_preload_one(merkle_level_kernel);
+    shard_preload_one(merkle_levels_kernel<1>);
+    shard_preload_one(merkle_levels_kernel<2>);
+    shard_preload_one(merkle_levels_kernel<3>);
     shard_preload_one(merkle_tail_kernel);
     shard_preload_one(merkle_pad_kernel);
     shard_preload_one(shard_barrier_kernel);

@@ -13,8 +13,8 @@
 // of earlier blocks enter t_n through the block's GEMM, those of the block itself through 28 lazily accumulated multiply-adds on the
 // integer pipes (mu_1..mu_7 < 2^52).  Against the FP64-resident form (poseidon_partial_f64: 22 dense MDS applications, ~580 issue slots
 // per round) the partial rounds cost the 22 S-boxes, 71 multiply-adds, 40 recombinations and ~530 IMMA per 32 permutations.
-// Tables, row layout and a lane-exact Python model of this data flow: tools/gen_poseidon_tc_consts.py (checked against the oracle in
-// tests/test_oracle_spec.py).
+// Tables, row layout and a lane-exact Python model of this data flow: tools/gen_poseidon_tc_consts.py (its model is checked on the CPU by the
+// test suite).
 //
 // Row of one permutation (PTC_ROW = 288 bytes, 16-byte aligned; 72 words = 8 mod 32 banks, so the A-fragment loads of 4 consecutive
 // rows tile the 32 banks):  [0,88) y_1..y_11 | 88: byte 1 (carries the additive constant) | 89..95: 0 | [96 + 8n, +8): slot n = GEMM part
