@@ -285,6 +285,174 @@ __global__ void __launch_bounds__(EVM_THREADS) evals_mma_kernel(const u64* __res
     }
 }
 
+// ---- second formulation (r02): the limb weight folded into the LEv operand ---------------------------------------------------
+// With A[m = (oc, b')][k = (row, b)] = byte b' of LEv[row][oc] * 2^(8b) mod p and B[k = (row, b)][n = col] = byte b of V[row][col] the
+// contraction index runs over (row, limb) and the B fragment of a lane IS the 8 bytes of V[row r0 + t][col g] as they lie in memory:
+// one 64-bit global load, no shared-memory staging and no byte transposition of the big operand.  The M index is (limb pair, oc) -- m-tile
+// i holds limbs 2i (tile rows 0..7 = the up to 8 (opening, coordinate) pairs) and 2i+1 (rows 8..15) -- so lane 4g+t ends up with all 8
+// limb sums of (oc g; columns 2t, 2t+1 of the n-tile) and recombines them alone.  The A fragments cost 7 shift-multiplies by 2^8 and 32
+// byte permutes per (oc, row); warp w of the CTA builds them for k-step w of a 32-row super-step into shared memory (double buffered,
+// one barrier per super-step) and all 8 warps -- 32 columns each -- use them.  s32 accumulators hold 4096 rows (4096 * 8 * 255^2 < 2^31),
+// then fold into per-lane field accumulators.  n_lev <= 2 (up to 8 rows per m-tile half); more openings take evals_mma_kernel.
+#define EV2_THREADS 256
+#define EV2_COLS 256             // columns per CTA: 8 warps x 4 n-tiles x 8
+#define EV2_FLUSH 128            // super-steps between folds of the s32 accumulators
+#define EV2_RING 8               // k-steps of V (4 rows x 32 columns) in each warp's private cp.async ring
+#define EV2_RPITCH 288           // bytes per staged row: 256 + 32, rows land 8 banks apart -> conflict-free 8-byte fragment loads
+#define EV2_STAGE (4 * EV2_RPITCH)
+#define EV2_SMEM (2 * 8 * 4 * 32 * 16 + 8 * EV2_RING * EV2_STAGE)
+
+GL_D u64 ev2_mul256(u64 x) { return gl_reduce96((u32)(x >> 56), x << 8); }      // x * 2^8 mod p, any u64 in / out
+GL_D void ev2_cp(void* smem_dst, const void* gmem_src, bool ok16, bool valid) {   // 16-byte (or 2 x 8-byte) copy, zero fill when !valid
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned n = valid ? 16u : 0u;
+    if (ok16) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem_src), "r"(n) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem_src), "r"(n >> 1) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa + 8), "l"(reinterpret_cast<const char*>(gmem_src) + 8), "r"(n >> 1) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(EV2_THREADS, 2) evals_mma2_kernel(const u64* __restrict__ buf, u64 size, int eb, u64 n, u64 rows_per_chunk,
+                                                                    const u64* __restrict__ lev, u32 n_lev, u64* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char ev2_smem[];
+    uint4 (*Abuf)[8 * 4 * 32] = reinterpret_cast<uint4 (*)[8 * 4 * 32]>(ev2_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    unsigned char* ring = ev2_smem + 2 * 8 * 4 * 32 * 16 + warp * (EV2_RING * EV2_STAGE);
+    const u32 n_oc = 3 * n_lev;
+    const u64 kb = (u64)blockIdx.y * rows_per_chunk;
+    const u64 ke = kb + rows_per_chunk < n ? kb + rows_per_chunk : n;           // both multiples of 32
+    const u64 nsuper = (ke > kb) ? (ke - kb) / 32 : 0;
+    const u64 cbase = (u64)blockIdx.x * EV2_COLS + 32 * warp;
+    const u64 rstride = size << eb;                                              // words between consecutive base rows
+    const u64* __restrict__ lp = (g < (int)n_oc) ? lev + (u64)(g / 3) * n * 3 + (g % 3) : nullptr;
+
+    // A fragments of k-step `warp` of super-step S -> Abuf[S & 1]
+    auto prep = [&](u64 S) {
+        const u64 r = kb + 32 * S + 4 * warp + t;
+        u64 x = (lp && r < ke) ? lp[r * 3] : 0;
+        u32 lo[8], hi[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            lo[b] = (u32)x;
+            hi[b] = (u32)(x >> 32);
+            x = ev2_mul256(x);
+        }
+        uint4* dst = &Abuf[S & 1][(warp * 4) * 32 + lane];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const u32* w = (i < 2) ? lo : hi;
+            const u32 sel = (i & 1) ? 0x7362u : 0x5140u;                         // (w0[b], w1[b], w0[b+1], w1[b+1]), b = 0 or 2
+            const u32 p01 = __byte_perm(w[0], w[1], sel), p23 = __byte_perm(w[2], w[3], sel);
+            const u32 p45 = __byte_perm(w[4], w[5], sel), p67 = __byte_perm(w[6], w[7], sel);
+            dst[i * 32] = make_uint4(__byte_perm(p01, p23, 0x5410), __byte_perm(p01, p23, 0x7632), __byte_perm(p45, p67, 0x5410),
+                                     __byte_perm(p45, p67, 0x7632));
+        }
+    };
+
+    int acc[4][4][4];                                                            // [m-tile][n-tile][c]
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[i][j][c] = 0;
+    u64 facc[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; j++) facc[j][0] = facc[j][1] = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                // limbs 2i: acc[i][j][e], 2i + 1: acc[i][j][2 + e]; each < 2^31
+                const u64 L = (u64)(u32)acc[0][j][e] + ((u64)(u32)acc[0][j][2 + e] << 8) + ((u64)(u32)acc[1][j][e] << 16) + ((u64)(u32)acc[1][j][2 + e] << 24);
+                const u64 H = (u64)(u32)acc[2][j][e] + ((u64)(u32)acc[2][j][2 + e] << 8) + ((u64)(u32)acc[3][j][e] << 16) + ((u64)(u32)acc[3][j][2 + e] << 24);
+                const u64 lo = L + (H << 32);                                   // L + 2^32 H = (H >> 32 + carry) 2^64 + lo
+                const u64 v = gl_reduce128((H >> 32) + (u64)(lo < L), lo);
+                facc[j][e] = gl_add(facc[j][e], v);
+                acc[0][j][e] = acc[0][j][2 + e] = acc[1][j][e] = acc[1][j][2 + e] = 0;
+                acc[2][j][e] = acc[2][j][2 + e] = acc[3][j][e] = acc[3][j][2 + e] = 0;
+            }
+    };
+
+    // V: every warp streams its own 32 columns through a private ring of EV2_RING k-steps with cp.async (the data never passes through
+    // registers, 7 KB per warp in flight).  Lane l copies the 16-byte chunks l and l + 32 of a k-step: chunk c = row c / 16, columns
+    // 2 (c % 16), +1.  Chunks past the row end are zero filled; odd row lengths (unaligned rows) copy 8 bytes at a time.
+    const bool ok16 = ((size & 1) == 0) && ((reinterpret_cast<size_t>(buf) & 15) == 0);
+    const u64 nk = nsuper * 8;
+    const int crow = lane >> 4, ccol = 2 * (lane & 15);
+    const bool v0 = cbase + ccol < size, v1 = cbase + ccol + 1 < size;
+    const u64* __restrict__ nsrc = buf + ((kb + crow) << eb) * size + cbase + ccol;   // next k-step to copy, chunk `lane`; chunk lane + 32 is 2 rows down
+    const u64 kstride = 4 * rstride, r2 = 2 * rstride;
+    u32 kleft = (u32)nk, nslot = 0, cslot = 0;
+    const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring) + crow * EV2_RPITCH + ccol * 8;
+    auto issue = [&]() {                                     // next k-step (if any) -> next ring slot; always commits a group
+        if (kleft) {
+            const unsigned da = ring_sa + nslot * EV2_STAGE;
+            if (ok16) {                                                          // even size: both columns of a chunk are in or out together
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(v0 ? nsrc : buf), "r"(v0 ? 16u : 0u) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + 2 * EV2_RPITCH), "l"(v0 ? nsrc + r2 : buf), "r"(v0 ? 16u : 0u) : "memory");
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const u64* sh = nsrc + h * r2;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(da + 2 * h * EV2_RPITCH), "l"(v0 ? sh : buf), "r"(v0 ? 8u : 0u) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(da + 2 * h * EV2_RPITCH + 8), "l"(v1 ? sh + 1 : buf), "r"(v1 ? 8u : 0u) : "memory");
+                }
+            }
+            nsrc += kstride;
+            kleft--;
+        }
+        nslot = (nslot + 1) & (EV2_RING - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (nsuper) prep(0);
+#pragma unroll
+    for (int k = 0; k < EV2_RING - 1; k++) issue();
+    const unsigned char* vbase = ring + t * EV2_RPITCH + g * 8;
+    for (u64 S0 = 0; S0 < nsuper; S0 += EV2_FLUSH) {
+        const u64 S1 = S0 + EV2_FLUSH < nsuper ? S0 + EV2_FLUSH : nsuper;
+#pragma unroll 1
+        for (u64 S = S0; S < S1; S++) {
+            __syncthreads();                                 // fragments of super-step S are written; everyone is done reading those of S - 1
+            if (S + 1 < nsuper) prep(S + 1);
+            const uint4* __restrict__ ab = &Abuf[S & 1][lane];
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(EV2_RING - 2) : "memory");      // this lane's copies of the k-step have landed
+                __syncwarp();                                                                // ... and every other lane's
+                const unsigned char* vb = vbase + cslot * EV2_STAGE;
+                cslot = (cslot + 1) & (EV2_RING - 1);
+                u64 vv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) vv[j] = *reinterpret_cast<const u64*>(vb + 64 * j);
+                __syncwarp();                                // the slot read one k-step ago is free in every lane: refill it
+                issue();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint4 a = ab[(ks * 4 + i) * 32];
+                    const u32 af[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) evm_mma(acc[i][j], af, (u32)vv[j], (u32)(vv[j] >> 32));
+                }
+            }
+        }
+        flush();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (g < (int)n_oc) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const u64 col = cbase + 8 * j + 2 * t + e;
+                if (col < size) partial[((u64)blockIdx.y * size + col) * n_oc + g] = gl_canon(facc[j][e]);
+            }
+    }
+}
+
 // out[e] from the dense per-chunk results: dim 1 -> (o, c) of the column; dim 3 -> R(col) + x R(col+1) + x^2 R(col+2) in F3, with
 // x (r0, r1, r2) = (r2, r0 + r2, r1).
 __global__ void evals_gather_kernel(const u64* __restrict__ partial, u32 chunks, u64 size, u32 n_lev, const EvalDesc* __restrict__ desc, u32 n_evals,

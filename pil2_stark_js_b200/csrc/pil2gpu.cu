@@ -623,6 +623,37 @@ int pil2gpu_compute_evals_dev(pil2gpu_ctx* ctx, const uint64_t* buf_dev, uint64_
     // the per-evaluation kernel (kept for small inputs and as the cross-check in the tests).
     const char* mode = getenv("PIL2GPU_EVALS");
     const bool use_mma = nBits >= 10 && n_lev <= 4 && !(mode && strcmp(mode, "scalar") == 0);
+    // (measured crossover at 2^22 rows: 128 columns 1.92 vs 2.72 ms, 64 columns 1.86 vs 1.53 ms -- its A-fragment work is per row, whatever the width)
+    if (use_mma && n_lev <= 2 && (size >= 96 || (mode && strcmp(mode, "mma2") == 0)) && !(mode && strcmp(mode, "mma1") == 0)) {
+        // second formulation (evals_mma2_kernel): the limb weight sits in the LEv operand, the buffer rows are MMA fragments as they lie
+        const u32 n_oc = 3 * n_lev;
+        const u64 colgroups = (size + EV2_COLS - 1) / EV2_COLS;
+        u64 chunks = (148 * 4) / colgroups;
+        if (chunks < 1) chunks = 1;
+        if (chunks > N / 32) chunks = N / 32;
+        const u64 rpc = (((N + chunks - 1) / chunks) + 31) & ~(u64)31;
+        chunks = (N + rpc - 1) / rpc;
+        const size_t desc_words = ((size_t)n_evals * sizeof(EvalDesc) + 7) / 8, part_words = chunks * size * n_oc, out_words = (size_t)n_evals * 3;
+        u64* scratch = nullptr;
+        CU(cudaMallocFromPoolAsync(&scratch, (desc_words + part_words + out_words) * sizeof(u64), ctx->pool, ctx->stream));
+        EvalDesc* ddesc = reinterpret_cast<EvalDesc*>(scratch);
+        u64 *partial = scratch + desc_words, *dout = partial + part_words;
+        cudaError_t e = cudaMemcpyAsync(ddesc, desc, (size_t)n_evals * sizeof(EvalDesc), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            dim3 grid((unsigned)colgroups, (unsigned)chunks, 1);
+            static bool ev2_attr = false;
+            if (!ev2_attr) { cudaFuncSetAttribute(evals_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV2_SMEM); ev2_attr = true; }
+            evals_mma2_kernel<<<grid, EV2_THREADS, EV2_SMEM, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, (const u64*)lev_dev, n_lev, partial);
+            evals_gather_kernel<<<(n_evals + 127) / 128, 128, 0, ctx->stream>>>(partial, (u32)chunks, size, n_lev, ddesc, n_evals, dout);
+            e = cudaMemcpyAsync(evals_out, dout, out_words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        cudaFreeAsync(scratch, ctx->stream);
+        if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "compute_evals: %s", cudaGetErrorString(e));
+        int rc = check_launch(ctx, 2, "compute_evals");
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        return PIL2GPU_OK;
+    }
     if (use_mma) {
         const u32 n_oc = 3 * n_lev, MT = (24 * n_lev + 15) / 16, M = MT * 16;
         u64 rpc = (N / 64) & ~(u64)(EVM_KSTEP - 1);

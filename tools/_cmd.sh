@@ -1,4 +1,5 @@
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
-for m in 1 2; do
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -DTC_MODE=$m -I pil2_stark_js_b200/csrc -o /tmp/ntt_tc_probe$m tools/probe/ntt_tc_probe.cu && echo "mode $m" && timeout 120 /tmp/ntt_tc_probe$m 200
+for c in 8 37 64 128; do
+echo "cols $c new:"; timeout 200 python tools/evals_probe.py 22 $c 2 2>&1 | tail -1
+echo "cols $c old:"; PIL2GPU_EVALS=mma1 timeout 200 python tools/evals_probe.py 22 $c 2 2>&1 | tail -1
 done
