@@ -82,6 +82,114 @@ __global__ void __launch_bounds__(FP_WARPS * 32) fripol_mma_kernel(const u64* __
             }
 }
 
+// ---- second formulation (r02): the rows are the B operand ------------------------------------------------------------------------
+// N = rows (n-tile = 8 rows), K = (column, limb b) -- the B fragment of a lane is one buffer element as it lies in memory -- and the
+// constants W'[(col, b)][oc] are the A operand with M = (limb pair, oc): m-tile i holds limbs 2i (tile rows 0..7 = the up to 8 outputs oc)
+// and 2i+1, so a lane ends up with all 8 limb sums of (oc g; rows 2t, 2t+1 of every n-tile) and recombines them alone (no shuffles, no
+// fragment register moves: the first formulation's A fragments interleave two rows and cost 8 moves per two MMAs).  A CTA is 8 warps x 32
+// rows.  Every warp streams its rows through a private cp.async ring in steps of 8 columns (64 bytes per row, 2 KB per step, 2 steps in
+// flight); the A fragments of a step (4 KB) are shared by the 8 warps through a CTA-wide ring filled one 16-byte copy per thread and step,
+// made visible by a barrier every second step.  n_groups <= 2 (oc <= 8); more groups take fripol_mma_kernel.
+#define FP2_THREADS 256
+#define FP2_DPITCH 96                         // bytes per staged row of a step: 64 + 32, rows land 8 banks apart (conflict-free fragment loads)
+#define FP2_DSTAGE (32 * FP2_DPITCH)
+#define FP2_DRING 3
+#define FP2_TPIECE 4096                       // A fragments of one step: 2 k-steps x 4 m-tiles x 32 lanes x 16 bytes
+#define FP2_TRING 6
+#define FP2_SMEM (FP2_TRING * FP2_TPIECE + 8 * FP2_DRING * FP2_DSTAGE)
+
+// AF: [piece][k-step of the piece][m-tile][lane] uint4, zero padded to npieces + 3 pieces.  S[row * NT + oc] (+)= sum.
+__global__ void __launch_bounds__(FP2_THREADS, 2) fripol_mma2_kernel(const u64* __restrict__ buf, u64 size, u64 rows, const uint4* __restrict__ AF,
+                                                                     u32 npieces, int NT, u64* __restrict__ S, int accumulate) {
+    extern __shared__ __align__(16) unsigned char fp2_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    unsigned char* tring = fp2_smem;
+    unsigned char* dring = fp2_smem + FP2_TRING * FP2_TPIECE + warp * (FP2_DRING * FP2_DSTAGE);
+    const u64 row0 = ((u64)blockIdx.x * 8 + warp) * 32;
+    int acc[4][4][4];                         // [m-tile][n-tile][c]
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[i][j][c] = 0;
+    // copies of this lane per step: chunks lane + 32 q (q < 4): row (lane >> 2) + 8 q, 16-byte part lane & 3 (columns 8 f + 2 part, + 1)
+    const bool ok16 = ((size & 1) == 0) && ((reinterpret_cast<size_t>(buf) & 15) == 0);
+    const int part = lane & 3;
+    const u64* src[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        u64 r = row0 + (lane >> 2) + 8 * q;
+        if (r >= rows) r = rows - 1;          // clamped rows are computed and discarded
+        src[q] = buf + r * size + 2 * part;
+    }
+    const unsigned dsa = (unsigned)__cvta_generic_to_shared(dring) + (lane >> 2) * FP2_DPITCH + part * 16;
+    const unsigned tsa = (unsigned)__cvta_generic_to_shared(tring) + threadIdx.x * 16;
+    u32 nf = 0;                               // next step to issue
+    auto issue = [&]() {                      // group nf: data of step nf, A fragments of step nf + 1 (step 0's ride along with group 0)
+        if (nf < npieces) {
+            const u64 c0 = (u64)8 * nf + 2 * part;
+            const unsigned da = dsa + (nf % FP2_DRING) * FP2_DSTAGE;
+            if (ok16) {
+                const bool v = c0 < size;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + q * 8 * FP2_DPITCH), "l"(v ? src[q] + 8 * nf : buf), "r"(v ? 16u : 0u) : "memory");
+            } else {
+                const bool v0 = c0 < size, v1 = c0 + 1 < size;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(da + q * 8 * FP2_DPITCH), "l"(v0 ? src[q] + 8 * nf : buf), "r"(v0 ? 8u : 0u) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(da + q * 8 * FP2_DPITCH + 8), "l"(v1 ? src[q] + 8 * nf + 1 : buf), "r"(v1 ? 8u : 0u) : "memory");
+                }
+            }
+            if (nf == 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tsa), "l"(AF + threadIdx.x) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tsa + ((nf + 1) % FP2_TRING) * FP2_TPIECE), "l"(AF + (size_t)(nf + 1) * 256 + threadIdx.x) : "memory");
+        }
+        nf++;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue();
+    issue();
+    for (u32 f = 0; f < npieces; f++) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // groups <= f have landed: data of step f, A fragments of steps <= f + 1
+        if ((f & 1) == 0) __syncthreads(); else __syncwarp();     // even steps publish the A fragments of steps f, f + 1 to the whole CTA
+        issue();                              // refills the slot of step f - 1: every lane is past that step (the sync above)
+        const unsigned char* db = dring + (f % FP2_DRING) * FP2_DSTAGE + g * FP2_DPITCH + t * 8;
+        const uint4* __restrict__ ab = reinterpret_cast<const uint4*>(tring + (f % FP2_TRING) * FP2_TPIECE) + lane;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            u64 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = *reinterpret_cast<const u64*>(db + 8 * j * FP2_DPITCH + 32 * h);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint4 a = ab[(h * 4 + i) * 32];
+                const u32 af[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) evm_mma(acc[i][j], af, (u32)v[j], (u32)(v[j] >> 32));
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (g < NT) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const u64 L = (u64)(u32)acc[0][j][e] + ((u64)(u32)acc[0][j][2 + e] << 8) + ((u64)(u32)acc[1][j][e] << 16) + ((u64)(u32)acc[1][j][2 + e] << 24);
+                const u64 H = (u64)(u32)acc[2][j][e] + ((u64)(u32)acc[2][j][2 + e] << 8) + ((u64)(u32)acc[3][j][e] << 16) + ((u64)(u32)acc[3][j][2 + e] << 24);
+                const u64 lo = L + (H << 32);
+                const u64 f = gl_reduce128((H >> 32) + (u64)(lo < L), lo);
+                const u64 r = row0 + 8 * j + 2 * t + e;
+                if (r < rows) {
+                    u64* o = S + r * NT + g;
+                    *o = gl_canon(accumulate ? gl_add(*o, f) : f);
+                }
+            }
+    }
+}
+
 struct FriPolFinish {
     u64 u[12][3];        // vf1 powers per group
     u64 c[12][3];        // sum_i w_i ev_i per group

@@ -925,6 +925,40 @@ int pil2gpu_fri_pol_dev(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_
                     v = glh_mul(v, 256);
                 }
             }
+        const char* fpmode = getenv("PIL2GPU_FRIPOL");
+        if (n_groups <= 2 && !(fpmode && strcmp(fpmode, "mma1") == 0)) {
+            // second formulation (fripol_mma2_kernel): rows as the B operand, A fragments in (limb pair, oc) order
+            const u32 ksteps = (u32)((size + 3) / 4), npieces = (ksteps + 1) / 2;
+            std::vector<uint4> AF((size_t)(npieces + 3) * 256, make_uint4(0, 0, 0, 0));
+            for (u32 s = 0; s < ksteps; s++)
+                for (int i = 0; i < 4; i++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int gid = lane >> 2, tig = lane & 3;
+                        const u64 col = (u64)4 * s + tig;
+                        if (gid >= NT || col >= size) continue;
+                        u32 a[4] = {0, 0, 0, 0};
+                        for (int ib = 0; ib < 4; ib++) {
+                            const unsigned char* lo = &Wb[((size_t)col * 8 + ib) * NT * 8 + gid * 8];
+                            const unsigned char* hi = &Wb[((size_t)col * 8 + 4 + ib) * NT * 8 + gid * 8];
+                            a[0] |= (u32)lo[2 * i] << (8 * ib);
+                            a[1] |= (u32)lo[2 * i + 1] << (8 * ib);
+                            a[2] |= (u32)hi[2 * i] << (8 * ib);
+                            a[3] |= (u32)hi[2 * i + 1] << (8 * ib);
+                        }
+                        AF[((size_t)(s >> 1) * 2 + (s & 1)) * 128 + i * 32 + lane] = make_uint4(a[0], a[1], a[2], a[3]);
+                    }
+            uint4* dAF = nullptr;
+            e = cudaMallocFromPoolAsync(&dAF, AF.size() * sizeof(uint4), ctx->pool, ctx->stream);
+            if (e != cudaSuccess) break;
+            bfs.push_back(reinterpret_cast<uint2*>(dAF));
+            e = cudaMemcpyAsync(dAF, AF.data(), AF.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream);   // pageable source: staged before return
+            if (e != cudaSuccess) break;
+            static bool fp2_attr = false;
+            if (!fp2_attr) { cudaFuncSetAttribute(fripol_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FP2_SMEM); fp2_attr = true; }
+            fripol_mma2_kernel<<<(unsigned)((E + 255) / 256), FP2_THREADS, FP2_SMEM, ctx->stream>>>((const u64*)bufs[bi].p, size, E, dAF, npieces, NT, S, bi > 0);
+            launches++;
+            continue;
+        }
         std::vector<uint2> BF((size_t)dsteps * 2 * NT * 32);
         for (u32 j = 0; j < dsteps; j++)
             for (int h = 0; h < 2; h++)

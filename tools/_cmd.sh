@@ -1,5 +1,4 @@
 cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
-for c in 8 37 64 128; do
-echo "cols $c new:"; timeout 200 python tools/evals_probe.py 22 $c 2 2>&1 | tail -1
-echo "cols $c old:"; PIL2GPU_EVALS=mma1 timeout 200 python tools/evals_probe.py 22 $c 2 2>&1 | tail -1
-done
+timeout 600 python -m pytest tests/test_gpu_f_rows.py tests/test_gpu_expressions.py -x -q -m gpu 2>&1 | tail -3
+echo "--- fripol new"; timeout 200 python tools/fripol_probe.py 23 256 2 2>&1 | tail -2
+echo "--- fripol old"; PIL2GPU_FRIPOL=mma1 timeout 200 python tools/fripol_probe.py 23 256 2 2>&1 | tail -2
