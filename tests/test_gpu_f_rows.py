@@ -144,7 +144,8 @@ def test_compute_lev_vs_oracle(ctx, n_bits, opening):
 @pytest.mark.parametrize("mode", ["mma", "mma1", "mma2", "scalar"])
 @pytest.mark.parametrize("n_bits,extend_bits,size,n_evals,openings", [
     (6, 1, 9, 5, [0, 1, -1]), (10, 1, 37, 40, [0, 1, -1]), (12, 2, 15, 300, [0, 1, -1]), (13, 1, 128, 100, [0, 1]), (3, 0, 4, 2, [0, 1, -1]),
-    (11, 1, 64, 64, [0]), (10, 0, 33, 50, [0, 1, -1, 2]), (15, 1, 8, 30, [0, 1]), (12, 1, 2, 4, [0, 1, 2, 3, 4])])
+    (11, 1, 64, 64, [0]), (10, 0, 33, 50, [0, 1, -1, 2]), (15, 1, 8, 30, [0, 1]), (12, 1, 2, 4, [0, 1, 2, 3, 4]),
+    (10, 1, 37, 40, [0, 1]), (12, 0, 301, 64, [0, 1]), (11, 2, 300, 50, [0]), (13, 1, 256, 90, [0, -1])])
 def test_compute_evals_vs_oracle(ctx, monkeypatch, mode, n_bits, extend_bits, size, n_evals, openings):
     """Evaluation sums through the tensor-core byte-limb GEMM (n_bits >= 10, <= 4 openings) and through the per-evaluation
     kernel (PIL2GPU_EVALS=scalar; also what small inputs and > 4 openings use): both bit-exact against the oracle."""
