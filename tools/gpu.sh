@@ -31,7 +31,7 @@ PY
       B="python bench.py --workload $WL --steps 1 --warmup 1 --no-e2e --no-cpu --no-extras --no-verify"
       $B > gpurun_out/${TAG}_plain_$WL.log 2>&1 || { tail -5 gpurun_out/${TAG}_plain_$WL.log; continue; }
       ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_$WL.csv $B > gpurun_out/${TAG}_ncu_launch_$WL.log 2>&1
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"${NCU_K:-ntt_pass|ntt_lde|merkle_leaf|merkle_tree}" -c ${NCU_C:-8} -f \
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"${NCU_K:-ntt_pass|ntt_lde|merkle_leaf|merkle_levels}" -c ${NCU_C:-8} -f \
           -o gpurun_out/${TAG}_prof_$WL $B > gpurun_out/${TAG}_ncu_full_$WL.log 2>&1
       tail -2 gpurun_out/${TAG}_ncu_full_$WL.log; ls -la gpurun_out/${TAG}_*;;
     multi)
