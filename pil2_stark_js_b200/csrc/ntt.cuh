@@ -379,7 +379,7 @@ __device__ __forceinline__ void ntt_item_decode(const NttItems& it, u32 item, u3
     if (it.ipc == 1) { y = item / it.tiles; tile_id = item - y * it.tiles; }
     else { tile_id = item / it.ychunks; y = item - tile_id * it.ychunks; }
 }
-template <bool DIF, bool INVERSE, bool SC = false, bool PIPE = true>
+template <bool DIF, bool INVERSE, bool SC = false, bool PIPE = true, bool NARROW = false>
 __global__ void __launch_bounds__(NTT_THREADS, PIPE ? 3 : NTT_PASS_MIN_CTAS) ntt_pass_kernel(const u64* in, u64* out, NttPass P, NttTables tb,   // in == out for the in-place passes: no __restrict__
                                                                const __grid_constant__ NttScatter sc, NttItems it) {
     extern __shared__ __align__(16) u64 ntt_smem[];
@@ -425,9 +425,9 @@ __global__ void __launch_bounds__(NTT_THREADS, PIPE ? 3 : NTT_PASS_MIN_CTAS) ntt
         __syncthreads();                                   // A: this item's rows are in shared memory; the previous store is finished
         if (PIPE && item + 1 < item_end) issue_load(item + 1, tiles[bsel ^ 1]);
         ulonglong2* reg = tile + (threadIdx.x >> 5) * RS;      // this warp's column pair
-        const u64 c0 = (u64)y * NTT_W;
-        const int cw = (int)((P.C - c0 < NTT_W) ? (P.C - c0) : NTT_W);
-        if (2 * (int)(threadIdx.x >> 5) < cw) {            // narrow buffers (quotient: 3-6 columns): warps whose column pair is padding skip the butterflies
+        // NARROW: buffers narrower than a tile (quotient, LEv: 3-6 columns) -- warps whose column pair is padding skip the butterflies.
+        // A separate instantiation: the test costs the wide kernels registers they do not have (48 at 5 CTAs / SM; measured +1.5 ms on cfg3's LDE).
+        if (!NARROW || 2 * (u64)(threadIdx.x >> 5) < P.C) {
             if (DIF && P.canon_in) {   // the caller's buffer may hold non-canonical words; DIF butterflies need canonical inputs
                 for (int k = threadIdx.x & 31; k < (1 << t); k += 32) {
                     ulonglong2 v = reg[ntt_pad(k)];
@@ -439,6 +439,8 @@ __global__ void __launch_bounds__(NTT_THREADS, PIPE ? 3 : NTT_PASS_MIN_CTAS) ntt
             ntt_warp_transform<DIF>(reg, TW, t);
         }
         __syncthreads();                                   // B
+        const u64 c0 = (u64)y * NTT_W;
+        const int cw = (int)((P.C - c0 < NTT_W) ? (P.C - c0) : NTT_W);
         const u64 pos0 = ((u64)base_hi << (lo + t)) | base_lo;
         ntt_tile_store<SC>(tile, out, P.C, c0, cw, t, P.scale ? 2 : ((!DIF && P.canon_out) ? 1 : 0), P.scale, pos0 * P.out_mul + z, P.out_mul << lo, sc);
         if (!PIPE && item + 1 < item_end) {
@@ -472,36 +474,31 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_FUSED_MIN_CTAS) ntt_lde_fused
     if (async) { ntt_cp_async_wait(); __syncthreads(); }
     ulonglong2* reg = tile + (threadIdx.x >> 5) * RS;
     ulonglong2* reg2 = tile2 + (threadIdx.x >> 5) * RS;
-    const bool live = 2 * (int)(threadIdx.x >> 5) < cw;          // warps whose column pair is padding skip the arithmetic (narrow buffers)
-    if (live) {
-        if (canon_in) {
-            for (int k = threadIdx.x & 31; k < rows; k += 32) {
-                ulonglong2 v = reg[ntt_pad(k)];
-                v.x = gl_canon(v.x); v.y = gl_canon(v.y);
-                reg[ntt_pad(k)] = v;
-            }
-            __syncwarp();
-        }
-        ntt_warp_transform<true>(reg, TW, t);          // coefficients, bit-reversed: position q holds a_{bitrev_n(q)}
-        for (int k = threadIdx.x & 31; k < rows; k += 32) {   // * 1/N, once (warp-private region)
+    if (canon_in) {
+        for (int k = threadIdx.x & 31; k < rows; k += 32) {
             ulonglong2 v = reg[ntt_pad(k)];
-            v.x = gl_mmul(v.x, n_inv_mont); v.y = gl_mmul(v.y, n_inv_mont);
+            v.x = gl_canon(v.x); v.y = gl_canon(v.y);
             reg[ntt_pad(k)] = v;
         }
         __syncwarp();
     }
+    ntt_warp_transform<true>(reg, TW, t);          // coefficients, bit-reversed: position q holds a_{bitrev_n(q)}
+    for (int k = threadIdx.x & 31; k < rows; k += 32) {   // * 1/N, once (warp-private region)
+        ulonglong2 v = reg[ntt_pad(k)];
+        v.x = gl_mmul(v.x, n_inv_mont); v.y = gl_mmul(v.y, n_inv_mont);
+        reg[ntt_pad(k)] = v;
+    }
+    __syncwarp();
     for (int r = 0; r < B; r++) {
         __syncthreads();                                           // every warp is done with the previous twiddle table
         ntt_build_tw<false>(TW, G, t, 0, 0, r, n, ext_bits, tb);   // ends with a barrier
-        if (live) {
-            ulonglong2* work = reg;                                // the last coset transforms the coefficients in place
-            if (r + 1 < B) {
-                work = reg2;
-                for (int k = threadIdx.x & 31; k < rows; k += 32) reg2[ntt_pad(k)] = reg[ntt_pad(k)];
-                __syncwarp();
-            }
-            ntt_warp_transform<false>(work, TW, t);
+        ulonglong2* work = reg;                                    // the last coset transforms the coefficients in place
+        if (r + 1 < B) {
+            work = reg2;
+            for (int k = threadIdx.x & 31; k < rows; k += 32) reg2[ntt_pad(k)] = reg[ntt_pad(k)];
+            __syncwarp();
         }
+        ntt_warp_transform<false>(work, TW, t);
         __syncthreads();
         ntt_tile_store<SC>((r + 1 < B) ? tile2 : tile, out, C, c0, cw, t, canon_out ? 1 : 0, 0, (q0 << (ext_bits - n)) + r, (u64)B, sc);
     }
@@ -563,6 +560,9 @@ static inline int ntt_launch_pass(const u64* in, u64* out, const NttPass& P, uns
     if (pipe) {
         if (ntt_set_smem(ntt_pass_kernel<DIF, INVERSE, SC, true>, smem) != cudaSuccess) return -1;
         ntt_pass_kernel<DIF, INVERSE, SC, true><<<grid, NTT_THREADS, smem, st>>>(in, out, P, tb, sc, it);
+    } else if (P.C < NTT_W && !SC) {
+        if (ntt_set_smem(ntt_pass_kernel<DIF, INVERSE, false, false, true>, smem) != cudaSuccess) return -1;
+        ntt_pass_kernel<DIF, INVERSE, false, false, true><<<grid, NTT_THREADS, smem, st>>>(in, out, P, tb, sc, it);
     } else {
         if (ntt_set_smem(ntt_pass_kernel<DIF, INVERSE, SC, false>, smem) != cudaSuccess) return -1;
         ntt_pass_kernel<DIF, INVERSE, SC, false><<<grid, NTT_THREADS, smem, st>>>(in, out, P, tb, sc, it);
