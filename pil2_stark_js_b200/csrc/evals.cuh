@@ -457,19 +457,25 @@ __global__ void __launch_bounds__(EV2_THREADS, 2) evals_mma2_kernel(const u64* _
 // x (r0, r1, r2) = (r2, r0 + r2, r1).
 __global__ void evals_gather_kernel(const u64* __restrict__ partial, u32 chunks, u64 size, u32 n_lev, const EvalDesc* __restrict__ desc, u32 n_evals,
                                     u64* __restrict__ out) {
-    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per evaluation: the lanes stride over the chunks, then a shuffle reduction
+    const u32 e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= n_evals) return;
     const EvalDesc d = desc[e];
     const u32 n_oc = 3 * n_lev;
     gl3 r[3];
     for (u32 j = 0; j < d.dim; j++) {
         gl3 a = {{0, 0, 0}};
-        for (u32 ch = 0; ch < chunks; ch++) {
+        for (u32 ch = lane; ch < chunks; ch += 32) {
             const u64* p = partial + ((u64)ch * size + d.offset + j) * n_oc + 3 * d.lev;
             a = gl3_add(a, gl3{{p[0], p[1], p[2]}});
         }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int c = 0; c < 3; c++) a.c[c] = gl_add(a.c[c], __shfl_xor_sync(0xFFFFFFFFu, a.c[c], off));
         r[j] = a;
     }
+    if (lane != 0) return;
     gl3 v = r[0];
     if (d.dim == 3) {
         const gl3 x1 = {{r[1].c[2], gl_add(r[1].c[0], r[1].c[2]), r[1].c[1]}};                    // x * r1

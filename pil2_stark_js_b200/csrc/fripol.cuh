@@ -17,7 +17,7 @@
 
 // D(16x8) += A(16x32, u8) * B(32x8, u8): same instruction as evm_mma
 // BF: fragment-ordered B, u32 pairs [(dstep * 2 + h) * NT + nt][lane][2]
-// S[row * NT + oc] (+)= field value of sum_{col, b} V-byte * W'
+// S[oc * rows + row] (+)= field value of sum_{col, b} V-byte * W'
 template <int NT>
 __global__ void __launch_bounds__(FP_WARPS * 32) fripol_mma_kernel(const u64* __restrict__ buf, u64 size, u64 rows, const uint2* __restrict__ BF,
                                                                     u32 dsteps, u64* __restrict__ S, int accumulate) {
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(FP_WARPS * 32) fripol_mma_kernel(const u64* __
                 f = gl_add(f, __shfl_xor_sync(0xFFFFFFFFu, f, 2));
                 const u64 r = row0 + m * 16 + half * 8 + gid;
                 if (tig == 0 && r < rows) {
-                    u64* o = S + r * NT + t;
+                    u64* o = S + (u64)t * rows + r;
                     *o = gl_canon(accumulate ? gl_add(*o, f) : f);
                 }
             }
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(FP_WARPS * 32) fripol_mma_kernel(const u64* __
 #define FP2_TRING 6
 #define FP2_SMEM (FP2_TRING * FP2_TPIECE + 8 * FP2_DRING * FP2_DSTAGE)
 
-// AF: [piece][k-step of the piece][m-tile][lane] uint4, zero padded to npieces + 3 pieces.  S[row * NT + oc] (+)= sum.
+// AF: [piece][k-step of the piece][m-tile][lane] uint4, zero padded to npieces + 3 pieces.  S[oc * rows + row] (+)= sum.
 __global__ void __launch_bounds__(FP2_THREADS, 2) fripol_mma2_kernel(const u64* __restrict__ buf, u64 size, u64 rows, const uint4* __restrict__ AF,
                                                                      u32 npieces, int NT, u64* __restrict__ S, int accumulate) {
     extern __shared__ __align__(16) unsigned char fp2_smem[];
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(FP2_THREADS, 2) fripol_mma2_kernel(const u64* 
                 const u64 f = gl_reduce128((H >> 32) + (u64)(lo < L), lo);
                 const u64 r = row0 + 8 * j + 2 * t + e;
                 if (r < rows) {
-                    u64* o = S + r * NT + g;
+                    u64* o = S + (u64)g * rows + r;
                     *o = gl_canon(accumulate ? gl_add(*o, f) : f);
                 }
             }
@@ -203,8 +203,8 @@ __global__ void fripol_finish_kernel(const u64* __restrict__ S, const u64* __res
     if (r >= rows) return;
     gl3 acc = {{0, 0, 0}};
     for (int g = 0; g < P.n_groups; g++) {
-        const u64* s = S + (r * P.n_groups + g) * 3;
-        const gl3 sg = {{gl_sub(s[0], P.c[g][0]), gl_sub(s[1], P.c[g][1]), gl_sub(s[2], P.c[g][2])}};
+        const u64* s = S + (u64)(3 * g) * rows + r;          // S is planar: S[oc * rows + row], oc = 3 g + c (coalesced on both sides)
+        const gl3 sg = {{gl_sub(s[0], P.c[g][0]), gl_sub(s[rows], P.c[g][1]), gl_sub(s[2 * rows], P.c[g][2])}};
         const u64* x = xdiv + 3 * (r * P.n_open + P.xidx[g]);
         const gl3 t = gl3_mul(gl3_mul(sg, gl3{{x[0], x[1], x[2]}}), gl3{{P.u[g][0], P.u[g][1], P.u[g][2]}});
         acc = gl3_add(acc, t);

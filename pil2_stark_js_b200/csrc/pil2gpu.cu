@@ -644,7 +644,7 @@ int pil2gpu_compute_evals_dev(pil2gpu_ctx* ctx, const uint64_t* buf_dev, uint64_
             static bool ev2_attr = false;
             if (!ev2_attr) { cudaFuncSetAttribute(evals_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV2_SMEM); ev2_attr = true; }
             evals_mma2_kernel<<<grid, EV2_THREADS, EV2_SMEM, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, (const u64*)lev_dev, n_lev, partial);
-            evals_gather_kernel<<<(n_evals + 127) / 128, 128, 0, ctx->stream>>>(partial, (u32)chunks, size, n_lev, ddesc, n_evals, dout);
+            evals_gather_kernel<<<(n_evals + 3) / 4, 128, 0, ctx->stream>>>(partial, (u32)chunks, size, n_lev, ddesc, n_evals, dout);
             e = cudaMemcpyAsync(evals_out, dout, out_words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
         }
         cudaFreeAsync(scratch, ctx->stream);
@@ -677,7 +677,7 @@ int pil2gpu_compute_evals_dev(pil2gpu_ctx* ctx, const uint64_t* buf_dev, uint64_
                 case 5: evals_mma_kernel<5><<<grid, EVM_THREADS, 0, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, LT, n_lev, partial); break;
                 default: evals_mma_kernel<6><<<grid, EVM_THREADS, 0, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, LT, n_lev, partial); break;
             }
-            evals_gather_kernel<<<(n_evals + 127) / 128, 128, 0, ctx->stream>>>(partial, (u32)chunks, size, n_lev, ddesc, n_evals, dout);
+            evals_gather_kernel<<<(n_evals + 3) / 4, 128, 0, ctx->stream>>>(partial, (u32)chunks, size, n_lev, ddesc, n_evals, dout);
             e = cudaMemcpyAsync(evals_out, dout, out_words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
         }
         cudaFreeAsync(scratch, ctx->stream);
