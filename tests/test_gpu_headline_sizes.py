@@ -113,3 +113,31 @@ def test_fri_chain_cfg4_vs_oracle(ctx):
             assert np.array_equal(nodes, C.merkelize(erows, 3 << (steps[s] - nxt), 1 << nxt)), f"tree of layer {s}"
         cur = p
     assert cur.shape == (16, 3)
+
+
+def test_evals_second_formulation_long_chunks_vs_oracle(ctx):
+    """Evaluation sums through evals_mma2_kernel at 2^22 rows x 128 columns: 592 K-chunks of ~7 k rows, so every CTA folds its s32 limb
+    accumulators into the field accumulators in mid-chunk (every 4096 rows) as it does at cfg3's size; dims 1 and 3, two openings.
+    Then the same shape with all-0xFF words in both operands: the limb sums reach 4096 * 8 * 255^2 = 2 130 739 200 < 2^31."""
+    n_bits, size = 22, 128
+    n = 1 << n_bits
+    xi = splitmix_field(5, 0, 3)
+    buf = splitmix_field(77, 0, size * n)
+    buf[:3] = [P - 1, P - 1, 0xFFFFFFFF]
+    ev = [(c, 1, o) for o in (0, 1) for c in (0, 1, 63, 64, 127)] + [(5, 3, 0), (125, 3, 1), (62, 3, 1)]
+    levs = ctx.compute_levs(xi, [0, 1], n_bits)
+    dbuf = ctx.upload(buf)
+    got = ctx.compute_evals(dbuf, size, n_bits, n_bits, ev, levs, 2)
+    levs_o = [C.lev(xi, o, n_bits) for o in (0, 1)]
+    want = C.evals({"b": (buf, size)}, [("b", o, d, l) for o, d, l in ev], levs_o, n_bits, 0)
+    assert np.array_equal(got, want)
+    dbuf.free(); levs.free()
+    del buf
+    ones = np.full(size * n, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)          # non-canonical on purpose: interpreted mod p
+    lev1 = np.full(3 * n, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    dlev, dbuf = ctx.upload(lev1), ctx.upload(ones)
+    got = ctx.compute_evals(dbuf, size, n_bits, n_bits, [(0, 1, 0), (127, 1, 0)], dlev, 1)
+    v = (2**64 - 1) % P
+    s = n * v * v % P
+    assert [int(x) for x in got[0]] == [s, s, s] and [int(x) for x in got[1]] == [s, s, s]
+    dlev.free(); dbuf.free()
