@@ -161,30 +161,20 @@ __global__ void __launch_bounds__(MERKLE_TC_THREADS, 1) merkle_leaf_tc_kernel(Ro
     }
 }
 // Launch helper: returns false when the tensor-core kernel does not apply (the caller uses merkle_leaf_kernel).
-static int merkle_tc_sms = 0;
+// Measured on B200 (profiles/r02_poseidon_tc.md): 107 ms against 97 ms for the FP64-resident kernel at 2^22 x 256 -- the tensor-core form
+// has 27 % fewer issue slots but only 4 warps per scheduler fit next to its tables, so it stays opt-in (PIL2GPU_LEAF_TC=1).
 static bool merkle_launch_leaf_tc(RowTiles t, u64 width, u64 height, u64* nodes, cudaStream_t st) {
     if (width <= 4 || height < MERKLE_TC_MIN_ROWS) return false;
-    if (merkle_tc_sms == 0) {
-        // Measured on B200 (profiles/r02_poseidon_tc.md): 107 ms against 97 ms for the FP64-resident kernel at 2^22 x 256 -- the
-        // tensor-core form has 27 % fewer issue slots but only 4 warps per scheduler fit next to its tables, so it stays opt-in.
-        const char* env = getenv("PIL2GPU_LEAF_TC");
-        const bool on = env ? (env[0] == '1') : (MERKLE_TC_DEFAULT != 0);
-        int dev = 0, sms = 0;
-        if (!on) {
-            merkle_tc_sms = -1;
-        } else if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
-            merkle_tc_sms = -1;
-        } else if (cudaFuncSetAttribute(merkle_leaf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POSEIDON_TC_SMEM(MERKLE_TC_THREADS)) !=
-                   cudaSuccess) {
-            (void)cudaGetLastError();
-            merkle_tc_sms = -1;
-        } else {
-            merkle_tc_sms = sms;
-        }
+    static const int on = [] { const char* env = getenv("PIL2GPU_LEAF_TC"); return env ? (env[0] == '1') : (MERKLE_TC_DEFAULT != 0); }();
+    if (!on) return false;
+    int dev = 0, sms = 0;                     // per device, on every launch: a process may drive several GPUs
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0 ||
+        cudaFuncSetAttribute(merkle_leaf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POSEIDON_TC_SMEM(MERKLE_TC_THREADS)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
     }
-    if (merkle_tc_sms < 0) return false;
     const u64 ntiles = (height + MERKLE_TC_THREADS - 1) / MERKLE_TC_THREADS;
-    const unsigned grid = (unsigned)(ntiles < (u64)merkle_tc_sms ? ntiles : (u64)merkle_tc_sms);
+    const unsigned grid = (unsigned)(ntiles < (u64)sms ? ntiles : (u64)sms);
     merkle_leaf_tc_kernel<<<grid, MERKLE_TC_THREADS, POSEIDON_TC_SMEM(MERKLE_TC_THREADS), st>>>(t, width, height, nodes);
     return true;
 }

@@ -641,11 +641,12 @@ int pil2gpu_compute_evals_dev(pil2gpu_ctx* ctx, const uint64_t* buf_dev, uint64_
         cudaError_t e = cudaMemcpyAsync(ddesc, desc, (size_t)n_evals * sizeof(EvalDesc), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) {
             dim3 grid((unsigned)colgroups, (unsigned)chunks, 1);
-            static bool ev2_attr = false;
-            if (!ev2_attr) { cudaFuncSetAttribute(evals_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV2_SMEM); ev2_attr = true; }
-            evals_mma2_kernel<<<grid, EV2_THREADS, EV2_SMEM, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, (const u64*)lev_dev, n_lev, partial);
-            evals_gather_kernel<<<(n_evals + 3) / 4, 128, 0, ctx->stream>>>(partial, (u32)chunks, size, n_lev, ddesc, n_evals, dout);
-            e = cudaMemcpyAsync(evals_out, dout, out_words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+            e = cudaFuncSetAttribute(evals_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV2_SMEM);   // per device: set on every launch
+            if (e == cudaSuccess) {
+                evals_mma2_kernel<<<grid, EV2_THREADS, EV2_SMEM, ctx->stream>>>((const u64*)buf_dev, size, eb, N, rpc, (const u64*)lev_dev, n_lev, partial);
+                evals_gather_kernel<<<(n_evals + 3) / 4, 128, 0, ctx->stream>>>(partial, (u32)chunks, size, n_lev, ddesc, n_evals, dout);
+                e = cudaMemcpyAsync(evals_out, dout, out_words * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+            }
         }
         cudaFreeAsync(scratch, ctx->stream);
         if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "compute_evals: %s", cudaGetErrorString(e));
@@ -953,8 +954,8 @@ int pil2gpu_fri_pol_dev(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_
             bfs.push_back(reinterpret_cast<uint2*>(dAF));
             e = cudaMemcpyAsync(dAF, AF.data(), AF.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream);   // pageable source: staged before return
             if (e != cudaSuccess) break;
-            static bool fp2_attr = false;
-            if (!fp2_attr) { cudaFuncSetAttribute(fripol_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FP2_SMEM); fp2_attr = true; }
+            e = cudaFuncSetAttribute(fripol_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FP2_SMEM);   // per device: set on every launch
+            if (e != cudaSuccess) break;
             fripol_mma2_kernel<<<(unsigned)((E + 255) / 256), FP2_THREADS, FP2_SMEM, ctx->stream>>>((const u64*)bufs[bi].p, size, E, dAF, npieces, NT, S, bi > 0);
             launches++;
             continue;
