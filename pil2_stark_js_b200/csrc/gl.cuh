@@ -190,19 +190,63 @@ GL_D gl3 gl3_scale(const gl3& a, u64 s) { return gl3{{gl_mul(a.c[0], s), gl_mul(
 // s_mont = s * 2^64 (canonical): plain product a * s
 GL_D gl3 gl3_mscale(const gl3& a, u64 s_mont) { return gl3{{gl_mmul(a.c[0], s_mont), gl_mmul(a.c[1], s_mont), gl_mmul(a.c[2], s_mont)}}; }
 GL_D gl3 gl3_canon(const gl3& a) { return gl3{{gl_canon(a.c[0]), gl_canon(a.c[1]), gl_canon(a.c[2])}}; }
+// Lazy accumulator of 64 x 64 products: three 64-bit columns (weights 1, 2^32, 2^64) with their carry counts.  A product costs
+// 4 IMAD.WIDE with carry-out + the carry adds (ptxas fuses mad.lo.cc / madc.hi.cc and merges the carries of neighbouring products).
+struct GlAcc {
+    u32 a0l, a0h, c0, a1l, a1h, c1, a2l, a2h, c2;
+};
+GL_D void gl_acc_madc(u32& lo, u32& hi, u32& c, u32 x, u32 y) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(lo), "+r"(hi), "+r"(c) : "r"(x), "r"(y));
+}
+GL_D void gl_acc_mac(GlAcc& A, u64 x, u64 y) {       // A += x * y, any u64 representatives
+    const u32 x0 = (u32)x, x1 = (u32)(x >> 32), y0 = (u32)y, y1 = (u32)(y >> 32);
+    gl_acc_madc(A.a0l, A.a0h, A.c0, x0, y0);
+    gl_acc_madc(A.a1l, A.a1h, A.c1, x0, y1);
+    gl_acc_madc(A.a1l, A.a1h, A.c1, x1, y0);
+    gl_acc_madc(A.a2l, A.a2h, A.c2, x1, y1);
+}
+// a0 + c0 2^64 + (a1 + c1 2^64) 2^32 + (a2 + c2 2^64) 2^64 mod p for up to ~2^28 accumulated products: the low 128 bits go through
+// gl_reduce128, what lies above 2^128 (top < 2^32) comes off as top * 2^32 (2^128 = -2^32 mod p) -- folded with 2^64 = 2^32 - 1 first, so
+// that the subtrahend is canonical.
+GL_D u64 gl_acc_reduce(const GlAcc& A) {
+    u32 l1, h0, h1, top;
+    asm("{\n\t"
+        "add.cc.u32   %0, %4, %5;\n\t"        // a0h + a1l
+        "addc.cc.u32  %1, %6, %7;\n\t"        // a2l + a1h + carry
+        "addc.cc.u32  %2, %8, 0;\n\t"
+        "addc.u32     %3, %9, 0;\n\t"         // c2 + carry
+        "add.cc.u32   %1, %1, %10;\n\t"       // + c0
+        "addc.cc.u32  %2, %2, %11;\n\t"       // + c1 (weight 2^96)
+        "addc.u32     %3, %3, 0;\n\t"
+        "}"
+        : "=&r"(l1), "=&r"(h0), "=&r"(h1), "=&r"(top)
+        : "r"(A.a0h), "r"(A.a1l), "r"(A.a2l), "r"(A.a1h), "r"(A.a2h), "r"(A.c2), "r"(A.c0), "r"(A.c1));
+    const u64 r = gl_reduce128(((u64)h1 << 32) | h0, ((u64)l1 << 32) | A.a0l);
+    return gl_subc(r, (u64)top << 32);             // top * 2^32 < p: canonical
+}
+
+// Product modulo x^3 - x - 1 (f3g.js:94-102): with c_k the coefficients of the plain polynomial product, x^3 = x + 1 and x^4 = x^2 + x give
+//     r0 = c0 + c3,  r1 = c1 + c3 + c4,  r2 = c2 + c4.
+// The 12 partial products are accumulated lazily (no reduction between them) and every coordinate is reduced once: ~170 instructions
+// against ~300 for the Karatsuba form with a reduction per product (6 multiplications + 15 modular additions).  Any u64 in and out.
 GL_D gl3 gl3_mul(const gl3& a, const gl3& b) {
-    // Karatsuba-style product modulo x^3 - x - 1, same operation count as f3g.js:94-102
-    u64 A = gl_mul(gl_add(a.c[0], a.c[1]), gl_add(b.c[0], b.c[1]));
-    u64 B = gl_mul(gl_add(a.c[0], a.c[2]), gl_add(b.c[0], b.c[2]));
-    u64 C = gl_mul(gl_add(a.c[1], a.c[2]), gl_add(b.c[1], b.c[2]));
-    u64 D = gl_mul(a.c[0], b.c[0]);
-    u64 E = gl_mul(a.c[1], b.c[1]);
-    u64 F = gl_mul(a.c[2], b.c[2]);
-    u64 G = gl_sub(D, E);
+    GlAcc r0 = {0, 0, 0, 0, 0, 0, 0, 0, 0}, r1 = r0, r2 = r0;
+    gl_acc_mac(r0, a.c[0], b.c[0]);
+    gl_acc_mac(r0, a.c[1], b.c[2]);
+    gl_acc_mac(r0, a.c[2], b.c[1]);
+    gl_acc_mac(r1, a.c[0], b.c[1]);
+    gl_acc_mac(r1, a.c[1], b.c[0]);
+    gl_acc_mac(r1, a.c[1], b.c[2]);
+    gl_acc_mac(r1, a.c[2], b.c[1]);
+    gl_acc_mac(r1, a.c[2], b.c[2]);
+    gl_acc_mac(r2, a.c[0], b.c[2]);
+    gl_acc_mac(r2, a.c[1], b.c[1]);
+    gl_acc_mac(r2, a.c[2], b.c[0]);
+    gl_acc_mac(r2, a.c[2], b.c[2]);
     gl3 r;
-    r.c[0] = gl_sub(gl_add(C, G), F);
-    r.c[1] = gl_sub(gl_sub(gl_sub(gl_add(A, C), E), E), D);
-    r.c[2] = gl_sub(B, G);
+    r.c[0] = gl_acc_reduce(r0);
+    r.c[1] = gl_acc_reduce(r1);
+    r.c[2] = gl_acc_reduce(r2);
     return r;
 }
 
