@@ -209,6 +209,12 @@ typedef struct pil2gpu_expr_buffer {
 } pil2gpu_expr_buffer;
 int pil2gpu_calculate_exps_dev(pil2gpu_ctx* ctx, const uint32_t* ops, uint32_t n_ops, const uint64_t* consts, uint32_t n_consts,
                                const pil2gpu_expr_buffer* bufs, uint32_t n_bufs, uint32_t domain_bits, int x_shift);
+/* The records are compiled at run time into a straight-line kernel (NVRTC, once per device and program -- what compileCode,
+ * prover_helpers.js:87-110, does with `new Function`); the interpreter remains as the fallback when libnvrtc is absent
+ * (PIL2GPU_EXPR=interp forces it, =jit turns a missing compiler into PIL2GPU_E_UNSUPPORTED).  pil2gpu_expr_jit_check returns the generated
+ * source (up to cap - 1 characters) and 0 when NVRTC compiles it for sm_100a; it needs no device. */
+int pil2gpu_expr_jit_check(const uint32_t* ops, uint32_t n_ops, const uint64_t* row_words, uint32_t n_bufs, uint32_t domain_bits, int x_shift,
+                           char* source_out, uint64_t cap);
 
 /* ---- FRI polynomial: computeFRIStark after the xDivXSubXi table, src/stark/stark_gen_helpers.js:325-334 ------------- */
 /* One entry of pilInfo.evMap, in evMap order (the Horner order of friPolinomial.js:26-40 depends on it): the polynomial's

@@ -84,6 +84,7 @@ _SIGS = {
     "pil2gpu_compute_q_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), u64p, c_u32,
                                         vp, vp]),
     "pil2gpu_calculate_exps_dev": (c_int, [vp, vp, c_u32, vp, c_u32, vp, c_u32, c_u32, c_int]),
+    "pil2gpu_expr_jit_check": (c_int, [vp, c_u32, vp, c_u32, c_u32, c_int, ctypes.c_char_p, c_u64]),
     "pil2gpu_fri_fold_range_dev": (c_int, [vp, vp, c_int, c_u32, c_u32, c_i32, c_u32, vp, c_u64, c_u64, vp, vp]),
     "pil2gpu_fri_fold_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u32, c_u32, c_i32, c_u32, vp, c_int, ctypes.POINTER(vp), u64p, c_u32,
                                        ctypes.POINTER(vp), u64p, c_u32, vp]),

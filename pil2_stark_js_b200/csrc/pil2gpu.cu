@@ -25,6 +25,7 @@
 #include "shard.cuh"
 #include "fripol.cuh"
 #include "expr.cuh"
+#include "expr_jit.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -821,6 +822,27 @@ int pil2gpu_calculate_exps_dev(pil2gpu_ctx* ctx, const uint32_t* ops, uint32_t n
         for (uint32_t j = 0; j < nsrc && !rc; j++) rc = check_operand(o + 7 + 3 * j, false, k, "source");
         if (rc) return rc;
     }
+    // Compiled path (expr_jit.cuh): the records become a straight-line kernel, built once per (device, program) with NVRTC.
+    // PIL2GPU_EXPR=interp forces the interpreter, =jit makes a missing / failing compiler an error instead of a fallback.
+    const char* xmode = getenv("PIL2GPU_EXPR");
+    if (!(xmode && strcmp(xmode, "interp") == 0)) {
+        cudaKernel_t jk = expr_jit_get(ops, n_ops, eb.row_words, domain_bits, x_shift != 0);
+        if (!jk && xmode && strcmp(xmode, "jit") == 0) return fail(PIL2GPU_E_UNSUPPORTED, "calculate_exps: %s", expr_jit_error.c_str());
+        if (jk) {
+            const size_t cb = (size_t)(n_consts ? n_consts : 1) * 3 * sizeof(u64);
+            u64* d_c = nullptr;
+            CU(cudaMallocFromPoolAsync(&d_c, cb, ctx->pool, ctx->stream));
+            cudaError_t je = n_consts ? cudaMemcpyAsync(d_c, consts, (size_t)n_consts * 3 * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+            const u64* d_cc = d_c;
+            const u64* bytepow = ctx->tb.bytepow;
+            void* args[] = {(void*)&d_cc, (void*)&eb, (void*)&bytepow};
+            if (je == cudaSuccess)
+                je = cudaLaunchKernel((const void*)jk, dim3((unsigned)((N + EXPR_THREADS - 1) / EXPR_THREADS)), dim3(EXPR_THREADS), args, 0, ctx->stream);
+            cudaFreeAsync(d_c, ctx->stream);
+            if (je != cudaSuccess) return fail(PIL2GPU_E_CUDA, "calculate_exps (compiled): %s", cudaGetErrorString(je));
+            return check_launch(ctx, 1, "calculate_exps");
+        }
+    }
     const size_t op_bytes = (size_t)n_ops * EXPR_OP_WORDS * sizeof(uint32_t), c_bytes = (size_t)(n_consts ? n_consts : 1) * 3 * sizeof(u64);
     char* scratch = nullptr;
     CU(cudaMallocFromPoolAsync(&scratch, ((op_bytes + 15) & ~(size_t)15) + c_bytes, ctx->pool, ctx->stream));
@@ -998,6 +1020,36 @@ int pil2gpu_fri_pol_dev(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_
     cudaFreeAsync(S, ctx->stream);
     if (e != cudaSuccess) return fail(PIL2GPU_E_CUDA, "fri_pol: %s", cudaGetErrorString(e));
     return check_launch(ctx, launches, "fri_pol");
+}
+
+// The CUDA source the compiled path generates for a program, and whether NVRTC accepts it for sm_100a (no device needed: tests / tooling).
+// source_out (may be NULL) receives up to cap - 1 characters + NUL; returns 0 = compiles, > 0 = NVRTC error code (message in
+// pil2gpu_last_error), PIL2GPU_E_UNSUPPORTED = no NVRTC on this machine.
+int pil2gpu_expr_jit_check(const uint32_t* ops, uint32_t n_ops, const uint64_t* row_words, uint32_t n_bufs, uint32_t domain_bits, int x_shift,
+                           char* source_out, uint64_t cap) {
+    if (!ops || n_ops == 0 || (!row_words && n_bufs) || n_bufs > EXPR_MAX_BUFS || domain_bits > 32) return fail(PIL2GPU_E_INVALID, "bad argument");
+    u64 rw[EXPR_MAX_BUFS] = {0};
+    for (uint32_t b = 0; b < n_bufs; b++) rw[b] = row_words[b];
+    for (uint32_t k = 0; k < n_ops; k++) {
+        const uint32_t* o = ops + (size_t)k * EXPR_OP_WORDS;
+        if (o[0] > EXPR_MULADD || o[1] > 3) return fail(PIL2GPU_E_INVALID, "record %u: invalid opcode / source count", k);
+        for (uint32_t j = 0; j <= o[1]; j++) {
+            const uint32_t* w = j == 0 ? o + 4 : o + 4 + 3 * j;
+            const uint32_t kind = w[0] & 255;
+            if (kind > EXPR_K_X || (kind == EXPR_K_TMP && w[1] >= EXPR_MAX_SLOTS) || (kind == EXPR_K_BUF && (w[0] >> 16) >= n_bufs))
+                return fail(PIL2GPU_E_INVALID, "record %u: invalid operand", k);
+        }
+    }
+    std::string src, log;
+    const int rc = expr_jit_compile_only(ops, n_ops, rw, domain_bits, x_shift != 0, &src, &log);
+    if (source_out && cap) {
+        const size_t n = src.size() < cap - 1 ? src.size() : (size_t)cap - 1;
+        memcpy(source_out, src.data(), n);
+        source_out[n] = 0;
+    }
+    if (rc == -1) return fail(PIL2GPU_E_UNSUPPORTED, "%s", log.c_str());
+    if (rc != 0) return fail(rc > 0 ? rc : PIL2GPU_E_CUDA, "NVRTC: %s", log.substr(0, 800).c_str());
+    return PIL2GPU_OK;
 }
 
 // Host-buffer form of the whole of computeFRIStark's arithmetic (:289-334): uploads every distinct extended buffer once, builds

@@ -102,3 +102,32 @@ def test_addon_argument_checks_execute_under_a_mock_napi(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ALL CHECKS PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
     assert r.stdout.count("ok  :") >= 25
+
+
+def test_expression_jit_source_compiles_offline():
+    """The run-time compiled form of the constraint-expression evaluator (csrc/expr_jit.cuh): the CUDA source generated for the golden
+    quotient program of the sm_all AIR (169 records) is accepted by NVRTC for sm_100a -- no device needed -- and mirrors the records:
+    one statement per record, temporaries as registers, the F3 x F3 products as gl3_mul."""
+    import ctypes, json, sys, types
+    import numpy as np
+    sys.path.insert(0, str(ROOT / "tests"))
+    from test_oracle_expressions import prover_side_program, make_domain_ctx
+    from pil2_stark_js_b200 import prover_helpers as H, _lib
+    L = _lib.load()
+    qcode = json.loads((ROOT / "tests" / "golden" / "sm_all_q_code.json").read_text())
+    d = make_domain_ctx(qcode, np.random.default_rng(1), 4, 5)
+    cc = H.compile_code(types.SimpleNamespace(**d), prover_side_program(qcode), "ext")
+    rw = np.array([r for _, r in cc.buffers], dtype=np.uint64)
+    buf = ctypes.create_string_buffer(1 << 20)
+    rc = L.pil2gpu_expr_jit_check(cc.ops.ctypes.data, len(cc.ops) // 16, rw.ctypes.data, len(rw), 5, 1, buf, 1 << 20)
+    src = buf.value.decode()
+    body = src[src.index('extern "C"'):]
+    assert body.count("\n    { const gl3 a = ") == 169 and body.count("gl3_mul(a, b)") == 38 and "xval" in body
+    L.pil2gpu_last_error.restype = ctypes.c_char_p
+    if rc == -5:                                                        # PIL2GPU_E_UNSUPPORTED: no libnvrtc on this machine
+        import pytest
+        pytest.skip(L.pil2gpu_last_error().decode())
+    assert rc == 0, L.pil2gpu_last_error().decode()
+    bad = np.zeros(16, dtype=np.uint32)
+    bad[0] = 9
+    assert L.pil2gpu_expr_jit_check(bad.ctypes.data, 1, None, 0, 4, 1, None, 0) == -1

@@ -24,6 +24,14 @@ def gpu():
     return m.default_context(0)
 
 
+@pytest.fixture(params=["jit", "interp"], autouse=True)
+def expr_mode(request, monkeypatch):
+    """Every test runs through the run-time compiled kernel (NVRTC; "jit" makes a missing compiler an error, so the GPU box proves the
+    compiled path is the one that ran) and through the interpreter."""
+    monkeypatch.setenv("PIL2GPU_EXPR", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def qcode():
     return json.loads((ROOT / "tests" / "golden" / "sm_all_q_code.json").read_text())
