@@ -209,6 +209,16 @@ typedef struct pil2gpu_expr_buffer {
 } pil2gpu_expr_buffer;
 int pil2gpu_calculate_exps_dev(pil2gpu_ctx* ctx, const uint32_t* ops, uint32_t n_ops, const uint64_t* consts, uint32_t n_consts,
                                const pil2gpu_expr_buffer* bufs, uint32_t n_bufs, uint32_t domain_bits, int x_shift);
+/* Host-buffer form (the reference's ctx arrays, prover_helpers.js:33-76): buffers with `read` != 0 are uploaded, those with `written` != 0
+ * come back after the program has run; every buffer holds 2^domain_bits rows of row_words words.  Synchronous. */
+typedef struct pil2gpu_expr_host_buffer {
+    uint64_t* ptr;
+    uint64_t row_words;
+    int32_t read;
+    int32_t written;
+} pil2gpu_expr_host_buffer;
+int pil2gpu_calculate_exps(pil2gpu_ctx* ctx, const uint32_t* ops, uint32_t n_ops, const uint64_t* consts, uint32_t n_consts,
+                           const pil2gpu_expr_host_buffer* bufs, uint32_t n_bufs, uint32_t domain_bits, int x_shift);
 /* The records are compiled at run time into a straight-line kernel (NVRTC, once per device and program -- what compileCode,
  * prover_helpers.js:87-110, does with `new Function`); the interpreter remains as the fallback when libnvrtc is absent
  * (PIL2GPU_EXPR=interp forces it, =jit turns a missing compiler into PIL2GPU_E_UNSUPPORTED).  pil2gpu_expr_jit_check returns the generated

@@ -704,6 +704,36 @@ napi_value FriPol(napi_env env, napi_callback_info info) {
     return rc ? fail_now(env, rc) : nullptr;
 }
 
+// calculateExps(ctx, ops: Int32Array (16 words per record, the u32 bit patterns of pil2gpu_calculate_exps), consts: BigUint64Array (3 per
+//               entry), bufs: BigUint64Array[] (2^domainBits rows each), meta: BigInt64Array (3 per buffer: row words, read, written),
+//               domainBits, xShift)                                                  calculateExps, prover_helpers.js:33-76
+// js/prover_helpers.js compiles the reference's {op, dest, src} records into `ops`; buffers flagged `written` are updated in place.
+napi_value CalculateExps(napi_env env, napi_callback_info info) {
+    Args a(env, info, 7);
+    pil2gpu_ctx* ctx = a.ctx(0);
+    int32_t* ops = nullptr; size_t nops = 0; uint64_t* consts = nullptr; size_t nc = 0; int64_t* meta = nullptr; size_t nmeta = 0;
+    Pages b;
+    a.i32_array(1, &ops, &nops); a.u64_array(2, &consts, &nc);
+    a.pages(3, b.p, b.w, &b.total);
+    a.i64_array(4, &meta, &nmeta);
+    const uint32_t domainBits = a.u32(5), xShift = a.u32(6);
+    a.need(nops > 0 && nops % 16 == 0, "ops holds 16 words per record");
+    a.need(nc % 3 == 0, "consts holds 3 words per entry");
+    a.need(domainBits <= 32 && nmeta == 3 * b.p.size() && b.p.size() <= 24, "bad buffer list (3 meta words per buffer, at most 24 buffers)");
+    if (!a.ok) return nullptr;
+    std::vector<pil2gpu_expr_host_buffer> hb(b.p.size());
+    for (size_t i = 0; a.ok && i < hb.size(); i++) {
+        const int64_t rw = meta[3 * i];
+        uint64_t want = 0;
+        a.need(rw > 0 && shl_fits((uint64_t)rw, domainBits, &want) && b.w[i] == want, "a buffer does not hold rowWords * 2^domainBits words");
+        hb[i].ptr = b.p[i]; hb[i].row_words = (uint64_t)rw; hb[i].read = meta[3 * i + 1] != 0; hb[i].written = meta[3 * i + 2] != 0;
+    }
+    if (!a.ok) return nullptr;
+    int rc = pil2gpu_calculate_exps(ctx, reinterpret_cast<const uint32_t*>(ops), (uint32_t)(nops / 16), consts, (uint32_t)(nc / 3), hb.data(),
+                                    (uint32_t)hb.size(), domainBits, (int)xShift);
+    return rc ? fail_now(env, rc) : nullptr;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // multi-GPU commit group (pil2gpu_shard_*): one handle per GPU, wired across worker processes (shardHandles / shardConnect: the
 // 128-byte handle pairs travel over the fork channel as BigUint64Array(16)) or inside one process (shardConnectLocal).
@@ -920,6 +950,7 @@ napi_value Init(napi_env env, napi_value exports) {
         {"computeEvals", nullptr, ComputeEvals, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"xDivXSubXi", nullptr, XDivXSubXi, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"friPol", nullptr, FriPol, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"calculateExps", nullptr, CalculateExps, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"shardCreate", nullptr, ShardCreate, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"shardHandles", nullptr, ShardHandles, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"shardConnect", nullptr, ShardConnect, nullptr, nullptr, nullptr, napi_default, nullptr},

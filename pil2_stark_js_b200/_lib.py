@@ -38,6 +38,11 @@ class ExprBuffer(ctypes.Structure):
     _fields_ = [("ptr_dev", ctypes.c_void_p), ("row_words", ctypes.c_uint64)]
 
 
+class ExprHostBuffer(ctypes.Structure):
+    """pil2gpu_expr_host_buffer (include/pil2gpu.h)"""
+    _fields_ = [("ptr", ctypes.c_void_p), ("row_words", ctypes.c_uint64), ("read", ctypes.c_int32), ("written", ctypes.c_int32)]
+
+
 class FriTerm(ctypes.Structure):
     """pil2gpu_fri_term (include/pil2gpu.h)"""
     _fields_ = [("buf_dev", ctypes.c_void_p), ("size", ctypes.c_uint64), ("offset", ctypes.c_uint64), ("dim", ctypes.c_uint32),
@@ -84,6 +89,7 @@ _SIGS = {
     "pil2gpu_compute_q_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u64, c_u64, c_u32, c_u32, c_int, ctypes.POINTER(vp), u64p, c_u32,
                                         vp, vp]),
     "pil2gpu_calculate_exps_dev": (c_int, [vp, vp, c_u32, vp, c_u32, vp, c_u32, c_u32, c_int]),
+    "pil2gpu_calculate_exps": (c_int, [vp, vp, c_u32, vp, c_u32, vp, c_u32, c_u32, c_int]),
     "pil2gpu_expr_jit_check": (c_int, [vp, c_u32, vp, c_u32, c_u32, c_int, ctypes.c_char_p, c_u64]),
     "pil2gpu_fri_fold_range_dev": (c_int, [vp, vp, c_int, c_u32, c_u32, c_i32, c_u32, vp, c_u64, c_u64, vp, vp]),
     "pil2gpu_fri_fold_paged": (c_int, [vp, ctypes.POINTER(vp), u64p, c_u32, c_u32, c_u32, c_i32, c_u32, vp, c_int, ctypes.POINTER(vp), u64p, c_u32,

@@ -1022,6 +1022,40 @@ int pil2gpu_fri_pol_dev(pil2gpu_ctx* ctx, const pil2gpu_fri_term* terms, uint32_
     return check_launch(ctx, launches, "fri_pol");
 }
 
+// Host-buffer form of calculateExps: every buffer is a host array of 2^domain_bits rows; buffers with `read` set are uploaded, the
+// program runs on the device, buffers with `written` set come back.  (The device-resident form is what a prover that keeps its extended
+// buffers in HBM calls; this one is the drop-in for the reference's host arrays, prover_helpers.js:33-76.)
+int pil2gpu_calculate_exps(pil2gpu_ctx* ctx, const uint32_t* ops, uint32_t n_ops, const uint64_t* consts, uint32_t n_consts,
+                           const pil2gpu_expr_host_buffer* bufs, uint32_t n_bufs, uint32_t domain_bits, int x_shift) {
+    ENTER(ctx);
+    if (n_ops == 0) return PIL2GPU_OK;
+    if (!bufs && n_bufs) return fail(PIL2GPU_E_INVALID, "null argument");
+    if (domain_bits > 32) return fail(PIL2GPU_E_INVALID, "domain of 2^%u rows exceeds the 2-adicity of the field", domain_bits);
+    if (n_bufs > EXPR_MAX_BUFS) return fail(PIL2GPU_E_UNSUPPORTED, "more than %d buffers", EXPR_MAX_BUFS);
+    const u64 N = 1ULL << domain_bits;
+    size_t words = 0;
+    for (uint32_t b = 0; b < n_bufs; b++) {
+        if (!bufs[b].ptr || bufs[b].row_words == 0) return fail(PIL2GPU_E_INVALID, "buffer %u: null pointer or empty rows", b);
+        words += ev2(N * bufs[b].row_words);
+    }
+    int rc = ensure_ws(ctx, words);
+    if (rc) return rc;
+    pil2gpu_expr_buffer dev[EXPR_MAX_BUFS];
+    size_t off = 0;
+    for (uint32_t b = 0; b < n_bufs; b++) {
+        dev[b].ptr_dev = ctx->ws + off;
+        dev[b].row_words = bufs[b].row_words;
+        if (bufs[b].read) CU(cudaMemcpyAsync(dev[b].ptr_dev, bufs[b].ptr, N * bufs[b].row_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+        off += ev2(N * bufs[b].row_words);
+    }
+    rc = pil2gpu_calculate_exps_dev(ctx, ops, n_ops, consts, n_consts, dev, n_bufs, domain_bits, x_shift);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    for (uint32_t b = 0; b < n_bufs; b++)
+        if (bufs[b].written) CU(cudaMemcpyAsync(bufs[b].ptr, dev[b].ptr_dev, N * bufs[b].row_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PIL2GPU_OK;
+}
+
 // The CUDA source the compiled path generates for a program, and whether NVRTC accepts it for sm_100a (no device needed: tests / tooling).
 // source_out (may be NULL) receives up to cap - 1 characters + NUL; returns 0 = compiles, > 0 = NVRTC error code (message in
 // pil2gpu_last_error), PIL2GPU_E_UNSUPPORTED = no NVRTC on this machine.

@@ -113,6 +113,7 @@ static napi_value big(uint64_t x) { napi_value v = mk(napi_value__::BIGINT); v->
 static napi_value nul() { return mk(napi_value__::NUL); }
 static napi_value ext(void* p) { napi_value v = mk(napi_value__::EXTERNAL); v->ext = p; return v; }
 static napi_value u64arr(size_t n) { napi_value v = mk(napi_value__::TYPEDARRAY); v->ta_type = napi_biguint64_array; v->length = n; v->data = calloc(n ? n : 1, 8); return v; }
+static napi_value i64arr(size_t n) { napi_value v = mk(napi_value__::TYPEDARRAY); v->ta_type = napi_bigint64_array; v->length = n; v->data = calloc(n ? n : 1, 8); return v; }
 static napi_value i32arr(size_t n) { napi_value v = mk(napi_value__::TYPEDARRAY); v->ta_type = napi_int32_array; v->length = n; v->data = calloc(n ? n : 1, 4); return v; }
 static napi_value arr(std::vector<napi_value> e) { napi_value v = mk(napi_value__::ARRAY); v->elems = e; return v; }
 
@@ -139,7 +140,7 @@ int main() {
     printf("registered %zu functions\n", env->exports.size());
     const char* must[] = {"create", "allocPinnedPage", "nttPaged", "ldePaged", "merkelizePaged", "extendAndMerkelizePaged", "computeQPaged", "friFoldPaged", "commit",
                           "treeRoot", "treeGroupProofs", "treeDownload", "treeFree", "treeFromPages", "poseidon", "linearHash", "merkleNNodes", "computeEvals",
-                          "xDivXSubXi", "friPol", "shardCreate", "shardHandles", "shardConnect", "shardConnectLocal", "shardCommit", "shardRoot", "shardOpen",
+                          "xDivXSubXi", "friPol", "calculateExps", "shardCreate", "shardHandles", "shardConnect", "shardConnectLocal", "shardCommit", "shardRoot", "shardOpen",
                           "shardProofs", "shardFree"};
     for (const char* m : must) if (!env->exports.count(m)) { printf("FAIL: %s missing\n", m); failures++; }
     napi_value fake_ctx = ext((void*)0x1);      // never dereferenced: every call below must be rejected before it reaches the library
@@ -167,6 +168,10 @@ int main() {
                  {fake_ctx, arr({u64arr(48)}), num(4), num(2), num(-1), num(4), u64arr(3), num(0), arr({u64arr(11)}), nul(), nul()}, "RangeError", "polOut");
     expect_throw(env, "xDivXSubXi: out wrong size", "xDivXSubXi", {fake_ctx, u64arr(3), i32arr(2), num(3), num(4), u64arr(95)}, "RangeError", "out");
     expect_throw(env, "computeEvals: buf wrong size", "computeEvals", {fake_ctx, u64arr(3), i32arr(2), num(3), num(4), u64arr(79), num(5), u64arr(2)}, "RangeError", "buf");
+    expect_throw(env, "calculateExps: ops not a multiple of 16", "calculateExps", {fake_ctx, i32arr(17), u64arr(3), arr({u64arr(32)}), i64arr(3), num(4), num(1)}, "RangeError", "ops");
+    { napi_value meta = i64arr(3); ((int64_t*)meta->data)[0] = 3; ((int64_t*)meta->data)[1] = 1;
+      expect_throw(env, "calculateExps: buffer of the wrong size", "calculateExps", {fake_ctx, i32arr(16), u64arr(3), arr({u64arr(47)}), meta, num(4), num(1)}, "RangeError", "rowWords"); }
+    expect_throw(env, "calculateExps: ops is a BigUint64Array", "calculateExps", {fake_ctx, u64arr(16), u64arr(3), arr({u64arr(32)}), i64arr(3), num(4), num(1)}, "TypeError", "Int32Array");
     expect_throw(env, "commit: source wrong size", "commit", {fake_ctx, arr({u64arr(15)}), num(2), num(3), num(4), num(0)}, "RangeError", "buffer");
     expect_throw(env, "nttPaged: fractional nPols", "nttPaged", {fake_ctx, arr({u64arr(16)}), arr({u64arr(16)}), num(2.5), num(3), num(0)}, "RangeError", "integer");
     // wrong types are TypeErrors; a null context is rejected

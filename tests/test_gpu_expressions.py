@@ -158,6 +158,32 @@ def test_random_programs_vs_oracle(gpu, qcode, dom, seed):
     assert "cm4_" + dom in cc.written
 
 
+def test_host_buffer_entry_point(gpu, qcode):
+    """pil2gpu_calculate_exps (what the N-API addon's calculateExps and js/prover_helpers.js call): host arrays in, the written buffers
+    updated in place, same values as the oracle; buffers not flagged `written` come back untouched."""
+    import ctypes
+    from pil2_stark_js_b200 import prover_helpers as H, _lib
+    rng = np.random.default_rng(21)
+    d = make_domain_ctx(qcode, rng, 6, 7)
+    code = prover_side_program(qcode)
+    want = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+    X.calculate_exps(want, code, "ext")
+    ctx = ns(d, gpu)
+    cc = H.compile_code(ctx, code, "ext")
+    host = [np.ascontiguousarray(H._host_buffer(ctx, name), dtype=np.uint64).reshape(-1).copy() for name, _ in cc.buffers]
+    before = [h.copy() for h in host]
+    arr = (_lib.ExprHostBuffer * len(host))()
+    for i, ((name, rw), h) in enumerate(zip(cc.buffers, host)):
+        arr[i] = _lib.ExprHostBuffer(h.ctypes.data, rw, 1, 1 if name in cc.written else 0)
+    rc = gpu._L.pil2gpu_calculate_exps(gpu.handle, cc.ops.ctypes.data, len(code), cc.consts.ctypes.data, cc.consts.size // 3, arr, len(host), 7, 1)
+    assert rc == 0, gpu._L.pil2gpu_last_error().decode()
+    for (name, _), h, b in zip(cc.buffers, host, before):
+        if name in cc.written:
+            assert np.array_equal(h, want[name].reshape(-1)), name
+        else:
+            assert np.array_equal(h, b), name
+
+
 def test_program_errors(gpu, qcode):
     from pil2_stark_js_b200 import prover_helpers as H, Pil2GpuError
     rng = np.random.default_rng(5)
