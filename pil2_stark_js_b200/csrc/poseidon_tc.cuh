@@ -32,7 +32,7 @@
 #define PTC_HIST_SMEM 1
 #endif
 #ifndef PTC_UNROLL_J
-#define PTC_UNROLL_J 8      // 8: the rounds of a block are straight-line code (exact multiply-add count); 1: one rolled round body
+#define PTC_UNROLL_J 1      // 1: one rolled round body (47 KB kernel, 107 ms at 2^22 x 256); 8: straight-line blocks (72 KB, 121 ms: instruction cache)
 #endif
 
 constexpr int ptc_unroll_j = PTC_UNROLL_J;
