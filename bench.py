@@ -617,11 +617,11 @@ def run_next_rows(g, L, check, vp, npp, torch, time_phase, reps, n_bits, cols, b
             words += rw << ext_bits
 
         def phase_expr():
-            check(L.pil2gpu_calculate_exps_dev(g.h, vp(cc.ops.ctypes.data), len(code), vp(cc.consts.ctypes.data), cc.consts.size // 3, ebufs, len(cc.buffers),
+            check(L.pil2gpu_calculate_exps_dev(g.h, vp(cc.ops.ctypes.data), cc.ops.size // 16, vp(cc.consts.ctypes.data), cc.consts.size // 3, ebufs, len(cc.buffers),
                                                ext_bits, 1))
         phase_expr()
         t_ex = time_phase(phase_expr, reps)
-        expr = {"s": t_ex, "shape": f"{len(code)}-record quotient program of the sm_all AIR (51 columns in 4 buffers, {cc.n_slots} live temporaries) over 2^{ext_bits} rows",
+        expr = {"s": t_ex, "shape": f"{len(code)}-record quotient program of the sm_all AIR ({cc.ops.size // 16} records after dropping dead temporaries; 51 columns in 4 buffers, {cc.n_slots} live temporaries) over 2^{ext_bits} rows",
                 "algorithmic_bytes": 8 * words, "GBps": 8 * words / t_ex / 1e9, "frac_hbm": 8 * words / t_ex / 1e9 / hbm_peak,
                 "records_per_s": len(code) * float(1 << ext_bits) / t_ex}
         del keep

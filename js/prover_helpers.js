@@ -61,6 +61,23 @@ function compileCode(ctx, code, dom) {
         const st = "cm" + p.stage;
         return [st + "_" + dom, p.stagePos, info.mapSectionsN[st], p.dim];
     };
+    // validation first (on the program as given: dead records are checked too)
+    const seen = new Set();
+    for (const c of code) {
+        if (!(c.op in OPCODES)) throw new Error("Invalid op:" + c.op);
+        const nsrc = c.op === "copy" ? 1 : (c.op === "muladd" ? 3 : 2);
+        if (c.src.length !== nsrc) throw new Error("op " + c.op + " takes " + nsrc + " sources");
+        for (const s of c.src) if (s.type === "tmp" && !seen.has(s.id)) throw new Error("temporary " + s.id + " read before it is written");
+        if (c.dest.type === "tmp") seen.add(c.dest.id);
+    }
+    // dead records: temporaries nobody reads (the code generator leaves some behind) are dropped, transitively
+    for (;;) {
+        const read = new Set();
+        code.forEach((c) => c.src.forEach((s) => { if (s.type === "tmp") read.add(s.id); }));
+        const live = code.filter((c) => c.dest.type !== "tmp" || read.has(c.dest.id));
+        if (live.length === code.length) break;
+        code = live;
+    }
     const lastUse = new Map();
     code.forEach((c, k) => c.src.forEach((s) => { if (s.type === "tmp") lastUse.set(s.id, k); }));
     const slotOf = new Map(), free = [], tmpDim = new Map();

@@ -85,6 +85,28 @@ def compile_code(ctx, code, dom):
         st = "cm%d" % p["stage"]
         return st + "_" + dom, p["stagePos"], info["mapSectionsN"][st], p["dim"]
 
+    # validation first (on the program as given: dead records are checked too)
+    seen = set()
+    for c in code:
+        if c["op"] not in OPCODES:
+            raise ValueError("Invalid op:" + str(c["op"]))
+        nsrc = {"copy": 1, "muladd": 3}.get(c["op"], 2)
+        if len(c["src"]) != nsrc:
+            raise ValueError("op %s takes %d sources" % (c["op"], nsrc))
+        for s in c["src"]:
+            if s["type"] == "tmp" and s["id"] not in seen:
+                raise ValueError("temporary %d read before it is written" % s["id"])
+        if c["dest"]["type"] == "tmp":
+            seen.add(c["dest"]["id"])
+    # dead records: a temporary nobody reads (the code generator leaves some behind: 23 of the 169 records of the sm_all quotient
+    # program) -- dropped, transitively, before slots are assigned
+    code = list(code)
+    while True:
+        read = {s["id"] for c in code for s in c["src"] if s["type"] == "tmp"}
+        live = [c for c in code if c["dest"]["type"] != "tmp" or c["dest"]["id"] in read]
+        if len(live) == len(code):
+            break
+        code = live
     # liveness of the temporaries: last record that reads each id
     last_use = {}
     for k, c in enumerate(code):
@@ -209,7 +231,7 @@ def calculateExps(ctx, code, dom, debug=False, ret=False, global_=False):
                 owned.append((name, b))
                 ptr = b.ptr.value
             arr[i] = _lib.ExprBuffer(ptr, row_words)
-        check(g._L.pil2gpu_calculate_exps_dev(g.handle, ctypes.c_void_p(cc.ops.ctypes.data), len(records), ctypes.c_void_p(cc.consts.ctypes.data) if cc.consts.size else None,
+        check(g._L.pil2gpu_calculate_exps_dev(g.handle, ctypes.c_void_p(cc.ops.ctypes.data), cc.ops.size // OP_WORDS, ctypes.c_void_p(cc.consts.ctypes.data) if cc.consts.size else None,
                                               cc.consts.size // 3, arr, len(cc.buffers), ctx.nBits if dom == "n" else ctx.nBitsExt, 1 if dom == "ext" else 0))
         for name, b in owned:
             if name in cc.written:

@@ -175,7 +175,7 @@ def test_host_buffer_entry_point(gpu, qcode):
     arr = (_lib.ExprHostBuffer * len(host))()
     for i, ((name, rw), h) in enumerate(zip(cc.buffers, host)):
         arr[i] = _lib.ExprHostBuffer(h.ctypes.data, rw, 1, 1 if name in cc.written else 0)
-    rc = gpu._L.pil2gpu_calculate_exps(gpu.handle, cc.ops.ctypes.data, len(code), cc.consts.ctypes.data, cc.consts.size // 3, arr, len(host), 7, 1)
+    rc = gpu._L.pil2gpu_calculate_exps(gpu.handle, cc.ops.ctypes.data, cc.ops.size // 16, cc.consts.ctypes.data, cc.consts.size // 3, arr, len(host), 7, 1)
     assert rc == 0, gpu._L.pil2gpu_last_error().decode()
     for (name, _), h, b in zip(cc.buffers, host, before):
         if name in cc.written:
@@ -195,9 +195,13 @@ def test_program_errors(gpu, qcode):
     with pytest.raises(ValueError):
         H.calculateExps(ctx, [{"op": "copy", "dest": {"type": "tmp", "id": 1, "dim": 1}, "src": [{"type": "tmp", "id": 0, "dim": 1}]}], "ext")
     wide = [{"op": "copy", "dest": {"type": "tmp", "id": k, "dim": 1}, "src": [{"type": "x"}]} for k in range(70)]
-    wide += [{"op": "add", "dest": {"type": "tmp", "id": 100 + k, "dim": 1}, "src": [{"type": "tmp", "id": k, "dim": 1}, {"type": "x"}]} for k in range(70)]
+    wide += [{"op": "add", "dest": {"type": "tmp", "id": 100 + k, "dim": 1},
+              "src": [{"type": "tmp", "id": k, "dim": 1}, {"type": "tmp", "id": 99 + k, "dim": 1} if k else {"type": "x"}]} for k in range(70)]
+    wide.append({"op": "copy", "dest": {"type": "q", "id": 0, "dim": 3}, "src": [{"type": "tmp", "id": 169, "dim": 1}]})
     with pytest.raises(ValueError):
         H.calculateExps(ctx, wide, "ext")                              # 70 temporaries alive at once
+    # records whose temporary nobody reads are dropped before slots are assigned: the same 140 records without the final store are an empty program
+    assert H.compile_code(ctx, wide[:-1], "ext").ops.size == 0
     # the C ABI validates the records itself
     bad = np.zeros(16, dtype=np.uint32)
     bad[0], bad[1] = 9, 2
