@@ -277,3 +277,33 @@ def test_golden_quotient_split_convention(golden):
         xin = S.f3_mul(xin, xi)
     recombined = S.f3_add([int(x) for x in ev[0]], S.f3_mul(xin, [int(x) for x in ev[1]]))
     assert recombined == S.eval_pol(coef, xi)
+
+
+def test_byte_limb_contraction_with_the_weight_in_the_small_operand():
+    """The identity behind the second tensor-core formulation of the evaluation sums and the FRI polynomial (csrc/evals.cuh
+    evals_mma2_kernel, csrc/fripol.cuh fripol_mma2_kernel): with A[(m), (row, b)] = byte m of (coef[row] * 2^(8b) mod p) and
+    B[(row, b)] = byte b of value[row] -- the bytes of the big operand exactly as they lie in memory -- the exact integer sums
+    D_m = sum_(row, b) A B recombine to sum_row coef[row] * value[row] mod p as sum_m 2^(8m) D_m, also when the operands are
+    non-canonical 64-bit words and when D_m is folded in chunks the way the kernels fold their s32 accumulators."""
+    import random
+    rnd = random.Random(31)
+    rows = 300
+    coef = [rnd.randrange(1 << 64) for _ in range(rows)]          # any 64-bit representatives
+    val = [rnd.randrange(1 << 64) for _ in range(rows)]
+    coef[0] = val[0] = (1 << 64) - 1
+    want = sum(c * v for c, v in zip(coef, val)) % S.P
+    total = 0
+    for lo in range(0, rows, 128):                                   # chunked: every chunk's limb sums are recombined and added mod p
+        D = [0] * 8
+        for r in range(lo, min(lo + 128, rows)):
+            x = coef[r]
+            for b in range(8):                                       # x = coef * 2^(8b) mod p, any representative below 2^64
+                vb = (val[r] >> (8 * b)) & 0xFF
+                for m in range(8):
+                    D[m] += ((x >> (8 * m)) & 0xFF) * vb
+                x = (x << 8) % S.P if b < 7 else x
+        assert max(D) < 1 << 31                                      # 128 rows * 8 limbs * 255^2: the s32 accumulators of a chunk hold
+        L = D[0] + (D[1] << 8) + (D[2] << 16) + (D[3] << 24)
+        H = D[4] + (D[5] << 8) + (D[6] << 16) + (D[7] << 24)
+        total = (total + L + (H << 32)) % S.P
+    assert total == want
