@@ -221,7 +221,8 @@ int pil2gpu_calculate_exps(pil2gpu_ctx* ctx, const uint32_t* ops, uint32_t n_ops
                            const pil2gpu_expr_host_buffer* bufs, uint32_t n_bufs, uint32_t domain_bits, int x_shift);
 /* The records are compiled at run time into a straight-line kernel (NVRTC, once per device and program -- what compileCode,
  * prover_helpers.js:87-110, does with `new Function`); the interpreter remains as the fallback when libnvrtc is absent
- * (PIL2GPU_EXPR=interp forces it, =jit turns a missing compiler into PIL2GPU_E_UNSUPPORTED).  pil2gpu_expr_jit_check returns the generated
+ * (PIL2GPU_EXPR=interp forces it, =jit turns a missing compiler into PIL2GPU_E_UNSUPPORTED; PIL2GPU_JIT_CACHE=<dir> keeps the compiled
+ * kernels across processes).  pil2gpu_expr_jit_check returns the generated
  * source (up to cap - 1 characters) and 0 when NVRTC compiles it for sm_100a; it needs no device. */
 int pil2gpu_expr_jit_check(const uint32_t* ops, uint32_t n_ops, const uint64_t* row_words, uint32_t n_bufs, uint32_t domain_bits, int x_shift,
                            char* source_out, uint64_t cap);

@@ -164,6 +164,33 @@ def test_random_programs_vs_oracle(gpu, qcode, dom, seed):
     assert "cm4_" + dom in cc.written
 
 
+def test_compiled_kernels_persist_in_the_cache_directory(qcode, tmp_path):
+    """PIL2GPU_JIT_CACHE: the first process compiles the golden program and leaves a cubin in the directory, a second process loads it
+    (no NVRTC call: much faster first evaluation) and computes the same q_ext."""
+    import os, subprocess, sys, time
+    code = (
+        "import json, sys, time, types, pathlib; import numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from test_oracle_expressions import prover_side_program, make_domain_ctx\n"
+        "import pil2_stark_js_b200 as m\nfrom pil2_stark_js_b200 import prover_helpers as H\n"
+        "qcode = json.loads(pathlib.Path(%r).read_text())\n"
+        "d = make_domain_ctx(qcode, np.random.default_rng(4), 6, 7)\n"
+        "ctx = types.SimpleNamespace(**d); ctx.gpu = m.default_context(0)\n"
+        "ctx.gpu.sync(); t0 = time.perf_counter(); H.calculateExps(ctx, prover_side_program(qcode), 'ext'); dt = time.perf_counter() - t0\n"
+        "np.save(sys.argv[1], ctx.q_ext); print(dt)\n"
+    ) % (str(ROOT), str(ROOT / "tests"), str(ROOT / "tests" / "golden" / "sm_all_q_code.json"))
+    env = dict(os.environ, PIL2GPU_EXPR="jit", PIL2GPU_JIT_CACHE=str(tmp_path))
+    out = []
+    for k in range(2):
+        r = subprocess.run([sys.executable, "-c", code, str(tmp_path / ("q%d.npy" % k))], env=env, capture_output=True, text=True, timeout=600)
+        if r.returncode != 0 and "NVRTC" in r.stderr and "not found" in r.stderr:
+            pytest.skip("NVRTC not available")
+        assert r.returncode == 0, r.stderr[-800:]
+        out.append(float(r.stdout.strip().splitlines()[-1]))
+        assert len(list(tmp_path.glob("pil2gpu_expr_*_sm100a.cubin"))) == 1
+    assert np.array_equal(np.load(tmp_path / "q0.npy"), np.load(tmp_path / "q1.npy"))
+    assert out[1] < 0.5 * out[0], out                                # the second process did not compile
+
+
 def test_host_buffer_entry_point(gpu, qcode):
     """pil2gpu_calculate_exps (what the N-API addon's calculateExps and js/prover_helpers.js call): host arrays in, the written buffers
     updated in place, same values as the oracle; buffers not flagged `written` come back untouched."""
