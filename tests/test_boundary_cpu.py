@@ -134,3 +134,26 @@ def test_expression_jit_source_compiles_offline():
     bad = np.zeros(16, dtype=np.uint32)
     bad[0] = 9
     assert L.pil2gpu_expr_jit_check(bad.ctypes.data, 1, None, 0, 4, 1, None, 0) == -1
+
+
+def test_js_shims_only_call_exported_addon_functions():
+    """Node is absent, so the JS shims never run here: at least every `addon.<name>` they call must be an export of the N-API addon, and
+    their brackets must balance (a crude stand-in for `node --check`)."""
+    import re
+    exported = set(re.findall(r'\{"(\w+)", nullptr, \w+, nullptr', (ROOT / "napi" / "pil2gpu_addon.cc").read_text()))
+    assert "calculateExps" in exported and len(exported) >= 30
+    for f in sorted((ROOT / "js").glob("*.js")):
+        src = f.read_text()
+        for name in set(re.findall(r"\baddon\.(\w+)\s*\(", src)):
+            assert name in exported, f"{f.name} calls addon.{name}, which the addon does not export"
+        s = re.sub(r"//[^\n]*", "", src)
+        s = re.sub(r"/\*.*?\*/", "", s, flags=re.S)
+        for q in ('"', "'", "`"):
+            s = re.sub(q + r"(?:\\.|[^" + q + r"\\])*" + q, q + q, s)
+        stack, pairs = [], {")": "(", "]": "[", "}": "{"}
+        for ch in s:
+            if ch in "([{":
+                stack.append(ch)
+            elif ch in ")]}":
+                assert stack and stack.pop() == pairs[ch], f"{f.name}: unbalanced {ch}"
+        assert not stack, f"{f.name}: unclosed {stack[-1]}"
