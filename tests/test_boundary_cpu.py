@@ -125,7 +125,7 @@ def test_expression_jit_source_compiles_offline():
     recs = cc.ops.reshape(-1, 16)
     n_f3_products = sum(1 for r in recs if r[0] in (2, 4) and ((r[7] >> 8) & 255) == 3 and ((r[10] >> 8) & 255) == 3)
     assert len(recs) == 146 and cc.n_slots == 17              # 23 of the program's 169 records compute temporaries nobody reads: dropped
-    assert body.count("\n    { const gl3 a = ") == len(recs) and body.count("gl3_mul(a, b)") == n_f3_products and "xval" in body
+    assert body.count("\n    { const gl3 a = ") == len(recs) and body.count("f3_mul(a, b)") == n_f3_products and "xval" in body
     L.pil2gpu_last_error.restype = ctypes.c_char_p
     if rc == -5:                                                        # PIL2GPU_E_UNSUPPORTED: no libnvrtc on this machine
         import pytest
