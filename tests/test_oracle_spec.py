@@ -257,3 +257,49 @@ def test_tensor_core_partial_rounds_model_vs_oracle():
     blocks, final = g.tables()
     inc = (root / "pil2_stark_js_b200/csrc/poseidon_tc_consts.inc").read_text()
     assert "0x%016xULL" % blocks[1][100] in inc and "0x%016xULL" % final[-1] in inc and "POSEIDON_TC_WORDS 8448" in inc
+
+
+def test_lazy_f3_product_accumulator_model():
+    """csrc/gl.cuh gl3_mul accumulates the 12 partial products of an F3 product lazily in three 64-bit columns with carry counts and
+    reduces each coordinate once (gl_acc_mac / gl_acc_reduce: low 128 bits through 2^64 = 2^32 - 1 and 2^96 = -1, what lies above 2^128
+    comes off as top * 2^32 since 2^128 = -2^32 mod p).  The same word-level steps in Python give the oracle's F3 product, for random
+    and for all-ones (non-canonical, maximal carries) operands."""
+    import random
+    M32, M64 = (1 << 32) - 1, (1 << 64) - 1
+
+    def mac(A, x, y):                                     # A = [a0, c0, a1, c1, a2, c2]: 64-bit columns + carry counts
+        x0, x1, y0, y1 = x & M32, x >> 32, y & M32, y >> 32
+        for col, p in ((0, x0 * y0), (2, x0 * y1), (2, x1 * y0), (4, x1 * y1)):
+            s = A[col] + p
+            A[col], A[col + 1] = s & M64, A[col + 1] + (s >> 64)
+
+    def reduce(A):
+        a0, c0, a1, c1, a2, c2 = A
+        l1 = (a0 >> 32) + (a1 & M32)
+        h0 = (a2 & M32) + (a1 >> 32) + (l1 >> 32)
+        h1 = (a2 >> 32) + (h0 >> 32)
+        top = c2 + (h1 >> 32)
+        h0 = (h0 & M32) + c0
+        h1 = (h1 & M32) + c1 + (h0 >> 32)
+        top += h1 >> 32
+        lo = ((l1 & M32) << 32) | (a0 & M32)
+        hi = ((h1 & M32) << 32) | (h0 & M32)
+        assert top < 1 << 31
+        # exactness of the decomposition, then the reduction identities
+        total = a0 + (c0 << 64) + ((a1 + (c1 << 64)) << 32) + ((a2 + (c2 << 64)) << 64)
+        assert total == lo + (hi << 64) + (top << 128)
+        r = (lo + (hi & M32) * ((1 << 32) - 1) - (hi >> 32)) % S.P           # gl_reduce128: 2^64 = 2^32 - 1, 2^96 = -1
+        return (r - (top << 32)) % S.P                                        # 2^128 = -2^32
+
+    def f3_mul_lazy(a, b):
+        r0, r1, r2 = [0] * 6, [0] * 6, [0] * 6
+        for acc, terms in ((r0, ((0, 0), (1, 2), (2, 1))), (r1, ((0, 1), (1, 0), (1, 2), (2, 1), (2, 2))), (r2, ((0, 2), (1, 1), (2, 0), (2, 2)))):
+            for i, j in terms:
+                mac(acc, a[i], b[j])
+        return [reduce(r0), reduce(r1), reduce(r2)]
+
+    rnd = random.Random(17)
+    cases = [([M64] * 3, [M64] * 3), ([S.P - 1] * 3, [S.P - 1] * 3), ([0, 1, 0], [0, 0, 1])]
+    cases += [([rnd.randrange(1 << 64) for _ in range(3)], [rnd.randrange(1 << 64) for _ in range(3)]) for _ in range(200)]
+    for a, b in cases:
+        assert f3_mul_lazy(a, b) == S.f3_mul([x % S.P for x in a], [x % S.P for x in b])
