@@ -303,3 +303,66 @@ def test_lazy_f3_product_accumulator_model():
     cases += [([rnd.randrange(1 << 64) for _ in range(3)], [rnd.randrange(1 << 64) for _ in range(3)]) for _ in range(200)]
     for a, b in cases:
         assert f3_mul_lazy(a, b) == S.f3_mul([x % S.P for x in a], [x % S.P for x in b])
+
+
+def test_three_level_post_order_walk_model():
+    """csrc/merkle.cuh merkle_levels_kernel: thread i walks the depth-LV subtree over input nodes [2^LV i, 2^LV (i+1)) in post-order with a
+    rolled loop (leaf pair, leaf pair, their parent, ...).  The same state machine in Python -- pending level, parked left siblings,
+    'a node exists iff its first input node does', missing nodes count as the zero pad -- reproduces every level of the oracle's tree
+    for ragged sizes and LV = 1, 2, 3."""
+    def level_offsets(p_in, n_in, lv):
+        off, n = [p_in], n_in
+        for _ in range(lv):
+            off.append(off[-1] + 4 * (n + (n & 1)))
+            n = (n + 1) // 2
+        return off
+
+    def walk(nodes, p_in, n_in, lv, i):
+        first = i << lv
+        if first >= n_in:
+            return
+        off = level_offsets(p_in, n_in, lv)
+        left, cur, k, pending = {}, [0, 0, 0, 0], 0, 0
+        for _ in range((1 << lv) - 1):
+            if pending == 0:
+                lvl, idx = 1, (first >> 1) + k
+                n0 = 2 * idx
+                a = list(nodes[p_in + 4 * n0:p_in + 4 * n0 + 4])
+                b = list(nodes[p_in + 4 * (n0 + 1):p_in + 4 * (n0 + 1) + 4])       # n0 + 1 == n_in: the stored zero pad
+                k += 1
+            else:
+                lvl, idx = pending + 1, (first >> (pending + 1)) + ((k - 1) >> pending)
+                a, b = left[pending], cur
+            if (idx << lvl) < n_in:
+                cur = [int(x) for x in S.poseidon_perm([int(x) for x in a] + [int(x) for x in b] + [0, 0, 0, 0])[:4]]
+                nodes[off[lvl] + 4 * idx:off[lvl] + 4 * idx + 4] = cur
+            else:
+                cur = [0, 0, 0, 0]
+            j = (k - 1) >> (lvl - 1)
+            if (j & 1) and lvl < lv:
+                pending = lvl
+            else:
+                if lvl < lv:
+                    left[lvl] = cur
+                pending = 0
+
+    import random
+    rng = random.Random(3)
+    for height in (8, 11, 13, 16, 21, 37):
+        leaves = [rng.randrange(S.P) for _ in range(4 * height)]
+        want = S.merkelize([int(x) for x in leaves], 4, height)["nodes"]   # width 4: the leaf digest of a row is the row itself
+        for lv in (1, 2, 3):
+            nodes = [0] * len(want)
+            nodes[:4 * height] = [int(x) for x in leaves]
+            p_in, n = 0, height
+            while n > 1:
+                remaining, m = 0, n
+                while m > 1:
+                    m, remaining = (m + 1) // 2, remaining + 1
+                step = min(lv, remaining)                                  # the launcher never walks past the root either
+                for i in range((n + (1 << step) - 1) >> step):
+                    walk(nodes, p_in, n, step, i)
+                for _ in range(step):
+                    p_in += 4 * (n + (n & 1))
+                    n = (n + 1) // 2
+            assert nodes == [int(x) for x in want], (height, lv)
